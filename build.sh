@@ -1,0 +1,17 @@
+#!/bin/bash
+# Builds the product shared library in-tree (it travels to the GPU box with the repo snapshot).
+set -e
+cd "$(dirname "$0")/bwa_mem_quickassist_b200"
+NVCC=${NVCC:-nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function"
+mkdir -p build
+for f in ksw_generic ksw_fast ksw_runtime; do
+  if [ csrc/$f.cu -nt build/$f.o ] || [ -n "$(find csrc include ../include -newer build/$f.o 2>/dev/null | head -1)" ] || [ ! -f build/$f.o ]; then
+    $NVCC $FLAGS -c csrc/$f.cu -o build/$f.o
+  fi
+done
+if [ ! -f build/ksw_pack.o ] || [ -n "$(find csrc ../include -newer build/ksw_pack.o | head -1)" ]; then
+  g++ -O3 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c csrc/ksw_pack.cpp -o build/ksw_pack.o
+fi
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libksw_b200.so build/ksw_generic.o build/ksw_fast.o build/ksw_runtime.o build/ksw_pack.o -lcudart_static -lpthread -ldl -lrt
+echo "built $(pwd)/libksw_b200.so"

@@ -1,0 +1,53 @@
+// ksw_dev.cuh — device-side records shared by the kernels and the host runtime.
+//
+// HBM layout of one packed batch (built by ksw_pack.cpp, consumed by the kernels):
+//
+//   d_jobs : DevJob[n]      32 B each, in *binned* order (fast class first, then generic;
+//                           inside a class sorted so that the 32 jobs of a warp have similar
+//                           row counts and band widths)
+//   d_pool : uint32[]       per job, 16-byte aligned:  query 2-bit words | target 2-bit words
+//                           base k of a sequence sits in word k/16 at bits 2*(k%16)
+//   d_npool: uint32[]       only for the (rare) jobs whose query or target holds an N (code 4):
+//                           [query N-mask words][target N-mask words], 1 bit per base; the base
+//                           itself is stored as 0 in the 2-bit stream
+//   d_res  : DevRes[n]      24 B each, indexed by the CALLER's job index (DevJob::idx)
+//
+// Algorithmic HBM bytes per job = 32 (record) + 16*ceil((ceil(qlen/16)+ceil(tlen/16))*4/16) (sequences)
+//                                 + 24 (result); for 101x101: 32 + 64 + 24 = 120 B.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KSW_HD __host__ __device__ __forceinline__
+#else
+#define KSW_HD inline
+#endif
+
+struct DevJob {
+	uint32_t seq_off;   // offset of the job's packed sequences in d_pool, in 16-byte units
+	uint32_t idx;       // caller's index of this job
+	int32_t  qlen, tlen;
+	int32_t  h0;        // already max(h0,0)              (ksw.c:384)
+	int32_t  w;         // already clamped by the reference rule (ksw.c:398-406), done on the host
+	uint32_t flags;     // bit0: query N-mask present, bit1: target N-mask present
+	uint32_t nmask_off; // word offset of the job's N masks in d_npool (valid iff flags != 0)
+};
+static_assert(sizeof(DevJob) == 32, "DevJob must be 32 bytes");
+
+struct DevRes {
+	int32_t score, qle, tle, gtle, gscore, max_off;
+};
+static_assert(sizeof(DevRes) == 24, "DevRes must be 24 bytes");
+
+struct KswParams {          // passed by value as a kernel parameter (constant bank)
+	int8_t  mat[25];
+	int8_t  pad[3];
+	int32_t o_del, e_del, o_ins, e_ins;
+	int32_t zdrop;
+};
+
+#define KSW_FLAG_QN 1u
+#define KSW_FLAG_TN 2u
+
+static KSW_HD uint32_t ksw_words2(int len) { return (uint32_t)((len + 15) >> 4); }
+static KSW_HD uint32_t ksw_words1(int len) { return (uint32_t)((len + 31) >> 5); }

@@ -1,0 +1,95 @@
+// ksw_fast.cu — the fast extension kernel for sm_100a: one job per lane, one warp per CTA,
+// H/E columns and PRMT score selectors of the 32 jobs interleaved in shared memory
+// (quad q of lane l at hq[q*32+l]: every LDS.128/STS.128 of a warp is conflict-free whatever
+// column each lane is at), DPX s16x2 arithmetic (see ksw_fast_core.h for the per-lane logic).
+//
+// Scheduling: persistent CTAs (SM count x CTAs that fit by shared memory); each lane pulls its
+// next job from a global counter (warp-aggregated atomicAdd) as soon as its previous job ends,
+// so lanes only wait for each other inside one DP row, never for a whole job.  Jobs arrive binned
+// (ksw_pack.cpp) so that neighbouring lanes sweep bands of similar width.
+#include <cuda_runtime.h>
+#include "ksw_dev.cuh"
+#include "ksw_fast_core.h"
+#include "ksw_launch.h"
+
+namespace {
+
+constexpr int T = KSW_FAST_THREADS;   // 32: one warp per CTA
+
+__global__ void __launch_bounds__(T)
+ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
+                const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap,
+                unsigned long long *__restrict__ counter, DevRes *__restrict__ res)
+{
+	extern __shared__ uint4 smem[];
+	const int lane = threadIdx.x;
+	uint4 *hq = smem;
+	uint32_t *sq = reinterpret_cast<uint32_t *>(hq + (size_t)nq_cap * T);
+	uint2 *mrow = reinterpret_cast<uint2 *>(sq + (size_t)nq_cap * T);
+	if (lane < 5) mrow[lane] = ksw_fast_matrow(P, lane);
+	__syncwarp();
+
+	KswFastConst K;
+	ksw_fast_make_const(P, K);
+	const KswFastMem<T> M{hq + lane, sq + lane};
+	KswFastLane L;
+	L.tlen = 0; L.i = 0;
+	enum { IDLE = 0, RUN = 1, DONE = 2 };
+	int state = IDLE;
+
+	while (true) {
+		const unsigned need = __ballot_sync(0xffffffffu, state == IDLE);
+		if (need) {
+			const int leader = __ffs(need) - 1;
+			unsigned long long base = 0;
+			if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (state == IDLE) {
+				const long long k = (long long)base + __popc(need & ((1u << lane) - 1u));
+				if (k < n_jobs) {
+					const DevJob jb = jobs[k];
+					ksw_fast_setup<T>(L, M, K, jb, pool, npool);
+					state = RUN;
+				} else state = DONE;
+			}
+		}
+		if (__all_sync(0xffffffffu, state == DONE)) break;
+		if (state == RUN) {
+			if (ksw_fast_row<T>(L, M, K, mrow)) {
+				DevRes r;
+				ksw_fast_result(L, r);
+				res[L.idx] = r;
+				state = IDLE;
+			}
+		}
+	}
+}
+
+} // namespace
+
+size_t ksw_fast_smem_bytes(int qmax)
+{
+	return (size_t)KSW_FAST_QUADS(qmax) * T * (sizeof(uint4) + sizeof(uint32_t)) + 5 * sizeof(uint2) + 8;
+}
+
+cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
+                            const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
+                            DevRes *res, cudaStream_t st)
+{
+	if (n_jobs <= 0) return cudaSuccess;
+	const size_t smem = ksw_fast_smem_bytes(qmax);
+	cudaError_t e = cudaFuncSetAttribute(ksw_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_fast_kernel, T, smem);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	long long blocks = (long long)sm_count * per_sm;
+	const long long need = (n_jobs + T - 1) / T;
+	if (blocks > need) blocks = need;
+	e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+	if (e != cudaSuccess) return e;
+	ksw_fast_kernel<<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
+	                                                    KSW_FAST_QUADS(qmax), counter, res);
+	return cudaGetLastError();
+}

@@ -1,0 +1,40 @@
+// ksw_pack.h — host packer: caller-order byte-coded jobs -> binned DevJob[] + 2-bit pool + N side pool.
+// Plain C++ (no CUDA calls) so that the same packer feeds the GPU runtime and the CPU emulation used
+// by the tests.  Two phases so the caller can size its (pinned) buffers in between.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/ksw_b200.h"
+#include "ksw_dev.cuh"
+
+#define KSW_FAST_CLASSES 3
+static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {128, 256, 512};
+
+struct KswPackPlan {
+	int64_t n = 0, n_fast = 0, n_generic = 0;
+	// the fast jobs come first, grouped in KSW_FAST_CLASSES query-length classes (one launch each,
+	// so a few long queries do not shrink everybody's occupancy); then the generic jobs
+	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0};
+	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0};
+	size_t pool_bytes = 0;             // bytes of the 2-bit pool (multiple of 16)
+	int qmax_generic = 0;
+	int maxsc = 0;
+	std::vector<uint32_t> order;       // binned position -> caller index
+	std::vector<uint32_t> seq_off;     // binned position -> pool offset in 16-byte units (n+1 entries)
+};
+
+// fast_qmax: largest qlen the fast kernel accepts (0 = fast kernel disabled: everything is generic)
+int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs, int fast_qmax,
+                  int n_threads, KswPackPlan &plan, std::string &err);
+
+// fills dj[0..n) and pool[0..pool_bytes/4); N masks of the rare jobs that have them are appended to nmask
+int ksw_pack_fill(const KswPackPlan &plan, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs,
+                  const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
+                  std::vector<uint32_t> &nmask, int n_threads);
+
+void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P);
+
+// the reference's band clamp (ksw.c:398-406), evaluated with the identical C expression
+int ksw_clamp_w(int qlen, int maxsc, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus);
+int ksw_mat_max(const int8_t *mat);

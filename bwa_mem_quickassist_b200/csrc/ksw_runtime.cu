@@ -1,0 +1,438 @@
+// ksw_runtime.cu — host side of the C ABI declared in include/ksw_b200.h:
+// contexts, the packer (2-bit + N side masks, length binning), H2D/D2H staging on a
+// per-context stream, kernel dispatch, and the scalar ksw_extend/ksw_extend2 wrappers.
+//
+// There is deliberately NO CPU implementation of the DP in this file: every result comes
+// from a kernel launch.  If CUDA is unusable the calls fail loudly.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ksw_b200.h"
+#include "ksw_dev.cuh"
+#include "ksw_launch.h"
+#include "ksw_pack.h"
+
+// ------------------------------------------------------------------ small helpers
+namespace {
+
+struct PinnedBuf {            // grow-only pinned host buffer
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 4096;
+		cudaError_t e = cudaMallocHost(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct DevBuf {               // grow-only device buffer
+	void *p = nullptr; size_t cap = 0;
+	cudaError_t reserve(size_t bytes) {
+		if (bytes <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 4096;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+// ------------------------------------------------------------------ opaque types
+struct ksw_b200_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+	int pack_threads = 8;
+	int64_t launches = 0;
+	// staging reused by ksw_b200_extend_batch / upload
+	PinnedBuf h_jobs, h_pool, h_npool, h_res;
+	// scratch of the generic kernel
+	DevBuf d_eh, d_qc, d_counter;
+	// cached batch buffers for the one-shot entry (avoid cudaMalloc per call)
+	ksw_b200_batch *cached = nullptr;
+};
+
+struct ksw_b200_batch {
+	int64_t n = 0, n_fast = 0, n_generic = 0;
+	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0};
+	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0};
+	KswParams P;
+	DevBuf d_jobs, d_pool, d_npool, d_res;
+	size_t pool_bytes = 0, npool_bytes = 0;
+	int qmax_generic = 0;
+};
+
+namespace {
+
+int fail(ksw_b200_ctx *ctx, int code, const std::string &msg)
+{
+	if (ctx) ctx->err = msg;
+	return code;
+}
+#define CU(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess)                                                                    \
+			return fail(ctx, 100 + (int)e__, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+	} while (0)
+
+struct HostPacked {
+	KswPackPlan plan;
+	size_t npool_bytes = 0;
+};
+
+int fast_qmax_enabled()
+{
+	static const int v = [] {
+		const char *s = getenv("KSW_B200_DISABLE_FAST");
+		return (s && *s && *s != '0') ? 0 : KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1];
+	}();
+	return v;
+}
+
+// Builds DevJob[] (binned order), the 2-bit pool and the N side pool in the ctx's pinned staging.
+int pack_host(ksw_b200_ctx *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+              const uint8_t *qpool, const uint8_t *tpool, HostPacked &hp)
+{
+	std::string err;
+	int rc = ksw_pack_plan(cfg, n, jobs, fast_qmax_enabled(), ctx->pack_threads, hp.plan, err);
+	if (rc) return fail(ctx, rc, err);
+	CU(ctx->h_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
+	CU(ctx->h_pool.reserve(std::max<size_t>(hp.plan.pool_bytes, 16)));
+	std::vector<uint32_t> nmask;
+	rc = ksw_pack_fill(hp.plan, cfg, jobs, qpool, tpool, (DevJob *)ctx->h_jobs.p, (uint32_t *)ctx->h_pool.p,
+	                   nmask, ctx->pack_threads);
+	if (rc) return fail(ctx, rc, "ksw_b200: packing failed");
+	hp.npool_bytes = nmask.size() * 4;
+	CU(ctx->h_npool.reserve(std::max<size_t>(hp.npool_bytes, 16)));
+	if (hp.npool_bytes) memcpy(ctx->h_npool.p, nmask.data(), hp.npool_bytes);
+	return 0;
+}
+
+int ensure_generic_scratch(ksw_b200_ctx *ctx, int qmax, int &n_blocks)
+{
+	// one column slab per resident thread; bound the slab to ~1 GiB
+	const size_t per_thread = (size_t)(qmax + 1) * (sizeof(int2) + 1);
+	size_t threads = (size_t)ctx->sm_count * 8 * KSW_GENERIC_THREADS;
+	const size_t budget = (size_t)1 << 30;
+	while (threads > KSW_GENERIC_THREADS && threads * per_thread > budget) threads >>= 1;
+	n_blocks = (int)(threads / KSW_GENERIC_THREADS);
+	CU(ctx->d_eh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
+	CU(ctx->d_qc.reserve(threads * (size_t)(qmax + 1)));
+	return 0;
+}
+
+int enqueue_kernels(ksw_b200_ctx *ctx, ksw_b200_batch *b)
+{
+	int64_t first = 0;
+	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
+		const int64_t nc = b->fast_class_n[c];
+		if (nc <= 0) continue;
+		CU(ctx->d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
+		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, nc, (const uint32_t *)b->d_pool.p,
+		                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[c], ctx->sm_count,
+		                   (unsigned long long *)ctx->d_counter.p + c, (DevRes *)b->d_res.p, ctx->stream));
+		ctx->launches++;
+		first += nc;
+	}
+	if (b->n_generic > 0) {
+		int n_blocks = 0;
+		int rc = ensure_generic_scratch(ctx, b->qmax_generic, n_blocks);
+		if (rc) return rc;
+		const int64_t need = (b->n_generic + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS;
+		if (need < n_blocks) n_blocks = (int)need;
+		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p + b->n_fast, b->n_generic, (const uint32_t *)b->d_pool.p,
+		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)ctx->d_eh.p, (uint8_t *)ctx->d_qc.p,
+		                      n_blocks, (DevRes *)b->d_res.p, ctx->stream));
+		ctx->launches++;
+	}
+	return 0;
+}
+
+int upload_into(ksw_b200_ctx *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch *b)
+{
+	HostPacked hp;
+	int rc = pack_host(ctx, cfg, n, jobs, qpool, tpool, hp);
+	if (rc) return rc;
+	const KswPackPlan &pl = hp.plan;
+	b->n = n; b->n_fast = pl.n_fast; b->n_generic = pl.n_generic;
+	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
+		b->fast_class_n[c] = pl.fast_class_n[c];
+		b->fast_class_qmax[c] = pl.fast_class_qmax[c];
+	}
+	b->qmax_generic = pl.qmax_generic;
+	b->pool_bytes = pl.pool_bytes; b->npool_bytes = hp.npool_bytes;
+	ksw_params_from_cfg(cfg, b->P);
+	CU(b->d_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
+	CU(b->d_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
+	CU(b->d_npool.reserve(std::max<size_t>(hp.npool_bytes, 16)));
+	CU(b->d_res.reserve(sizeof(DevRes) * (size_t)std::max<int64_t>(n, 1)));
+	if (n > 0) {
+		CU(cudaMemcpyAsync(b->d_jobs.p, ctx->h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+		if (pl.pool_bytes)
+			CU(cudaMemcpyAsync(b->d_pool.p, ctx->h_pool.p, pl.pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		if (hp.npool_bytes)
+			CU(cudaMemcpyAsync(b->d_npool.p, ctx->h_npool.p, hp.npool_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	return 0;
+}
+
+void batch_release(ksw_b200_batch *b)
+{
+	if (!b) return;
+	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release();
+	delete b;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int ksw_b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
+{
+	if (!out) return 1;
+	*out = nullptr;
+	ksw_b200_ctx *ctx = new ksw_b200_ctx();
+	ctx->device = device;
+	cudaError_t e = cudaSetDevice(device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if (e != cudaSuccess) {
+		fprintf(stderr, "[ksw_b200] cannot create context on device %d: %s\n", device, cudaGetErrorString(e));
+		delete ctx;
+		return 100 + (int)e;
+	}
+	unsigned hw = std::thread::hardware_concurrency();
+	ctx->pack_threads = (int)std::max(1u, std::min(hw ? hw : 8u, 32u));
+	*out = ctx;
+	return 0;
+}
+
+void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	batch_release(ctx->cached);
+	ctx->h_jobs.release(); ctx->h_pool.release(); ctx->h_npool.release(); ctx->h_res.release();
+	ctx->d_eh.release(); ctx->d_qc.release(); ctx->d_counter.release();
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char *ksw_b200_strerror(const ksw_b200_ctx_t *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ksw_b200_ctx_set_pack_threads(ksw_b200_ctx_t *ctx, int n_threads)
+{
+	if (!ctx || n_threads < 1) return 1;
+	ctx->pack_threads = n_threads;
+	return 0;
+}
+
+int64_t ksw_b200_ctx_launch_count(const ksw_b200_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+int ksw_b200_ctx_sync(ksw_b200_ctx_t *ctx)
+{
+	if (!ctx) return 1;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+int ksw_b200_batch_upload(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch_t **out)
+{
+	if (!ctx || !cfg || !out || n < 0) return 1;
+	*out = nullptr;
+	CU(cudaSetDevice(ctx->device));
+	ksw_b200_batch *b = new ksw_b200_batch();
+	int rc = upload_into(ctx, cfg, n, jobs, qpool, tpool, b);
+	if (rc == 0) {
+		cudaError_t e = cudaStreamSynchronize(ctx->stream);     // staging is reused by the next upload
+		if (e != cudaSuccess) rc = fail(ctx, 100 + (int)e, std::string("upload sync: ") + cudaGetErrorString(e));
+	}
+	if (rc) { batch_release(b); return rc; }
+	*out = b;
+	return 0;
+}
+
+int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b)
+{
+	if (!ctx || !b) return 1;
+	CU(cudaSetDevice(ctx->device));
+	return enqueue_kernels(ctx, b);
+}
+
+int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms)
+{
+	if (!ctx || !b || iters < 1 || !ms) return 1;
+	CU(cudaSetDevice(ctx->device));
+	for (int i = 0; i < iters; ++i) {
+		CU(cudaEventRecord(ctx->ev0, ctx->stream));
+		int rc = enqueue_kernels(ctx, b);
+		if (rc) return rc;
+		CU(cudaEventRecord(ctx->ev1, ctx->stream));
+		CU(cudaEventSynchronize(ctx->ev1));
+		CU(cudaEventElapsedTime(&ms[i], ctx->ev0, ctx->ev1));
+	}
+	return 0;
+}
+
+int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_res_t *res)
+{
+	if (!ctx || !b || (!res && b->n)) return 1;
+	CU(cudaSetDevice(ctx->device));
+	if (b->n == 0) { CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+	const size_t bytes = sizeof(DevRes) * (size_t)b->n;
+	CU(ctx->h_res.reserve(bytes));
+	CU(cudaMemcpyAsync(ctx->h_res.p, b->d_res.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	memcpy(res, ctx->h_res.p, bytes);
+	return 0;
+}
+
+int ksw_b200_batch_info(const ksw_b200_batch_t *b, int64_t *n_fast, int64_t *n_generic, int64_t *packed_bytes)
+{
+	if (!b) return 1;
+	if (n_fast) *n_fast = b->n_fast;
+	if (n_generic) *n_generic = b->n_generic;
+	if (packed_bytes) *packed_bytes = (int64_t)(b->pool_bytes + b->npool_bytes + sizeof(DevJob) * (size_t)b->n);
+	return 0;
+}
+
+void ksw_b200_batch_free(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b)
+{
+	if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+	batch_release(b);
+}
+
+int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
+{
+	if (!ctx || !cfg || n < 0) return 1;
+	if (n == 0) return 0;
+	if (!jobs || !res) return 1;
+	CU(cudaSetDevice(ctx->device));
+	if (!ctx->cached) ctx->cached = new ksw_b200_batch();
+	ksw_b200_batch *b = ctx->cached;
+	int rc = upload_into(ctx, cfg, n, jobs, qpool, tpool, b);
+	if (rc) return rc;
+	rc = enqueue_kernels(ctx, b);
+	if (rc) return rc;
+	return ksw_b200_batch_download(ctx, b, res);
+}
+
+int ksw_b200_dpx_peak(ksw_b200_ctx_t *ctx, int which, double *lane_ops_per_s, float *ms_out)
+{
+	if (!ctx || !lane_ops_per_s) return 1;
+	CU(cudaSetDevice(ctx->device));
+	const int blocks = ctx->sm_count * 8, iters = 4096;
+	unsigned *d = nullptr;
+	CU(cudaMalloc(&d, (size_t)blocks * 256 * 4));
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; ++rep) {
+		CU(cudaEventRecord(ctx->ev0, ctx->stream));
+		CU(ksw_launch_dpx_peak(which, d, blocks, iters, ctx->stream));
+		CU(cudaEventRecord(ctx->ev1, ctx->stream));
+		CU(cudaEventSynchronize(ctx->ev1));
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		if (rep > 0 && ms < best) best = ms;
+		ctx->launches++;
+	}
+	cudaFree(d);
+	const double ops = (double)blocks * 256.0 * iters * 32.0;   // 8 chains x 4 DPX instructions per iteration
+	*lane_ops_per_s = ops / (best * 1e-3);
+	if (ms_out) *ms_out = best;
+	return 0;
+}
+
+int ksw_b200_clamp_w(int qlen, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus)
+{
+	return ksw_clamp_w(qlen, ksw_mat_max(mat), o_del, e_del, o_ins, e_ins, w, end_bonus);
+}
+
+// ---- scalar drop-ins (ksw.h:107-108).  One lazily created context per host thread.
+static ksw_b200_ctx *scalar_ctx()
+{
+	static thread_local struct Holder {
+		ksw_b200_ctx *c = nullptr;
+		~Holder() { if (c) ksw_b200_ctx_destroy(c); }
+	} h;
+	if (!h.c) {
+		int dev = 0;
+		if (const char *s = getenv("KSW_B200_DEVICE")) dev = atoi(s);
+		if (ksw_b200_ctx_create(dev, &h.c) != 0) {
+			fprintf(stderr, "[ksw_b200] fatal: no usable CUDA device for ksw_extend (there is no CPU fallback)\n");
+			abort();
+		}
+		h.c->pack_threads = 1;
+	}
+	return h.c;
+}
+
+int ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
+                int *qle, int *tle, int *gtle, int *gscore, int *max_off)
+{
+	ksw_b200_ctx *ctx = scalar_ctx();
+	ksw_b200_cfg_t cfg;
+	memcpy(cfg.mat, mat, 25);
+	cfg.m = m; cfg.o_del = o_del; cfg.e_del = e_del; cfg.o_ins = o_ins; cfg.e_ins = e_ins;
+	cfg.zdrop = zdrop; cfg.end_bonus = end_bonus;
+	ksw_b200_job_t job;
+	job.q_off = 0; job.t_off = 0; job.qlen = qlen; job.tlen = tlen; job.h0 = h0; job.w = w;
+	ksw_b200_res_t r;
+	int rc = ksw_b200_extend_batch(ctx, &cfg, 1, &job, query, target, &r);
+	if (rc) {
+		fprintf(stderr, "[ksw_b200] fatal: ksw_extend2 failed on the GPU (%d): %s\n", rc, ksw_b200_strerror(ctx));
+		abort();
+	}
+	if (qle) *qle = r.qle;
+	if (tle) *tle = r.tle;
+	if (gtle) *gtle = r.gtle;
+	if (gscore) *gscore = r.gscore;
+	if (max_off) *max_off = r.max_off;
+	return r.score;
+}
+
+int ksw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+               int gapo, int gape, int w, int end_bonus, int zdrop, int h0,
+               int *qle, int *tle, int *gtle, int *gscore, int *max_off)
+{
+	return ksw_extend2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, end_bonus, zdrop, h0,
+	                   qle, tle, gtle, gscore, max_off);
+}
+
+} // extern "C"

@@ -1,0 +1,211 @@
+"""ctypes binding of include/ksw_b200.h (the drop-in boundary of the ksw_extend path).
+
+Names and argument meaning mirror the reference's C interface (bwa-0.7.8/ksw.h:107-108 for the
+scalar calls; the batched entry replaces the loop over ksw_extend2 in mem_chain2aln,
+bwa-0.7.8/bwamem.c:826,854).  No algorithm lives here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+JOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"),
+                   ("h0", "<i4"), ("w", "<i4")])            # ksw_b200_job_t
+RES_DT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
+                   ("gscore", "<i4"), ("max_off", "<i4")])  # ksw_b200_res_t
+
+
+class KswB200Error(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):                                      # ksw_b200_cfg_t
+    _fields_ = [("mat", C.c_int8 * 25), ("m", C.c_int32), ("o_del", C.c_int32), ("e_del", C.c_int32),
+                ("o_ins", C.c_int32), ("e_ins", C.c_int32), ("zdrop", C.c_int32), ("end_bonus", C.c_int32)]
+
+
+def make_cfg(a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100, end_bonus=5, mat=None) -> Cfg:
+    """Scoring as `bwa mem` builds it: bwa_fill_scmat (bwa-0.7.8/bwa.c:77-86) + mem_opt_init defaults
+    (bwa-0.7.8/bwamem.c:45-75)."""
+    cfg = Cfg()
+    if mat is None:
+        k = 0
+        for i in range(4):
+            for j in range(4):
+                cfg.mat[k] = a if i == j else -b
+                k += 1
+            cfg.mat[k] = -1
+            k += 1
+        for j in range(5):
+            cfg.mat[k] = -1
+            k += 1
+    else:
+        m = np.asarray(mat, dtype=np.int8).reshape(25)
+        for i in range(25):
+            cfg.mat[i] = int(m[i])
+    cfg.m = 5
+    cfg.o_del, cfg.e_del, cfg.o_ins, cfg.e_ins = o_del, e_del, o_ins, e_ins
+    cfg.zdrop, cfg.end_bonus = zdrop, end_bonus
+    return cfg
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libksw_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libksw_b200.so.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise KswB200Error(f"{p} is missing: run ./build.sh (or __graft_entry__.build()); "
+                           "there is no CPU fallback for the extension path")
+    lib = C.CDLL(p)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.ksw_b200_device_count.restype = i32
+    lib.ksw_b200_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.ksw_b200_ctx_destroy.argtypes = [vp]
+    lib.ksw_b200_ctx_destroy.restype = None
+    lib.ksw_b200_strerror.argtypes = [vp]
+    lib.ksw_b200_strerror.restype = C.c_char_p
+    lib.ksw_b200_ctx_set_pack_threads.argtypes = [vp, i32]
+    lib.ksw_b200_ctx_launch_count.argtypes = [vp]
+    lib.ksw_b200_ctx_launch_count.restype = i64
+    lib.ksw_b200_ctx_sync.argtypes = [vp]
+    lib.ksw_b200_extend_batch.argtypes = [vp, C.POINTER(Cfg), i64, vp, vp, vp, vp]
+    lib.ksw_b200_batch_upload.argtypes = [vp, C.POINTER(Cfg), i64, vp, vp, vp, C.POINTER(vp)]
+    lib.ksw_b200_batch_run.argtypes = [vp, vp]
+    lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
+    lib.ksw_b200_batch_download.argtypes = [vp, vp, vp]
+    lib.ksw_b200_batch_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    lib.ksw_b200_batch_free.argtypes = [vp, vp]
+    lib.ksw_b200_batch_free.restype = None
+    lib.ksw_b200_dpx_peak.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    lib.ksw_b200_clamp_w.argtypes = [i32, vp] + [i32] * 6
+    scalar = [i32, vp, i32, vp, i32, vp]
+    lib.ksw_extend.argtypes = scalar + [i32] * 6 + [C.POINTER(i32)] * 5
+    lib.ksw_extend2.argtypes = scalar + [i32] * 8 + [C.POINTER(i32)] * 5
+    _lib = lib
+    return lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ResidentBatch:
+    def __init__(self, owner: "KswB200", handle, n: int):
+        self.owner, self.handle, self.n = owner, handle, n
+
+    def info(self):
+        nf, ng, pb = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self.owner.lib.ksw_b200_batch_info(self.handle, C.byref(nf), C.byref(ng), C.byref(pb))
+        return {"n_fast": nf.value, "n_generic": ng.value, "packed_bytes": pb.value}
+
+    def free(self):
+        if self.handle:
+            self.owner.lib.ksw_b200_batch_free(self.owner.ctx, self.handle)
+            self.handle = None
+
+
+class KswB200:
+    """One extension context == one (host thread, GPU) pair, as the C ABI defines it."""
+
+    def __init__(self, device: int = 0, pack_threads: int | None = None):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.lib.ksw_b200_ctx_create(device, C.byref(self.ctx))
+        if rc != 0:
+            raise KswB200Error(f"ksw_b200_ctx_create(device={device}) failed with code {rc}: no usable B200; "
+                               "the extension path has no CPU fallback")
+        if pack_threads:
+            self.lib.ksw_b200_ctx_set_pack_threads(self.ctx, int(pack_threads))
+
+    def close(self):
+        if self.ctx:
+            self.lib.ksw_b200_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise KswB200Error(f"{what} failed ({rc}): {self.lib.ksw_b200_strerror(self.ctx).decode()}")
+
+    @staticmethod
+    def _norm(jobs, qpool, tpool):
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        tpool = np.ascontiguousarray(tpool, dtype=np.uint8)
+        return jobs, qpool, tpool
+
+    def extend_batch(self, cfg: Cfg, jobs, qpool, tpool) -> np.ndarray:
+        """Host buffers in, host results out (pack + H2D + kernels + D2H inside the call)."""
+        jobs, qpool, tpool = self._norm(jobs, qpool, tpool)
+        res = np.zeros(jobs.shape[0], dtype=RES_DT)
+        self._check(self.lib.ksw_b200_extend_batch(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool),
+                                                   _p(tpool), _p(res)), "ksw_b200_extend_batch")
+        return res
+
+    def upload(self, cfg: Cfg, jobs, qpool, tpool) -> ResidentBatch:
+        jobs, qpool, tpool = self._norm(jobs, qpool, tpool)
+        h = C.c_void_p()
+        self._check(self.lib.ksw_b200_batch_upload(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool),
+                                                   _p(tpool), C.byref(h)), "ksw_b200_batch_upload")
+        return ResidentBatch(self, h, int(jobs.shape[0]))
+
+    def run(self, batch: ResidentBatch):
+        self._check(self.lib.ksw_b200_batch_run(self.ctx, batch.handle), "ksw_b200_batch_run")
+
+    def run_timed(self, batch: ResidentBatch, iters: int) -> np.ndarray:
+        ms = np.zeros(iters, dtype=np.float32)
+        self._check(self.lib.ksw_b200_batch_run_timed(self.ctx, batch.handle, iters, _p(ms)),
+                    "ksw_b200_batch_run_timed")
+        return ms
+
+    def download(self, batch: ResidentBatch) -> np.ndarray:
+        res = np.zeros(batch.n, dtype=RES_DT)
+        self._check(self.lib.ksw_b200_batch_download(self.ctx, batch.handle, _p(res)), "ksw_b200_batch_download")
+        return res
+
+    def sync(self):
+        self._check(self.lib.ksw_b200_ctx_sync(self.ctx), "ksw_b200_ctx_sync")
+
+    def launch_count(self) -> int:
+        return int(self.lib.ksw_b200_ctx_launch_count(self.ctx))
+
+    def dpx_peak(self, which: int = 0):
+        ops, ms = C.c_double(0), C.c_float(0)
+        self._check(self.lib.ksw_b200_dpx_peak(self.ctx, which, C.byref(ops), C.byref(ms)), "ksw_b200_dpx_peak")
+        return ops.value, ms.value
+
+
+def ksw_extend2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0):
+    """Scalar drop-in with the reference's argument order (ksw.h:108).  Returns
+    (score, qle, tle, gtle, gscore, max_off)."""
+    lib = load_library()
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    t = np.ascontiguousarray(target, dtype=np.uint8)
+    mt = np.ascontiguousarray(mat, dtype=np.int8)
+    out = [C.c_int(0) for _ in range(5)]
+    sc = lib.ksw_extend2(qlen, _p(q), tlen, _p(t), m, _p(mt), o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0,
+                         *[C.byref(x) for x in out])
+    return (sc,) + tuple(x.value for x in out)
+
+
+def ksw_extend(qlen, query, tlen, target, m, mat, gapo, gape, w, end_bonus, zdrop, h0):
+    """Scalar drop-in (ksw.h:107)."""
+    return ksw_extend2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, end_bonus, zdrop, h0)

@@ -1,0 +1,119 @@
+/*
+ * ksw_b200.h — C ABI of the B200-native seed-extension path.
+ *
+ * This is the drop-in boundary for BWA-MEM 0.7.8's banded affine-gap extension
+ * (reference: bwa-0.7.8/ksw.c:379-481, declared at bwa-0.7.8/ksw.h:107-108):
+ *
+ *   - ksw_extend / ksw_extend2 keep the reference's scalar signatures verbatim
+ *     (ksw.h:107-108), but run the one job on the GPU.  No CPU fallback exists:
+ *     if no CUDA device / kernel image is available the call aborts like the
+ *     reference's err_fatal (bwa-0.7.8/utils.c:90).
+ *   - ksw_b200_extend_batch is the batched entry that sits beside them.  It
+ *     replaces a loop of ksw_extend2 calls (the two call sites in
+ *     mem_chain2aln, bwa-0.7.8/bwamem.c:826 and :854).  The record layout
+ *     follows the fork's own, unused, accelerator sketch ext_param_t /
+ *     ext_res_t (bwamem.c:553-577) but is per *side*, because the right
+ *     extension's h0 is the left extension's score (bwamem.c:842,854).
+ *
+ * Plain C types only; no CUDA or torch types cross this boundary.
+ * All functions return 0 on success and a non-zero code on a CUDA/usage error
+ * (message via ksw_b200_strerror); the scalar reference API has no error path,
+ * so the scalar wrappers treat any error as fatal.
+ */
+#ifndef KSW_B200_H
+#define KSW_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- records ------------------------------------------------------------ */
+
+/* Scoring shared by every job of a batch == the by-value arguments every
+ * ksw_extend2 call in mem_chain2aln passes from mem_opt_t (bwamem.c:826,854):
+ * mat (opt->mat, 5x5, indexed [target*5+query], bwa.c:77-86), gap costs,
+ * zdrop, and end_bonus (pen_clip5 for a left pass, pen_clip3 for a right pass). */
+typedef struct {
+	int8_t  mat[25];
+	int32_t m;                 /* alphabet size; must be 5 (every reference caller passes 5) */
+	int32_t o_del, e_del, o_ins, e_ins;
+	int32_t zdrop;             /* <= 0 disables z-drop (ksw.c:455) */
+	int32_t end_bonus;
+} ksw_b200_cfg_t;
+
+/* One extension job (one side of one seed).  Sequences are byte codes 0..4
+ * (A,C,G,T,N) exactly as the reference passes them; they live in two caller-owned
+ * pools so that a batch is three flat arrays. */
+typedef struct {
+	uint64_t q_off, t_off;     /* byte offsets of query / target in the pools */
+	int32_t  qlen, tlen;       /* qlen >= 1, tlen >= 0 */
+	int32_t  h0;               /* score carried in (seed score or the left score) */
+	int32_t  w;                /* band width before the reference's clamp (ksw.c:398-406) */
+} ksw_b200_job_t;
+
+/* The six outputs of ksw_extend2 (return value, *_qle, *_tle, *_gtle, *_gscore, *_max_off). */
+typedef struct {
+	int32_t score, qle, tle, gtle, gscore, max_off;
+} ksw_b200_res_t;
+
+typedef struct ksw_b200_ctx ksw_b200_ctx_t;       /* one per (host thread, GPU) */
+typedef struct ksw_b200_batch ksw_b200_batch_t;   /* a packed batch resident in HBM */
+
+/* ---- scalar entries: the reference signatures, unchanged (ksw.h:107-108) -- */
+int ksw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+               int gapo, int gape, int w, int end_bonus, int zdrop, int h0,
+               int *qle, int *tle, int *gtle, int *gscore, int *max_off);
+int ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
+                int *qle, int *tle, int *gtle, int *gscore, int *max_off);
+
+/* ---- contexts -------------------------------------------------------------- */
+int  ksw_b200_device_count(void);
+int  ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out);
+void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx);
+const char *ksw_b200_strerror(const ksw_b200_ctx_t *ctx);   /* last error text of this ctx ("" if none) */
+/* number of host threads used to pack sequences (default: min(hardware threads, 32)) */
+int  ksw_b200_ctx_set_pack_threads(ksw_b200_ctx_t *ctx, int n_threads);
+/* cumulative number of kernels this ctx has launched (for bench accounting) */
+int64_t ksw_b200_ctx_launch_count(const ksw_b200_ctx_t *ctx);
+
+/* ---- batched entry: host buffers in, host results out ----------------------- */
+/* Packs (2-bit + N masks), length-bins, copies H2D from pinned staging on the
+ * ctx stream, runs the extension kernels, copies results D2H into res[0..n) in the
+ * caller's job order, and returns when they are there.  res need not be pinned. */
+int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n,
+                          const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
+                          ksw_b200_res_t *res);
+
+/* ---- split form: upload once, run many times (bench / two-pass drivers) ----- */
+int ksw_b200_batch_upload(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n,
+                          const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
+                          ksw_b200_batch_t **out);
+/* enqueue the kernels for a resident batch on the ctx stream (asynchronous) */
+int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);
+/* run `iters` times, each bracketed by CUDA events on the ctx stream; ms[i] = device time of run i */
+int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms);
+/* wait for the stream and copy results (caller's job order) to host */
+int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_res_t *res);
+/* statistics of a resident batch: n_fast / n_generic jobs, packed bytes in HBM */
+int ksw_b200_batch_info(const ksw_b200_batch_t *b, int64_t *n_fast, int64_t *n_generic, int64_t *packed_bytes);
+void ksw_b200_batch_free(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);
+int ksw_b200_ctx_sync(ksw_b200_ctx_t *ctx);
+
+/* ---- measurement helper ------------------------------------------------------ */
+/* Issue-rate microbenchmark of the DPX family used by the kernels (VIADDMNMX.S16x2[.RELU],
+ * VIMNMX.S16x2): returns warp-level lane-operations per second sustained by the whole GPU
+ * (SURVEY.md §8d "peak to divide by").  which: 0 = s16x2 mix, 1 = s32 mix. */
+int ksw_b200_dpx_peak(ksw_b200_ctx_t *ctx, int which, double *lane_ops_per_s, float *ms);
+
+/* the reference's band clamp (ksw.c:398-406), exposed for tests of the host packer */
+int ksw_b200_clamp_w(int qlen, const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins,
+                     int w, int end_bonus);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSW_B200_H */

@@ -1,0 +1,57 @@
+/*
+ * oracle/ref_shim.c — TEST INFRASTRUCTURE.  Batch driver around the REFERENCE's own
+ * ksw_extend2 (bwa-0.7.8/ksw.c:379, compiled unmodified from /root/reference by
+ * oracle/Makefile into oracle/_ref/libksw_ref.so).  Contains no algorithm: it only
+ * loops over jobs (optionally on several pthreads) and calls the reference symbol.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <pthread.h>
+
+/* prototype as declared in the reference header bwa-0.7.8/ksw.h:108 */
+int ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m,
+                const int8_t *mat, int o_del, int e_del, int o_ins, int e_ins, int w,
+                int end_bonus, int zdrop, int h0, int *qle, int *tle, int *gtle,
+                int *gscore, int *max_off);
+
+typedef struct { int32_t score, qle, tle, gtle, gscore, max_off; } ref_res_t;
+typedef struct { uint64_t q_off, t_off; int32_t qlen, tlen, h0, w; } ref_job_t;
+typedef struct { int8_t mat[25]; int32_t m, o_del, e_del, o_ins, e_ins, zdrop, end_bonus; } ref_cfg_t;
+
+typedef struct {
+	const ref_cfg_t *cfg; const ref_job_t *jobs; const uint8_t *qpool, *tpool;
+	ref_res_t *res; int64_t n, begin, stride;
+} arg_t;
+
+static void *worker(void *p)
+{
+	arg_t *a = (arg_t *)p;
+	const ref_cfg_t *c = a->cfg;
+	int64_t k;
+	for (k = a->begin; k < a->n; k += a->stride) {
+		const ref_job_t *j = &a->jobs[k];
+		ref_res_t *r = &a->res[k];
+		r->score = ksw_extend2(j->qlen, a->qpool + j->q_off, j->tlen, a->tpool + j->t_off, c->m, c->mat,
+		                       c->o_del, c->e_del, c->o_ins, c->e_ins, j->w, c->end_bonus, c->zdrop, j->h0,
+		                       &r->qle, &r->tle, &r->gtle, &r->gscore, &r->max_off);
+	}
+	return 0;
+}
+
+int ksw_ref_extend_batch(const ref_cfg_t *cfg, int64_t n, const ref_job_t *jobs, const uint8_t *qpool,
+                         const uint8_t *tpool, ref_res_t *res, int n_threads)
+{
+	int t;
+	pthread_t *tid; arg_t *args;
+	if (n_threads < 1) n_threads = 1;
+	tid = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
+	args = (arg_t *)malloc(sizeof(arg_t) * n_threads);
+	for (t = 0; t < n_threads; ++t) {
+		arg_t a = { cfg, jobs, qpool, tpool, res, n, t, n_threads };
+		args[t] = a;
+		pthread_create(&tid[t], 0, worker, &args[t]);
+	}
+	for (t = 0; t < n_threads; ++t) pthread_join(tid[t], 0);
+	free(tid); free(args);
+	return 0;
+}

@@ -1,0 +1,51 @@
+// tests/emu/fast_emu.cpp — TEST INFRASTRUCTURE.  Compiles the product's packer (ksw_pack.cpp) and
+// the per-lane logic of the fast kernel (ksw_fast_core.h) as plain C++ with software DPX, so that the
+// exact kernel source can be fuzzed against the oracle on a machine without a GPU.  Jobs the packer
+// routes to the generic kernel are reported with score = INT32_MIN (the emulation covers only the
+// fast path).  Never linked into the product library.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <climits>
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_pack.h"
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_fast_core.h"
+
+extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                                  const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res,
+                                  int64_t *n_fast_out, int threads)
+{
+	KswPackPlan plan;
+	std::string err;
+	int rc = ksw_pack_plan(cfg, n, jobs, KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1], threads, plan, err);
+	if (rc) return rc;
+	std::vector<DevJob> dj(n ? n : 1);
+	std::vector<uint32_t> pool(plan.pool_bytes / 4 + 4), nmask;
+	rc = ksw_pack_fill(plan, cfg, jobs, qpool, tpool, dj.data(), pool.data(), nmask, threads);
+	if (rc) return rc;
+	if (nmask.empty()) nmask.push_back(0);
+	KswParams P;
+	ksw_params_from_cfg(cfg, P);
+	KswFastConst K;
+	ksw_fast_make_const(P, K);
+	ksw_u2 mrow[5];
+	for (int t = 0; t < 5; ++t) mrow[t] = ksw_fast_matrow(P, t);
+	if (n_fast_out) *n_fast_out = plan.n_fast;
+	for (int64_t k = 0; k < n; ++k) res[k].score = INT_MIN;
+	for (int64_t p = 0; p < plan.n_fast; ++p) {
+		const DevJob &jb = dj[p];
+		const int nq = KSW_FAST_QUADS(jb.qlen);
+		std::vector<ksw_u4> hq(nq);
+		std::vector<uint32_t> sq(nq);
+		// poison so that reads of never-written state show up as mismatches
+		for (auto &v : hq) v.x = v.y = v.z = v.w = 0x5a5a5a5au;
+		KswFastMem<1> M{hq.data(), sq.data()};
+		KswFastLane L;
+		ksw_fast_setup<1>(L, M, K, jb, pool.data(), nmask.data());
+		while (!ksw_fast_row<1>(L, M, K, mrow)) {}
+		DevRes r;
+		ksw_fast_result(L, r);
+		memcpy(&res[jb.idx], &r, sizeof(r));
+	}
+	return 0;
+}

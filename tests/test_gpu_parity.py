@@ -1,0 +1,124 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle, bit-exact on all six
+outputs (score, qle, tle, gtle, gscore, max_off) for every job.  Integer work: tolerance is zero."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import kswtest as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, b: K.Batch, expect_fast=None):
+    want = K.run_oracle(b)
+    got = ctx.extend_batch(b.cfg, b.jobs, b.qpool, b.tpool)
+    mm = K.first_mismatch(want, got.view(K.RES_DT))
+    assert mm is None, f"first mismatch at job {mm[0]} ({mm[1]} jobs differ): {mm[2]}; job={b.jobs[mm[0]]}"
+    if expect_fast is not None:
+        rb = ctx.upload(b.cfg, b.jobs, b.qpool, b.tpool)
+        info = rb.info()
+        rb.free()
+        assert (info["n_fast"] > 0) == expect_fast, info
+
+
+def test_adversarial(gpu_ctx, oracle_built):
+    _check(gpu_ctx, K.gen_adversarial(), expect_fast=True)
+
+
+def test_fuzz_default_scoring(gpu_ctx, oracle_built):
+    _check(gpu_ctx, K.gen_fuzz(30000, seed=11))
+
+
+def test_fuzz_nondefault_asymmetric_gaps(gpu_ctx, oracle_built):
+    cfg = K.make_cfg(a=2, b=3, o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=30, end_bonus=9)
+    _check(gpu_ctx, K.gen_fuzz(20000, seed=12, cfg=cfg))
+
+
+def test_fuzz_zdrop_disabled_bwasw_style(gpu_ctx, oracle_built):
+    # bwasw calls ksw_extend with zdrop=-1, end_bonus=0 (bwtsw2_aux.c:133,161)
+    _check(gpu_ctx, K.gen_fuzz(10000, seed=13, cfg=K.make_cfg(zdrop=-1, end_bonus=0)))
+
+
+def test_fuzz_long_queries_mix_fast_and_generic(gpu_ctx, oracle_built):
+    _check(gpu_ctx, K.gen_fuzz(3000, seed=14, max_q=900))
+
+
+def test_int16_overflow_goes_generic(gpu_ctx, oracle_built):
+    # h0 + qlen*a beyond the s16 budget must be routed to the int32 kernel and stay exact
+    b = K.gen_fuzz(2000, seed=15, h0_max=40000)
+    _check(gpu_ctx, b)
+    cfg = K.make_cfg(a=100, b=120, o_del=200, e_del=30, o_ins=250, e_ins=20, zdrop=3000, end_bonus=50)
+    _check(gpu_ctx, K.gen_fuzz(2000, seed=16, cfg=cfg, h0_max=3000))
+
+
+def test_general_matrix(gpu_ctx, oracle_built):
+    rng = np.random.default_rng(5)
+    mat = rng.integers(-9, 8, 25).astype(np.int8)
+    mat[[0, 6, 12, 18]] = [5, 6, 7, 4]
+    _check(gpu_ctx, K.gen_fuzz(10000, seed=17, cfg=K.make_cfg(mat=mat, o_del=5, e_del=2, o_ins=3, e_ins=2, zdrop=50)))
+
+
+def test_config2_sample(gpu_ctx, oracle_built):
+    _check(gpu_ctx, K.gen_config2(200000, seed=20), expect_fast=True)
+
+
+def test_empty_and_single(gpu_ctx, oracle_built):
+    b = K.gen_fuzz(1, seed=3)
+    _check(gpu_ctx, b)
+    empty = K.Batch(b.cfg, b.jobs[:0].copy(), b.qpool, b.tpool)
+    assert gpu_ctx.extend_batch(empty.cfg, empty.jobs, empty.qpool, empty.tpool).shape[0] == 0
+
+
+def test_scalar_dropins(gpu_ctx, oracle_built):
+    import bwa_mem_quickassist_b200 as B
+    b = K.gen_fuzz(40, seed=21)
+    want = K.run_oracle(b)
+    mat = K.cfg_mat(b.cfg)
+    for k in range(b.n):
+        j = b.jobs[k]
+        q = b.qpool[j["q_off"]: j["q_off"] + j["qlen"]]
+        t = b.tpool[j["t_off"]: j["t_off"] + j["tlen"]]
+        got = B.ksw_extend2(int(j["qlen"]), q, int(j["tlen"]), t, 5, mat, 6, 1, 6, 1, int(j["w"]), 5, 100, int(j["h0"]))
+        assert got == tuple(int(want[f][k]) for f in K.RES_DT.names)
+        got = B.ksw_extend(int(j["qlen"]), q, int(j["tlen"]), t, 5, mat, 6, 1, int(j["w"]), 5, 100, int(j["h0"]))
+        assert got == tuple(int(want[f][k]) for f in K.RES_DT.names)
+
+
+def test_generic_kernel_alone(oracle_built):
+    """Same jobs with the fast kernel disabled (separate process: the switch is read once)."""
+    code = (
+        "import sys; sys.path[:0]=['tests','.']\n"
+        "import kswtest as K, bwa_mem_quickassist_b200 as B\n"
+        "ctx=B.KswB200(0)\n"
+        "for b in (K.gen_adversarial(), K.gen_fuzz(8000, seed=31), K.gen_config2(20000, seed=32)):\n"
+        "    rb=ctx.upload(b.cfg,b.jobs,b.qpool,b.tpool); assert rb.info()['n_fast']==0; rb.free()\n"
+        "    mm=K.first_mismatch(K.run_oracle(b), ctx.extend_batch(b.cfg,b.jobs,b.qpool,b.tpool).view(K.RES_DT))\n"
+        "    assert mm is None, mm\n"
+        "print('ok')\n")
+    env = dict(os.environ, KSW_B200_DISABLE_FAST="1")
+    out = subprocess.run([sys.executable, "-c", code], cwd=K.ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_size_independent_properties_full_rows(gpu_ctx, oracle_built):
+    """At sizes the oracle is not run on: identical sequences must score h0+qlen with qle=tle=qlen and
+    gscore=score (closed form), and splitting/permuting a batch must not change any job's result."""
+    n, L = 300000, 101
+    rng = np.random.default_rng(77)
+    t = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    jobs = np.zeros(n, dtype=K.JOB_DT)
+    jobs["q_off"] = np.arange(n, dtype=np.uint64) * np.uint64(L)
+    jobs["t_off"] = jobs["q_off"]
+    jobs["qlen"] = L; jobs["tlen"] = L; jobs["w"] = 100
+    jobs["h0"] = rng.integers(19, 101, n)
+    cfg = K.make_cfg()
+    r = gpu_ctx.extend_batch(cfg, jobs, t.reshape(-1), t.reshape(-1))
+    assert (r["score"] == jobs["h0"] + L).all() and (r["qle"] == L).all() and (r["tle"] == L).all()
+    assert (r["gscore"] == r["score"]).all() and (r["gtle"] == L).all() and (r["max_off"] == 0).all()
+    perm = rng.permutation(n)
+    r2 = gpu_ctx.extend_batch(cfg, jobs[perm], t.reshape(-1), t.reshape(-1))
+    for f in K.RES_DT.names:
+        assert (r2[f] == r[f][perm]).all()
