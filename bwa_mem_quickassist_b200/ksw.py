@@ -81,8 +81,8 @@ def load_library():
     lib.ksw_b200_ctx_launch_count.argtypes = [vp]
     lib.ksw_b200_ctx_launch_count.restype = i64
     lib.ksw_b200_ctx_sync.argtypes = [vp]
-    lib.ksw_b200_extend_batch.argtypes = [vp, C.POINTER(Cfg), i64, vp, vp, vp, vp]
-    lib.ksw_b200_batch_upload.argtypes = [vp, C.POINTER(Cfg), i64, vp, vp, vp, C.POINTER(vp)]
+    lib.ksw_b200_extend_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.ksw_b200_batch_upload.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(vp)]
     lib.ksw_b200_batch_run.argtypes = [vp, vp]
     lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
     lib.ksw_b200_batch_download.argtypes = [vp, vp, vp]

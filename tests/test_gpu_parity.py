@@ -79,8 +79,8 @@ def test_scalar_dropins(gpu_ctx, oracle_built):
     mat = K.cfg_mat(b.cfg)
     for k in range(b.n):
         j = b.jobs[k]
-        q = b.qpool[j["q_off"]: j["q_off"] + j["qlen"]]
-        t = b.tpool[j["t_off"]: j["t_off"] + j["tlen"]]
+        q = b.qpool[int(j["q_off"]): int(j["q_off"]) + int(j["qlen"])]
+        t = b.tpool[int(j["t_off"]): int(j["t_off"]) + int(j["tlen"])]
         got = B.ksw_extend2(int(j["qlen"]), q, int(j["tlen"]), t, 5, mat, 6, 1, 6, 1, int(j["w"]), 5, 100, int(j["h0"]))
         assert got == tuple(int(want[f][k]) for f in K.RES_DT.names)
         got = B.ksw_extend(int(j["qlen"]), q, int(j["tlen"]), t, 5, mat, 6, 1, int(j["w"]), 5, 100, int(j["h0"]))
