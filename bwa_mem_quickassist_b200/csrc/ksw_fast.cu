@@ -24,14 +24,15 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 	extern __shared__ uint4 smem[];
 	const int lane = threadIdx.x;
 	uint4 *hq = smem;
-	uint32_t *sq = reinterpret_cast<uint32_t *>(hq + (size_t)nq_cap * T);
-	uint2 *mrow = reinterpret_cast<uint2 *>(sq + (size_t)nq_cap * T);
+	uint16_t *sa = reinterpret_cast<uint16_t *>(hq + (size_t)nq_cap * T);
+	uint16_t *sb = sa + (size_t)nq_cap * T;
+	uint2 *mrow = reinterpret_cast<uint2 *>(sb + (size_t)nq_cap * T);
 	if (lane < 5) mrow[lane] = ksw_fast_matrow(P, lane);
 	__syncwarp();
 
 	KswFastConst K;
 	ksw_fast_make_const(P, K);
-	const KswFastMem<T> M{hq + lane, sq + lane};
+	const KswFastMem<T> M{hq + lane, sa + lane, sb + lane};
 	KswFastLane L;
 	L.tlen = 0; L.i = 0;
 	enum { IDLE = 0, RUN = 1, DONE = 2 };

@@ -138,11 +138,12 @@ static KSW_HD ksw_u2 ksw_fast_matrow(const KswParams &P, int t)
 // halfword index of column c's H inside its quad's uint4 {HA, EA, HB, EB}; E is at +2
 static KSW_HD int ksw_fast_hslot(int c) { const int k = c & 3; return k < 2 ? k : 7 - k; }
 
-// Shared-memory view of one lane: quad q lives at hq[q*T], its two PRMT selectors at sq[q*T].
+// Shared-memory view of one lane: quad q lives at hq[q*T]; the PRMT selectors of its pair A / pair B
+// at sa[q*T] / sb[q*T] (two separate 16-bit arrays so that each is one LDS.U16 and no ALU extract).
 template <int T>
 struct KswFastMem {
 	ksw_u4 *hq;
-	uint32_t *sq;
+	uint16_t *sa, *sb;
 	KSW_HD uint16_t *h16(int c) const { return reinterpret_cast<uint16_t *>(&hq[(c >> 2) * T]) + ksw_fast_hslot(c); }
 };
 
@@ -189,16 +190,80 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 		v4.z = (uint32_t)hv[3] | ((uint32_t)hv[2] << 16);   // pair B: lo c3, hi c2
 		v4.w = 0u;
 		M.hq[q * T] = v4;
-		M.sq[q * T] = (sb[0] | (sb[1] << 8)) | ((sb[3] | (sb[2] << 8)) << 16);
+		M.sa[q * T] = (uint16_t)(sb[0] | (sb[1] << 8));
+		M.sb[q * T] = (uint16_t)(sb[3] | (sb[2] << 8));
 	}
 }
 
 // ----------------------------------------------------------------------------- one row
+struct KswFastRowRegs {       // registers carried along a row
+	uint32_t X;               // F entering the next column (lo half at quad entry)
+	uint32_t Hc;              // lo half = H(i, c0-1): carry for the shifted H store
+	uint32_t m, zmin;         // per-half running max / min of the row
+	int mjl, mjh;             // last column where the lo / hi half reached its running max
+	uint32_t hA, hB;          // H of the last processed quad
+};
+
+// One quad (4 cells).  EDGE quads (first / last of the band) mask their out-of-band columns.
+template <int T, bool EDGE>
+static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, const KswFastConst &K, const ksw_u2 mr,
+                                 const int q, const int lo, const int hi)
+{
+	using namespace kswdpx;
+	ksw_u4 v = M.hq[q * T];
+	const uint32_t selA = M.sa[q * T], selB = M.sb[q * T];
+	const int c0 = q << 2;
+	uint32_t keepA = 0xffffffffu, keepB = 0xffffffffu;
+	if (EDGE) {
+		// in-band test per column; phantom columns get H = -8192, E = 0
+		const uint32_t in0 = (uint32_t)(c0 >= lo && c0 < hi), in1 = (uint32_t)(c0 + 1 >= lo && c0 + 1 < hi);
+		const uint32_t in2 = (uint32_t)(c0 + 2 >= lo && c0 + 2 < hi), in3 = (uint32_t)(c0 + 3 >= lo && c0 + 3 < hi);
+		keepA = in0 * 0xffffu + in1 * 0xffff0000u;
+		keepB = in3 * 0xffffu + in2 * 0xffff0000u;
+		v.x = (v.x & keepA) | (KSW_NEGPK & ~keepA); v.y &= keepA;
+		v.z = (v.z & keepB) | (KSW_NEGPK & ~keepB); v.w &= keepB;
+	}
+	const uint32_t scA = prmt(mr.x, mr.y, selA), scB = prmt(mr.x, mr.y, selB);
+	const uint32_t hpA = addmax2(v.x, scA, v.y), hpB = addmax2(v.z, scB, v.w);
+	// relu(h' - oe_ins): the third operand only has to be <= 0, a live constant saves a zero register
+	const uint32_t gA = addmax2_relu(hpA, K.neg_oei, K.neg_oei), gB = addmax2_relu(hpB, K.neg_oei, K.neg_oei);
+	// F chain: c0 (A.lo) -> c1 (A.hi) -> c2 (B.hi) -> c3 (B.lo) -> next quad
+	const uint32_t t1 = addmax2(R.X, K.neg_ei, gA);        // lo = F(c1)
+	const uint32_t FA = prmt(R.X, t1, 0x5410u);            // (F(c0), F(c1))
+	const uint32_t t2 = addmax2(FA, K.neg_ei, gA);         // hi = F(c2)
+	const uint32_t t3 = addmax2(t2, K.neg_ei, gB);         // hi = F(c3)
+	const uint32_t FB = prmt(t2, t3, 0x3276u);             // (lo = F(c3), hi = F(c2))
+	R.X = addmax2(FB, K.neg_ei, gB);                       // lo = F(c0 of the next quad)
+	const uint32_t hA = max2(hpA, FA), hB = max2(hpB, FB);
+	// E(i+1,j) = max(E - e_del, relu(H - oe_del))
+	const uint32_t eA = addmax2(v.y, K.neg_ed, addmax2_relu(hA, K.neg_oed, K.neg_oed));
+	const uint32_t eB = addmax2(v.w, K.neg_ed, addmax2_relu(hB, K.neg_oed, K.neg_oed));
+	// row maximum with last-index-wins ties, tracked per half (each half sees its columns in rising order)
+	bool ph, pl;
+	R.m = bmax2(hA, R.m, ph, pl);
+	if (pl) R.mjl = c0;
+	if (ph) R.mjh = c0 + 1;
+	R.m = bmax2(hB, R.m, ph, pl);
+	if (ph) R.mjh = c0 + 2;
+	if (pl) R.mjl = c0 + 3;
+	// zero detector over the in-band cells
+	if (EDGE) R.zmin = min3_2(R.zmin, hA | (~keepA & 0x7fff7fffu), hB | (~keepB & 0x7fff7fffu));
+	else R.zmin = min3_2(R.zmin, hA, hB);
+	// store: eh[j].h = H(i, j-1), eh[j].e = E(i+1, j)
+	ksw_u4 o;
+	o.x = prmt(R.Hc, hA, 0x5410u);                         // (H(c0-1), H(c0))
+	o.y = eA;
+	o.z = prmt(hA, hB, 0x3276u);                           // (lo: H(c2) for column c3, hi: H(c1) for column c2)
+	o.w = eB;
+	M.hq[q * T] = o;
+	R.Hc = hB;                                             // lo half = H(c3)
+	R.hA = hA; R.hB = hB;
+}
+
 // Processes row L.i.  Returns true when the job is finished (results are then in L).
 template <int T>
 static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const KswFastConst &K, const ksw_u2 *mrow)
 {
-	using namespace kswdpx;
 	const int i = L.i;
 	if (i >= L.tlen) return true;
 	// target base of this row
@@ -228,67 +293,21 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 	}
 
 	const int q0 = lo >> 2, q1 = (hi - 1) >> 2;
-	uint32_t X = 0;                 // F entering the next column (lo half at quad entry)
-	uint32_t Hc = 0;                // H(i, c0-1) in its lo half (carry for the shifted H store)
-	uint32_t m = 0, zmin = 0x7fff7fffu;
-	int mjl = -1, mjh = -1;
-	uint32_t hA = 0, hB = 0;
-
-	for (int q = q0; q <= q1; ++q) {
-		ksw_u4 v = M.hq[q * T];
-		const uint16_t *sp = reinterpret_cast<const uint16_t *>(&M.sq[q * T]);
-		const uint32_t selA = sp[0], selB = sp[1];
-		const int c0 = q << 2;
-		uint32_t keepA = 0xffffffffu, keepB = 0xffffffffu;
-		const bool edge = (q == q0) | (q == q1);
-		if (edge) {
-			// in-band test per column; phantom columns get H = -8192, E = 0
-			const uint32_t in0 = (uint32_t)(c0 >= lo && c0 < hi), in1 = (uint32_t)(c0 + 1 >= lo && c0 + 1 < hi);
-			const uint32_t in2 = (uint32_t)(c0 + 2 >= lo && c0 + 2 < hi), in3 = (uint32_t)(c0 + 3 >= lo && c0 + 3 < hi);
-			keepA = in0 * 0xffffu + in1 * 0xffff0000u;
-			keepB = in3 * 0xffffu + in2 * 0xffff0000u;
-			v.x = (v.x & keepA) | (KSW_NEGPK & ~keepA); v.y &= keepA;
-			v.z = (v.z & keepB) | (KSW_NEGPK & ~keepB); v.w &= keepB;
-		}
-		const uint32_t scA = prmt(mr.x, mr.y, selA), scB = prmt(mr.x, mr.y, selB);
-		const uint32_t hpA = addmax2(v.x, scA, v.y), hpB = addmax2(v.z, scB, v.w);
-		const uint32_t gA = addmax2_relu(hpA, K.neg_oei, 0u), gB = addmax2_relu(hpB, K.neg_oei, 0u);
-		// F chain: c0 (A.lo) -> c1 (A.hi) -> c2 (B.hi) -> c3 (B.lo) -> next quad
-		const uint32_t t1 = addmax2(X, K.neg_ei, gA);          // lo = F(c1)
-		const uint32_t FA = prmt(X, t1, 0x5410u);              // (F(c0), F(c1))
-		const uint32_t t2 = addmax2(FA, K.neg_ei, gA);         // hi = F(c2)
-		const uint32_t t3 = addmax2(t2, K.neg_ei, gB);         // hi = F(c3)
-		const uint32_t FB = prmt(t2, t3, 0x3276u);             // (lo = F(c3), hi = F(c2))
-		X = addmax2(FB, K.neg_ei, gB);                         // lo = F(c0 of the next quad)
-		hA = max2(hpA, FA); hB = max2(hpB, FB);
-		// E(i+1,j)
-		const uint32_t eA = addmax2(v.y, K.neg_ed, addmax2_relu(hA, K.neg_oed, 0u));
-		const uint32_t eB = addmax2(v.w, K.neg_ed, addmax2_relu(hB, K.neg_oed, 0u));
-		// row maximum with last-index-wins ties, tracked per half (each half sees its columns in rising order)
-		bool ph, pl;
-		m = bmax2(hA, m, ph, pl);
-		if (pl) mjl = c0;
-		if (ph) mjh = c0 + 1;
-		m = bmax2(hB, m, ph, pl);
-		if (ph) mjh = c0 + 2;
-		if (pl) mjl = c0 + 3;
-		// zero detector over the in-band cells
-		if (edge) zmin = min3_2(zmin, hA | (~keepA & 0x7fff7fffu), hB | (~keepB & 0x7fff7fffu));
-		else zmin = min3_2(zmin, hA, hB);
-		// store: eh[j].h = H(i, j-1), eh[j].e = E(i+1, j)
-		ksw_u4 o;
-		o.x = prmt(Hc, hA, 0x5410u);                           // (H(c0-1), H(c0))
-		o.y = eA;
-		o.z = prmt(hA, hB, 0x3276u);                           // (lo: H(c2) for column c3, hi: H(c1) for column c2)
-		o.w = eB;
-		M.hq[q * T] = o;
-		Hc = hB;                                               // lo half = H(c3)
+	KswFastRowRegs R;
+	R.X = 0; R.Hc = 0; R.m = 0; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
+	ksw_fast_quad<T, true>(R, M, K, mr, q0, lo, hi);
+	if (q1 > q0) {
+#ifdef __CUDACC__
+#pragma unroll 2
+#endif
+		for (int q = q0 + 1; q < q1; ++q) ksw_fast_quad<T, false>(R, M, K, mr, q, lo, hi);
+		ksw_fast_quad<T, true>(R, M, K, mr, q1, lo, hi);
 	}
 	// H(i, hi-1): the reference's h1 after the loop
 	int left;
 	{
 		const int k = (hi - 1) & 3;
-		const uint32_t r = k < 2 ? hA : hB;
+		const uint32_t r = k < 2 ? R.hA : R.hB;
 		left = (int)((k == 0 || k == 3) ? (r & 0xffffu) : (r >> 16));
 	}
 	// edge writes of the reference (ksw.c:429 for column lo, ksw.c:446 for column hi)
@@ -302,9 +321,9 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		if (left >= L.end_sc) L.end_i = i;
 		L.end_sc = L.end_sc > left ? L.end_sc : left;
 	}
-	const int m_lo = (int)(int16_t)(m & 0xffffu), m_hi = (int)(int16_t)(m >> 16);
+	const int m_lo = (int)(int16_t)(R.m & 0xffffu), m_hi = (int)(int16_t)(R.m >> 16);
 	const int rmax = m_lo > m_hi ? m_lo : m_hi;
-	int rarg = m_lo > m_hi ? mjl : (m_hi > m_lo ? mjh : (mjl > mjh ? mjl : mjh));
+	const int rarg = m_lo > m_hi ? R.mjl : (m_hi > m_lo ? R.mjh : (R.mjl > R.mjh ? R.mjl : R.mjh));
 	if (rmax == 0) return true;                                // ksw.c:451
 	if (rmax > L.best) {                                       // ksw.c:452-454
 		L.best = rmax; L.best_i = i; L.best_j = rarg;
@@ -316,7 +335,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		else         { if (L.best - rmax - (dj - di) * K.e_ins > K.zdrop) return true; }
 	}
 	// band trim (ksw.c:463-466)
-	const bool any_zero = ((zmin & 0xffffu) == 0u) | ((zmin >> 16) == 0u);
+	const bool any_zero = ((R.zmin & 0xffffu) == 0u) | ((R.zmin >> 16) == 0u);
 	if (!any_zero) {
 		// every eh[j].h for j in (lo, hi] is non-zero, so only the first-column slot eh[lo].h can stop the
 		// downward scan, and the upward scan runs off the end

@@ -36,10 +36,10 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 		const DevJob &jb = dj[p];
 		const int nq = KSW_FAST_QUADS(jb.qlen);
 		std::vector<ksw_u4> hq(nq);
-		std::vector<uint32_t> sq(nq);
+		std::vector<uint16_t> sa(nq), sb(nq);
 		// poison so that reads of never-written state show up as mismatches
 		for (auto &v : hq) v.x = v.y = v.z = v.w = 0x5a5a5a5au;
-		KswFastMem<1> M{hq.data(), sq.data()};
+		KswFastMem<1> M{hq.data(), sa.data(), sb.data()};
 		KswFastLane L;
 		ksw_fast_setup<1>(L, M, K, jb, pool.data(), nmask.data());
 		while (!ksw_fast_row<1>(L, M, K, mrow)) {}
