@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — the ksw_extend hot path on B200, per the driver's contract.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--jobs J] [--impl reference]
+
+Workload (BASELINE.json configs[1]): J = 10 M synthetic 101 bp query/target pairs per GPU, w = 100,
+default scoring, h0 ~ U[19,100] (bwa_mem_quickassist_b200/synth.py).  One *step* = one pass of the
+batched extension over the whole batch.
+
+  value   GCUPS over *visited* DP cells (sum over executed rows of end-beg, ksw.c:418-421; counted by
+          the kernels themselves and cross-checked against the oracle on the CPU sample), inputs
+          already packed and resident in HBM, kernels timed with CUDA events on the launching stream.
+  e2e     the same metric through the C-ABI call a host program makes (ksw_b200_extend_batch with
+          HOST buffers): 2-bit packing, H2D from pinned staging, kernels, D2H, every step.
+  roofline      cell-update rate against the DPX issue peak measured live by the library's probe
+                kernel (peak_CUPS = lane-ops/s x 2 cells / 8 issue slots); the path is
+                integer-issue bound, so the HBM figure is reported beside it as a sanity line.
+  cpu_baseline  the reference's own ksw_extend2 (oracle/_ref, compiled unmodified from the reference
+                sources) on all host cores over a bounded sample of the same jobs; it is also the
+                bit-exact check of the GPU results for that sample.
+
+With N > 1 (torchrun, one rank per GPU) every rank runs the same per-GPU workload (weak scaling; the
+path shards by jobs with no exchange step, so there is no data-path collective); timing is the max
+over ranks.  `--impl reference` times only the CPU reference (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+METRIC = "ksw_extend GCUPS (visited cells)"
+UNIT = "GCUPS"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--jobs", type=int, default=10_000_000, help="jobs per GPU (config 2: 10 M)")
+    ap.add_argument("--e2e-jobs", type=int, default=0, help="jobs per e2e step (default: same as --jobs)")
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="jobs in the CPU baseline sample")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seed", type=int, default=12345)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(n, seed):
+    from bwa_mem_quickassist_b200.synth import config2_jobs
+    return config2_jobs(n, seed=seed)
+
+
+def cpu_reference(cfg, jobs, qpool, tpool, threads):
+    """Times the reference's own ksw_extend2 (oracle/_ref) — or the oracle port if the compiled
+    reference did not travel — over the given jobs on `threads` host threads."""
+    import kswtest as K
+    b = K.Batch(cfg, jobs, qpool, tpool)
+    kind = "reference" if K.have_ref() else "port"
+    t0 = time.perf_counter()
+    res = K.run_ref(b, threads=threads) if kind == "reference" else K.run_oracle(b, threads=threads)
+    dt = time.perf_counter() - t0
+    return kind, res, dt
+
+
+def visited_cells_oracle(cfg, jobs, qpool, tpool, threads):
+    import kswtest as K
+    _, cells = K.run_oracle(K.Batch(cfg, jobs, qpool, tpool), threads=threads, want_cells=True)
+    return cells
+
+
+def run_reference_arm(a):
+    """`--impl reference`: the CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import kswtest as K
+    K.build_oracle() if not os.path.exists(K.ORACLE_SO) else None
+    threads = os.cpu_count() or 1
+    n = min(a.cpu_sample, a.jobs)
+    jobs, qpool, tpool = make_workload(n, a.seed)
+    cfg = K.make_cfg()
+    cells = int(visited_cells_oracle(cfg, jobs, qpool, tpool, threads).sum())
+    times = []
+    kind = "port"
+    for s in range(a.warmup + a.steps):
+        kind, _, dt = cpu_reference(cfg, jobs, qpool, tpool, threads)
+        if s >= a.warmup:
+            times.append(dt)
+    tot = sum(times)
+    gcups = cells * len(times) / tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"config2: {n} x (qlen=101,tlen=101) w=100 default scoring, bounded sample of the "
+                               f"{a.jobs}-job batch", "jobs_per_step": n},
+        "ext_per_s": n * len(times) / tot,
+        "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n} jobs per step, all host threads"},
+        "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+
+    import bwa_mem_quickassist_b200 as B
+    import kswtest as K
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = B.KswB200(local)
+    cfg = B.make_cfg()
+    jobs, qpool, tpool = make_workload(a.jobs, a.seed + rank)      # every rank its own shard of reads
+    n = a.jobs
+
+    # ---- live DPX issue peak (the roofline denominator), measured before the timed region
+    lane_ops, _ = ctx.dpx_peak(0)
+    peak_gcups = lane_ops * 2.0 / 8.0 / 1e9
+
+    # ---- resident path: pack + upload once, time the kernels
+    launches0 = ctx.launch_count()
+    rb = ctx.upload(cfg, jobs, qpool, tpool)
+    info = rb.info()
+    for _ in range(a.warmup):
+        ctx.run(rb)
+    ctx.sync()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms = ctx.run_timed(rb, a.steps)                                # CUDA events on the ctx stream, per step
+    ctx.sync()
+    l1 = ctx.launch_count()
+    barrier()
+    clocks = sampler.stop()
+    t_dev = float(ms.sum()) * 1e-3
+    t_max = max_over_ranks(t_dev)
+    cells_job = ctx.download_cells(rb)
+    cells = float(cells_job.astype(np.int64).sum())
+    res_gpu = ctx.download(rb)
+    nominal = float((jobs["qlen"].astype(np.int64) * jobs["tlen"]).sum())
+    cells_all = sum_over_ranks(cells)
+    nominal_all = sum_over_ranks(nominal)
+    value = cells_all * a.steps / t_max / 1e9
+    kernel_launches = l1 - l0
+    rb.free()
+
+    # ---- end to end through the C ABI with host buffers (pack + H2D + kernels + D2H inside)
+    ne = a.e2e_jobs or n
+    ej, eq, et = (jobs, qpool, tpool) if ne == n else (jobs[:ne], qpool, tpool)
+    e_cells = float(cells_job[:ne].astype(np.int64).sum())
+    for _ in range(min(a.warmup, 2)):
+        ctx.extend_batch(cfg, ej, eq, et)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res_e2e = ctx.extend_batch(cfg, ej, eq, et)
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e_max = max_over_ranks(t_e2e)
+    h2d, d2h = ctx.last_transfer()
+    e2e_value = sum_over_ranks(e_cells) * a.steps / t_e2e_max / 1e9
+    same = all((res_e2e[f] == res_gpu[f][:ne]).all() for f in B.RES_DT.names)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) + bit-exact check of that sample
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        ns = min(a.cpu_sample, n)
+        kind, res_cpu, dt = cpu_reference(K.make_cfg(), jobs[:ns], qpool, tpool, threads)
+        ocells = visited_cells_oracle(K.make_cfg(), jobs[:ns], qpool, tpool, threads)
+        ok = all((res_cpu[f] == res_gpu[f][:ns]).all() for f in B.RES_DT.names)
+        ok_cells = bool((ocells == cells_job[:ns].astype(np.int64)).all())
+        parity = {"sample_jobs": ns, "bit_exact": bool(ok), "cells_match_oracle": ok_cells, "e2e_equals_resident": bool(same)}
+        cpu = {"value": float(ocells.sum()) / dt / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"first {ns} jobs of the batch, {threads} host threads, one pass",
+               "ext_per_s": ns / dt}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = float(info["packed_bytes"] + 24 * n + 4 * n)      # job records + 2-bit pool in, results + cell counts out
+        per_gpu_gcups = value / world
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16x2 (int16 pairs; int32 kernel for out-of-range jobs)", "data": "synthetic",
+            "config": {"workload": f"config2: {n} jobs/GPU x (qlen=101,tlen=101), w=100, zdrop=100, end_bonus=5, "
+                                   "a=1 b=4 o=6 e=1, h0~U[19,100]", "jobs_per_gpu": n, "l2_policy": "inputs larger than L2 "
+                                   f"({info['packed_bytes'] / 1e6:.0f} MB packed per GPU)",
+                       "fast_jobs": info["n_fast"], "generic_jobs": info["n_generic"]},
+            "ext_per_s": n * world * a.steps / t_max,
+            "gcups_nominal_qlen_x_tlen": nominal_all * a.steps / t_max / 1e9,
+            "visited_cells_per_job": cells / n,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ext_per_s": ne * world * a.steps / t_e2e_max, "jobs_per_step_per_gpu": ne,
+                    "ms_per_step": 1e3 * t_e2e_max / a.steps,
+                    "what": "ksw_b200_extend_batch on host byte-code buffers: pack + H2D + kernels + D2H"},
+            "gpu_launches": int(kernel_launches),
+            "roofline": {"bound": "dpx_issue", "achieved": per_gpu_gcups, "peak": peak_gcups, "unit": "GCUPS/GPU",
+                         "frac": per_gpu_gcups / peak_gcups, "traffic": None,
+                         "peak_source": f"live DPX probe: {lane_ops / 1e12:.2f} T lane-ops/s x 2 cells / 8 issue slots "
+                                        "(SURVEY.md 8d); not in MEASURED_PEAKS.json"},
+            "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes * a.steps / t_dev / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg_bytes * a.steps / t_dev / 1e9 / hbm_peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,7 +19,7 @@ constexpr int T = KSW_FAST_THREADS;   // 32: one warp per CTA
 __global__ void __launch_bounds__(T)
 ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
                 const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap,
-                unsigned long long *__restrict__ counter, DevRes *__restrict__ res)
+                unsigned long long *__restrict__ counter, DevRes *__restrict__ res, uint32_t *__restrict__ cells)
 {
 	extern __shared__ uint4 smem[];
 	const int lane = threadIdx.x;
@@ -60,6 +60,7 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 				DevRes r;
 				ksw_fast_result(L, r);
 				res[L.idx] = r;
+				cells[L.idx] = L.cells;
 				state = IDLE;
 			}
 		}
@@ -75,7 +76,7 @@ size_t ksw_fast_smem_bytes(int qmax)
 
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
-                            DevRes *res, cudaStream_t st)
+                            DevRes *res, uint32_t *cells, cudaStream_t st)
 {
 	if (n_jobs <= 0) return cudaSuccess;
 	const size_t smem = ksw_fast_smem_bytes(qmax);
@@ -91,6 +92,6 @@ cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *
 	e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
 	if (e != cudaSuccess) return e;
 	ksw_fast_kernel<<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
-	                                                    KSW_FAST_QUADS(qmax), counter, res);
+	                                                    KSW_FAST_QUADS(qmax), counter, res, cells);
 	return cudaGetLastError();
 }

@@ -110,6 +110,7 @@ struct KswFastLane {
 	// running state (ksw.c:408-410)
 	int32_t i, lo, hi;
 	int32_t best, best_i, best_j, end_i, end_sc, off;
+	uint32_t cells;          // visited DP cells: sum over executed rows of (hi - lo), the GCUPS unit
 	uint32_t tw, tw_next;    // current / prefetched target word (16 bases each)
 };
 
@@ -160,6 +161,7 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 	L.qlen = jb.qlen; L.tlen = jb.tlen; L.h0 = jb.h0; L.w = jb.w; L.idx = jb.idx;
 	L.i = 0; L.lo = 0; L.hi = jb.qlen;
 	L.best = jb.h0; L.best_i = -1; L.best_j = -1; L.end_i = -1; L.end_sc = -1; L.off = 0;
+	L.cells = 0;
 	L.tw = jb.tlen > 0 ? L.t2[0] : 0u;
 	L.tw_next = jb.tlen > 16 ? L.t2[1] : 0u;
 
@@ -292,6 +294,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		return true;
 	}
 
+	L.cells += (uint32_t)(hi - lo);
 	const int q0 = lo >> 2, q1 = (hi - 1) >> 2;
 	KswFastRowRegs R;
 	R.X = 0; R.Hc = 0; R.m = 0; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;

@@ -23,7 +23,8 @@ __device__ __forceinline__ int seq_code(const uint32_t *w2, const uint32_t *nmas
 // warp, which sweep similar columns at the same time, touch neighbouring addresses.
 __global__ void __launch_bounds__(128)
 ksw_generic_kernel(const DevJob *__restrict__ jobs, int64_t n_jobs, const uint32_t *__restrict__ pool,
-                   const uint32_t *__restrict__ npool, KswParams P, int2 *__restrict__ eh, uint8_t *__restrict__ qc, DevRes *__restrict__ res)
+                   const uint32_t *__restrict__ npool, KswParams P, int2 *__restrict__ eh, uint8_t *__restrict__ qc, DevRes *__restrict__ res,
+                   uint32_t *__restrict__ cells)
 {
 	const int64_t n_threads = (int64_t)gridDim.x * blockDim.x;
 	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,6 +54,7 @@ ksw_generic_kernel(const DevJob *__restrict__ jobs, int64_t n_jobs, const uint32
 		}
 		int best = h0, best_i = -1, best_j = -1, end_i = -1, end_sc = -1, off = 0;   // ksw.c:408-410
 		int lo = 0, hi = qlen;
+		uint32_t ncell = 0;
 		for (int i = 0; i < tlen; ++i) {
 			const int t = seq_code(t2, tn, i);
 			const int8_t *srow = P.mat + t * 5;
@@ -60,6 +62,7 @@ ksw_generic_kernel(const DevJob *__restrict__ jobs, int64_t n_jobs, const uint32
 			int f = 0, rmax = 0, rarg = -1;
 			lo = max(lo, i - w);
 			hi = min(min(hi, i + w + 1), qlen);
+			if (hi > lo) ncell += (uint32_t)(hi - lo);
 			for (int j = lo; j < hi; ++j) {
 				int2 c = EH(j);
 				int h = c.x + srow[QC(j)];                           // no zero guard (ksw.c:430)
@@ -97,6 +100,7 @@ ksw_generic_kernel(const DevJob *__restrict__ jobs, int64_t n_jobs, const uint32
 		r.score = best; r.qle = best_j + 1; r.tle = best_i + 1;
 		r.gtle = end_i + 1; r.gscore = end_sc; r.max_off = off;
 		res[jb.idx] = r;
+		cells[jb.idx] = ncell;
 	}
 }
 
@@ -138,10 +142,10 @@ dpx_peak_kernel(unsigned *out, int iters, unsigned seed)
 
 cudaError_t ksw_launch_generic(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                const KswParams &P,
-                               int2 *eh, uint8_t *qc, int n_blocks, DevRes *res, cudaStream_t st)
+                               int2 *eh, uint8_t *qc, int n_blocks, DevRes *res, uint32_t *cells, cudaStream_t st)
 {
 	if (n_jobs <= 0) return cudaSuccess;
-	ksw_generic_kernel<<<n_blocks, KSW_GENERIC_THREADS, 0, st>>>(jobs, n_jobs, pool, npool, P, eh, qc, res);
+	ksw_generic_kernel<<<n_blocks, KSW_GENERIC_THREADS, 0, st>>>(jobs, n_jobs, pool, npool, P, eh, qc, res, cells);
 	return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@
 // generic int32 kernel: eh/qc are scratch slabs of (qmax+1) * n_blocks*KSW_GENERIC_THREADS entries
 cudaError_t ksw_launch_generic(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                const KswParams &P,
-                               int2 *eh, uint8_t *qc, int n_blocks, DevRes *res, cudaStream_t st);
+                               int2 *eh, uint8_t *qc, int n_blocks, DevRes *res, uint32_t *cells, cudaStream_t st);
 
 // DPX issue-rate probe; each thread issues iters*32 DPX instructions
 cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iters, cudaStream_t st);
@@ -19,5 +19,5 @@ cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iter
 // fast s16x2 kernel over jobs[0..n_jobs) whose qlen <= qmax; counter: one device uint64 scratch word
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
-                            DevRes *res, cudaStream_t st);
+                            DevRes *res, uint32_t *cells, cudaStream_t st);
 size_t ksw_fast_smem_bytes(int qmax);

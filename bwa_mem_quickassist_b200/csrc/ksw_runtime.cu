@@ -64,6 +64,7 @@ struct ksw_b200_ctx {
 	int64_t launches = 0;
 	// staging reused by ksw_b200_extend_batch / upload
 	PinnedBuf h_jobs, h_pool, h_npool, h_res;
+	int64_t last_h2d = 0, last_d2h = 0;   // bytes moved by the last ksw_b200_extend_batch call
 	// scratch of the generic kernel
 	DevBuf d_eh, d_qc, d_counter;
 	// cached batch buffers for the one-shot entry (avoid cudaMalloc per call)
@@ -75,7 +76,7 @@ struct ksw_b200_batch {
 	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0};
 	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0};
 	KswParams P;
-	DevBuf d_jobs, d_pool, d_npool, d_res;
+	DevBuf d_jobs, d_pool, d_npool, d_res, d_cells;
 	size_t pool_bytes = 0, npool_bytes = 0;
 	int qmax_generic = 0;
 };
@@ -149,7 +150,8 @@ int enqueue_kernels(ksw_b200_ctx *ctx, ksw_b200_batch *b)
 		CU(ctx->d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
 		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, nc, (const uint32_t *)b->d_pool.p,
 		                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[c], ctx->sm_count,
-		                   (unsigned long long *)ctx->d_counter.p + c, (DevRes *)b->d_res.p, ctx->stream));
+		                   (unsigned long long *)ctx->d_counter.p + c, (DevRes *)b->d_res.p,
+		                   (uint32_t *)b->d_cells.p, ctx->stream));
 		ctx->launches++;
 		first += nc;
 	}
@@ -161,7 +163,7 @@ int enqueue_kernels(ksw_b200_ctx *ctx, ksw_b200_batch *b)
 		if (need < n_blocks) n_blocks = (int)need;
 		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p + b->n_fast, b->n_generic, (const uint32_t *)b->d_pool.p,
 		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)ctx->d_eh.p, (uint8_t *)ctx->d_qc.p,
-		                      n_blocks, (DevRes *)b->d_res.p, ctx->stream));
+		                      n_blocks, (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, ctx->stream));
 		ctx->launches++;
 	}
 	return 0;
@@ -186,6 +188,7 @@ int upload_into(ksw_b200_ctx *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const k
 	CU(b->d_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
 	CU(b->d_npool.reserve(std::max<size_t>(hp.npool_bytes, 16)));
 	CU(b->d_res.reserve(sizeof(DevRes) * (size_t)std::max<int64_t>(n, 1)));
+	CU(b->d_cells.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 1)));
 	if (n > 0) {
 		CU(cudaMemcpyAsync(b->d_jobs.p, ctx->h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
 		if (pl.pool_bytes)
@@ -199,7 +202,7 @@ int upload_into(ksw_b200_ctx *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const k
 void batch_release(ksw_b200_batch *b)
 {
 	if (!b) return;
-	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release();
+	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release(); b->d_cells.release();
 	delete b;
 }
 
@@ -350,7 +353,26 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 	if (rc) return rc;
 	rc = enqueue_kernels(ctx, b);
 	if (rc) return rc;
+	ctx->last_h2d = (int64_t)(sizeof(DevJob) * (size_t)n + b->pool_bytes + b->npool_bytes);
+	ctx->last_d2h = (int64_t)(sizeof(DevRes) * (size_t)n);
 	return ksw_b200_batch_download(ctx, b, res);
+}
+
+int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes)
+{
+	if (!ctx) return 1;
+	if (h2d_bytes) *h2d_bytes = ctx->last_h2d;
+	if (d2h_bytes) *d2h_bytes = ctx->last_d2h;
+	return 0;
+}
+
+int ksw_b200_batch_download_cells(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, uint32_t *cells)
+{
+	if (!ctx || !b || (!cells && b->n)) return 1;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (b->n) CU(cudaMemcpy(cells, b->d_cells.p, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToHost));
+	return 0;
 }
 
 int ksw_b200_dpx_peak(ksw_b200_ctx_t *ctx, int which, double *lane_ops_per_s, float *ms_out)

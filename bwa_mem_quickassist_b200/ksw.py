@@ -86,6 +86,8 @@ def load_library():
     lib.ksw_b200_batch_run.argtypes = [vp, vp]
     lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
     lib.ksw_b200_batch_download.argtypes = [vp, vp, vp]
+    lib.ksw_b200_batch_download_cells.argtypes = [vp, vp, vp]
+    lib.ksw_b200_ctx_last_transfer.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.ksw_b200_batch_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.ksw_b200_batch_free.argtypes = [vp, vp]
     lib.ksw_b200_batch_free.restype = None
@@ -180,6 +182,17 @@ class KswB200:
         res = np.zeros(batch.n, dtype=RES_DT)
         self._check(self.lib.ksw_b200_batch_download(self.ctx, batch.handle, _p(res)), "ksw_b200_batch_download")
         return res
+
+    def download_cells(self, batch: ResidentBatch) -> np.ndarray:
+        cells = np.zeros(batch.n, dtype=np.uint32)
+        self._check(self.lib.ksw_b200_batch_download_cells(self.ctx, batch.handle, _p(cells)),
+                    "ksw_b200_batch_download_cells")
+        return cells
+
+    def last_transfer(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.lib.ksw_b200_ctx_last_transfer(self.ctx, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def sync(self):
         self._check(self.lib.ksw_b200_ctx_sync(self.ctx), "ksw_b200_ctx_sync")

@@ -88,6 +88,9 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
                           const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
                           ksw_b200_res_t *res);
 
+/* bytes the last ksw_b200_extend_batch call copied host->device and device->host */
+int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
 /* ---- split form: upload once, run many times (bench / two-pass drivers) ----- */
 int ksw_b200_batch_upload(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n,
                           const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
@@ -98,6 +101,9 @@ int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);
 int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms);
 /* wait for the stream and copy results (caller's job order) to host */
 int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_res_t *res);
+/* visited DP cells per job (caller's order): sum over the rows the reference loop executes of
+ * (end - beg), ksw.c:418-421 — the unit of the GCUPS metric.  Valid after a run. */
+int ksw_b200_batch_download_cells(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, uint32_t *cells);
 /* statistics of a resident batch: n_fast / n_generic jobs, packed bytes in HBM */
 int ksw_b200_batch_info(const ksw_b200_batch_t *b, int64_t *n_fast, int64_t *n_generic, int64_t *packed_bytes);
 void ksw_b200_batch_free(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);

@@ -1,0 +1,45 @@
+"""Generates tests/golden/ksw_extend_golden.npz from the REFERENCE's own ksw_extend2
+(oracle/_ref/libksw_ref.so = bwa-0.7.8/ksw.c compiled unmodified by oracle/Makefile).
+
+Run in the build container (where /root/reference is mounted):  python tests/golden/make_golden.py
+The reference ships no known-answer vectors for this path, so these outputs of the
+compiled reference are the golden vectors; the oracle restatement, the CPU emulation of the kernel
+source and the CUDA path are all checked against them.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import kswtest as K  # noqa: E402
+
+
+def main():
+    K.build_oracle()
+    assert K.have_ref(), "oracle/_ref/libksw_ref.so missing: /root/reference must be mounted to regenerate"
+    sets = {
+        "adversarial": K.gen_adversarial(seed=7),
+        "fuzz_default": K.gen_fuzz(3000, seed=101),
+        "fuzz_asym": K.gen_fuzz(1500, seed=102, cfg=K.make_cfg(a=2, b=3, o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=30, end_bonus=9)),
+        "fuzz_bwasw": K.gen_fuzz(1000, seed=103, cfg=K.make_cfg(zdrop=-1, end_bonus=0)),
+        "config2": K.gen_config2(3000, seed=104),
+        "highindel250": K.gen_fuzz(1000, seed=105, max_q=250, related=1.0, w_choices=(100,), h0_max=120),
+    }
+    out = {}
+    for name, b in sets.items():
+        res = K.run_ref(b, threads=4)
+        out[f"{name}.jobs"] = b.jobs
+        out[f"{name}.qpool"] = b.qpool
+        out[f"{name}.tpool"] = b.tpool
+        out[f"{name}.cfg"] = np.frombuffer(bytes(b.cfg), dtype=np.uint8).copy()
+        out[f"{name}.res"] = res
+        print(name, b.n, "jobs")
+    path = os.path.join(HERE, "ksw_extend_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

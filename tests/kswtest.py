@@ -8,11 +8,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 from dataclasses import dataclass
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "libksw_oracle.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libksw_ref.so")
@@ -176,37 +179,11 @@ def mutate(rng: np.random.Generator, seq: np.ndarray, sub: float, indel: float, 
 
 def gen_config2(n: int, seed: int = 12345, qlen: int = 101, tlen: int = 101, sub=0.01, indel=0.001,
                 cfg: Cfg | None = None, w: int = 100, h0_lo: int = 19, h0_hi: int = 100) -> Batch:
-    """BASELINE.json config 2 shape (vectorised): target uniform random, query = target with 1 %
-    substitutions and 0.1 % single-base indels, h0 ~ U[19,100], w=100, default scoring."""
-    rng = np.random.default_rng(seed)
-    cfg = cfg or make_cfg()
-    L = max(qlen, tlen) + 8
-    base = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
-    t = np.ascontiguousarray(base[:, :tlen])
-    # substitutions
-    q = base.copy()
-    s = rng.random((n, L)) < sub
-    q[s] = (q[s] + rng.integers(1, 4, size=int(s.sum()), dtype=np.uint8)) & 3
-    # one optional single-base indel event per query at rate ~ indel*qlen (rare double events ignored)
-    ev = rng.random(n) < indel * qlen
-    pos = rng.integers(1, qlen - 1, size=n)
-    ins = rng.random(n) < 0.5
-    rows = np.flatnonzero(ev)
-    for r_ in rows:                                # few rows (≈10 %), short python loop
-        p = int(pos[r_])
-        if ins[r_]:
-            q[r_, p + 1:] = q[r_, p:-1].copy()
-            q[r_, p] = rng.integers(0, 4)
-        else:
-            q[r_, p:-1] = q[r_, p + 1:].copy()
-    q = np.ascontiguousarray(q[:, :qlen])
-    jobs = np.zeros(n, dtype=JOB_DT)
-    jobs["q_off"] = np.arange(n, dtype=np.uint64) * np.uint64(qlen)
-    jobs["t_off"] = np.arange(n, dtype=np.uint64) * np.uint64(tlen)
-    jobs["qlen"], jobs["tlen"] = qlen, tlen
-    jobs["h0"] = rng.integers(h0_lo, h0_hi + 1, size=n)
-    jobs["w"] = w
-    return Batch(cfg, jobs, q.reshape(-1), t.reshape(-1))
+    """BASELINE.json config 2 shape (the generator bench.py uses): target uniform random, query = target
+    with 1 % substitutions and 0.1 % single-base indels, h0 ~ U[19,100], w=100, default scoring."""
+    from bwa_mem_quickassist_b200.synth import config2_jobs
+    jobs, q, t = config2_jobs(n, seed=seed, qlen=qlen, tlen=tlen, sub=sub, indel=indel, w=w, h0_lo=h0_lo, h0_hi=h0_hi)
+    return Batch(cfg or make_cfg(), jobs.astype(JOB_DT), q, t)
 
 
 def gen_fuzz(n: int, seed: int, cfg: Cfg | None = None, max_q: int = 250, n_frac: float = 0.02,
@@ -288,3 +265,47 @@ def gen_adversarial(seed: int = 7, cfg: Cfg | None = None) -> Batch:
             for h0 in (0, 3, 19, 60):
                 add(q, t, h0, 100); add(q, t, h0, 7)
     return _pools_from_lists(qs, ts, np.array(h0s), np.array(ws), cfg)
+
+
+# ------------------------------------------------------------------ golden fixture
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ksw_extend_golden.npz")
+
+
+def load_golden():
+    """{name: (Batch, reference results)} from the committed fixture (made by tests/golden/make_golden.py
+    from the compiled reference)."""
+    z = np.load(GOLDEN)
+    names = sorted({k.split(".")[0] for k in z.files})
+    out = {}
+    for nm in names:
+        cfg = Cfg.from_buffer_copy(z[f"{nm}.cfg"].tobytes())
+        b = Batch(cfg, z[f"{nm}.jobs"].astype(JOB_DT), z[f"{nm}.qpool"], z[f"{nm}.tpool"])
+        out[nm] = (b, z[f"{nm}.res"].astype(RES_DT))
+    return out
+
+
+# ------------------------------------------------------------------ CPU emulation of the fast kernel source
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(EMU_DIR, "libfast_emu.so")
+
+
+def emu_lib():
+    if "emu" not in _libs:
+        subprocess.run(["make", "-C", EMU_DIR, "--no-print-directory"], check=True, stdout=subprocess.DEVNULL)
+        lib = C.CDLL(EMU_SO)
+        lib.ksw_fast_emu_batch.restype = C.c_int
+        lib.ksw_fast_emu_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int]
+        _libs["emu"] = lib
+    return _libs["emu"]
+
+
+def run_emu(b: Batch, threads: int = 4):
+    """Results of the product packer + fast-kernel lane code compiled for the CPU.  Jobs the packer routes
+    to the generic kernel come back with score == INT32_MIN.  Returns (res, n_fast)."""
+    res = np.zeros(b.n, dtype=RES_DT)
+    nf = C.c_int64(0)
+    rc = emu_lib().ksw_fast_emu_batch(C.byref(b.cfg), b.n, _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), _ptr(res),
+                                      C.byref(nf), threads)
+    assert rc == 0, rc
+    return res, int(nf.value)

@@ -65,6 +65,22 @@ def test_config2_sample(gpu_ctx, oracle_built):
     _check(gpu_ctx, K.gen_config2(200000, seed=20), expect_fast=True)
 
 
+def test_visited_cell_counts_match_oracle(gpu_ctx, oracle_built):
+    for b in (K.gen_config2(50000, seed=41), K.gen_fuzz(5000, seed=42, max_q=700)):
+        _, cells = K.run_oracle(b, want_cells=True)
+        rb = gpu_ctx.upload(b.cfg, b.jobs, b.qpool, b.tpool)
+        gpu_ctx.run(rb)
+        got = gpu_ctx.download_cells(rb)
+        rb.free()
+        assert (got.astype(np.int64) == cells).all()
+
+
+def test_golden_vectors(gpu_ctx):
+    for name, (b, want) in K.load_golden().items():
+        got = gpu_ctx.extend_batch(b.cfg, b.jobs, b.qpool, b.tpool)
+        assert K.first_mismatch(want, got.view(K.RES_DT)) is None, name
+
+
 def test_empty_and_single(gpu_ctx, oracle_built):
     b = K.gen_fuzz(1, seed=3)
     _check(gpu_ctx, b)
