@@ -7,22 +7,30 @@
 
 namespace {
 
+// splits [0,n) into contiguous ranges, one per pool thread (serial when pool is null or n is small)
 template <class F>
-void parallel_for(int64_t n, int n_threads, F &&fn)
+void parallel_ranges(KswPool *pool, int64_t n, F &&fn)
 {
 	if (n <= 0) return;
-	n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (n + 4095) / 4096));
-	if (n_threads == 1) { fn(0, (int64_t)0, n); return; }
-	std::vector<std::thread> th;
-	th.reserve(n_threads);
-	const int64_t per = (n + n_threads - 1) / n_threads;
-	for (int t = 0; t < n_threads; ++t) {
-		const int64_t b = t * per, e = std::min<int64_t>(n, b + per);
-		if (b >= e) break;
-		th.emplace_back([&fn, t, b, e] { fn(t, b, e); });
-	}
-	for (auto &x : th) x.join();
+	int T = pool ? pool->size() : 1;
+	T = (int)std::max<int64_t>(1, std::min<int64_t>(T, (n + 16383) / 16384));
+	const int64_t per = (n + T - 1) / T;
+	auto body = [&](int t) {
+		const int64_t b = std::min<int64_t>(n, t * per), e = std::min<int64_t>(n, b + per);
+		if (b < e) fn(t, b, e);
+	};
+	if (T == 1) body(0); else pool->run(T, body);
 }
+
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("bmi2"))) inline uint32_t squeeze16_pext(uint64_t a, uint64_t b)
+{
+	return (uint32_t)__builtin_ia32_pext_di(a, 0x0303030303030303ull) |
+	       ((uint32_t)__builtin_ia32_pext_di(b, 0x0303030303030303ull) << 16);
+}
+const bool g_has_bmi2 = __builtin_cpu_supports("bmi2");
+#define KSW_HAVE_PEXT 1
+#endif
 
 // 2-bit packing of `len` byte codes into ceil(len/16) words.  Returns true if a code > 3 (N) was
 // seen; those bases are stored as 0 and flagged in nmask (ceil(len/32) words, caller-zeroed).
@@ -38,6 +46,9 @@ inline bool pack2(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
 			uint64_t a, b;
 			memcpy(&a, s + k, 8); memcpy(&b, s + k + 8, 8);
 			if ((a | b) & 0xFCFCFCFCFCFCFCFCull) slow = true;
+#ifdef KSW_HAVE_PEXT
+			else if (g_has_bmi2) word = squeeze16_pext(a, b);
+#endif
 			else {
 				// gather the low 2 bits of each of 8 bytes into 16 contiguous bits
 				auto squeeze = [](uint64_t v) -> uint32_t {
@@ -103,7 +114,7 @@ void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P)
 }
 
 int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs, int fast_qmax,
-                  int n_threads, KswPackPlan &plan, std::string &err)
+                  KswPool *pool, KswPackPlan &plan, std::string &err)
 {
 	if (cfg->m != 5) { err = "ksw_b200: only m == 5 is supported (every reference caller passes 5)"; return 2; }
 	if (n > 0x7fffffffLL) { err = "ksw_b200: more than 2^31-1 jobs in one batch"; return 2; }
@@ -111,98 +122,156 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 	int minsc = 0;
 	for (int i = 0; i < 25; ++i) minsc = std::min<int>(minsc, cfg->mat[i]);
 	plan.n = n; plan.maxsc = maxsc;
+	if ((int64_t)plan.pos_of.size() < n) { plan.pos_of.resize(n); plan.off_of.resize(n); plan.units_of.resize(n); plan.key.resize(n); }
 
-	// bin key from the lengths alone (no sequence bytes are touched in this phase):
-	// class bits | rows (coarse) | carried-in score — the two things that drive the band a job sweeps.
-	// Keys are inverted so that long jobs come first (short tail at the end of the launch).
+	// Bin key from the lengths alone (no sequence bytes are touched in this phase):
+	// generic bit | query-length class | rows (coarse) | carried-in score — the things that drive the band
+	// a job sweeps.  Keys are inverted so that long jobs come first (short tail at the end of a launch).
+	// Parallel counting sort: per-thread histograms over contiguous caller ranges, then a stable scatter.
 	constexpr int NKEY = 1 << 16;
-	std::vector<uint16_t> key(n);
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(pool ? pool->size() : 1, (n + 65535) / 65536));
+	const int64_t per = (n + T - 1) / T;
+	std::vector<uint16_t> &key = plan.key;
+	std::vector<std::vector<uint32_t>> &cnt = plan.cnt;
+	std::vector<std::vector<uint64_t>> &usum = plan.usum;
+	if ((int)cnt.size() < T) { cnt.resize(T); usum.resize(T); }
+	std::vector<int> qmax_cls(T * (KSW_FAST_CLASSES + 1), 0);
+	std::vector<int> krange(2 * T, 0);
+	// threads beyond T keep stale histograms from a larger earlier call: clear the range they may hold
+	for (int t = T; t < (int)cnt.size(); ++t)
+		if ((int)cnt[t].size() == NKEY && plan.key_hi >= plan.key_lo) {
+			std::fill(cnt[t].begin() + plan.key_lo, cnt[t].begin() + plan.key_hi + 1, 0u);
+			std::fill(usum[t].begin() + plan.key_lo, usum[t].begin() + plan.key_hi + 1, (uint64_t)0);
+		}
 	std::atomic<int> bad{0};
-	parallel_for(n, n_threads, [&](int, int64_t b, int64_t e) {
+	auto range_of = [&](int t, int64_t &b, int64_t &e) { b = std::min<int64_t>(n, t * per); e = std::min<int64_t>(n, b + per); };
+	auto run_T = [&](auto &&fn) {
+		if (T == 1) { fn(0); return; }
+		pool->run(T, fn);
+	};
+	run_T([&](int t) {
+		int64_t b, e; range_of(t, b, e);
+		if ((int)cnt[t].size() != NKEY) { cnt[t].assign(NKEY, 0); usum[t].assign(NKEY, 0); }
+		else if (plan.key_hi >= plan.key_lo) {
+			std::fill(cnt[t].begin() + plan.key_lo, cnt[t].begin() + plan.key_hi + 1, 0u);
+			std::fill(usum[t].begin() + plan.key_lo, usum[t].begin() + plan.key_hi + 1, (uint64_t)0);
+		}
+		int *qm = &qmax_cls[t * (KSW_FAST_CLASSES + 1)];
+		int klo = NKEY, khi = -1;
 		for (int64_t k = b; k < e; ++k) {
 			const ksw_b200_job_t &j = jobs[k];
-			if (j.qlen < 1 || j.tlen < 0) { bad = 1; key[k] = 0; continue; }
+			if (j.qlen < 1 || j.tlen < 0) { bad = 1; key[k] = 0; plan.units_of[k] = 0; continue; }
 			const int h0 = j.h0 < 0 ? 0 : j.h0;
 			const bool fast = fast_eligible(cfg, fast_qmax, maxsc, minsc, j.qlen, h0);
 			uint32_t qc = 0;
 			while (qc + 1 < KSW_FAST_CLASSES && j.qlen > KSW_FAST_CLASS_QMAX[qc]) ++qc;
 			const uint32_t tl = 127u - ((uint32_t)std::min(j.tlen, 2032) >> 4);   // 7 bits
 			const uint32_t hb = 63u - ((uint32_t)std::min(h0, 504) >> 3);         // 6 bits
-			key[k] = (uint16_t)((fast ? (qc << 13) : 0x8000u) | (tl << 6) | hb);
+			const uint16_t ky = (uint16_t)((fast ? (qc << 13) : 0x8000u) | (tl << 6) | hb);
+			const uint32_t units = (ksw_words2(j.qlen) + ksw_words2(j.tlen) + 3) >> 2;
+			key[k] = ky; plan.units_of[k] = units;
+			cnt[t][ky]++; usum[t][ky] += units;
+			klo = std::min<int>(klo, ky); khi = std::max<int>(khi, ky);
+			int &slot = qm[fast ? (int)qc : KSW_FAST_CLASSES];
+			slot = std::max(slot, j.qlen);
 		}
+		krange[2 * t] = klo; krange[2 * t + 1] = khi;
 	});
 	if (bad) { err = "ksw_b200: job with qlen < 1 or tlen < 0"; return 2; }
 
-	std::vector<int64_t> hist(NKEY + 1, 0);
-	for (int64_t k = 0; k < n; ++k) hist[(size_t)key[k] + 1]++;
-	for (int i = 0; i < NKEY; ++i) hist[i + 1] += hist[i];
-	plan.n_fast = hist[0x8000];
-	plan.n_generic = n - plan.n_fast;
-	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
-		const int hi_key = c + 1 < KSW_FAST_CLASSES ? ((c + 1) << 13) : 0x8000;
-		plan.fast_class_n[c] = hist[hi_key] - hist[c << 13];
-		plan.fast_class_qmax[c] = 0;
+	// exclusive prefix over (key, thread): start position / start pool offset of every (key, thread) run
+	// (only the key range that occurs is walked; class boundaries are picked up on the way)
+	int klo = NKEY, khi = -1;
+	for (int t = 0; t < T; ++t) { klo = std::min(klo, krange[2 * t]); khi = std::max(khi, krange[2 * t + 1]); }
+	plan.key_lo = klo; plan.key_hi = khi;
+	uint64_t pos = 0, off = 0;
+	int64_t below[KSW_FAST_CLASSES + 2];     // number of jobs with key < c<<13, and < 0x8000 in the last entry
+	for (int c = 0; c <= KSW_FAST_CLASSES + 1; ++c) below[c] = -1;
+	auto boundary_of = [](int c) { return c <= KSW_FAST_CLASSES ? (c << 13) : 0x8000; };
+	for (int ky = klo; ky <= khi; ++ky) {
+		for (int c = 0; c <= KSW_FAST_CLASSES + 1; ++c)
+			if (below[c] < 0 && ky >= boundary_of(c)) below[c] = (int64_t)pos;
+		for (int t = 0; t < T; ++t) {
+			const uint32_t c = cnt[t][ky];
+			const uint64_t u = usum[t][ky];
+			cnt[t][ky] = (uint32_t)pos; usum[t][ky] = off;
+			pos += c; off += u;
+		}
 	}
-	plan.order.resize(n);
+	for (int c = 0; c <= KSW_FAST_CLASSES + 1; ++c) if (below[c] < 0) below[c] = (int64_t)pos;
+	if (off > 0xffffffffull) { err = "ksw_b200: packed pool exceeds 64 GiB"; return 2; }
+	// keys: class c spans [c<<13, (c+1)<<13) (0x6000-0x7fff unused), the generic block starts at 0x8000
 	{
-		std::vector<int64_t> cur(hist.begin(), hist.end() - 1);
-		for (int64_t k = 0; k < n; ++k) plan.order[cur[key[k]]++] = (uint32_t)k;
+		plan.n_fast = below[KSW_FAST_CLASSES + 1];
+		plan.n_generic = n - plan.n_fast;
+		for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
+			plan.fast_class_n[c] = std::min(below[c + 1], plan.n_fast) - std::min(below[c], plan.n_fast);
+			plan.fast_class_qmax[c] = 0;
+			for (int t = 0; t < T; ++t)
+				plan.fast_class_qmax[c] = std::max(plan.fast_class_qmax[c], qmax_cls[t * (KSW_FAST_CLASSES + 1) + c]);
+		}
+		plan.qmax_generic = 0;
+		for (int t = 0; t < T; ++t)
+			plan.qmax_generic = std::max(plan.qmax_generic, qmax_cls[t * (KSW_FAST_CLASSES + 1) + KSW_FAST_CLASSES]);
 	}
-	plan.seq_off.resize(n + 1);
-	uint64_t off = 0;
-	int qmg = 0;
-	int64_t class_end[KSW_FAST_CLASSES];
-	{
-		int64_t acc = 0;
-		for (int c = 0; c < KSW_FAST_CLASSES; ++c) { acc += plan.fast_class_n[c]; class_end[c] = acc; }
-	}
-	int cls = 0;
-	for (int64_t p = 0; p < n; ++p) {
-		const ksw_b200_job_t &j = jobs[plan.order[p]];
-		plan.seq_off[p] = (uint32_t)off;
-		off += (ksw_words2(j.qlen) + ksw_words2(j.tlen) + 3) >> 2;
-		if (off > 0xffffffffull) { err = "ksw_b200: packed pool exceeds 64 GiB"; return 2; }
-		if (p < plan.n_fast) {
-			while (p >= class_end[cls]) ++cls;
-			plan.fast_class_qmax[cls] = std::max(plan.fast_class_qmax[cls], j.qlen);
-		} else qmg = std::max(qmg, j.qlen);
-	}
-	plan.seq_off[n] = (uint32_t)off;
 	plan.pool_bytes = (size_t)off * 16;
-	plan.qmax_generic = qmg;
+
+	// stable scatter: each thread walks its caller range again
+	run_T([&](int t) {
+		int64_t b, e; range_of(t, b, e);
+		uint32_t *c = cnt[t].data();
+		uint64_t *u = usum[t].data();
+		for (int64_t k = b; k < e; ++k) {
+			const uint16_t ky = key[k];
+			plan.pos_of[k] = c[ky]++;
+			plan.off_of[k] = (uint32_t)u[ky];
+			u[ky] += plan.units_of[k];
+		}
+	});
 	return 0;
 }
 
 int ksw_pack_fill(const KswPackPlan &plan, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs,
                   const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
-                  std::vector<uint32_t> &nmask, int n_threads)
+                  std::vector<uint32_t> &nmask, KswPool *tp)
 {
 	const int64_t n = plan.n;
-	const int T = std::max(n_threads, 1);
+	const int T = tp ? tp->size() : 1;
 	struct NList { std::vector<uint32_t> words; std::vector<std::pair<int64_t, uint32_t>> where; };
 	std::vector<NList> nl(T);
-	parallel_for(n, T, [&](int t, int64_t b, int64_t e) {
+	// caller order: the byte-coded sequences (the bulk of the traffic) are streamed sequentially, the packed
+	// records are written to their binned positions
+	parallel_ranges(tp, n, [&](int t, int64_t b, int64_t e) {
 		std::vector<uint32_t> qm, tm;
-		for (int64_t p = b; p < e; ++p) {
-			const ksw_b200_job_t &j = jobs[plan.order[p]];
+		int last_qlen = -1, last_w = 0, last_weff = 0;
+		for (int64_t k = b; k < e; ++k) {
+			const ksw_b200_job_t &j = jobs[k];
+			const uint32_t p = plan.pos_of[k];
 			DevJob d;
-			d.seq_off = plan.seq_off[p];
-			d.idx = plan.order[p];
+			d.seq_off = plan.off_of[k];
+			d.idx = (uint32_t)k;
 			d.qlen = j.qlen; d.tlen = j.tlen;
 			d.h0 = j.h0 < 0 ? 0 : j.h0;                                                     // ksw.c:384
-			d.w = ksw_clamp_w(j.qlen, plan.maxsc, cfg->o_del, cfg->e_del, cfg->o_ins, cfg->e_ins, j.w, cfg->end_bonus);
+			if (j.qlen != last_qlen || j.w != last_w) {
+				last_weff = ksw_clamp_w(j.qlen, plan.maxsc, cfg->o_del, cfg->e_del, cfg->o_ins, cfg->e_ins, j.w, cfg->end_bonus);
+				last_qlen = j.qlen; last_w = j.w;
+			}
+			d.w = last_weff;
 			d.flags = 0; d.nmask_off = 0;
-			uint32_t *dst = pool + (size_t)plan.seq_off[p] * 4;
+			uint32_t *dst = pool + (size_t)d.seq_off * 4;
 			const uint32_t qw = ksw_words2(j.qlen), tw = ksw_words2(j.tlen);
-			qm.assign(ksw_words1(j.qlen), 0); tm.assign(ksw_words1(j.tlen), 0);
+			const uint32_t qmw = ksw_words1(j.qlen), tmw = ksw_words1(j.tlen);
+			if (qm.size() < qmw) qm.resize(qmw);
+			if (tm.size() < tmw) tm.resize(tmw);
+			std::fill_n(qm.data(), qmw, 0u); std::fill_n(tm.data(), tmw, 0u);
 			const bool qn = pack2(qpool + j.q_off, j.qlen, dst, qm.data());
 			const bool tn = pack2(tpool + j.t_off, j.tlen, dst + qw, tm.data());
-			for (uint32_t x = qw + tw; x < (plan.seq_off[p + 1] - plan.seq_off[p]) * 4u; ++x) dst[x] = 0;
+			for (uint32_t x = qw + tw; x < plan.units_of[k] * 4u; ++x) dst[x] = 0;
 			if (qn || tn) {
 				d.flags = (qn ? KSW_FLAG_QN : 0u) | (tn ? KSW_FLAG_TN : 0u);
-				nl[t].where.emplace_back(p, (uint32_t)nl[t].words.size());
-				if (qn) nl[t].words.insert(nl[t].words.end(), qm.begin(), qm.end());
-				if (tn) nl[t].words.insert(nl[t].words.end(), tm.begin(), tm.end());
+				nl[t].where.emplace_back((int64_t)p, (uint32_t)nl[t].words.size());
+				if (qn) nl[t].words.insert(nl[t].words.end(), qm.begin(), qm.begin() + qmw);
+				if (tn) nl[t].words.insert(nl[t].words.end(), tm.begin(), tm.begin() + tmw);
 			}
 			dj[p] = d;
 		}
@@ -215,4 +284,72 @@ int ksw_pack_fill(const KswPackPlan &plan, const ksw_b200_cfg_t *cfg, const ksw_
 		for (auto &w : l.where) dj[w.first].nmask_off = (uint32_t)(base + w.second);
 	}
 	return 0;
+}
+
+// ------------------------------------------------------------------ KswPool
+#include <condition_variable>
+#include <mutex>
+
+struct KswPool::Impl {
+	std::vector<std::thread> th;
+	std::mutex mu;
+	std::condition_variable cv_go, cv_done;
+	void (*fn)(void *, int) = nullptr;
+	void *arg = nullptr;
+	int n_tasks = 0;
+	uint64_t gen = 0;
+	int pending = 0;
+	bool stop = false;
+};
+
+KswPool::KswPool(int n_threads) : impl_(new Impl()), n_(std::max(1, n_threads))
+{
+	for (int t = 1; t < n_; ++t)
+		impl_->th.emplace_back([this, t] {
+			uint64_t seen = 0;
+			for (;;) {
+				void (*fn)(void *, int); void *arg; bool mine;
+				{
+					std::unique_lock<std::mutex> lk(impl_->mu);
+					impl_->cv_go.wait(lk, [&] { return impl_->stop || impl_->gen != seen; });
+					if (impl_->stop) return;
+					seen = impl_->gen;
+					fn = impl_->fn; arg = impl_->arg; mine = t < impl_->n_tasks;
+				}
+				if (mine) {
+					fn(arg, t);
+					std::unique_lock<std::mutex> lk(impl_->mu);
+					if (--impl_->pending == 0) impl_->cv_done.notify_one();
+				}
+			}
+		});
+}
+
+KswPool::~KswPool()
+{
+	{
+		std::unique_lock<std::mutex> lk(impl_->mu);
+		impl_->stop = true;
+	}
+	impl_->cv_go.notify_all();
+	for (auto &x : impl_->th) x.join();
+	delete impl_;
+}
+
+void KswPool::run(int n_tasks, void (*fn)(void *, int), void *arg)
+{
+	n_tasks = std::max(1, std::min(n_tasks, n_));
+	if (n_tasks > 1) {
+		std::unique_lock<std::mutex> lk(impl_->mu);
+		impl_->fn = fn; impl_->arg = arg; impl_->n_tasks = n_tasks;
+		impl_->pending = n_tasks - 1;
+		++impl_->gen;
+		lk.unlock();
+		impl_->cv_go.notify_all();
+	}
+	fn(arg, 0);
+	if (n_tasks > 1) {
+		std::unique_lock<std::mutex> lk(impl_->mu);
+		impl_->cv_done.wait(lk, [&] { return impl_->pending == 0; });
+	}
 }

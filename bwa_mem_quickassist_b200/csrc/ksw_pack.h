@@ -5,8 +5,27 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <type_traits>
 #include "../../include/ksw_b200.h"
 #include "ksw_dev.cuh"
+
+// Persistent fork-join worker pool (thread creation per call costs more than packing a small chunk).
+class KswPool {
+public:
+	explicit KswPool(int n_threads);
+	~KswPool();
+	int size() const { return n_; }
+	// runs fn(t) for t in [0, n_tasks) (n_tasks <= size()), task 0 on the calling thread; returns when all are done
+	void run(int n_tasks, void (*fn)(void *, int), void *arg);
+	template <class F> void run(int n_tasks, F &&f)
+	{
+		run(n_tasks, [](void *a, int t) { (*static_cast<typename std::remove_reference<F>::type *>(a))(t); }, (void *)&f);
+	}
+private:
+	struct Impl;
+	Impl *impl_;
+	int n_;
+};
 
 #define KSW_FAST_CLASSES 3
 static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {128, 256, 512};
@@ -20,18 +39,25 @@ struct KswPackPlan {
 	size_t pool_bytes = 0;             // bytes of the 2-bit pool (multiple of 16)
 	int qmax_generic = 0;
 	int maxsc = 0;
-	std::vector<uint32_t> order;       // binned position -> caller index
-	std::vector<uint32_t> seq_off;     // binned position -> pool offset in 16-byte units (n+1 entries)
+	// per caller index k (so that the fill pass streams the caller's buffers sequentially):
+	std::vector<uint32_t> pos_of;      // binned position of job k
+	std::vector<uint32_t> off_of;      // pool offset of job k in 16-byte units
+	std::vector<uint32_t> units_of;    // 16-byte units job k occupies
+	// scratch kept between calls (a plan object is meant to be reused: fresh pages are expensive)
+	std::vector<uint16_t> key;
+	std::vector<std::vector<uint32_t>> cnt;
+	std::vector<std::vector<uint64_t>> usum;
+	int key_lo = 0, key_hi = -1;       // range of keys the scratch histograms currently hold (to re-zero lazily)
 };
 
 // fast_qmax: largest qlen the fast kernel accepts (0 = fast kernel disabled: everything is generic)
 int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs, int fast_qmax,
-                  int n_threads, KswPackPlan &plan, std::string &err);
+                  KswPool *pool, KswPackPlan &plan, std::string &err);
 
 // fills dj[0..n) and pool[0..pool_bytes/4); N masks of the rare jobs that have them are appended to nmask
 int ksw_pack_fill(const KswPackPlan &plan, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs,
                   const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
-                  std::vector<uint32_t> &nmask, int n_threads);
+                  std::vector<uint32_t> &nmask, KswPool *tp);
 
 void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P);
 

@@ -1,16 +1,16 @@
 // ksw_runtime.cu — host side of the C ABI declared in include/ksw_b200.h:
-// contexts, the packer (2-bit + N side masks, length binning), H2D/D2H staging on a
-// per-context stream, kernel dispatch, and the scalar ksw_extend/ksw_extend2 wrappers.
+// contexts, H2D/D2H staging on per-context streams, kernel dispatch, the chunked
+// pack/copy/compute pipeline of the one-shot batched entry, and the scalar
+// ksw_extend/ksw_extend2 wrappers.  (The packer itself is ksw_pack.cpp.)
 //
 // There is deliberately NO CPU implementation of the DP in this file: every result comes
 // from a kernel launch.  If CUDA is unusable the calls fail loudly.
 #include <cuda_runtime.h>
 #include <algorithm>
-#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,27 +51,15 @@ struct DevBuf {               // grow-only device buffer
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+double now_ms()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ opaque types
-struct ksw_b200_ctx {
-	int device = 0;
-	int sm_count = 148;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-	std::string err;
-	int pack_threads = 8;
-	int64_t launches = 0;
-	// staging reused by ksw_b200_extend_batch / upload
-	PinnedBuf h_jobs, h_pool, h_npool, h_res;
-	int64_t last_h2d = 0, last_d2h = 0;   // bytes moved by the last ksw_b200_extend_batch call
-	// scratch of the generic kernel
-	DevBuf d_eh, d_qc, d_counter;
-	// cached batch buffers for the one-shot entry (avoid cudaMalloc per call)
-	ksw_b200_batch *cached = nullptr;
-};
-
-struct ksw_b200_batch {
+struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
 	int64_t n = 0, n_fast = 0, n_generic = 0;
 	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0};
 	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0};
@@ -79,6 +67,36 @@ struct ksw_b200_batch {
 	DevBuf d_jobs, d_pool, d_npool, d_res, d_cells;
 	size_t pool_bytes = 0, npool_bytes = 0;
 	int qmax_generic = 0;
+};
+
+namespace {
+
+// One pipeline stage set: pinned staging, a reusable plan, a device batch, a stream, kernel scratch.
+struct Slot {
+	cudaStream_t stream = nullptr;
+	PinnedBuf h_jobs, h_pool, h_npool, h_res;
+	KswPackPlan plan;
+	std::vector<uint32_t> nmask;
+	ksw_b200_batch batch;
+	DevBuf d_eh, d_qc, d_counter;          // scratch of the generic kernel / job counters of the fast kernel
+	bool busy = false;                     // results of a chunk are in flight into h_res
+	int64_t first = 0, n = 0;              // caller range of that chunk
+};
+
+} // namespace
+
+struct ksw_b200_ctx {
+	int device = 0;
+	int sm_count = 148;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+	int pack_threads = 8;
+	KswPool *pool = nullptr;               // (re)created lazily with pack_threads workers
+	int64_t chunk_jobs = 1 << 20;
+	int trace = 0;
+	int64_t launches = 0;
+	int64_t last_h2d = 0, last_d2h = 0;    // bytes moved by the last ksw_b200_extend_batch call
+	Slot slot[2];                           // slot[0] also serves upload / run / download of resident batches
 };
 
 namespace {
@@ -95,10 +113,12 @@ int fail(ksw_b200_ctx *ctx, int code, const std::string &msg)
 			return fail(ctx, 100 + (int)e__, std::string(#call) + ": " + cudaGetErrorString(e__)); \
 	} while (0)
 
-struct HostPacked {
-	KswPackPlan plan;
-	size_t npool_bytes = 0;
-};
+KswPool *pool_of(ksw_b200_ctx *ctx)
+{
+	if (ctx->pool && ctx->pool->size() != ctx->pack_threads) { delete ctx->pool; ctx->pool = nullptr; }
+	if (!ctx->pool) ctx->pool = new KswPool(ctx->pack_threads);
+	return ctx->pool;
+}
 
 int fast_qmax_enabled()
 {
@@ -109,26 +129,56 @@ int fast_qmax_enabled()
 	return v;
 }
 
-// Builds DevJob[] (binned order), the 2-bit pool and the N side pool in the ctx's pinned staging.
-int pack_host(ksw_b200_ctx *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
-              const uint8_t *qpool, const uint8_t *tpool, HostPacked &hp)
+void batch_release_buffers(ksw_b200_batch *b)
+{
+	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release(); b->d_cells.release();
+}
+
+// pack jobs[0..n) into the slot's pinned staging and start the H2D copies into `b` on the slot's stream
+int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                    const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch *b, double *t_plan, double *t_fill)
 {
 	std::string err;
-	int rc = ksw_pack_plan(cfg, n, jobs, fast_qmax_enabled(), ctx->pack_threads, hp.plan, err);
+	const double t0 = now_ms();
+	int rc = ksw_pack_plan(cfg, n, jobs, fast_qmax_enabled(), pool_of(ctx), s.plan, err);
 	if (rc) return fail(ctx, rc, err);
-	CU(ctx->h_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
-	CU(ctx->h_pool.reserve(std::max<size_t>(hp.plan.pool_bytes, 16)));
-	std::vector<uint32_t> nmask;
-	rc = ksw_pack_fill(hp.plan, cfg, jobs, qpool, tpool, (DevJob *)ctx->h_jobs.p, (uint32_t *)ctx->h_pool.p,
-	                   nmask, ctx->pack_threads);
+	const KswPackPlan &pl = s.plan;
+	const double t1 = now_ms();
+	CU(s.h_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
+	CU(s.h_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
+	rc = ksw_pack_fill(pl, cfg, jobs, qpool, tpool, (DevJob *)s.h_jobs.p, (uint32_t *)s.h_pool.p, s.nmask, pool_of(ctx));
 	if (rc) return fail(ctx, rc, "ksw_b200: packing failed");
-	hp.npool_bytes = nmask.size() * 4;
-	CU(ctx->h_npool.reserve(std::max<size_t>(hp.npool_bytes, 16)));
-	if (hp.npool_bytes) memcpy(ctx->h_npool.p, nmask.data(), hp.npool_bytes);
+	const size_t npool_bytes = s.nmask.size() * 4;
+	CU(s.h_npool.reserve(std::max<size_t>(npool_bytes, 16)));
+	if (npool_bytes) memcpy(s.h_npool.p, s.nmask.data(), npool_bytes);
+	const double t2 = now_ms();
+	if (t_plan) *t_plan += t1 - t0;
+	if (t_fill) *t_fill += t2 - t1;
+
+	b->n = n; b->n_fast = pl.n_fast; b->n_generic = pl.n_generic;
+	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
+		b->fast_class_n[c] = pl.fast_class_n[c];
+		b->fast_class_qmax[c] = pl.fast_class_qmax[c];
+	}
+	b->qmax_generic = pl.qmax_generic;
+	b->pool_bytes = pl.pool_bytes; b->npool_bytes = npool_bytes;
+	ksw_params_from_cfg(cfg, b->P);
+	CU(b->d_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
+	CU(b->d_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
+	CU(b->d_npool.reserve(std::max<size_t>(npool_bytes, 16)));
+	CU(b->d_res.reserve(sizeof(DevRes) * (size_t)std::max<int64_t>(n, 1)));
+	CU(b->d_cells.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 1)));
+	if (n > 0) {
+		CU(cudaMemcpyAsync(b->d_jobs.p, s.h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
+		if (pl.pool_bytes)
+			CU(cudaMemcpyAsync(b->d_pool.p, s.h_pool.p, pl.pool_bytes, cudaMemcpyHostToDevice, s.stream));
+		if (npool_bytes)
+			CU(cudaMemcpyAsync(b->d_npool.p, s.h_npool.p, npool_bytes, cudaMemcpyHostToDevice, s.stream));
+	}
 	return 0;
 }
 
-int ensure_generic_scratch(ksw_b200_ctx *ctx, int qmax, int &n_blocks)
+int ensure_generic_scratch(ksw_b200_ctx *ctx, Slot &s, int qmax, int &n_blocks)
 {
 	// one column slab per resident thread; bound the slab to ~1 GiB
 	const size_t per_thread = (size_t)(qmax + 1) * (sizeof(int2) + 1);
@@ -136,74 +186,63 @@ int ensure_generic_scratch(ksw_b200_ctx *ctx, int qmax, int &n_blocks)
 	const size_t budget = (size_t)1 << 30;
 	while (threads > KSW_GENERIC_THREADS && threads * per_thread > budget) threads >>= 1;
 	n_blocks = (int)(threads / KSW_GENERIC_THREADS);
-	CU(ctx->d_eh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
-	CU(ctx->d_qc.reserve(threads * (size_t)(qmax + 1)));
+	CU(s.d_eh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
+	CU(s.d_qc.reserve(threads * (size_t)(qmax + 1)));
 	return 0;
 }
 
-int enqueue_kernels(ksw_b200_ctx *ctx, ksw_b200_batch *b)
+// launches the kernels of batch b on slot s's stream (one fast launch per query-length class + generic)
+int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 {
 	int64_t first = 0;
 	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
 		const int64_t nc = b->fast_class_n[c];
 		if (nc <= 0) continue;
-		CU(ctx->d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
+		CU(s.d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
 		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, nc, (const uint32_t *)b->d_pool.p,
 		                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[c], ctx->sm_count,
-		                   (unsigned long long *)ctx->d_counter.p + c, (DevRes *)b->d_res.p,
-		                   (uint32_t *)b->d_cells.p, ctx->stream));
+		                   (unsigned long long *)s.d_counter.p + c, (DevRes *)b->d_res.p,
+		                   (uint32_t *)b->d_cells.p, s.stream));
 		ctx->launches++;
 		first += nc;
 	}
 	if (b->n_generic > 0) {
 		int n_blocks = 0;
-		int rc = ensure_generic_scratch(ctx, b->qmax_generic, n_blocks);
+		int rc = ensure_generic_scratch(ctx, s, b->qmax_generic, n_blocks);
 		if (rc) return rc;
 		const int64_t need = (b->n_generic + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS;
 		if (need < n_blocks) n_blocks = (int)need;
 		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p + b->n_fast, b->n_generic, (const uint32_t *)b->d_pool.p,
-		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)ctx->d_eh.p, (uint8_t *)ctx->d_qc.p,
-		                      n_blocks, (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, ctx->stream));
+		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)s.d_eh.p, (uint8_t *)s.d_qc.p,
+		                      n_blocks, (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, s.stream));
 		ctx->launches++;
 	}
 	return 0;
 }
 
-int upload_into(ksw_b200_ctx *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
-                const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch *b)
+// waits for the chunk in flight on slot s and hands its results to the caller
+int retire_slot(ksw_b200_ctx *ctx, Slot &s, ksw_b200_res_t *res, double *t_wait)
 {
-	HostPacked hp;
-	int rc = pack_host(ctx, cfg, n, jobs, qpool, tpool, hp);
-	if (rc) return rc;
-	const KswPackPlan &pl = hp.plan;
-	b->n = n; b->n_fast = pl.n_fast; b->n_generic = pl.n_generic;
-	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
-		b->fast_class_n[c] = pl.fast_class_n[c];
-		b->fast_class_qmax[c] = pl.fast_class_qmax[c];
+	if (!s.busy) return 0;
+	const double t0 = now_ms();
+	CU(cudaStreamSynchronize(s.stream));
+	if (t_wait) *t_wait += now_ms() - t0;
+	// pinned staging -> caller's array, split over the pack threads (a 100 MB memcpy is not free)
+	{
+		char *dst = (char *)(res + s.first);
+		const char *src = (const char *)s.h_res.p;
+		const size_t bytes = sizeof(DevRes) * (size_t)s.n;
+		KswPool *tp = pool_of(ctx);
+		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)tp->size(), bytes >> 20));
+		const size_t per = (bytes + T - 1) / T;
+		auto body = [&](int t) {
+			const size_t b = std::min(bytes, (size_t)t * per), e = std::min(bytes, b + per);
+			if (b < e) memcpy(dst + b, src + b, e - b);
+		};
+		if (T == 1) body(0); else tp->run(T, body);
 	}
-	b->qmax_generic = pl.qmax_generic;
-	b->pool_bytes = pl.pool_bytes; b->npool_bytes = hp.npool_bytes;
-	ksw_params_from_cfg(cfg, b->P);
-	CU(b->d_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
-	CU(b->d_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
-	CU(b->d_npool.reserve(std::max<size_t>(hp.npool_bytes, 16)));
-	CU(b->d_res.reserve(sizeof(DevRes) * (size_t)std::max<int64_t>(n, 1)));
-	CU(b->d_cells.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 1)));
-	if (n > 0) {
-		CU(cudaMemcpyAsync(b->d_jobs.p, ctx->h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-		if (pl.pool_bytes)
-			CU(cudaMemcpyAsync(b->d_pool.p, ctx->h_pool.p, pl.pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		if (hp.npool_bytes)
-			CU(cudaMemcpyAsync(b->d_npool.p, ctx->h_npool.p, hp.npool_bytes, cudaMemcpyHostToDevice, ctx->stream));
-	}
+	s.busy = false;
 	return 0;
-}
-
-void batch_release(ksw_b200_batch *b)
-{
-	if (!b) return;
-	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release(); b->d_cells.release();
-	delete b;
 }
 
 } // namespace
@@ -225,7 +264,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	ksw_b200_ctx *ctx = new ksw_b200_ctx();
 	ctx->device = device;
 	cudaError_t e = cudaSetDevice(device);
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -236,6 +275,8 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	}
 	unsigned hw = std::thread::hardware_concurrency();
 	ctx->pack_threads = (int)std::max(1u, std::min(hw ? hw : 8u, 32u));
+	if (const char *s = getenv("KSW_B200_CHUNK")) ctx->chunk_jobs = std::max<int64_t>(1024, atoll(s));
+	if (const char *s = getenv("KSW_B200_TRACE")) ctx->trace = atoi(s);
 	*out = ctx;
 	return 0;
 }
@@ -244,13 +285,16 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	batch_release(ctx->cached);
-	ctx->h_jobs.release(); ctx->h_pool.release(); ctx->h_npool.release(); ctx->h_res.release();
-	ctx->d_eh.release(); ctx->d_qc.release(); ctx->d_counter.release();
+	for (Slot &s : ctx->slot) {
+		if (s.stream) cudaStreamSynchronize(s.stream);
+		batch_release_buffers(&s.batch);
+		s.h_jobs.release(); s.h_pool.release(); s.h_npool.release(); s.h_res.release();
+		s.d_eh.release(); s.d_qc.release(); s.d_counter.release();
+		if (s.stream) cudaStreamDestroy(s.stream);
+	}
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx->pool;
 	delete ctx;
 }
 
@@ -263,13 +307,20 @@ int ksw_b200_ctx_set_pack_threads(ksw_b200_ctx_t *ctx, int n_threads)
 	return 0;
 }
 
+int ksw_b200_ctx_set_chunk_jobs(ksw_b200_ctx_t *ctx, int64_t chunk_jobs)
+{
+	if (!ctx || chunk_jobs < 1) return 1;
+	ctx->chunk_jobs = chunk_jobs;
+	return 0;
+}
+
 int64_t ksw_b200_ctx_launch_count(const ksw_b200_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
 
 int ksw_b200_ctx_sync(ksw_b200_ctx_t *ctx)
 {
 	if (!ctx) return 1;
 	CU(cudaSetDevice(ctx->device));
-	CU(cudaStreamSynchronize(ctx->stream));
+	for (Slot &s : ctx->slot) CU(cudaStreamSynchronize(s.stream));
 	return 0;
 }
 
@@ -279,13 +330,14 @@ int ksw_b200_batch_upload(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 	if (!ctx || !cfg || !out || n < 0) return 1;
 	*out = nullptr;
 	CU(cudaSetDevice(ctx->device));
+	Slot &s = ctx->slot[0];
 	ksw_b200_batch *b = new ksw_b200_batch();
-	int rc = upload_into(ctx, cfg, n, jobs, qpool, tpool, b);
+	int rc = pack_and_upload(ctx, s, cfg, n, jobs, qpool, tpool, b, nullptr, nullptr);
 	if (rc == 0) {
-		cudaError_t e = cudaStreamSynchronize(ctx->stream);     // staging is reused by the next upload
+		cudaError_t e = cudaStreamSynchronize(s.stream);       // the staging is reused by the next upload
 		if (e != cudaSuccess) rc = fail(ctx, 100 + (int)e, std::string("upload sync: ") + cudaGetErrorString(e));
 	}
-	if (rc) { batch_release(b); return rc; }
+	if (rc) { batch_release_buffers(b); delete b; return rc; }
 	*out = b;
 	return 0;
 }
@@ -294,18 +346,19 @@ int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b)
 {
 	if (!ctx || !b) return 1;
 	CU(cudaSetDevice(ctx->device));
-	return enqueue_kernels(ctx, b);
+	return enqueue_kernels(ctx, ctx->slot[0], b);
 }
 
 int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms)
 {
 	if (!ctx || !b || iters < 1 || !ms) return 1;
 	CU(cudaSetDevice(ctx->device));
+	Slot &s = ctx->slot[0];
 	for (int i = 0; i < iters; ++i) {
-		CU(cudaEventRecord(ctx->ev0, ctx->stream));
-		int rc = enqueue_kernels(ctx, b);
+		CU(cudaEventRecord(ctx->ev0, s.stream));
+		int rc = enqueue_kernels(ctx, s, b);
 		if (rc) return rc;
-		CU(cudaEventRecord(ctx->ev1, ctx->stream));
+		CU(cudaEventRecord(ctx->ev1, s.stream));
 		CU(cudaEventSynchronize(ctx->ev1));
 		CU(cudaEventElapsedTime(&ms[i], ctx->ev0, ctx->ev1));
 	}
@@ -316,12 +369,22 @@ int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_r
 {
 	if (!ctx || !b || (!res && b->n)) return 1;
 	CU(cudaSetDevice(ctx->device));
-	if (b->n == 0) { CU(cudaStreamSynchronize(ctx->stream)); return 0; }
+	Slot &s = ctx->slot[0];
+	if (b->n == 0) { CU(cudaStreamSynchronize(s.stream)); return 0; }
 	const size_t bytes = sizeof(DevRes) * (size_t)b->n;
-	CU(ctx->h_res.reserve(bytes));
-	CU(cudaMemcpyAsync(ctx->h_res.p, b->d_res.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-	CU(cudaStreamSynchronize(ctx->stream));
-	memcpy(res, ctx->h_res.p, bytes);
+	CU(s.h_res.reserve(bytes));
+	CU(cudaMemcpyAsync(s.h_res.p, b->d_res.p, bytes, cudaMemcpyDeviceToHost, s.stream));
+	CU(cudaStreamSynchronize(s.stream));
+	memcpy(res, s.h_res.p, bytes);
+	return 0;
+}
+
+int ksw_b200_batch_download_cells(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, uint32_t *cells)
+{
+	if (!ctx || !b || (!cells && b->n)) return 1;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->slot[0].stream));
+	if (b->n) CU(cudaMemcpy(cells, b->d_cells.p, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToHost));
 	return 0;
 }
 
@@ -336,10 +399,12 @@ int ksw_b200_batch_info(const ksw_b200_batch_t *b, int64_t *n_fast, int64_t *n_g
 
 void ksw_b200_batch_free(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b)
 {
-	if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-	batch_release(b);
+	if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->slot[0].stream); }
+	if (b) { batch_release_buffers(b); delete b; }
 }
 
+// One-shot batched entry.  The batch is cut into chunks of ctx->chunk_jobs jobs (caller order); chunk c+1 is
+// packed on the host threads while chunk c is being copied / computed on the GPU (two slots, two streams).
 int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
                           const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
 {
@@ -347,15 +412,36 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 	if (n == 0) return 0;
 	if (!jobs || !res) return 1;
 	CU(cudaSetDevice(ctx->device));
-	if (!ctx->cached) ctx->cached = new ksw_b200_batch();
-	ksw_b200_batch *b = ctx->cached;
-	int rc = upload_into(ctx, cfg, n, jobs, qpool, tpool, b);
-	if (rc) return rc;
-	rc = enqueue_kernels(ctx, b);
-	if (rc) return rc;
-	ctx->last_h2d = (int64_t)(sizeof(DevJob) * (size_t)n + b->pool_bytes + b->npool_bytes);
+	const double t_begin = now_ms();
+	double t_plan = 0, t_fill = 0, t_wait = 0;
+	int64_t h2d = 0;
+	const int64_t chunk = ctx->chunk_jobs;
+	int which = 0;
+	for (int64_t first = 0; first < n; first += chunk, which ^= 1) {
+		const int64_t nc = std::min(chunk, n - first);
+		Slot &s = ctx->slot[which];
+		int rc = retire_slot(ctx, s, res, &t_wait);              // its staging and device buffers are about to be reused
+		if (rc) return rc;
+		rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, &t_plan, &t_fill);
+		if (rc) return rc;
+		rc = enqueue_kernels(ctx, s, &s.batch);
+		if (rc) return rc;
+		CU(s.h_res.reserve(sizeof(DevRes) * (size_t)nc));
+		CU(cudaMemcpyAsync(s.h_res.p, s.batch.d_res.p, sizeof(DevRes) * (size_t)nc, cudaMemcpyDeviceToHost, s.stream));
+		s.busy = true; s.first = first; s.n = nc;
+		h2d += (int64_t)(sizeof(DevJob) * (size_t)nc + s.batch.pool_bytes + s.batch.npool_bytes);
+	}
+	// retire in submission order
+	for (int k = 0; k < 2; ++k) {
+		int rc = retire_slot(ctx, ctx->slot[which ^ k], res, &t_wait);
+		if (rc) return rc;
+	}
+	ctx->last_h2d = h2d;
 	ctx->last_d2h = (int64_t)(sizeof(DevRes) * (size_t)n);
-	return ksw_b200_batch_download(ctx, b, res);
+	if (ctx->trace)
+		fprintf(stderr, "[ksw_b200] extend_batch n=%lld chunk=%lld: total %.2f ms (plan %.2f, fill %.2f, wait-gpu %.2f)\n",
+		        (long long)n, (long long)chunk, now_ms() - t_begin, t_plan, t_fill, t_wait);
+	return 0;
 }
 
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes)
@@ -366,27 +452,19 @@ int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, in
 	return 0;
 }
 
-int ksw_b200_batch_download_cells(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, uint32_t *cells)
-{
-	if (!ctx || !b || (!cells && b->n)) return 1;
-	CU(cudaSetDevice(ctx->device));
-	CU(cudaStreamSynchronize(ctx->stream));
-	if (b->n) CU(cudaMemcpy(cells, b->d_cells.p, sizeof(uint32_t) * (size_t)b->n, cudaMemcpyDeviceToHost));
-	return 0;
-}
-
 int ksw_b200_dpx_peak(ksw_b200_ctx_t *ctx, int which, double *lane_ops_per_s, float *ms_out)
 {
 	if (!ctx || !lane_ops_per_s) return 1;
 	CU(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->slot[0].stream;
 	const int blocks = ctx->sm_count * 8, iters = 4096;
 	unsigned *d = nullptr;
 	CU(cudaMalloc(&d, (size_t)blocks * 256 * 4));
 	float best = 1e30f;
 	for (int rep = 0; rep < 4; ++rep) {
-		CU(cudaEventRecord(ctx->ev0, ctx->stream));
-		CU(ksw_launch_dpx_peak(which, d, blocks, iters, ctx->stream));
-		CU(cudaEventRecord(ctx->ev1, ctx->stream));
+		CU(cudaEventRecord(ctx->ev0, st));
+		CU(ksw_launch_dpx_peak(which, d, blocks, iters, st));
+		CU(cudaEventRecord(ctx->ev1, st));
 		CU(cudaEventSynchronize(ctx->ev1));
 		float ms = 0;
 		CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));

@@ -78,6 +78,7 @@ def load_library():
     lib.ksw_b200_strerror.argtypes = [vp]
     lib.ksw_b200_strerror.restype = C.c_char_p
     lib.ksw_b200_ctx_set_pack_threads.argtypes = [vp, i32]
+    lib.ksw_b200_ctx_set_chunk_jobs.argtypes = [vp, i64]
     lib.ksw_b200_ctx_launch_count.argtypes = [vp]
     lib.ksw_b200_ctx_launch_count.restype = i64
     lib.ksw_b200_ctx_sync.argtypes = [vp]
@@ -132,6 +133,12 @@ class KswB200:
         if pack_threads:
             self.lib.ksw_b200_ctx_set_pack_threads(self.ctx, int(pack_threads))
 
+    def set_chunk_jobs(self, n: int):
+        self.lib.ksw_b200_ctx_set_chunk_jobs(self.ctx, int(n))
+
+    def set_pack_threads(self, n: int):
+        self.lib.ksw_b200_ctx_set_pack_threads(self.ctx, int(n))
+
     def close(self):
         if self.ctx:
             self.lib.ksw_b200_ctx_destroy(self.ctx)
@@ -154,10 +161,15 @@ class KswB200:
         tpool = np.ascontiguousarray(tpool, dtype=np.uint8)
         return jobs, qpool, tpool
 
-    def extend_batch(self, cfg: Cfg, jobs, qpool, tpool) -> np.ndarray:
-        """Host buffers in, host results out (pack + H2D + kernels + D2H inside the call)."""
+    def extend_batch(self, cfg: Cfg, jobs, qpool, tpool, out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers in, host results out (pack + H2D + kernels + D2H inside the call).
+        `out` (RES_DT, len(jobs)) lets a caller reuse its result array, as a C caller would."""
         jobs, qpool, tpool = self._norm(jobs, qpool, tpool)
-        res = np.zeros(jobs.shape[0], dtype=RES_DT)
+        if out is not None:
+            assert out.dtype == RES_DT and out.shape[0] == jobs.shape[0] and out.flags.c_contiguous
+            res = out
+        else:
+            res = np.zeros(jobs.shape[0], dtype=RES_DT)
         self._check(self.lib.ksw_b200_extend_batch(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool),
                                                    _p(tpool), _p(res)), "ksw_b200_extend_batch")
         return res

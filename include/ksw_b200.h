@@ -77,6 +77,9 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx);
 const char *ksw_b200_strerror(const ksw_b200_ctx_t *ctx);   /* last error text of this ctx ("" if none) */
 /* number of host threads used to pack sequences (default: min(hardware threads, 32)) */
 int  ksw_b200_ctx_set_pack_threads(ksw_b200_ctx_t *ctx, int n_threads);
+/* jobs per pipeline chunk of ksw_b200_extend_batch (default 2^20): chunk c+1 is packed on the host while
+ * chunk c is copied and computed on the GPU */
+int  ksw_b200_ctx_set_chunk_jobs(ksw_b200_ctx_t *ctx, int64_t chunk_jobs);
 /* cumulative number of kernels this ctx has launched (for bench accounting) */
 int64_t ksw_b200_ctx_launch_count(const ksw_b200_ctx_t *ctx);
 

@@ -17,11 +17,12 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 {
 	KswPackPlan plan;
 	std::string err;
-	int rc = ksw_pack_plan(cfg, n, jobs, KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1], threads, plan, err);
+	KswPool tp(threads);
+	int rc = ksw_pack_plan(cfg, n, jobs, KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1], &tp, plan, err);
 	if (rc) return rc;
 	std::vector<DevJob> dj(n ? n : 1);
 	std::vector<uint32_t> pool(plan.pool_bytes / 4 + 4), nmask;
-	rc = ksw_pack_fill(plan, cfg, jobs, qpool, tpool, dj.data(), pool.data(), nmask, threads);
+	rc = ksw_pack_fill(plan, cfg, jobs, qpool, tpool, dj.data(), pool.data(), nmask, &tp);
 	if (rc) return rc;
 	if (nmask.empty()) nmask.push_back(0);
 	KswParams P;
