@@ -40,6 +40,30 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
+    # mem_chain2aln level: regions from the reference's own mem_chain2aln (oracle/_ref/libbwa_ref.so)
+    assert K.have_bwa_ref()
+    csets = {
+        "default": K.gen_chains(300, seed=11),
+        "narrow_w": K.gen_chains(300, seed=12, opt=K.make_ext_opt(w=12), indel=0.01, max_indel=14),
+        "hi_indel250": K.gen_chains(200, seed=13, sub=0.04, indel=0.02, max_indel=12, read_lens=(250,)),
+        "asym": K.gen_chains(200, seed=14, opt=K.make_ext_opt(a=2, b=5, o_del=4, e_del=2, o_ins=8, e_ins=1, pen_clip5=7,
+                                                                pen_clip3=3, w=60, zdrop=40)),
+        "with_n": K.gen_chains(200, seed=15, n_frac=0.03),
+    }
+    out = {}
+    for name, cs in csets.items():
+        regs, reg_read = K.run_chain_ref(cs)
+        for f in ("pac", "read_off", "read_len", "qpool", "chain_read", "chain_seed0", "chain_nseeds", "seeds"):
+            out[f"{name}.{f}"] = getattr(cs, f)
+        out[f"{name}.l_pac"] = np.array([cs.l_pac], dtype=np.int64)
+        out[f"{name}.opt"] = np.frombuffer(bytes(cs.opt), dtype=np.uint8).copy()
+        out[f"{name}.regs"] = regs
+        out[f"{name}.reg_read"] = reg_read
+        print(name, cs.n_reads, "reads", cs.n_chains, "chains", len(regs), "regions")
+    path = os.path.join(HERE, "chain2aln_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
 
 if __name__ == "__main__":
     main()

@@ -309,3 +309,220 @@ def run_emu(b: Batch, threads: int = 4):
                                       C.byref(nf), threads)
     assert rc == 0, rc
     return res, int(nf.value)
+
+
+# ------------------------------------------------------------------ chains -> regions (mem_chain2aln level)
+SEED_DT = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])                      # mem_seed_t
+REG_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),
+                   ("sub", "<i4"), ("csub", "<i4"), ("sub_n", "<i4"), ("w", "<i4"), ("seedcov", "<i4"),
+                   ("secondary", "<i4"), ("hash", "<u8")])                                   # mem_alnreg_t
+assert SEED_DT.itemsize == 16 and REG_DT.itemsize == 64
+
+
+class ExtOpt(C.Structure):
+    """b200_ext_opt_t / o_opt_t / flat_opt_t: the mem_opt_t fields the extension path reads."""
+    _fields_ = [("a", C.c_int), ("b", C.c_int), ("o_del", C.c_int), ("e_del", C.c_int), ("o_ins", C.c_int),
+                ("e_ins", C.c_int), ("pen_clip5", C.c_int), ("pen_clip3", C.c_int), ("w", C.c_int), ("zdrop", C.c_int),
+                ("mat", C.c_int8 * 25)]
+
+
+def make_ext_opt(a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, pen_clip5=5, pen_clip3=5, w=100, zdrop=100) -> ExtOpt:
+    o = ExtOpt()
+    o.a, o.b, o.o_del, o.e_del, o.o_ins, o.e_ins = a, b, o_del, e_del, o_ins, e_ins
+    o.pen_clip5, o.pen_clip3, o.w, o.zdrop = pen_clip5, pen_clip3, w, zdrop
+    m = fill_scmat(a, b)
+    for i in range(25):
+        o.mat[i] = int(m[i])
+    return o
+
+
+@dataclass
+class ChainSet:
+    opt: ExtOpt
+    l_pac: int
+    pac: np.ndarray          # uint8, 2-bit packed forward strand (bntseq.c:191)
+    read_off: np.ndarray     # int64
+    read_len: np.ndarray     # int32
+    qpool: np.ndarray        # uint8 codes
+    chain_read: np.ndarray   # int32, non-decreasing
+    chain_seed0: np.ndarray  # int64
+    chain_nseeds: np.ndarray  # int32
+    seeds: np.ndarray        # SEED_DT
+
+    @property
+    def n_reads(self):
+        return int(self.read_len.shape[0])
+
+    @property
+    def n_chains(self):
+        return int(self.chain_read.shape[0])
+
+    def flat_args(self):
+        return [self.l_pac, _ptr(self.pac), self.n_reads, _ptr(self.read_off), _ptr(self.read_len), _ptr(self.qpool),
+                self.n_chains, _ptr(self.chain_read), _ptr(self.chain_seed0), _ptr(self.chain_nseeds), _ptr(self.seeds)]
+
+
+def pack_pac(genome: np.ndarray) -> np.ndarray:
+    """2-bit packing as the reference stores .pac: base l in byte l>>2 at bits ((~l)&3)<<1 (bntseq.c:191)."""
+    n = len(genome)
+    g = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+    g[:n] = genome
+    g = g.reshape(-1, 4)
+    pac = (g[:, 0] << 6) | (g[:, 1] << 4) | (g[:, 2] << 2) | g[:, 3]
+    return np.ascontiguousarray(np.concatenate([pac, np.zeros(1, np.uint8)]).astype(np.uint8))
+
+
+def gen_chains(n_reads: int, seed: int, l_pac: int = 30000, read_lens=(100, 150, 250), sub=0.02, indel=0.003,
+               max_indel=8, opt: ExtOpt | None = None, k: int = 19, n_frac=0.0) -> ChainSet:
+    """Synthetic reads against a random genome with a few repeats; seeds = maximal exact matches (>= k) found with
+    a k-mer index over the doubled (forward + reverse-complement) coordinate space of the reference; chains =
+    greedy groups of same-strand seeds on nearby diagonals.  Any such chain is a legal mem_chain2aln input."""
+    rng = np.random.default_rng(seed)
+    opt = opt or make_ext_opt()
+    genome = rng.integers(0, 4, l_pac).astype(np.uint8)
+    for _ in range(6):                                   # repeats -> several chains per read, contained seeds
+        ln = int(rng.integers(60, 400)); a = int(rng.integers(0, l_pac - ln)); b = int(rng.integers(0, l_pac - ln))
+        seg = genome[a:a + ln].copy()
+        flip = rng.random(ln) < 0.01
+        seg[flip] = (seg[flip] + 1) & 3
+        genome[b:b + ln] = seg
+    dbl = np.concatenate([genome, (3 - genome[::-1])]).astype(np.uint8)
+    L2 = 2 * l_pac
+    # k-mer index over the doubled space (windows that straddle l_pac are skipped)
+    codes = np.zeros(L2 - k + 1, dtype=np.uint64)
+    for i in range(k):
+        codes = (codes << np.uint64(2)) | dbl[i:L2 - k + 1 + i].astype(np.uint64)
+    index: dict = {}
+    for pos, c in enumerate(codes.tolist()):
+        if pos < l_pac < pos + k:
+            continue
+        index.setdefault(c, []).append(pos)
+    reads, chain_read, chain_seed0, chain_nseeds, seeds = [], [], [], [], []
+    for r in range(n_reads):
+        L = int(rng.choice(read_lens))
+        strand = int(rng.integers(0, 2))
+        p0 = int(rng.integers(0, l_pac - L - 1)) + strand * l_pac
+        read = mutate(rng, dbl[p0:p0 + L + 40], sub, indel, max_indel)[:L]
+        if len(read) < L:
+            read = np.concatenate([read, rng.integers(0, 4, L - len(read)).astype(np.uint8)])
+        if n_frac and rng.random() < 0.3:
+            read = np.where(rng.random(L) < n_frac, 4, read).astype(np.uint8)
+        found = set()
+        rc = np.zeros(max(L - k + 1, 0), dtype=np.uint64)
+        ok = np.ones(max(L - k + 1, 0), dtype=bool)
+        for i in range(k):
+            part = read[i:L - k + 1 + i]
+            ok &= part < 4
+            rc = (rc << np.uint64(2)) | (part & 3).astype(np.uint64)
+        for q, (c, good) in enumerate(zip(rc.tolist(), ok.tolist())):
+            if not good:
+                continue
+            for pos in index.get(c, ()):
+                qb, rb = q, pos
+                lim_lo = 0 if pos < l_pac else l_pac
+                lim_hi = l_pac if pos < l_pac else L2
+                while qb > 0 and rb > lim_lo and read[qb - 1] == dbl[rb - 1]:
+                    qb -= 1; rb -= 1
+                qe, re_ = q + k, pos + k
+                while qe < L and re_ < lim_hi and read[qe] == dbl[re_]:
+                    qe += 1; re_ += 1
+                found.add((rb, qb, qe - qb))
+        sl = sorted(found)
+        # greedy chaining: same strand, diagonal within 120, reference distance within 1000
+        chains: list = []
+        for (rb, qb, ln) in sl:
+            placed = False
+            for ch in chains:
+                rb0, qb0, _ = ch[-1]
+                if (rb0 < l_pac) == (rb < l_pac) and abs((rb - qb) - (rb0 - qb0)) < 120 and abs(rb - rb0) < 1000:
+                    ch.append((rb, qb, ln)); placed = True
+                    break
+            if not placed:
+                chains.append([(rb, qb, ln)])
+        chains.sort(key=lambda ch: -sum(s[2] for s in ch))
+        reads.append(read)
+        for ch in chains[:6]:
+            chain_read.append(r); chain_seed0.append(len(seeds)); chain_nseeds.append(len(ch))
+            seeds.extend(ch)
+    rl = np.array([len(x) for x in reads], dtype=np.int32)
+    ro = np.concatenate([[0], np.cumsum(rl)[:-1]]).astype(np.int64)
+    sd = np.zeros(len(seeds), dtype=SEED_DT)
+    if seeds:
+        arr = np.array(seeds, dtype=np.int64)
+        sd["rbeg"], sd["qbeg"], sd["len"] = arr[:, 0], arr[:, 1], arr[:, 2]
+    return ChainSet(opt, l_pac, pack_pac(genome), ro, rl, np.ascontiguousarray(np.concatenate(reads).astype(np.uint8)),
+                    np.array(chain_read, dtype=np.int32), np.array(chain_seed0, dtype=np.int64),
+                    np.array(chain_nseeds, dtype=np.int32), sd)
+
+
+def _run_chain_flat(fn, cs: ChainSet, extra_head=(), want_calls=False):
+    cap = int(cs.seeds.shape[0]) + 8
+    out = np.zeros(cap, dtype=REG_DT)
+    out_read = np.zeros(cap, dtype=np.int32)
+    n_out = C.c_int64(0)
+    n_calls = C.c_int64(0)
+    args = list(extra_head) + [C.byref(cs.opt)] + cs.flat_args() + [C.c_int64(cap), _ptr(out), _ptr(out_read), C.byref(n_out)]
+    if want_calls:
+        args.append(C.byref(n_calls))
+    rc = fn(*args)
+    assert rc == 0, rc
+    n = int(n_out.value)
+    return (out[:n].copy(), out_read[:n].copy(), int(n_calls.value)) if want_calls else (out[:n].copy(), out_read[:n].copy())
+
+
+_FLAT_TAIL = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+              C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def run_chain_oracle(cs: ChainSet):
+    fn = oracle_lib().oracle_chain2aln_flat
+    fn.restype = C.c_int
+    fn.argtypes = _FLAT_TAIL + [C.c_void_p]
+    return _run_chain_flat(fn, cs, want_calls=True)
+
+
+BWA_REF_SO = os.path.join(ORACLE_DIR, "_ref", "libbwa_ref.so")
+
+
+def have_bwa_ref() -> bool:
+    return os.path.exists(BWA_REF_SO)
+
+
+def run_chain_ref(cs: ChainSet):
+    if "bwaref" not in _libs:
+        _libs["bwaref"] = C.CDLL(BWA_REF_SO)
+    fn = _libs["bwaref"].ref_chain2aln_flat
+    fn.restype = C.c_int
+    fn.argtypes = _FLAT_TAIL
+    return _run_chain_flat(fn, cs)
+
+
+def run_chain_gpu(ctx, cs: ChainSet):
+    """The product's batched driver (b200_chain2aln_flat) on a KswB200 context."""
+    fn = ctx.lib.b200_chain2aln_flat
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] + _FLAT_TAIL
+    return _run_chain_flat(fn, cs, extra_head=[ctx.ctx])
+
+
+def regs_equal(a, b):
+    (ra, ia), (rb, ib) = a, b
+    if ra.shape != rb.shape or not (ia == ib).all():
+        return False
+    return all((ra[f] == rb[f]).all() for f in REG_DT.names)
+
+
+CHAIN_GOLDEN = os.path.join(ROOT, "tests", "golden", "chain2aln_golden.npz")
+
+
+def load_chain_golden():
+    """{name: (ChainSet, (regions, region_read))} made by tests/golden/make_golden.py from the reference's own
+    mem_chain2aln."""
+    z = np.load(CHAIN_GOLDEN)
+    out = {}
+    for nm in sorted({k.split(".")[0] for k in z.files}):
+        opt = ExtOpt.from_buffer_copy(z[f"{nm}.opt"].tobytes())
+        cs = ChainSet(opt, int(z[f"{nm}.l_pac"][0]), z[f"{nm}.pac"], z[f"{nm}.read_off"], z[f"{nm}.read_len"], z[f"{nm}.qpool"],
+                      z[f"{nm}.chain_read"], z[f"{nm}.chain_seed0"], z[f"{nm}.chain_nseeds"], z[f"{nm}.seeds"].astype(SEED_DT))
+        out[nm] = (cs, (z[f"{nm}.regs"].astype(REG_DT), z[f"{nm}.reg_read"]))
+    return out
