@@ -16,5 +16,5 @@ fi
 if [ ! -f build/bwamem_ext.o ] || [ -n "$(find csrc ../include -newer build/bwamem_ext.o | head -1)" ]; then
   gcc -O2 -std=gnu99 -fPIC -Wall -c csrc/bwamem_ext.c -o build/bwamem_ext.o
 fi
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libksw_b200.so build/ksw_generic.o build/ksw_fast.o build/ksw_runtime.o build/ksw_pack.o build/bwamem_ext.o -lcudart_static -lpthread -ldl -lrt
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libksw_b200.so build/ksw_generic.o build/ksw_fast.o build/ksw_runtime.o build/ksw_pack.o build/bwamem_ext.o -Xlinker -Bsymbolic-functions -lcudart_static -lpthread -ldl -lrt
 echo "built $(pwd)/libksw_b200.so"

@@ -1,0 +1,127 @@
+"""Whole-program check support: synthetic genome + reads, run stock / fork / B200-bound `bwa mem`, compare SAM.
+Methodology of the reference's own A/B harness (pipeline.sh vs pipeline_ref.sh: same command, DUT vs REF SAM)
+and of NEWS:27-28 (whole-SAM identity).  Test infrastructure only."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+BWA_STOCK = os.path.join(REFDIR, "bwa_stock")
+BWA_FORK = os.path.join(REFDIR, "bwa_fork")
+BWA_B200 = os.path.join(REFDIR, "bwa_b200")
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = np.array([3, 2, 1, 0], dtype=np.uint8)
+
+
+def have_binaries(*paths) -> bool:
+    return all(os.path.exists(p) and os.access(p, os.X_OK) for p in paths)
+
+
+def write_genome(path: str, length: int, seed: int, n_contigs: int = 1) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 4, length).astype(np.uint8)
+    with open(path, "w") as f:
+        per = length // n_contigs
+        for c in range(n_contigs):
+            seg = g[c * per:(c + 1) * per if c < n_contigs - 1 else length]
+            f.write(f">chr{c + 1}\n")
+            s = ACGT[seg].tobytes().decode()
+            for i in range(0, len(s), 80):
+                f.write(s[i:i + 80] + "\n")
+    return g
+
+
+def _mutate(rng, seq, sub, indel_events, indel_max):
+    """substitutions per base; `indel_events` per-base rate of an insertion or deletion of length U[1,indel_max]"""
+    out = []
+    i, n = 0, len(seq)
+    r = rng.random(2 * n + 4)
+    k = 0
+    while i < n:
+        x = r[k]; k += 1
+        if x < indel_events / 2:
+            i += int(rng.integers(1, indel_max + 1))
+            continue
+        if x < indel_events:
+            out.extend(rng.integers(0, 4, int(rng.integers(1, indel_max + 1))).tolist())
+        c = int(seq[i])
+        if r[k] < sub:
+            c = (c + int(rng.integers(1, 4))) & 3
+        k += 1
+        out.append(c); i += 1
+    return np.array(out, dtype=np.uint8)
+
+
+def _fq(f, name, codes):
+    s = ACGT[codes].tobytes().decode()
+    f.write(f"@{name}\n{s}\n+\n{'I' * len(s)}\n")
+
+
+def write_reads_se(path, genome, n, length, seed, sub=0.01, indel=0.001, indel_max=1, n_rate=0.0):
+    rng = np.random.default_rng(seed)
+    G = len(genome)
+    with open(path, "w") as f:
+        for r in range(n):
+            p = int(rng.integers(0, G - length - 20))
+            frag = genome[p:p + length + 20]
+            if rng.random() < 0.5:
+                frag = COMP[frag[::-1]]
+            rd = _mutate(rng, frag, sub, indel, indel_max)[:length]
+            s = ACGT[rd].tobytes().decode()
+            if n_rate and rng.random() < 0.2:
+                s = "".join("N" if rng.random() < n_rate else ch for ch in s)
+            f.write(f"@r{r}\n{s}\n+\n{'I' * len(s)}\n")
+
+
+def write_reads_pe(path1, path2, genome, n_pairs, length, seed, sub=0.01, indel=0.001, indel_max=1, ins_mean=None, ins_sd=None):
+    rng = np.random.default_rng(seed)
+    G = len(genome)
+    ins_mean = ins_mean or 2.5 * length
+    ins_sd = ins_sd or 0.25 * length
+    with open(path1, "w") as f1, open(path2, "w") as f2:
+        for r in range(n_pairs):
+            isz = max(length + 10, int(rng.normal(ins_mean, ins_sd)))
+            p = int(rng.integers(0, G - isz - 40))
+            frag = genome[p:p + isz + 40]
+            if rng.random() < 0.5:
+                frag = COMP[frag[::-1]]
+            a = _mutate(rng, frag[:length + 30], sub, indel, indel_max)[:length]
+            b = _mutate(rng, COMP[frag[:isz][::-1]][:length + 30], sub, indel, indel_max)[:length]
+            _fq(f1, f"p{r}", a)
+            _fq(f2, f"p{r}", b)
+
+
+def run(cmd, stdout_path=None, env=None, timeout=1800):
+    with open(stdout_path, "wb") if stdout_path else open(os.devnull, "wb") as out:
+        p = subprocess.run(cmd, stdout=out, stderr=subprocess.PIPE, env=env, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError(f"{' '.join(cmd)} failed ({p.returncode}): {p.stderr.decode()[-2000:]}")
+    return p.stderr.decode()
+
+
+def bwa_index(fa):
+    run([BWA_STOCK, "index", fa])
+
+
+def bwa_mem(binary, fa, reads, out_sam, threads=4, extra=(), env=None):
+    return run([binary, "mem", "-t", str(threads), *extra, fa, *reads], stdout_path=out_sam, env=env)
+
+
+def sam_body(path):
+    """SAM lines without @PG (the only line allowed to differ: main.c:66-68 puts the command line there)."""
+    with open(path, "rb") as f:
+        return [ln for ln in f if not ln.startswith(b"@PG")]
+
+
+def sam_equal(a, b):
+    la, lb = sam_body(a), sam_body(b)
+    if la == lb:
+        return True, None
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            return False, (i, x[:300], y[:300])
+    return False, (min(len(la), len(lb)), b"<length differs>", f"{len(la)} vs {len(lb)}".encode())

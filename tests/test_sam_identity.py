@@ -1,0 +1,83 @@
+"""Whole-program parity (BASELINE.json: "the resulting SAM must be byte-identical to stock bwa mem apart from the
+@PG line").  CPU: the harness itself (fork == stock, as SURVEY.md §0 found).  GPU: `bwa mem` with pass 1 bound to the
+B200 library (integration/bwamem_b200_glue.c) against stock 0.7.8, same -t, SE and PE, several -b / -t."""
+import os
+
+import pytest
+
+import samtest as S
+
+need_bins = pytest.mark.skipif(not S.have_binaries(S.BWA_STOCK, S.BWA_FORK),
+                               reason="oracle/_ref bwa binaries not built (reference sources not mounted at build time)")
+
+
+@pytest.fixture(scope="module")
+def small_se(tmp_path_factory):
+    d = tmp_path_factory.mktemp("se")
+    fa = str(d / "ref.fa")
+    g = S.write_genome(fa, 300000, seed=1)
+    S.bwa_index(fa)
+    fq = str(d / "r.fq")
+    S.write_reads_se(fq, g, 3000, 100, seed=2, n_rate=0.02)
+    return d, fa, fq
+
+
+@need_bins
+def test_harness_fork_equals_stock_cpu(small_se):
+    d, fa, fq = small_se
+    S.bwa_mem(S.BWA_STOCK, fa, [fq], str(d / "stock.sam"), threads=2)
+    S.bwa_mem(S.BWA_FORK, fa, [fq], str(d / "fork.sam"), threads=2, extra=["-b", "64"])
+    ok, why = S.sam_equal(str(d / "stock.sam"), str(d / "fork.sam"))
+    assert ok, why
+    assert len(S.sam_body(str(d / "stock.sam"))) > 3000
+
+
+need_b200 = pytest.mark.skipif(not S.have_binaries(S.BWA_STOCK, S.BWA_B200), reason="oracle/_ref/bwa_b200 not built")
+
+
+@pytest.mark.gpu
+@need_b200
+def test_se100_config1_byte_identical(tmp_path):
+    # BASELINE.json configs[0]: single-end 100 bp, 1 % subst, 0.1 % indel, 1 Mbp reference
+    fa = str(tmp_path / "ref.fa")
+    g = S.write_genome(fa, 1_000_000, seed=12345)
+    S.bwa_index(fa)
+    fq = str(tmp_path / "r.fq")
+    S.write_reads_se(fq, g, 20000, 100, seed=12346, sub=0.01, indel=0.001)
+    S.bwa_mem(S.BWA_STOCK, fa, [fq], str(tmp_path / "stock.sam"), threads=4)
+    for tag, extra, thr in (("b1", [], 4), ("b5000", ["-b", "5000"], 4), ("t1", ["-b", "100000"], 1)):
+        out = str(tmp_path / f"b200_{tag}.sam")
+        if thr != 4:
+            S.bwa_mem(S.BWA_STOCK, fa, [fq], str(tmp_path / "stock_t.sam"), threads=thr)
+        S.bwa_mem(S.BWA_B200, fa, [fq], out, threads=thr, extra=extra)
+        ok, why = S.sam_equal(str(tmp_path / ("stock.sam" if thr == 4 else "stock_t.sam")), out)
+        assert ok, (tag, why)
+
+
+@pytest.mark.gpu
+@need_b200
+def test_pe150_byte_identical(tmp_path):
+    fa = str(tmp_path / "ref.fa")
+    g = S.write_genome(fa, 2_000_000, seed=21, n_contigs=3)
+    S.bwa_index(fa)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    S.write_reads_pe(f1, f2, g, 15000, 150, seed=22, ins_mean=375, ins_sd=37)
+    S.bwa_mem(S.BWA_STOCK, fa, [f1, f2], str(tmp_path / "stock.sam"), threads=4)
+    S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4, extra=["-b", "3000"])
+    ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
+    assert ok, why
+
+
+@pytest.mark.gpu
+@need_b200
+def test_pe250_high_indel_byte_identical(tmp_path):
+    # BASELINE.json configs[3] shape: 2x250, 3 % subst, 2 % indel events of length U[1,12] (wide bands, z-drop heavy)
+    fa = str(tmp_path / "ref.fa")
+    g = S.write_genome(fa, 2_000_000, seed=31)
+    S.bwa_index(fa)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    S.write_reads_pe(f1, f2, g, 6000, 250, seed=32, sub=0.03, indel=0.02, indel_max=12)
+    S.bwa_mem(S.BWA_STOCK, fa, [f1, f2], str(tmp_path / "stock.sam"), threads=4)
+    S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4)
+    ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
+    assert ok, why
