@@ -16,6 +16,7 @@ namespace {
 
 constexpr int T = KSW_FAST_THREADS;   // 32: one warp per CTA
 
+template <bool KEYED>
 __global__ void __launch_bounds__(T)
 ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
                 const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap,
@@ -24,15 +25,20 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 	extern __shared__ uint4 smem[];
 	const int lane = threadIdx.x;
 	uint4 *hq = smem;
-	uint16_t *sa = reinterpret_cast<uint16_t *>(hq + (size_t)nq_cap * T);
-	uint16_t *sb = sa + (size_t)nq_cap * T;
-	uint2 *mrow = reinterpret_cast<uint2 *>(sb + (size_t)nq_cap * T);
-	if (lane < 5) mrow[lane] = ksw_fast_matrow(P, lane);
+	uint32_t *sq = reinterpret_cast<uint32_t *>(hq + (size_t)nq_cap * T);
+	uint2 *mrow = reinterpret_cast<uint2 *>(sq + (size_t)nq_cap * T);
+	KswFastEdge *edge = reinterpret_cast<KswFastEdge *>(mrow + 6);
+	if (lane < 5) {
+		mrow[lane] = ksw_fast_matrow(P, lane);
+		KswFastEdge e;
+		ksw_fast_edge_entry(lane, e);
+		edge[lane] = e;
+	}
 	__syncwarp();
 
 	KswFastConst K;
 	ksw_fast_make_const(P, K);
-	const KswFastMem<T> M{hq + lane, sa + lane, sb + lane};
+	const KswFastMem<T> M{hq + lane, sq + lane, edge};
 	KswFastLane L;
 	L.tlen = 0; L.i = 0;
 	enum { IDLE = 0, RUN = 1, DONE = 2 };
@@ -56,7 +62,7 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 		}
 		if (__all_sync(0xffffffffu, state == DONE)) break;
 		if (state == RUN) {
-			if (ksw_fast_row<T>(L, M, K, mrow)) {
+			if (ksw_fast_row<T, KEYED>(L, M, K, mrow)) {
 				DevRes r;
 				ksw_fast_result(L, r);
 				res[L.idx] = r;
@@ -71,19 +77,19 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 
 size_t ksw_fast_smem_bytes(int qmax)
 {
-	return (size_t)KSW_FAST_QUADS(qmax) * T * (sizeof(uint4) + sizeof(uint32_t)) + 5 * sizeof(uint2) + 8;
+	return (size_t)KSW_FAST_QUADS(qmax) * T * (sizeof(uint4) + sizeof(uint32_t)) + 6 * sizeof(uint2) + 5 * sizeof(KswFastEdge);
 }
 
-cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
-                            const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
-                            DevRes *res, uint32_t *cells, cudaStream_t st)
+template <bool KEYED>
+static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
+                                 const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
+                                 DevRes *res, uint32_t *cells, cudaStream_t st)
 {
-	if (n_jobs <= 0) return cudaSuccess;
 	const size_t smem = ksw_fast_smem_bytes(qmax);
-	cudaError_t e = cudaFuncSetAttribute(ksw_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(ksw_fast_kernel<KEYED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_fast_kernel, T, smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_fast_kernel<KEYED>, T, smem);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
 	long long blocks = (long long)sm_count * per_sm;
@@ -91,7 +97,16 @@ cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *
 	if (blocks > need) blocks = need;
 	e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
 	if (e != cudaSuccess) return e;
-	ksw_fast_kernel<<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
-	                                                    KSW_FAST_QUADS(qmax), counter, res, cells);
+	ksw_fast_kernel<KEYED><<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
+	                                                           KSW_FAST_QUADS(qmax), counter, res, cells);
 	return cudaGetLastError();
+}
+
+cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
+                            const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter,
+                            DevRes *res, uint32_t *cells, cudaStream_t st)
+{
+	if (n_jobs <= 0) return cudaSuccess;
+	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, res, cells, st)
+	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, res, cells, st);
 }

@@ -16,7 +16,9 @@
 //              F      : 2 x VIADDMNMX.S16x2 + 1 PRMT                 F(j+1) = max(F(j)-e_ins, g(j))   (*)
 //              h      = VIMNMX.S16x2(h', F)                                                      ksw.c:432
 //              E'     = VIADDMNMX.S16x2(E, -e_del, RELU(h - oe_del)) 2 DPX                       ksw.c:436-439
-//              (m,mj) : VIMNMX.S16x2 with predicate outputs + 2 predicated index moves          ksw.c:434-435
+//              (m,mj) : KEYED jobs (qlen <= 124, scores < 512): key = h*128 + column (1 IMAD on the FMA pipe),
+//                       VIMNMX.U16x2 on the keys — the larger column wins ties, as in the reference;
+//                       other jobs: VIMNMX.S16x2 with predicate outputs + 2 predicated index moves   ksw.c:434-435
 //              zero?  : VIMNMX3.S16x2 min over the row (1 per quad)  feeds the band trim        ksw.c:463-466
 //   (*) the reference computes F(j+1) = max(F(j)-e_ins, max(H(j)-oe_ins,0)) with H = max(h',F);
 //       since o_ins >= 0 implies F-oe_ins <= F-e_ins this equals max(F(j)-e_ins, h'(j)-oe_ins, 0)
@@ -46,6 +48,7 @@ namespace kswdpx {
 __device__ __forceinline__ uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t addmax2_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ uint32_t maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 __device__ __forceinline__ uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo) { return __vibmax_s16x2(a, b, &ge_hi, &ge_lo); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
@@ -70,6 +73,11 @@ KSW_EMU uint32_t addmax2_relu(uint32_t a, uint32_t b, uint32_t c)
 	return pk16(mx(mx((int16_t)(lo16(a) + lo16(b)), lo16(c)), 0), mx(mx((int16_t)(hi16(a) + hi16(b)), hi16(c)), 0));
 }
 KSW_EMU uint32_t max2(uint32_t a, uint32_t b) { return pk16(mx(lo16(a), lo16(b)), mx(hi16(a), hi16(b))); }
+KSW_EMU uint32_t maxu2(uint32_t a, uint32_t b)
+{
+	const uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+	return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+}
 KSW_EMU uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c)
 {
 	return pk16(mn(mn(lo16(a), lo16(b)), lo16(c)), mn(mn(hi16(a), hi16(b)), hi16(c)));
@@ -139,12 +147,41 @@ static KSW_HD ksw_u2 ksw_fast_matrow(const KswParams &P, int t)
 // halfword index of column c's H inside its quad's uint4 {HA, EA, HB, EB}; E is at +2
 static KSW_HD int ksw_fast_hslot(int c) { const int k = c & 3; return k < 2 ? k : 7 - k; }
 
-// Shared-memory view of one lane: quad q lives at hq[q*T]; the PRMT selectors of its pair A / pair B
-// at sa[q*T] / sb[q*T] (two separate 16-bit arrays so that each is one LDS.U16 and no ALU extract).
+// Edge look-up table (one copy per CTA in shared memory), indexed by r = a column position inside a quad, 0..4:
+//   ge / lt   : halfword masks of the quad's columns >= r / < r in the (A: lo c0, hi c1; B: lo c3, hi c2) layout
+//   only      : halfword mask of column r alone (all-zero for r == 4)
+//   sel_left  : PRMT selector that extracts H of column r-1 from (hA, hB) into the low half, zero-extended
+struct KswFastEdge {
+	uint32_t geA, geB, onlyA, onlyB;
+	uint32_t ltA, ltB, sel_left, pad;
+};
+
+static KSW_HD void ksw_fast_edge_entry(int r, KswFastEdge &e)
+{
+	// column k of a quad: k=0 -> A.lo, 1 -> A.hi, 2 -> B.hi, 3 -> B.lo
+	const uint32_t colA[4] = {0x0000ffffu, 0xffff0000u, 0u, 0u};
+	const uint32_t colB[4] = {0u, 0u, 0xffff0000u, 0x0000ffffu};
+	e.geA = e.geB = e.ltA = e.ltB = 0u;
+	for (int k = 0; k < 4; ++k) {
+		if (k >= r) { e.geA |= colA[k]; e.geB |= colB[k]; }
+		else        { e.ltA |= colA[k]; e.ltB |= colB[k]; }
+	}
+	e.onlyA = r < 4 ? colA[r] : 0u;
+	e.onlyB = r < 4 ? colB[r] : 0u;
+	// bytes of (hA, hB): 0,1 = A.lo  2,3 = A.hi  4,5 = B.lo  6,7 = B.hi; the upper result bytes replicate the sign
+	// (always 0: H >= 0), i.e. selector nibbles {lo, hi, 8|hi, 8|hi}
+	const uint32_t sel[4] = {0x9910u, 0xbb32u, 0xff76u, 0xdd54u};
+	e.sel_left = r >= 1 ? sel[r - 1] : sel[0];
+	e.pad = 0u;
+}
+
+// Shared-memory view of one lane: quad q lives at hq[q*T]; the PRMT selectors of its two pairs in one word
+// at sq[q*T] (low 16 bits: pair A, high 16 bits: pair B; PRMT ignores selector bits above 15).
 template <int T>
 struct KswFastMem {
 	ksw_u4 *hq;
-	uint16_t *sa, *sb;
+	uint32_t *sq;
+	const KswFastEdge *edge;     // 5 entries, shared by the CTA
 	KSW_HD uint16_t *h16(int c) const { return reinterpret_cast<uint16_t *>(&hq[(c >> 2) * T]) + ksw_fast_hslot(c); }
 };
 
@@ -192,8 +229,7 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 		v4.z = (uint32_t)hv[3] | ((uint32_t)hv[2] << 16);   // pair B: lo c3, hi c2
 		v4.w = 0u;
 		M.hq[q * T] = v4;
-		M.sa[q * T] = (uint16_t)(sb[0] | (sb[1] << 8));
-		M.sb[q * T] = (uint16_t)(sb[3] | (sb[2] << 8));
+		M.sq[q * T] = (sb[0] | (sb[1] << 8)) | ((sb[3] | (sb[2] << 8)) << 16);
 	}
 }
 
@@ -201,31 +237,35 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 struct KswFastRowRegs {       // registers carried along a row
 	uint32_t X;               // F entering the next column (lo half at quad entry)
 	uint32_t Hc;              // lo half = H(i, c0-1): carry for the shifted H store
-	uint32_t m, zmin;         // per-half running max / min of the row
-	int mjl, mjh;             // last column where the lo / hi half reached its running max
+	uint32_t m, zmin;         // running max (keys if KEYED) / running min of the row, per half
+	int mjl, mjh;             // !KEYED: last column where the lo / hi half reached its running max
+	uint32_t colA, colB;      // KEYED: packed column numbers of the current quad's pairs
 	uint32_t hA, hB;          // H of the last processed quad
 };
 
-// One quad (4 cells).  EDGE quads (first / last of the band) mask their out-of-band columns.
-template <int T, bool EDGE>
+#if defined(__CUDA_ARCH__)
+static __device__ __forceinline__ uint32_t ksw_hi16_of(uint32_t w) { return __umulhi(w, 0x10000u); }   // FMA pipe, not ALU
+#else
+static inline uint32_t ksw_hi16_of(uint32_t w) { return w >> 16; }
+#endif
+
+// One quad (4 cells).  EDGE: 0 = interior quad, 1 = a quad at the band edge: its out-of-band ("phantom")
+// columns are masked with keepA/keepB, the reference's edge writes are folded into its store.
+template <int T, bool KEYED, bool EDGE>
 static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, const KswFastConst &K, const ksw_u2 mr,
-                                 const int q, const int lo, const int hi)
+                                 const int q, const uint32_t keepA, const uint32_t keepB,
+                                 const uint32_t firstA, const uint32_t firstB, const uint32_t left0pk,
+                                 const uint32_t endA, const uint32_t endB)
 {
 	using namespace kswdpx;
 	ksw_u4 v = M.hq[q * T];
-	const uint32_t selA = M.sa[q * T], selB = M.sb[q * T];
-	const int c0 = q << 2;
-	uint32_t keepA = 0xffffffffu, keepB = 0xffffffffu;
+	const uint32_t sw = M.sq[q * T];
 	if (EDGE) {
-		// in-band test per column; phantom columns get H = -8192, E = 0
-		const uint32_t in0 = (uint32_t)(c0 >= lo && c0 < hi), in1 = (uint32_t)(c0 + 1 >= lo && c0 + 1 < hi);
-		const uint32_t in2 = (uint32_t)(c0 + 2 >= lo && c0 + 2 < hi), in3 = (uint32_t)(c0 + 3 >= lo && c0 + 3 < hi);
-		keepA = in0 * 0xffffu + in1 * 0xffff0000u;
-		keepB = in3 * 0xffffu + in2 * 0xffff0000u;
+		// phantom columns get H = -8192, E = 0
 		v.x = (v.x & keepA) | (KSW_NEGPK & ~keepA); v.y &= keepA;
 		v.z = (v.z & keepB) | (KSW_NEGPK & ~keepB); v.w &= keepB;
 	}
-	const uint32_t scA = prmt(mr.x, mr.y, selA), scB = prmt(mr.x, mr.y, selB);
+	const uint32_t scA = prmt(mr.x, mr.y, sw), scB = prmt(mr.x, mr.y, ksw_hi16_of(sw));
 	const uint32_t hpA = addmax2(v.x, scA, v.y), hpB = addmax2(v.z, scB, v.w);
 	// relu(h' - oe_ins): the third operand only has to be <= 0, a live constant saves a zero register
 	const uint32_t gA = addmax2_relu(hpA, K.neg_oei, K.neg_oei), gB = addmax2_relu(hpB, K.neg_oei, K.neg_oei);
@@ -238,34 +278,78 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 	R.X = addmax2(FB, K.neg_ei, gB);                       // lo = F(c0 of the next quad)
 	const uint32_t hA = max2(hpA, FA), hB = max2(hpB, FB);
 	// E(i+1,j) = max(E - e_del, relu(H - oe_del))
-	const uint32_t eA = addmax2(v.y, K.neg_ed, addmax2_relu(hA, K.neg_oed, K.neg_oed));
-	const uint32_t eB = addmax2(v.w, K.neg_ed, addmax2_relu(hB, K.neg_oed, K.neg_oed));
-	// row maximum with last-index-wins ties, tracked per half (each half sees its columns in rising order)
-	bool ph, pl;
-	R.m = bmax2(hA, R.m, ph, pl);
-	if (pl) R.mjl = c0;
-	if (ph) R.mjh = c0 + 1;
-	R.m = bmax2(hB, R.m, ph, pl);
-	if (ph) R.mjh = c0 + 2;
-	if (pl) R.mjl = c0 + 3;
+	uint32_t eA = addmax2(v.y, K.neg_ed, addmax2_relu(hA, K.neg_oed, K.neg_oed));
+	uint32_t eB = addmax2(v.w, K.neg_ed, addmax2_relu(hB, K.neg_oed, K.neg_oed));
+	// row maximum, ties to the last column (ksw.c:434)
+	if (KEYED) {
+		R.m = maxu2(R.m, hA * 128u + R.colA);
+		R.m = maxu2(R.m, hB * 128u + R.colB);
+		R.colA += 0x00040004u; R.colB += 0x00040004u;
+	} else {
+		// per half (each half sees its columns in rising order)
+		const int c0 = q << 2;
+		bool ph, pl;
+		R.m = bmax2(hA, R.m, ph, pl);
+		if (pl) R.mjl = c0;
+		if (ph) R.mjh = c0 + 1;
+		R.m = bmax2(hB, R.m, ph, pl);
+		if (ph) R.mjh = c0 + 2;
+		if (pl) R.mjl = c0 + 3;
+	}
 	// zero detector over the in-band cells
 	if (EDGE) R.zmin = min3_2(R.zmin, hA | (~keepA & 0x7fff7fffu), hB | (~keepB & 0x7fff7fffu));
 	else R.zmin = min3_2(R.zmin, hA, hB);
 	// store: eh[j].h = H(i, j-1), eh[j].e = E(i+1, j)
 	ksw_u4 o;
 	o.x = prmt(R.Hc, hA, 0x5410u);                         // (H(c0-1), H(c0))
-	o.y = eA;
 	o.z = prmt(hA, hB, 0x3276u);                           // (lo: H(c2) for column c3, hi: H(c1) for column c2)
-	o.w = eB;
+	if (EDGE) {
+		// eh[beg].h = first-column value (ksw.c:429) where this quad holds column lo; eh[end].e = 0 (ksw.c:446)
+		// where it holds column hi (eh[end].h = h1 is what the shifted store writes there anyway)
+		o.x = (o.x & ~firstA) | (left0pk & firstA);
+		o.z = (o.z & ~firstB) | (left0pk & firstB);
+		eA &= ~endA; eB &= ~endB;
+	}
+	o.y = eA; o.w = eB;
 	M.hq[q * T] = o;
 	R.Hc = hB;                                             // lo half = H(c3)
 	R.hA = hA; R.hB = hB;
 }
 
-// Processes row L.i.  Returns true when the job is finished (results are then in L).
+// whether a word of two non-negative int16 holds a zero half
+static KSW_HD bool ksw_has_zero16(uint32_t x) { return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u; }
+
+// the reference's trim scans (ksw.c:463-466) over the stored eh[].h, skipping whole zero-free quads
 template <int T>
+static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, int rarg, int lo, int hi, int &new_lo, int &new_hi)
+{
+	int j = rarg;
+	while (j >= lo) {
+		if ((j & 3) == 3 && j - 3 >= lo) {
+			const ksw_u4 v = M.hq[(j >> 2) * T];
+			if (!ksw_has_zero16(v.x) && !ksw_has_zero16(v.z)) { j -= 4; continue; }
+		}
+		if (*M.h16(j) == 0) break;
+		--j;
+	}
+	new_lo = j + 1;
+	j = rarg + 2;
+	while (j <= hi) {
+		if ((j & 3) == 0 && j + 3 <= hi) {
+			const ksw_u4 v = M.hq[(j >> 2) * T];
+			if (!ksw_has_zero16(v.x) && !ksw_has_zero16(v.z)) { j += 4; continue; }
+		}
+		if (*M.h16(j) == 0) break;
+		++j;
+	}
+	new_hi = j;
+}
+
+// Processes row L.i.  Returns true when the job is finished (results are then in L).
+template <int T, bool KEYED>
 static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const KswFastConst &K, const ksw_u2 *mrow)
 {
+	using namespace kswdpx;
 	const int i = L.i;
 	if (i >= L.tlen) return true;
 	// target base of this row
@@ -293,49 +377,64 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		}
 		return true;
 	}
-
 	L.cells += (uint32_t)(hi - lo);
 	const int q0 = lo >> 2, q1 = (hi - 1) >> 2;
+	const int hi_rel = hi - (q1 << 2);                         // 1..4: where column hi sits relative to the last quad
+	const KswFastEdge eL = M.edge[lo & 3], eR = M.edge[hi_rel];
+	const uint32_t left0pk = (uint32_t)left0 * 0x10001u;
 	KswFastRowRegs R;
 	R.X = 0; R.Hc = 0; R.m = 0; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
-	ksw_fast_quad<T, true>(R, M, K, mr, q0, lo, hi);
-	if (q1 > q0) {
+	if (KEYED) {
+		const uint32_t c0 = (uint32_t)(q0 << 2);
+		R.colA = (c0 | ((c0 + 1u) << 16));
+		R.colB = ((c0 + 3u) | ((c0 + 2u) << 16));
+	} else { R.colA = R.colB = 0; }
+	if (q1 == q0) {
+		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, eL.geA & eR.ltA, eL.geB & eR.ltB, eL.onlyA, eL.onlyB, left0pk, eR.onlyA, eR.onlyB);
+	} else {
+		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, eL.geA, eL.geB, eL.onlyA, eL.onlyB, left0pk, 0u, 0u);
 #ifdef __CUDACC__
 #pragma unroll 2
 #endif
-		for (int q = q0 + 1; q < q1; ++q) ksw_fast_quad<T, false>(R, M, K, mr, q, lo, hi);
-		ksw_fast_quad<T, true>(R, M, K, mr, q1, lo, hi);
+		for (int q = q0 + 1; q < q1; ++q) ksw_fast_quad<T, KEYED, false>(R, M, K, mr, q, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q1, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
 	}
 	// H(i, hi-1): the reference's h1 after the loop
-	int left;
-	{
-		const int k = (hi - 1) & 3;
-		const uint32_t r = k < 2 ? R.hA : R.hB;
-		left = (int)((k == 0 || k == 3) ? (r & 0xffffu) : (r >> 16));
-	}
-	// edge writes of the reference (ksw.c:429 for column lo, ksw.c:446 for column hi)
-	*M.h16(lo) = (uint16_t)left0;
-	{
-		uint16_t *p = M.h16(hi);
-		p[0] = (uint16_t)left;
-		p[2] = 0;                                              // E slot is two halfwords after the H slot
+	const int left = (int)prmt(R.hA, R.hB, eR.sel_left);
+	if (hi_rel == 4) {
+		// column hi opens the next quad: eh[end].h = h1, eh[end].e = 0 (ksw.c:446); the other half-words of that
+		// 64-bit slot belong to column hi+1, which is rewritten before it is read again
+		ksw_u2 *p = reinterpret_cast<ksw_u2 *>(&M.hq[(q1 + 1) * T]);
+		ksw_u2 w2; w2.x = (uint32_t)left; w2.y = 0u;
+		*p = w2;
 	}
 	if (hi == L.qlen) {                                        // ksw.c:447-450, ties -> last row
 		if (left >= L.end_sc) L.end_i = i;
 		L.end_sc = L.end_sc > left ? L.end_sc : left;
 	}
-	const int m_lo = (int)(int16_t)(R.m & 0xffffu), m_hi = (int)(int16_t)(R.m >> 16);
-	const int rmax = m_lo > m_hi ? m_lo : m_hi;
-	const int rarg = m_lo > m_hi ? R.mjl : (m_hi > m_lo ? R.mjh : (R.mjl > R.mjh ? R.mjl : R.mjh));
+	int rmax, rarg;
+	if (KEYED) {
+		const uint32_t k_lo = R.m & 0xffffu, k_hi = R.m >> 16;
+		const uint32_t kmax = k_lo > k_hi ? k_lo : k_hi;
+		rmax = (int)(kmax >> 7); rarg = (int)(kmax & 127u);
+	} else {
+		const int m_lo = (int)(int16_t)(R.m & 0xffffu), m_hi = (int)(int16_t)(R.m >> 16);
+		rmax = m_lo > m_hi ? m_lo : m_hi;
+		rarg = m_lo > m_hi ? R.mjl : (m_hi > m_lo ? R.mjh : (R.mjl > R.mjh ? R.mjl : R.mjh));
+	}
 	if (rmax == 0) return true;                                // ksw.c:451
-	if (rmax > L.best) {                                       // ksw.c:452-454
-		L.best = rmax; L.best_i = i; L.best_j = rarg;
-		const int d = rarg > i ? rarg - i : i - rarg;
-		L.off = L.off > d ? L.off : d;
-	} else if (K.zdrop > 0) {                                  // ksw.c:455-461
+	{   // ksw.c:452-461, written without divergent paths: new best, or the z-drop test against the old best
+		const bool better = rmax > L.best;
 		const int di = i - L.best_i, dj = rarg - L.best_j;
-		if (di > dj) { if (L.best - rmax - (di - dj) * K.e_del > K.zdrop) return true; }
-		else         { if (L.best - rmax - (dj - di) * K.e_ins > K.zdrop) return true; }
+		const int gap = di > dj ? (di - dj) * K.e_del : (dj - di) * K.e_ins;
+		const bool drop = !better && K.zdrop > 0 && (L.best - rmax - gap > K.zdrop);
+		const int d = rarg > i ? rarg - i : i - rarg;
+		const int off2 = L.off > d ? L.off : d;
+		L.best_i = better ? i : L.best_i;
+		L.best_j = better ? rarg : L.best_j;
+		L.off = better ? off2 : L.off;
+		L.best = better ? rmax : L.best;
+		if (drop) return true;
 	}
 	// band trim (ksw.c:463-466)
 	const bool any_zero = ((R.zmin & 0xffffu) == 0u) | ((R.zmin >> 16) == 0u);
@@ -345,11 +444,9 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		L.lo = left0 ? lo : lo + 1;
 		L.hi = hi + 1;
 	} else {
-		int j;
-		for (j = rarg; j >= lo && *M.h16(j); --j) ;
-		L.lo = j + 1;
-		for (j = rarg + 2; j <= hi && *M.h16(j); ++j) ;
-		L.hi = j;
+		int nl, nh;
+		ksw_fast_trim_scan<T>(M, rarg, lo, hi, nl, nh);
+		L.lo = nl; L.hi = nh;
 	}
 	L.i = i + 1;
 	return L.i >= L.tlen;

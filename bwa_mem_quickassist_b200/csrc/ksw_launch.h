@@ -16,8 +16,9 @@ cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iter
 
 #define KSW_FAST_THREADS 32
 
-// fast s16x2 kernel over jobs[0..n_jobs) whose qlen <= qmax; counter: one device uint64 scratch word
+// fast s16x2 kernel over jobs[0..n_jobs) whose qlen <= qmax; keyed: every job satisfies the class-0 bounds of
+// ksw_pack.h; counter: one device uint64 scratch word
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
-                            const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
+                            const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter,
                             DevRes *res, uint32_t *cells, cudaStream_t st);
 size_t ksw_fast_smem_bytes(int qmax);

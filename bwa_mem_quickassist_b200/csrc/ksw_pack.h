@@ -27,15 +27,18 @@ private:
 	int n_;
 };
 
-#define KSW_FAST_CLASSES 3
-static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {128, 256, 512};
+// Fast-kernel job classes (one launch each): class 0 = "keyed" jobs (qlen <= 124 and every score < 512, so the
+// row arg-max can be tracked as h*128+column in 16 bits); classes 1..3 by query length.
+#define KSW_FAST_CLASSES 4
+static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {124, 128, 256, 512};
+#define KSW_FAST_KEYED_MAXSCORE 511
 
 struct KswPackPlan {
 	int64_t n = 0, n_fast = 0, n_generic = 0;
 	// the fast jobs come first, grouped in KSW_FAST_CLASSES query-length classes (one launch each,
 	// so a few long queries do not shrink everybody's occupancy); then the generic jobs
-	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0};
-	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0};
+	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0, 0};
+	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0, 0};
 	size_t pool_bytes = 0;             // bytes of the 2-bit pool (multiple of 16)
 	int qmax_generic = 0;
 	int maxsc = 0;

@@ -61,8 +61,8 @@ double now_ms()
 // ------------------------------------------------------------------ opaque types
 struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
 	int64_t n = 0, n_fast = 0, n_generic = 0;
-	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0};
-	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0};
+	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0, 0};
+	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0, 0};
 	KswParams P;
 	DevBuf d_jobs, d_pool, d_npool, d_res, d_cells;
 	size_t pool_bytes = 0, npool_bytes = 0;
@@ -200,7 +200,7 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 		if (nc <= 0) continue;
 		CU(s.d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
 		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, nc, (const uint32_t *)b->d_pool.p,
-		                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[c], ctx->sm_count,
+		                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[c], c == 0, ctx->sm_count,
 		                   (unsigned long long *)s.d_counter.p + c, (DevRes *)b->d_res.p,
 		                   (uint32_t *)b->d_cells.p, s.stream));
 		ctx->launches++;

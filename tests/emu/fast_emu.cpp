@@ -13,7 +13,7 @@
 
 extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
                                   const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res,
-                                  int64_t *n_fast_out, int threads)
+                                  int64_t *n_fast_out, int threads, int64_t *n_keyed_out)
 {
 	KswPackPlan plan;
 	std::string err;
@@ -33,20 +33,24 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 	for (int t = 0; t < 5; ++t) mrow[t] = ksw_fast_matrow(P, t);
 	if (n_fast_out) *n_fast_out = plan.n_fast;
 	for (int64_t k = 0; k < n; ++k) res[k].score = INT_MIN;
+	KswFastEdge edge[5];
+	for (int r = 0; r < 5; ++r) ksw_fast_edge_entry(r, edge[r]);
 	for (int64_t p = 0; p < plan.n_fast; ++p) {
 		const DevJob &jb = dj[p];
+		const bool keyed = p < plan.fast_class_n[0];
 		const int nq = KSW_FAST_QUADS(jb.qlen);
-		std::vector<ksw_u4> hq(nq);
-		std::vector<uint16_t> sa(nq), sb(nq);
-		// poison so that reads of never-written state show up as mismatches
+		std::vector<ksw_u4> hq(nq + 1);
+		std::vector<uint32_t> sq(nq + 1);
 		for (auto &v : hq) v.x = v.y = v.z = v.w = 0x5a5a5a5au;
-		KswFastMem<1> M{hq.data(), sa.data(), sb.data()};
+		KswFastMem<1> M{hq.data(), sq.data(), edge};
 		KswFastLane L;
 		ksw_fast_setup<1>(L, M, K, jb, pool.data(), nmask.data());
-		while (!ksw_fast_row<1>(L, M, K, mrow)) {}
+		if (keyed) { while (!ksw_fast_row<1, true>(L, M, K, mrow)) {} }
+		else { while (!ksw_fast_row<1, false>(L, M, K, mrow)) {} }
 		DevRes r;
 		ksw_fast_result(L, r);
 		memcpy(&res[jb.idx], &r, sizeof(r));
 	}
+	if (n_keyed_out) *n_keyed_out = plan.fast_class_n[0];
 	return 0;
 }

@@ -295,7 +295,7 @@ def emu_lib():
         lib = C.CDLL(EMU_SO)
         lib.ksw_fast_emu_batch.restype = C.c_int
         lib.ksw_fast_emu_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                           C.c_void_p, C.c_int]
+                                           C.c_void_p, C.c_int, C.c_void_p]
         _libs["emu"] = lib
     return _libs["emu"]
 
@@ -305,9 +305,11 @@ def run_emu(b: Batch, threads: int = 4):
     to the generic kernel come back with score == INT32_MIN.  Returns (res, n_fast)."""
     res = np.zeros(b.n, dtype=RES_DT)
     nf = C.c_int64(0)
+    nk = C.c_int64(0)
     rc = emu_lib().ksw_fast_emu_batch(C.byref(b.cfg), b.n, _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), _ptr(res),
-                                      C.byref(nf), threads)
+                                      C.byref(nf), threads, C.byref(nk))
     assert rc == 0, rc
+    run_emu.last_keyed = int(nk.value)
     return res, int(nf.value)
 
 
