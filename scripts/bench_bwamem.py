@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Whole-program side-by-side: stock `bwa mem -t N` (bwa 0.7.8 from the tarball) and the
+B200-bound build on synthetic data of the BASELINE.json shapes, same flags, same -t; wall time, reads/s, and the
+SAM diff (minus @PG).  Seeding/chaining/SAM stay on the host (Amdahl: SURVEY.md §6), so this is a report, not the
+metric.  Usage: python scripts/bench_bwamem.py [--scale 1.0] [--threads N] [--out profiles/x.json]"""
+import argparse, json, os, sys, tempfile, time
+
+sys.path[:0] = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests")]
+import samtest as S
+
+
+def timed(binary, fa, reads, out, threads, extra=(), env=None):
+    t0 = time.perf_counter()
+    err = S.bwa_mem(binary, fa, reads, out, threads=threads, extra=extra, env=env)
+    return time.perf_counter() - t0, err
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 4)
+    ap.add_argument("--batch", type=int, default=20000)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    sc = a.scale
+    cfgs = [
+        ("config1 SE100 1Mbp 1%sub 0.1%indel", dict(genome=1_000_000, pe=False, n=int(200_000 * sc), L=100, sub=0.01, indel=0.001, imax=1)),
+        ("config3-shape PE150 (scaled genome)", dict(genome=5_000_000, pe=True, n=int(100_000 * sc), L=150, sub=0.01, indel=0.001, imax=1)),
+        ("config4-shape PE250 high-indel (scaled genome)", dict(genome=5_000_000, pe=True, n=int(30_000 * sc), L=250, sub=0.03, indel=0.02, imax=12)),
+    ]
+    rows = []
+    with tempfile.TemporaryDirectory() as d:
+        for name, c in cfgs:
+            fa = os.path.join(d, "ref.fa")
+            g = S.write_genome(fa, c["genome"], seed=1)
+            S.bwa_index(fa)
+            if c["pe"]:
+                reads = [os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq")]
+                S.write_reads_pe(reads[0], reads[1], g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
+                n_reads = 2 * c["n"]
+            else:
+                reads = [os.path.join(d, "r.fq")]
+                S.write_reads_se(reads[0], g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
+                n_reads = c["n"]
+            t_stock, _ = timed(S.BWA_STOCK, fa, reads, os.path.join(d, "stock.sam"), a.threads)
+            t_b200, _ = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)])
+            ok, why = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200.sam"))
+            row = {"config": name, "reads": n_reads, "threads": a.threads, "stock_s": round(t_stock, 3), "b200_s": round(t_b200, 3),
+                   "stock_reads_per_s": round(n_reads / t_stock), "b200_reads_per_s": round(n_reads / t_b200),
+                   "sam_identical_minus_PG": bool(ok)}
+            print(json.dumps(row), flush=True)
+            rows.append(row)
+    if a.out:
+        json.dump(rows, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
