@@ -24,6 +24,7 @@
 #include "bwamem.c"                       /* the reference source, found through -I$(REF) */
 #undef mem_process_seqs
 
+#include <pthread.h>
 #include "bwamem_b200.h"
 
 typedef struct {
@@ -32,12 +33,20 @@ typedef struct {
 	const uint8_t *pac;
 } b200_thread_t;
 
-static __thread b200_thread_t b200_tls;
+/* kt_for_batch creates fresh pthreads for every chunk (kthread_batch.c:54), so the per-worker state is kept
+ * in a table indexed by the worker id, not in thread-local storage */
+#define B200_MAX_WORKERS 1024
+static b200_thread_t b200_workers[B200_MAX_WORKERS];
 static int b200_n_gpus = -1;
+/* wall-clock seconds summed over worker threads: seeding+chaining, planning, GPU passes, replay+dedup */
+static double b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, b200_t_init;
+static void b200_add_time(double *acc, double dt) { __sync_synchronize(); { static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER; pthread_mutex_lock(&mu); *acc += dt; pthread_mutex_unlock(&mu); } }
 
 static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int tid)
 {
-	b200_thread_t *t = &b200_tls;
+	b200_thread_t *t;
+	if (tid < 0 || tid >= B200_MAX_WORKERS) err_fatal(__func__, "more than %d worker threads", B200_MAX_WORKERS);
+	t = &b200_workers[tid];
 	if (!t->ctx) {
 		if (b200_n_gpus < 0) b200_n_gpus = ksw_b200_device_count();
 		if (b200_n_gpus < 1 || ksw_b200_ctx_create(tid % b200_n_gpus, &t->ctx) != 0)
@@ -56,25 +65,49 @@ static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bn
 	return t;
 }
 
+/* CUDA context creation costs seconds on a large GPU; start it while `bwa mem` is still loading the index.
+ * (glibc passes argc/argv to constructors.) */
+static void *b200_warmup_thread(void *arg)
+{
+	int d, n = ksw_b200_device_count();
+	(void)arg;
+	for (d = 0; d < n; ++d) {
+		ksw_b200_ctx_t *c = 0;
+		if (ksw_b200_ctx_create(d, &c) == 0) ksw_b200_ctx_destroy(c);
+	}
+	return 0;
+}
+__attribute__((constructor)) static void b200_warmup(int argc, char **argv)
+{
+	pthread_t th;
+	if (argc >= 2 && strcmp(argv[1], "mem") == 0 && !getenv("KSW_B200_NO_WARMUP"))
+		if (pthread_create(&th, 0, b200_warmup_thread, 0) == 0) pthread_detach(th);
+}
+
 typedef struct { int handle; int short_ok; mem_alnreg_t short_reg; } b200_chain_state_t;
 
 static void worker1_b200(void *data, int start, int batch_size, int tid)
 {
 	worker_t *w = (worker_t *)data;
 	const mem_opt_t *opt = w->opt;
+	double tinit = realtime();
 	b200_thread_t *t = b200_thread_state(opt, w->bns, w->pac, tid);
 	mem_chain_v *chn = (mem_chain_v *)malloc(sizeof(mem_chain_v) * batch_size);
 	b200_chain_state_t **cst = (b200_chain_state_t **)malloc(sizeof(void *) * batch_size);
 	int b, i, rc;
+	double t0 = realtime(), t1, ts = 0, tp = 0;
+	b200_add_time(&b200_t_init, t0 - tinit);
 
 	b200_ext_plan_reset(t->plan);
 	for (b = 0; b < batch_size; ++b) {
 		bseq1_t *s = &w->seqs[start + b];
 		int rd;
+		t1 = realtime();
 		for (i = 0; i < s->l_seq; ++i)                     /* bwamem.c:1093-1094 */
 			s->seq[i] = s->seq[i] < 4 ? s->seq[i] : nst_nt4_table[(int)s->seq[i]];
 		chn[b] = mem_chain(opt, w->bwt, w->bns->l_pac, s->l_seq, (uint8_t *)s->seq);
 		chn[b].n = mem_chain_flt(opt, chn[b].n, chn[b].a);
+		ts += realtime() - t1;
 		rd = b200_ext_plan_add_read(t->plan, s->l_seq, (uint8_t *)s->seq);
 		cst[b] = (b200_chain_state_t *)calloc(chn[b].n ? chn[b].n : 1, sizeof(b200_chain_state_t));
 		for (i = 0; i < (int)chn[b].n; ++i) {
@@ -88,8 +121,12 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 			free(tmp.a);
 		}
 	}
+	tp = realtime() - t0 - ts;
+	t1 = realtime();
 	rc = b200_ext_plan_run(t->plan, t->ctx);
 	if (rc != 0) err_fatal(__func__, "GPU extension pass failed (%d): %s", rc, ksw_b200_strerror(t->ctx));
+	b200_add_time(&b200_t_seed, ts); b200_add_time(&b200_t_plan, tp); b200_add_time(&b200_t_gpu, realtime() - t1);
+	t1 = realtime();
 	for (b = 0; b < batch_size; ++b) {
 		bseq1_t *s = &w->seqs[start + b];
 		mem_alnreg_v regs;
@@ -105,6 +142,7 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 		w->regs[start + b] = regs;
 	}
 	free(chn); free(cst);
+	b200_add_time(&b200_t_replay, realtime() - t1);
 }
 
 void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed,
@@ -115,7 +153,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	worker_t w;
 	mem_alnreg_v *regs;
 	mem_pestat_t pes[4];
-	double ctime, rtime;
+	double ctime, rtime, t_pass1 = 0;
 	int batch = opt->batch_size, min_batch = 4096;
 	const char *e = getenv("KSW_B200_MIN_BATCH");
 
@@ -127,6 +165,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	w.seqs = seqs; w.regs = regs; w.n_processed = n_processed;
 	w.pes = &pes[0];
 	kt_for_batch(opt->n_threads, worker1_b200, &w, n, batch);                       /* pass 1: extension on the GPU */
+	t_pass1 = realtime() - rtime;
 	if (opt->flag & MEM_F_PE) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
 		else mem_pestat(opt, bns->l_pac, n, regs, pes);
@@ -134,6 +173,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	kt_for(opt->n_threads, worker2, &w, (opt->flag & MEM_F_PE) ? n >> 1 : n);          /* pass 2: unchanged */
 	free(regs);
 	if (bwa_verbose >= 3)
-		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec (extension on B200)\n", __func__, n,
-		        cputime() - ctime, realtime() - rtime);
+		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec (extension on B200; thread-seconds so far: "
+		        "init %.2f, seed+chain %.2f, plan %.2f, gpu passes %.2f, replay %.2f; pass1 %.3f s real)\n", __func__, n,
+		        cputime() - ctime, realtime() - rtime, b200_t_init, b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, t_pass1);
 }

@@ -15,18 +15,28 @@ def timed(binary, fa, reads, out, threads, extra=(), env=None):
     return time.perf_counter() - t0, err
 
 
+def chunk_times(err):
+    """(reads, real seconds) of every mem_process_seqs chunk, from the reference's own log line (bwamem.c:1320)."""
+    out = []
+    for ln in err.splitlines():
+        if "Processed" in ln and "real sec" in ln:
+            f = ln.split()
+            out.append((int(f[f.index("Processed") + 1]), float(f[f.index("real") - 1])))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 4)
-    ap.add_argument("--batch", type=int, default=20000)
+    ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     sc = a.scale
     cfgs = [
-        ("config1 SE100 1Mbp 1%sub 0.1%indel", dict(genome=1_000_000, pe=False, n=int(200_000 * sc), L=100, sub=0.01, indel=0.001, imax=1)),
-        ("config3-shape PE150 (scaled genome)", dict(genome=5_000_000, pe=True, n=int(100_000 * sc), L=150, sub=0.01, indel=0.001, imax=1)),
-        ("config4-shape PE250 high-indel (scaled genome)", dict(genome=5_000_000, pe=True, n=int(30_000 * sc), L=250, sub=0.03, indel=0.02, imax=12)),
+        ("config1 SE100 1Mbp 1%sub 0.1%indel", dict(genome=1_000_000, pe=False, n=int(4_000_000 * sc), L=100, sub=0.01, indel=0.001, imax=1)),
+        ("config3-shape PE150 (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(1_500_000 * sc), L=150, sub=0.01, indel=0.001, imax=1)),
+        ("config4-shape PE250 high-indel (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(600_000 * sc), L=250, sub=0.03, indel=0.002, imax=12)),
     ]
     rows = []
     with tempfile.TemporaryDirectory() as d:
@@ -36,17 +46,24 @@ def main():
             S.bwa_index(fa)
             if c["pe"]:
                 reads = [os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq")]
-                S.write_reads_pe(reads[0], reads[1], g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
+                S.write_reads_fast(reads, g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
                 n_reads = 2 * c["n"]
             else:
                 reads = [os.path.join(d, "r.fq")]
-                S.write_reads_se(reads[0], g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
+                S.write_reads_fast(reads, g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
                 n_reads = c["n"]
-            t_stock, _ = timed(S.BWA_STOCK, fa, reads, os.path.join(d, "stock.sam"), a.threads)
-            t_b200, _ = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)])
+            t_stock, e_stock = timed(S.BWA_STOCK, fa, reads, os.path.join(d, "stock.sam"), a.threads)
+            t_b200, e_b200 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)])
             ok, why = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200.sam"))
-            row = {"config": name, "reads": n_reads, "threads": a.threads, "stock_s": round(t_stock, 3), "b200_s": round(t_b200, 3),
+            cs, cb = chunk_times(e_stock), chunk_times(e_b200)
+            # steady state = chunks after the first (the first B200 chunk pays CUDA context creation, which a real run
+            # hides behind loading a GB-sized index)
+            ss = sum(r for r, _ in cs[1:]) / max(sum(t for _, t in cs[1:]), 1e-9) if len(cs) > 1 else None
+            sb = sum(r for r, _ in cb[1:]) / max(sum(t for _, t in cb[1:]), 1e-9) if len(cb) > 1 else None
+            row = {"config": name, "reads": n_reads, "threads": a.threads, "stock_wall_s": round(t_stock, 3), "b200_wall_s": round(t_b200, 3),
                    "stock_reads_per_s": round(n_reads / t_stock), "b200_reads_per_s": round(n_reads / t_b200),
+                   "stock_chunks": cs, "b200_chunks": cb,
+                   "stock_steady_reads_per_s": round(ss) if ss else None, "b200_steady_reads_per_s": round(sb) if sb else None,
                    "sam_identical_minus_PG": bool(ok)}
             print(json.dumps(row), flush=True)
             rows.append(row)

@@ -125,3 +125,95 @@ def sam_equal(a, b):
         if x != y:
             return False, (i, x[:300], y[:300])
     return False, (min(len(la), len(lb)), b"<length differs>", f"{len(la)} vs {len(lb)}".encode())
+
+
+# ------------------------------------------------------------------ vectorised read simulator (millions of reads in seconds)
+def _mutate_matrix(rng, frag, L, sub, indel, indel_max):
+    """frag: (n, L+pad) uint8 fragments (read direction).  Returns (n, L): substitutions at rate `sub` per base and at
+    most one indel event per read (probability indel*L) of length U[1,indel_max]."""
+    n, W = frag.shape
+    q = frag.copy()
+    k = int(rng.binomial(n * W, sub))
+    pos = rng.integers(0, n * W, size=k)
+    flat = q.reshape(-1)
+    flat[pos] = (flat[pos] + rng.integers(1, 4, size=k, dtype=np.uint8)) & 3
+    rows = np.flatnonzero(rng.random(n) < min(1.0, indel * L))
+    if rows.size:
+        col = np.arange(W, dtype=np.int32)[None, :]
+        p = rng.integers(1, L - 1, size=rows.size).astype(np.int32)[:, None]
+        ln = rng.integers(1, indel_max + 1, size=rows.size).astype(np.int32)[:, None]
+        ins = (rng.random(rows.size) < 0.5)[:, None]
+        # deletion from the read: read[c] = frag[c + ln] for c >= p; insertion: read[c] = frag[c - ln] for c >= p + ln,
+        # random bases in [p, p + ln)
+        shift = np.where(ins, np.where(col >= p + ln, -ln, 0), np.where(col >= p, ln, 0))
+        idx = np.clip(col + shift, 0, W - 1)
+        sub_rows = np.take_along_axis(q[rows], idx, axis=1)
+        rnd = rng.integers(0, 4, size=sub_rows.shape, dtype=np.uint8)
+        inside = ins & (col >= p) & (col < p + ln)
+        sub_rows = np.where(inside, rnd, sub_rows)
+        q[rows] = sub_rows
+    return q[:, :L]
+
+
+def _write_fastq_fixed(path, prefix, reads):
+    """reads: (n, L) uint8 codes; names are fixed width so the whole file is one numpy fill."""
+    n, L = reads.shape
+    names = np.char.add(prefix, np.char.zfill(np.arange(n).astype("U9"), 9)).astype("S")
+    wn = names.dtype.itemsize
+    rec = 1 + wn + 1 + L + 3 + L + 1
+    buf = np.full((n, rec), ord("\n"), dtype=np.uint8)
+    buf[:, 0] = ord("@")
+    buf[:, 1:1 + wn] = np.frombuffer(names.tobytes(), dtype=np.uint8).reshape(n, wn)
+    o = 1 + wn + 1
+    buf[:, o:o + L] = ACGT[reads]
+    buf[:, o + L + 1] = ord("+")
+    buf[:, o + L + 3:o + L + 3 + L] = ord("I")
+    buf.tofile(path)
+
+
+def write_reads_fast(paths, genome, n, length, seed, sub=0.01, indel=0.001, indel_max=1, ins_mean=None, ins_sd=None, chunk=500_000):
+    """SE if len(paths) == 1 else PE (FR orientation, insert ~ N(ins_mean, ins_sd))."""
+    rng = np.random.default_rng(seed)
+    G = len(genome)
+    pe = len(paths) == 2
+    pad = 2 * indel_max + 4
+    ins_mean = ins_mean or 2.5 * length
+    ins_sd = ins_sd or 0.25 * length
+    for p in paths:
+        open(p, "wb").close()
+    done = 0
+    while done < n:
+        m = min(chunk, n - done)
+        W = length + pad
+        col = np.arange(W, dtype=np.int64)[None, :]
+        if pe:
+            isz = np.maximum(length + 10, rng.normal(ins_mean, ins_sd, m).astype(np.int64))
+            start = rng.integers(0, G - isz.max() - W - 2, size=m)
+            rev = rng.random(m) < 0.5
+            # fragment on the forward strand is genome[start, start+isz); read 1 from its 5' end, read 2 = revcomp of its 3' end
+            f1 = genome[start[:, None] + col]
+            f2 = COMP[genome[(start + isz)[:, None] - 1 - col]]
+            # flipped pairs: the fragment is taken from the reverse strand, i.e. the roles swap
+            a = np.where(rev[:, None], f2, f1)
+            b = np.where(rev[:, None], f1, f2)
+            r1 = _mutate_matrix(rng, a, length, sub, indel, indel_max)
+            r2 = _mutate_matrix(rng, b, length, sub, indel, indel_max)
+            for path, r in ((paths[0], r1), (paths[1], r2)):
+                tmp = path + ".part"
+                _write_fastq_fixed(tmp, f"p{done // chunk:03d}_", r)
+                with open(path, "ab") as out, open(tmp, "rb") as src:
+                    out.write(src.read())
+                os.remove(tmp)
+        else:
+            start = rng.integers(0, G - W - 2, size=m)
+            rev = rng.random(m) < 0.5
+            fw = genome[start[:, None] + col]
+            rc = COMP[genome[(start + W)[:, None] - 1 - col]]
+            frag = np.where(rev[:, None], rc, fw)
+            r = _mutate_matrix(rng, frag, length, sub, indel, indel_max)
+            tmp = paths[0] + ".part"
+            _write_fastq_fixed(tmp, f"r{done // chunk:03d}_", r)
+            with open(paths[0], "ab") as out, open(tmp, "rb") as src:
+                out.write(src.read())
+            os.remove(tmp)
+        done += m

@@ -43,7 +43,7 @@ def test_se100_config1_byte_identical(tmp_path):
     g = S.write_genome(fa, 1_000_000, seed=12345)
     S.bwa_index(fa)
     fq = str(tmp_path / "r.fq")
-    S.write_reads_se(fq, g, 20000, 100, seed=12346, sub=0.01, indel=0.001)
+    S.write_reads_fast([fq], g, 60000, 100, seed=12346, sub=0.01, indel=0.001)
     S.bwa_mem(S.BWA_STOCK, fa, [fq], str(tmp_path / "stock.sam"), threads=4)
     for tag, extra, thr in (("b1", [], 4), ("b5000", ["-b", "5000"], 4), ("t1", ["-b", "100000"], 1)):
         out = str(tmp_path / f"b200_{tag}.sam")
@@ -61,7 +61,7 @@ def test_pe150_byte_identical(tmp_path):
     g = S.write_genome(fa, 2_000_000, seed=21, n_contigs=3)
     S.bwa_index(fa)
     f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
-    S.write_reads_pe(f1, f2, g, 15000, 150, seed=22, ins_mean=375, ins_sd=37)
+    S.write_reads_fast([f1, f2], g, 40000, 150, seed=22, ins_mean=375, ins_sd=37)
     S.bwa_mem(S.BWA_STOCK, fa, [f1, f2], str(tmp_path / "stock.sam"), threads=4)
     S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4, extra=["-b", "3000"])
     ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
@@ -76,7 +76,13 @@ def test_pe250_high_indel_byte_identical(tmp_path):
     g = S.write_genome(fa, 2_000_000, seed=31)
     S.bwa_index(fa)
     f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
-    S.write_reads_pe(f1, f2, g, 6000, 250, seed=32, sub=0.03, indel=0.02, indel_max=12)
+    S.write_reads_fast([f1, f2], g, 15000, 250, seed=32, sub=0.03, indel=0.004, indel_max=12)
+    # plus reads with several indel events each (the per-base simulator)
+    f1b, f2b = str(tmp_path / "s1.fq"), str(tmp_path / "s2.fq")
+    S.write_reads_pe(f1b, f2b, g, 3000, 250, seed=33, sub=0.03, indel=0.02, indel_max=12)
+    for a_, b_ in ((f1, f1b), (f2, f2b)):
+        with open(a_, "ab") as out, open(b_, "rb") as src:
+            out.write(src.read())
     S.bwa_mem(S.BWA_STOCK, fa, [f1, f2], str(tmp_path / "stock.sam"), threads=4)
     S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4)
     ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
