@@ -204,7 +204,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ctx = B.KswB200(local)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    ctx = B.KswB200(local, pack_threads=max(1, min(32, (os.cpu_count() or 8) // max(local_world, 1))))   # ranks share the host cores
     cfg = B.make_cfg()
     jobs, qpool, tpool = make_workload(a.jobs, a.seed + rank)      # every rank its own shard of reads
     n = a.jobs
