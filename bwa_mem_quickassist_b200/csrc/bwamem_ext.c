@@ -239,9 +239,35 @@ static void right_job(const b200_ext_plan_t *p, const chain_rec_t *ch, const b20
 	j->w = w;
 }
 
+/* Trace facility (the batched counterpart of the reference's `-v 4` extension trace, bwamem.c:821-828): with
+ * KSW_B200_DUMP=<prefix> every pass appends its job batch to <prefix>.<pid>.bin as
+ * [magic "KSWJ"][cfg][n][qpool bytes][tpool bytes][jobs][qpool][tpool] for offline replay (scripts/bench_jobs.py). */
+#include <stdio.h>
+#include <unistd.h>
+static void dump_jobs(const b200_ext_plan_t *p, const ksw_b200_cfg_t *cfg)
+{
+	const char *pre = getenv("KSW_B200_DUMP");
+	char path[4096];
+	FILE *f;
+	uint64_t hdr[3];
+	if (!pre || !*pre) return;
+	snprintf(path, sizeof(path), "%s.%d.bin", pre, (int)getpid());
+	f = fopen(path, "ab");
+	if (!f) return;
+	hdr[0] = p->jobs.n; hdr[1] = p->qpool.n; hdr[2] = p->tpool.n;
+	fwrite("KSWJ", 1, 4, f);
+	fwrite(cfg, sizeof(*cfg), 1, f);
+	fwrite(hdr, sizeof(hdr), 1, f);
+	fwrite(p->jobs.a, sizeof(ksw_b200_job_t), p->jobs.n, f);
+	fwrite(p->qpool.a, 1, p->qpool.n, f);
+	fwrite(p->tpool.a, 1, p->tpool.n, f);
+	fclose(f);
+}
+
 static int run_jobs(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg)
 {
 	if (p->jobs.n == 0) return 0;
+	dump_jobs(p, cfg);
 	vec_reserve(p->res, p->jobs.n);
 	return ksw_b200_extend_batch(ctx, cfg, (int64_t)p->jobs.n, p->jobs.a, p->qpool.a, p->tpool.a, p->res.a);
 }

@@ -46,6 +46,8 @@ struct KswParams {          // passed by value as a kernel parameter (constant b
 	int32_t zdrop;
 };
 
+#define KSW_FAST_QUADS(qlen) (((qlen) >> 2) + 1)   /* 4-column quads of the fast kernel that cover columns 0..qlen */
+
 #define KSW_FLAG_QN 1u
 #define KSW_FLAG_TN 2u
 

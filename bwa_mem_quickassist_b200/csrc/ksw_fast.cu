@@ -17,7 +17,7 @@ namespace {
 constexpr int T = KSW_FAST_THREADS;   // 32: one warp per CTA
 
 template <bool KEYED>
-__global__ void __launch_bounds__(T)
+__global__ void __launch_bounds__(T, 12)
 ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
                 const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap,
                 unsigned long long *__restrict__ counter, DevRes *__restrict__ res, uint32_t *__restrict__ cells)
@@ -51,14 +51,33 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 			unsigned long long base = 0;
 			if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
 			base = __shfl_sync(0xffffffffu, base, leader);
+			DevJob jb;
+			jb.seq_off = 0; jb.idx = 0; jb.qlen = 0; jb.tlen = 0; jb.h0 = 0; jb.w = 0; jb.flags = 0; jb.nmask_off = 0;
+			bool got = false;
 			if (state == IDLE) {
 				const long long k = (long long)base + __popc(need & ((1u << lane) - 1u));
-				if (k < n_jobs) {
-					const DevJob jb = jobs[k];
-					ksw_fast_setup<T>(L, M, K, jb, pool, npool);
-					state = RUN;
-				} else state = DONE;
+				if (k < n_jobs) { jb = jobs[k]; got = true; }
+				else state = DONE;
 			}
+			const unsigned fetched = __ballot_sync(0xffffffffu, got);
+			if (__popc(fetched) >= 8) {
+				// many lanes start together (e.g. at launch, or equal-length jobs): each builds its own state
+				if (got) ksw_fast_setup_quads<T>(hq, sq, lane, 0, 1, K, jb.seq_off, jb.qlen, jb.h0, jb.flags, jb.nmask_off, pool, npool);
+			} else {
+				// a few stragglers: all 32 lanes build the state of each newly fetched job, one job after the other,
+				// instead of 31 lanes idling through a one-lane setup
+				for (unsigned todo = fetched; todo; todo &= todo - 1) {
+					const int owner = __ffs(todo) - 1;
+					const uint32_t o_seq = __shfl_sync(0xffffffffu, jb.seq_off, owner);
+					const int o_qlen = __shfl_sync(0xffffffffu, jb.qlen, owner);
+					const int o_h0 = __shfl_sync(0xffffffffu, jb.h0, owner);
+					const uint32_t o_flags = __shfl_sync(0xffffffffu, jb.flags, owner);
+					const uint32_t o_nmask = __shfl_sync(0xffffffffu, jb.nmask_off, owner);
+					ksw_fast_setup_quads<T>(hq, sq, owner, lane, T, K, o_seq, o_qlen, o_h0, o_flags, o_nmask, pool, npool);
+				}
+			}
+			__syncwarp();
+			if (got) { ksw_fast_init_lane(L, jb, pool, npool); state = RUN; }
 		}
 		if (__all_sync(0xffffffffu, state == DONE)) break;
 		if (state == RUN) {

@@ -123,7 +123,6 @@ struct KswFastLane {
 };
 
 #define KSW_NEGPK 0xE000E000u          /* -8192 in both halves */
-#define KSW_FAST_QUADS(qlen) (((qlen) >> 2) + 1)   /* quads that cover columns 0..qlen */
 
 static KSW_HD uint32_t ksw_pk2(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
 
@@ -186,13 +185,10 @@ struct KswFastMem {
 };
 
 // ----------------------------------------------------------------------------- job setup
-// Fills row -1 (ksw.c:394-396), clears E, builds the PRMT selectors from the 2-bit query.
-template <int T>
-static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const KswFastConst &K, const DevJob &jb,
-                                  const uint32_t *pool, const uint32_t *npool)
+// Lane registers of a freshly fetched job (ksw.c:408-410) and the first target words.
+static KSW_HD void ksw_fast_init_lane(KswFastLane &L, const DevJob &jb, const uint32_t *pool, const uint32_t *npool)
 {
 	const uint32_t *q2 = pool + (size_t)jb.seq_off * 4;
-	const uint32_t *qn = (jb.flags & KSW_FLAG_QN) ? npool + jb.nmask_off : nullptr;
 	L.t2 = q2 + ksw_words2(jb.qlen);
 	L.tn = (jb.flags & KSW_FLAG_TN) ? npool + jb.nmask_off + ((jb.flags & KSW_FLAG_QN) ? ksw_words1(jb.qlen) : 0) : nullptr;
 	L.qlen = jb.qlen; L.tlen = jb.tlen; L.h0 = jb.h0; L.w = jb.w; L.idx = jb.idx;
@@ -201,14 +197,26 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 	L.cells = 0;
 	L.tw = jb.tlen > 0 ? L.t2[0] : 0u;
 	L.tw_next = jb.tlen > 16 ? L.t2[1] : 0u;
+}
 
-	const int nq = KSW_FAST_QUADS(jb.qlen);
-	const int h0 = jb.h0;
-	uint32_t qw = 0, nw = 0;
-	for (int q = 0; q < nq; ++q) {
+// Shared-memory state of one job: row -1 (ksw.c:394-396), E = 0, and the PRMT selectors built from the 2-bit
+// query.  COOPERATIVE: the quads of the job are dealt round-robin to the `n_helpers` lanes that call this with
+// helper = 0..n_helpers-1 (on the GPU all 32 lanes of the warp build the state of one lane's job, so a lane that
+// fetches a job alone does not make the other 31 idle through the whole setup); `owner` is the lane the job
+// belongs to, hq/sq are the CTA's arrays (not offset by lane).
+template <int T>
+static KSW_HD void ksw_fast_setup_quads(ksw_u4 *hq, uint32_t *sq, const int owner, const int helper, const int n_helpers,
+                                        const KswFastConst &K, const uint32_t seq_off, const int qlen, const int h0,
+                                        const uint32_t flags, const uint32_t nmask_off,
+                                        const uint32_t *pool, const uint32_t *npool)
+{
+	const uint32_t *q2 = pool + (size_t)seq_off * 4;
+	const uint32_t *qn = (flags & KSW_FLAG_QN) ? npool + nmask_off : nullptr;
+	const int nq = KSW_FAST_QUADS(qlen);
+	for (int q = helper; q < nq; q += n_helpers) {
 		const int c0 = q << 2;
-		if ((q & 3) == 0) qw = (c0 < jb.qlen) ? q2[c0 >> 4] : 0u;           // 16 bases = 4 quads per word
-		if (qn && (q & 7) == 0) nw = (c0 < jb.qlen) ? qn[c0 >> 5] : 0u;
+		const uint32_t qw = (c0 < qlen) ? q2[c0 >> 4] : 0u;                  // 16 bases = 4 quads per word
+		const uint32_t nw = (qn && c0 < qlen) ? qn[c0 >> 5] : 0u;
 		int hv[4];
 		uint32_t sb[4];
 #ifdef __CUDACC__
@@ -219,8 +227,8 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 			int v = c == 0 ? h0 : h0 - K.oe_ins - (c - 1) * K.e_ins;         // closed form of ksw.c:394-396
 			hv[k] = v > 0 ? v : 0;
 			uint32_t code = (qw >> (((c & 15)) << 1)) & 3u;
-			if (qn && ((nw >> (c & 31)) & 1u)) code = 4u;
-			if (c >= jb.qlen) code = 0u;
+			if ((nw >> (c & 31)) & 1u) code = 4u;
+			if (c >= qlen) code = 0u;
 			sb[k] = code | ((8u | code) << 4);                                // byte lookup + sign replicate
 		}
 		ksw_u4 v4;
@@ -228,8 +236,8 @@ static KSW_HD void ksw_fast_setup(KswFastLane &L, const KswFastMem<T> &M, const 
 		v4.y = 0u;
 		v4.z = (uint32_t)hv[3] | ((uint32_t)hv[2] << 16);   // pair B: lo c3, hi c2
 		v4.w = 0u;
-		M.hq[q * T] = v4;
-		M.sq[q * T] = (sb[0] | (sb[1] << 8)) | ((sb[3] | (sb[2] << 8)) << 16);
+		hq[q * T + owner] = v4;
+		sq[q * T + owner] = (sb[0] | (sb[1] << 8)) | ((sb[3] | (sb[2] << 8)) << 16);
 	}
 }
 

@@ -191,20 +191,39 @@ int ensure_generic_scratch(ksw_b200_ctx *ctx, Slot &s, int qmax, int &n_blocks)
 	return 0;
 }
 
-// launches the kernels of batch b on slot s's stream (one fast launch per query-length class + generic)
+// launches the kernels of batch b on slot s's stream: the fast classes (contiguous in the binned order) are grouped
+// into as few launches as is free — a class is folded into the next one when it is small or when the next class's
+// actual longest query needs (almost) the same shared memory — then the generic kernel
 int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 {
 	int64_t first = 0;
-	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
-		const int64_t nc = b->fast_class_n[c];
-		if (nc <= 0) continue;
+	int c = 0;
+	while (c < KSW_FAST_CLASSES) {
+		if (b->fast_class_n[c] <= 0) { ++c; continue; }
+		int64_t n_grp = b->fast_class_n[c];
+		int qmax = b->fast_class_qmax[c];
+		bool keyed = c == 0;
+		int e = c + 1;
+		while (e < KSW_FAST_CLASSES) {
+			if (b->fast_class_n[e] <= 0) { ++e; continue; }
+			const bool small = n_grp < (int64_t)ctx->sm_count * 13 * 32 * 4 || b->fast_class_n[e] < (int64_t)ctx->sm_count * 13 * 32 * 4;
+			const bool same_smem = KSW_FAST_QUADS(b->fast_class_qmax[e]) <= KSW_FAST_QUADS(qmax) + KSW_FAST_QUADS(qmax) / 8;
+			// never give up the keyed variant of a big class 0 for a small neighbour; fold class 0 only if it is small itself
+			if (keyed && n_grp >= (int64_t)ctx->sm_count * 13 * 32 * 4) break;
+			if (!(small || same_smem)) break;
+			n_grp += b->fast_class_n[e];
+			qmax = std::max(qmax, b->fast_class_qmax[e]);
+			keyed = false;
+			++e;
+		}
 		CU(s.d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
-		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, nc, (const uint32_t *)b->d_pool.p,
-		                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[c], c == 0, ctx->sm_count,
+		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, n_grp, (const uint32_t *)b->d_pool.p,
+		                   (const uint32_t *)b->d_npool.p, b->P, qmax, keyed, ctx->sm_count,
 		                   (unsigned long long *)s.d_counter.p + c, (DevRes *)b->d_res.p,
 		                   (uint32_t *)b->d_cells.p, s.stream));
 		ctx->launches++;
-		first += nc;
+		first += n_grp;
+		c = e;
 	}
 	if (b->n_generic > 0) {
 		int n_blocks = 0;

@@ -44,7 +44,8 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 		for (auto &v : hq) v.x = v.y = v.z = v.w = 0x5a5a5a5au;
 		KswFastMem<1> M{hq.data(), sq.data(), edge};
 		KswFastLane L;
-		ksw_fast_setup<1>(L, M, K, jb, pool.data(), nmask.data());
+		ksw_fast_setup_quads<1>(hq.data(), sq.data(), 0, 0, 1, K, jb.seq_off, jb.qlen, jb.h0, jb.flags, jb.nmask_off, pool.data(), nmask.data());
+		ksw_fast_init_lane(L, jb, pool.data(), nmask.data());
 		if (keyed) { while (!ksw_fast_row<1, true>(L, M, K, mrow)) {} }
 		else { while (!ksw_fast_row<1, false>(L, M, K, mrow)) {} }
 		DevRes r;
