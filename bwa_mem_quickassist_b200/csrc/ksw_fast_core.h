@@ -15,7 +15,10 @@
 //              g      = VIADDMNMX.S16x2.RELU(h', -oe_ins, 0)
 //              F      : 2 x VIADDMNMX.S16x2 + 1 PRMT                 F(j+1) = max(F(j)-e_ins, g(j))   (*)
 //              h      = VIMNMX.S16x2(h', F)                                                      ksw.c:432
-//              E'     = VIADDMNMX.S16x2(E, -e_del, RELU(h - oe_del)) 2 DPX                       ksw.c:436-439
+//              E'     = VIMNMX3.S16x2(E - e_del, h - oe_del, 0): ONE ALU-pipe op; the two subtractions are plain
+//                       32-bit IADDs that the compiler places on the FMA pipe.  They are borrow-free because every
+//                       H/E/F value is kept with a constant bias B = o_del+e_del in both halves (B instead of 0 is
+//                       the floor of all the max() clamps)                                        ksw.c:436-439
 //              (m,mj) : KEYED jobs (qlen <= 124, scores < 512): key = h*128 + column (1 IMAD on the FMA pipe),
 //                       VIMNMX.U16x2 on the keys — the larger column wins ties, as in the reference;
 //                       other jobs: VIMNMX.S16x2 with predicate outputs + 2 predicated index moves   ksw.c:434-435
@@ -50,6 +53,7 @@ __device__ __forceinline__ uint32_t addmax2_relu(uint32_t a, uint32_t b, uint32_
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 __device__ __forceinline__ uint32_t maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 __device__ __forceinline__ uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo) { return __vibmax_s16x2(a, b, &ge_hi, &ge_lo); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
@@ -82,6 +86,10 @@ KSW_EMU uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c)
 {
 	return pk16(mn(mn(lo16(a), lo16(b)), lo16(c)), mn(mn(hi16(a), hi16(b)), hi16(c)));
 }
+KSW_EMU uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c)
+{
+	return pk16(mx(mx(lo16(a), lo16(b)), lo16(c)), mx(mx(hi16(a), hi16(b)), hi16(c)));
+}
 KSW_EMU uint32_t bmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo)
 {
 	ge_lo = lo16(a) >= lo16(b); ge_hi = hi16(a) >= hi16(b);
@@ -105,7 +113,10 @@ KSW_EMU uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)   // PTX prmt.b32, gen
 
 // ----------------------------------------------------------------------------- lane state
 struct KswFastConst {
-	uint32_t neg_ei, neg_oei, neg_ed, neg_oed;   // both halves: -e_ins, -(o_ins+e_ins), -e_del, -(o_del+e_del)
+	uint32_t neg_ei, neg_oei;                    // both halves: -e_ins, -(o_ins+e_ins)
+	uint32_t ed32, oed32;                        // both halves: e_del, o_del+e_del (subtracted with 32-bit IADDs)
+	uint32_t Bpk;                                // both halves: the bias B = o_del+e_del carried by every H/E/F value
+	int32_t B;
 	int32_t o_del, e_del, e_ins, oe_ins, zdrop;
 };
 
@@ -129,7 +140,8 @@ static KSW_HD uint32_t ksw_pk2(int v) { return ((uint32_t)v & 0xffffu) | ((uint3
 static KSW_HD void ksw_fast_make_const(const KswParams &P, KswFastConst &K)
 {
 	K.neg_ei = ksw_pk2(-P.e_ins); K.neg_oei = ksw_pk2(-(P.o_ins + P.e_ins));
-	K.neg_ed = ksw_pk2(-P.e_del); K.neg_oed = ksw_pk2(-(P.o_del + P.e_del));
+	K.ed32 = ksw_pk2(P.e_del); K.oed32 = ksw_pk2(P.o_del + P.e_del);
+	K.B = P.o_del + P.e_del; K.Bpk = ksw_pk2(K.B);
 	K.o_del = P.o_del; K.e_del = P.e_del; K.e_ins = P.e_ins; K.oe_ins = P.o_ins + P.e_ins; K.zdrop = P.zdrop;
 }
 
@@ -225,7 +237,7 @@ static KSW_HD void ksw_fast_setup_quads(ksw_u4 *hq, uint32_t *sq, const int owne
 		for (int k = 0; k < 4; ++k) {
 			const int c = c0 + k;
 			int v = c == 0 ? h0 : h0 - K.oe_ins - (c - 1) * K.e_ins;         // closed form of ksw.c:394-396
-			hv[k] = v > 0 ? v : 0;
+			hv[k] = (v > 0 ? v : 0) + K.B;
 			uint32_t code = (qw >> (((c & 15)) << 1)) & 3u;
 			if ((nw >> (c & 31)) & 1u) code = 4u;
 			if (c >= qlen) code = 0u;
@@ -233,9 +245,9 @@ static KSW_HD void ksw_fast_setup_quads(ksw_u4 *hq, uint32_t *sq, const int owne
 		}
 		ksw_u4 v4;
 		v4.x = (uint32_t)hv[0] | ((uint32_t)hv[1] << 16);   // pair A: lo c0, hi c1
-		v4.y = 0u;
+		v4.y = K.Bpk;                                       // E = 0 (+ bias)
 		v4.z = (uint32_t)hv[3] | ((uint32_t)hv[2] << 16);   // pair B: lo c3, hi c2
-		v4.w = 0u;
+		v4.w = K.Bpk;
 		hq[q * T + owner] = v4;
 		sq[q * T + owner] = (sb[0] | (sb[1] << 8)) | ((sb[3] | (sb[2] << 8)) << 16);
 	}
@@ -269,14 +281,14 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 	ksw_u4 v = M.hq[q * T];
 	const uint32_t sw = M.sq[q * T];
 	if (EDGE) {
-		// phantom columns get H = -8192, E = 0
-		v.x = (v.x & keepA) | (KSW_NEGPK & ~keepA); v.y &= keepA;
-		v.z = (v.z & keepB) | (KSW_NEGPK & ~keepB); v.w &= keepB;
+		// phantom columns get H = -8192, E = 0 (+ bias)
+		v.x = (v.x & keepA) | (KSW_NEGPK & ~keepA); v.y = (v.y & keepA) | (K.Bpk & ~keepA);
+		v.z = (v.z & keepB) | (KSW_NEGPK & ~keepB); v.w = (v.w & keepB) | (K.Bpk & ~keepB);
 	}
 	const uint32_t scA = prmt(mr.x, mr.y, sw), scB = prmt(mr.x, mr.y, ksw_hi16_of(sw));
 	const uint32_t hpA = addmax2(v.x, scA, v.y), hpB = addmax2(v.z, scB, v.w);
-	// relu(h' - oe_ins): the third operand only has to be <= 0, a live constant saves a zero register
-	const uint32_t gA = addmax2_relu(hpA, K.neg_oei, K.neg_oei), gB = addmax2_relu(hpB, K.neg_oei, K.neg_oei);
+	// max(h' - oe_ins, 0), with the bias: the floor is B
+	const uint32_t gA = addmax2(hpA, K.neg_oei, K.Bpk), gB = addmax2(hpB, K.neg_oei, K.Bpk);
 	// F chain: c0 (A.lo) -> c1 (A.hi) -> c2 (B.hi) -> c3 (B.lo) -> next quad
 	const uint32_t t1 = addmax2(R.X, K.neg_ei, gA);        // lo = F(c1)
 	const uint32_t FA = prmt(R.X, t1, 0x5410u);            // (F(c0), F(c1))
@@ -285,9 +297,9 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 	const uint32_t FB = prmt(t2, t3, 0x3276u);             // (lo = F(c3), hi = F(c2))
 	R.X = addmax2(FB, K.neg_ei, gB);                       // lo = F(c0 of the next quad)
 	const uint32_t hA = max2(hpA, FA), hB = max2(hpB, FB);
-	// E(i+1,j) = max(E - e_del, relu(H - oe_del))
-	uint32_t eA = addmax2(v.y, K.neg_ed, addmax2_relu(hA, K.neg_oed, K.neg_oed));
-	uint32_t eB = addmax2(v.w, K.neg_ed, addmax2_relu(hB, K.neg_oed, K.neg_oed));
+	// E(i+1,j) = max(E - e_del, H - oe_del, 0); every half is >= B >= oe_del, so the 32-bit subtractions cannot borrow
+	uint32_t eA = max3_2(v.y - K.ed32, hA - K.oed32, K.Bpk);
+	uint32_t eB = max3_2(v.w - K.ed32, hB - K.oed32, K.Bpk);
 	// row maximum, ties to the last column (ksw.c:434)
 	if (KEYED) {
 		R.m = maxu2(R.m, hA * 128u + R.colA);
@@ -316,7 +328,7 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 		// where it holds column hi (eh[end].h = h1 is what the shifted store writes there anyway)
 		o.x = (o.x & ~firstA) | (left0pk & firstA);
 		o.z = (o.z & ~firstB) | (left0pk & firstB);
-		eA &= ~endA; eB &= ~endB;
+		eA = (eA & ~endA) | (K.Bpk & endA); eB = (eB & ~endB) | (K.Bpk & endB);
 	}
 	o.y = eA; o.w = eB;
 	M.hq[q * T] = o;
@@ -324,20 +336,24 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 	R.hA = hA; R.hB = hB;
 }
 
-// whether a word of two non-negative int16 holds a zero half
-static KSW_HD bool ksw_has_zero16(uint32_t x) { return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u; }
+// whether a word of two int16 >= B holds a half equal to B (a zero score)
+static KSW_HD bool ksw_has_zero16(uint32_t x, uint32_t Bpk)
+{
+	x -= Bpk;
+	return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u;
+}
 
 // the reference's trim scans (ksw.c:463-466) over the stored eh[].h, skipping whole zero-free quads
 template <int T>
-static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, int rarg, int lo, int hi, int &new_lo, int &new_hi)
+static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, const KswFastConst &K, int rarg, int lo, int hi, int &new_lo, int &new_hi)
 {
 	int j = rarg;
 	while (j >= lo) {
 		if ((j & 3) == 3 && j - 3 >= lo) {
 			const ksw_u4 v = M.hq[(j >> 2) * T];
-			if (!ksw_has_zero16(v.x) && !ksw_has_zero16(v.z)) { j -= 4; continue; }
+			if (!ksw_has_zero16(v.x, K.Bpk) && !ksw_has_zero16(v.z, K.Bpk)) { j -= 4; continue; }
 		}
-		if (*M.h16(j) == 0) break;
+		if (*M.h16(j) == (uint16_t)K.B) break;
 		--j;
 	}
 	new_lo = j + 1;
@@ -345,9 +361,9 @@ static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, int rarg, int lo, 
 	while (j <= hi) {
 		if ((j & 3) == 0 && j + 3 <= hi) {
 			const ksw_u4 v = M.hq[(j >> 2) * T];
-			if (!ksw_has_zero16(v.x) && !ksw_has_zero16(v.z)) { j += 4; continue; }
+			if (!ksw_has_zero16(v.x, K.Bpk) && !ksw_has_zero16(v.z, K.Bpk)) { j += 4; continue; }
 		}
-		if (*M.h16(j) == 0) break;
+		if (*M.h16(j) == (uint16_t)K.B) break;
 		++j;
 	}
 	new_hi = j;
@@ -389,9 +405,9 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 	const int q0 = lo >> 2, q1 = (hi - 1) >> 2;
 	const int hi_rel = hi - (q1 << 2);                         // 1..4: where column hi sits relative to the last quad
 	const KswFastEdge eL = M.edge[lo & 3], eR = M.edge[hi_rel];
-	const uint32_t left0pk = (uint32_t)left0 * 0x10001u;
+	const uint32_t left0pk = (uint32_t)(left0 + K.B) * 0x10001u;
 	KswFastRowRegs R;
-	R.X = 0; R.Hc = 0; R.m = 0; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
+	R.X = K.Bpk; R.Hc = 0; R.m = 0; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
 	if (KEYED) {
 		const uint32_t c0 = (uint32_t)(q0 << 2);
 		R.colA = (c0 | ((c0 + 1u) << 16));
@@ -408,12 +424,13 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q1, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
 	}
 	// H(i, hi-1): the reference's h1 after the loop
-	const int left = (int)prmt(R.hA, R.hB, eR.sel_left);
+	const int left_b = (int)prmt(R.hA, R.hB, eR.sel_left);     // still biased
+	const int left = left_b - K.B;
 	if (hi_rel == 4) {
 		// column hi opens the next quad: eh[end].h = h1, eh[end].e = 0 (ksw.c:446); the other half-words of that
 		// 64-bit slot belong to column hi+1, which is rewritten before it is read again
 		ksw_u2 *p = reinterpret_cast<ksw_u2 *>(&M.hq[(q1 + 1) * T]);
-		ksw_u2 w2; w2.x = (uint32_t)left; w2.y = 0u;
+		ksw_u2 w2; w2.x = (uint32_t)left_b; w2.y = K.Bpk;
 		*p = w2;
 	}
 	if (hi == L.qlen) {                                        // ksw.c:447-450, ties -> last row
@@ -424,10 +441,10 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 	if (KEYED) {
 		const uint32_t k_lo = R.m & 0xffffu, k_hi = R.m >> 16;
 		const uint32_t kmax = k_lo > k_hi ? k_lo : k_hi;
-		rmax = (int)(kmax >> 7); rarg = (int)(kmax & 127u);
+		rmax = (int)(kmax >> 7) - K.B; rarg = (int)(kmax & 127u);
 	} else {
 		const int m_lo = (int)(int16_t)(R.m & 0xffffu), m_hi = (int)(int16_t)(R.m >> 16);
-		rmax = m_lo > m_hi ? m_lo : m_hi;
+		rmax = (m_lo > m_hi ? m_lo : m_hi) - K.B;
 		rarg = m_lo > m_hi ? R.mjl : (m_hi > m_lo ? R.mjh : (R.mjl > R.mjh ? R.mjl : R.mjh));
 	}
 	if (rmax == 0) return true;                                // ksw.c:451
@@ -445,7 +462,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		if (drop) return true;
 	}
 	// band trim (ksw.c:463-466)
-	const bool any_zero = ((R.zmin & 0xffffu) == 0u) | ((R.zmin >> 16) == 0u);
+	const bool any_zero = ((R.zmin & 0xffffu) == (uint32_t)K.B) | ((R.zmin >> 16) == (uint32_t)K.B);
 	if (!any_zero) {
 		// every eh[j].h for j in (lo, hi] is non-zero, so only the first-column slot eh[lo].h can stop the
 		// downward scan, and the upward scan runs off the end
@@ -453,7 +470,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		L.hi = hi + 1;
 	} else {
 		int nl, nh;
-		ksw_fast_trim_scan<T>(M, rarg, lo, hi, nl, nh);
+		ksw_fast_trim_scan<T>(M, K, rarg, lo, hi, nl, nh);
 		L.lo = nl; L.hi = nh;
 	}
 	L.i = i + 1;

@@ -164,7 +164,7 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 			const int h0 = j.h0 < 0 ? 0 : j.h0;
 			const bool fast = fast_eligible(cfg, fast_qmax, maxsc, minsc, j.qlen, h0);
 			uint32_t qc = 0;
-			if (!(j.qlen <= KSW_FAST_CLASS_QMAX[0] && (int64_t)h0 + (int64_t)j.qlen * maxsc <= KSW_FAST_KEYED_MAXSCORE)) {
+			if (!(j.qlen <= KSW_FAST_CLASS_QMAX[0] && (int64_t)h0 + (int64_t)j.qlen * maxsc + cfg->o_del + cfg->e_del <= KSW_FAST_KEYED_MAXSCORE)) {
 				qc = 1;
 				while (qc + 1 < KSW_FAST_CLASSES && j.qlen > KSW_FAST_CLASS_QMAX[qc]) ++qc;
 			}
