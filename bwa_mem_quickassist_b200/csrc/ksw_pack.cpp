@@ -32,42 +32,52 @@ const bool g_has_bmi2 = __builtin_cpu_supports("bmi2");
 #define KSW_HAVE_PEXT 1
 #endif
 
-// 2-bit packing of `len` byte codes into ceil(len/16) words.  Returns true if a code > 3 (N) was
-// seen; those bases are stored as 0 and flagged in nmask (ceil(len/32) words, caller-zeroed).
+// gather the low 2 bits of each of 16 byte codes into one word (base k at bits 2k)
+inline uint32_t squeeze16(uint64_t a, uint64_t b)
+{
+#ifdef KSW_HAVE_PEXT
+	if (g_has_bmi2) return squeeze16_pext(a, b);
+#endif
+	auto squeeze = [](uint64_t v) -> uint32_t {
+		v = (v | (v >> 6)) & 0x000F000F000F000Full;
+		v = (v | (v >> 12)) & 0x000000FF000000FFull;
+		v = (v | (v >> 24)) & 0xFFFFull;
+		return (uint32_t)v;
+	};
+	return squeeze(a) | (squeeze(b) << 16);
+}
+
+// 2-bit packing of `len` byte codes into ceil(len/16) words.  Returns true if a code > 3 (N) was seen; those bases
+// are stored as 0 and flagged in nmask (ceil(len/32) words), which is zeroed here on the first N and otherwise untouched.
 inline bool pack2(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
 {
 	bool has_n = false;
-	const int nw = (len + 15) >> 4;
-	for (int wi = 0, k = 0; wi < nw; ++wi, k += 16) {
+	const int full = len >> 4;
+	auto slow_word = [&](const uint8_t *p, int k0, int lim) -> uint32_t {
 		uint32_t word = 0;
-		const int lim = std::min(16, len - k);
-		bool slow = lim < 16;
-		if (!slow) {
-			uint64_t a, b;
-			memcpy(&a, s + k, 8); memcpy(&b, s + k + 8, 8);
-			if ((a | b) & 0xFCFCFCFCFCFCFCFCull) slow = true;
-#ifdef KSW_HAVE_PEXT
-			else if (g_has_bmi2) word = squeeze16_pext(a, b);
-#endif
-			else {
-				// gather the low 2 bits of each of 8 bytes into 16 contiguous bits
-				auto squeeze = [](uint64_t v) -> uint32_t {
-					v = (v | (v >> 6)) & 0x000F000F000F000Full;
-					v = (v | (v >> 12)) & 0x000000FF000000FFull;
-					v = (v | (v >> 24)) & 0xFFFFull;
-					return (uint32_t)v;
-				};
-				word = squeeze(a) | (squeeze(b) << 16);
+		for (int x = 0; x < lim; ++x) {
+			uint32_t c = p[x];
+			if (c > 3) {
+				if (!has_n) { has_n = true; std::fill_n(nmask, (len + 31) >> 5, 0u); }
+				nmask[(k0 + x) >> 5] |= 1u << ((k0 + x) & 31);
+				c = 0;
 			}
+			word |= c << (2 * x);
 		}
-		if (slow) {
-			for (int x = 0; x < lim; ++x) {
-				uint32_t c = s[k + x];
-				if (c > 3) { has_n = true; nmask[(k + x) >> 5] |= 1u << ((k + x) & 31); c = 0; }
-				word |= c << (2 * x);
-			}
-		}
-		out[wi] = word;
+		return word;
+	};
+	for (int wi = 0; wi < full; ++wi) {
+		uint64_t a, b;
+		memcpy(&a, s + 16 * wi, 8); memcpy(&b, s + 16 * wi + 8, 8);
+		out[wi] = ((a | b) & 0xFCFCFCFCFCFCFCFCull) ? slow_word(s + 16 * wi, 16 * wi, 16) : squeeze16(a, b);
+	}
+	const int rem = len & 15;
+	if (rem) {
+		uint8_t tail[16] = {0};
+		memcpy(tail, s + 16 * full, (size_t)rem);
+		uint64_t a, b;
+		memcpy(&a, tail, 8); memcpy(&b, tail + 8, 8);
+		out[full] = ((a | b) & 0xFCFCFCFCFCFCFCFCull) ? slow_word(s + 16 * full, 16 * full, rem) : squeeze16(a, b);
 	}
 	return has_n;
 }
@@ -156,7 +166,7 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 			std::fill(cnt[t].begin() + plan.key_lo, cnt[t].begin() + plan.key_hi + 1, 0u);
 			std::fill(usum[t].begin() + plan.key_lo, usum[t].begin() + plan.key_hi + 1, (uint64_t)0);
 		}
-		int *qm = &qmax_cls[t * (KSW_FAST_CLASSES + 1)];
+		int qm[KSW_FAST_CLASSES + 1] = {0};               // thread-local; written back once (no false sharing)
 		int klo = NKEY, khi = -1;
 		for (int64_t k = b; k < e; ++k) {
 			const ksw_b200_job_t &j = jobs[k];
@@ -179,6 +189,7 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 			slot = std::max(slot, j.qlen);
 		}
 		krange[2 * t] = klo; krange[2 * t + 1] = khi;
+		for (int c = 0; c <= KSW_FAST_CLASSES; ++c) qmax_cls[t * (KSW_FAST_CLASSES + 1) + c] = qm[c];
 	});
 	if (bad) { err = "ksw_b200: job with qlen < 1 or tlen < 0"; return 2; }
 
@@ -266,7 +277,6 @@ int ksw_pack_fill(const KswPackPlan &plan, const ksw_b200_cfg_t *cfg, const ksw_
 			const uint32_t qmw = ksw_words1(j.qlen), tmw = ksw_words1(j.tlen);
 			if (qm.size() < qmw) qm.resize(qmw);
 			if (tm.size() < tmw) tm.resize(tmw);
-			std::fill_n(qm.data(), qmw, 0u); std::fill_n(tm.data(), tmw, 0u);
 			const bool qn = pack2(qpool + j.q_off, j.qlen, dst, qm.data());
 			const bool tn = pack2(tpool + j.t_off, j.tlen, dst + qw, tm.data());
 			for (uint32_t x = qw + tw; x < plan.units_of[k] * 4u; ++x) dst[x] = 0;

@@ -528,3 +528,25 @@ def load_chain_golden():
                       z[f"{nm}.chain_read"], z[f"{nm}.chain_seed0"], z[f"{nm}.chain_nseeds"], z[f"{nm}.seeds"].astype(SEED_DT))
         out[nm] = (cs, (z[f"{nm}.regs"].astype(REG_DT), z[f"{nm}.reg_read"]))
     return out
+
+
+def gen_boundaries(seed: int = 99, cfg: Cfg | None = None) -> Batch:
+    """Jobs that sit exactly on the packer's class boundaries: the keyed bound (h0 + qlen*a + o_del + e_del == 511 and
+    512), the query-length classes (124/125, 128/129, 256/257, 512/513) and the int16 budget (h0 + qlen*a == 20000 and
+    20001), with perfect matches so that the largest scores are really reached, plus near-perfect variants."""
+    rng = np.random.default_rng(seed)
+    cfg = cfg or make_cfg()
+    a = int(cfg.mat[0]); B = cfg.o_del + cfg.e_del
+    qs, ts, h0s, ws = [], [], [], []
+    for ql in (1, 3, 4, 5, 123, 124, 125, 127, 128, 129, 255, 256, 257, 511, 512, 513):
+        t = rng.integers(0, 4, ql + 30).astype(np.uint8)
+        q = t[:ql].copy()
+        q2 = q.copy()
+        if ql > 8:
+            q2[ql // 2] = (q2[ql // 2] + 1) & 3
+        for h0 in sorted({0, 1, max(0, 511 - B - ql * a - 1), max(0, 511 - B - ql * a), max(0, 511 - B - ql * a + 1),
+                          max(0, 20000 - ql * a - 1), max(0, 20000 - ql * a), max(0, 20000 - ql * a + 1), 32000}):
+            for qq in (q, q2):
+                qs.append(qq); ts.append(t); h0s.append(h0); ws.append(100)
+                qs.append(qq); ts.append(t[:ql]); h0s.append(h0); ws.append(1000)
+    return _pools_from_lists(qs, ts, np.array(h0s), np.array(ws), cfg)

@@ -54,6 +54,11 @@ def test_int16_overflow_goes_generic(gpu_ctx, oracle_built):
     _check(gpu_ctx, K.gen_fuzz(2000, seed=16, cfg=cfg, h0_max=3000))
 
 
+def test_class_boundaries(gpu_ctx, oracle_built):
+    _check(gpu_ctx, K.gen_boundaries())
+    _check(gpu_ctx, K.gen_boundaries(cfg=K.make_cfg(a=3, b=5, o_del=9, e_del=2, o_ins=4, e_ins=3, zdrop=200, end_bonus=7)))
+
+
 def test_general_matrix(gpu_ctx, oracle_built):
     rng = np.random.default_rng(5)
     mat = rng.integers(-9, 8, 25).astype(np.int8)

@@ -47,6 +47,20 @@ def test_packer_routes_out_of_range_jobs_to_generic(oracle_built):
     assert (got2["score"][long_q.jobs["qlen"] > 512] == np.iinfo(np.int32).min).all()
 
 
+def test_fast_lane_source_on_class_boundaries(oracle_built):
+    for cfg in (K.make_cfg(), K.make_cfg(a=3, b=5, o_del=9, e_del=2, o_ins=4, e_ins=3, zdrop=200, end_bonus=7)):
+        b = K.gen_boundaries(cfg=cfg)
+        want = K.run_oracle(b)
+        got, n_fast = K.run_emu(b)
+        sel = got["score"] != np.iinfo(np.int32).min
+        assert 0 < n_fast < b.n and K.run_emu.last_keyed > 0          # all three routes are exercised
+        mm = K.first_mismatch(want[sel], got[sel])
+        assert mm is None, mm
+        # the largest score the keyed class may see is exactly its bound
+        a = int(cfg.mat[0])
+        assert (want["score"][sel] <= 20000).all()
+
+
 def _header_functions():
     txt = open(os.path.join(K.ROOT, "include", "ksw_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
