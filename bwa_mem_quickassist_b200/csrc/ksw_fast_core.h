@@ -273,13 +273,12 @@ static inline uint32_t ksw_hi16_of(uint32_t w) { return w >> 16; }
 // columns are masked with keepA/keepB, the reference's edge writes are folded into its store.
 template <int T, bool KEYED, bool EDGE>
 static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, const KswFastConst &K, const ksw_u2 mr,
-                                 const int q, const uint32_t keepA, const uint32_t keepB,
+                                 const int q, ksw_u4 v, const uint32_t sw, const uint32_t keepA, const uint32_t keepB,
                                  const uint32_t firstA, const uint32_t firstB, const uint32_t left0pk,
                                  const uint32_t endA, const uint32_t endB)
 {
 	using namespace kswdpx;
-	ksw_u4 v = M.hq[q * T];
-	const uint32_t sw = M.sq[q * T];
+	// (v, sw) = hq[q], sq[q], loaded by the caller one quad ahead so that the LDS latency hides behind the previous quad
 	if (EDGE) {
 		// phantom columns get H = -8192, E = 0 (+ bias)
 		v.x = (v.x & keepA) | (KSW_NEGPK & ~keepA); v.y = (v.y & keepA) | (K.Bpk & ~keepA);
@@ -413,15 +412,23 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		R.colA = (c0 | ((c0 + 1u) << 16));
 		R.colB = ((c0 + 3u) | ((c0 + 2u) << 16));
 	} else { R.colA = R.colB = 0; }
+	ksw_u4 v = M.hq[q0 * T];
+	uint32_t sw = M.sq[q0 * T];
 	if (q1 == q0) {
-		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, eL.geA & eR.ltA, eL.geB & eR.ltB, eL.onlyA, eL.onlyB, left0pk, eR.onlyA, eR.onlyB);
+		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, v, sw, eL.geA & eR.ltA, eL.geB & eR.ltB, eL.onlyA, eL.onlyB, left0pk, eR.onlyA, eR.onlyB);
 	} else {
-		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, eL.geA, eL.geB, eL.onlyA, eL.onlyB, left0pk, 0u, 0u);
+		ksw_u4 vn = M.hq[(q0 + 1) * T];                        // software prefetch, one quad ahead
+		uint32_t swn = M.sq[(q0 + 1) * T];
+		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, v, sw, eL.geA, eL.geB, eL.onlyA, eL.onlyB, left0pk, 0u, 0u);
 #ifdef __CUDACC__
 #pragma unroll 2
 #endif
-		for (int q = q0 + 1; q < q1; ++q) ksw_fast_quad<T, KEYED, false>(R, M, K, mr, q, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
-		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q1, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
+		for (int q = q0 + 1; q < q1; ++q) {
+			v = vn; sw = swn;
+			vn = M.hq[(q + 1) * T]; swn = M.sq[(q + 1) * T];
+			ksw_fast_quad<T, KEYED, false>(R, M, K, mr, q, v, sw, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+		}
+		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q1, vn, swn, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
 	}
 	// H(i, hi-1): the reference's h1 after the loop
 	const int left_b = (int)prmt(R.hA, R.hB, eR.sel_left);     // still biased
