@@ -19,7 +19,7 @@ constexpr int T = KSW_FAST_THREADS;   // 32: one warp per CTA
 template <bool KEYED>
 __global__ void __launch_bounds__(T, 12)
 ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
-                const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap,
+                const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap, const int chunk,
                 unsigned long long *__restrict__ counter, DevRes *__restrict__ res, uint32_t *__restrict__ cells)
 {
 	extern __shared__ uint4 smem[];
@@ -44,21 +44,36 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 	enum { IDLE = 0, RUN = 1, DONE = 2 };
 	int state = IDLE;
 
+	// Job supply: the warp takes CHUNK (32..256, chosen by the launcher: >= 16 chunks per warp) consecutive jobs of the binned list at a time (one atomicAdd per chunk) and its
+	// lanes draw from that chunk, so the 32 jobs a warp works on at any moment are neighbours in the binned order
+	// (similar band width and length) even after the lanes have drifted apart in time.
+	const long long CHUNK = chunk;
+	long long wcur = 0, wend = 0;                                  // warp-uniform cursor into the current chunk
+	bool exhausted = false;
+
 	while (true) {
-		const unsigned need = __ballot_sync(0xffffffffu, state == IDLE);
+		unsigned need = __ballot_sync(0xffffffffu, state == IDLE);
 		if (need) {
-			const int leader = __ffs(need) - 1;
-			unsigned long long base = 0;
-			if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
-			base = __shfl_sync(0xffffffffu, base, leader);
 			DevJob jb;
 			jb.seq_off = 0; jb.idx = 0; jb.qlen = 0; jb.tlen = 0; jb.h0 = 0; jb.w = 0; jb.flags = 0; jb.nmask_off = 0;
 			bool got = false;
-			if (state == IDLE) {
-				const long long k = (long long)base + __popc(need & ((1u << lane) - 1u));
-				if (k < n_jobs) { jb = jobs[k]; got = true; }
-				else state = DONE;
+			for (int round = 0; round < 2 && need; ++round) {
+				if (wcur >= wend && !exhausted) {
+					unsigned long long base = 0;
+					if (lane == 0) base = atomicAdd(counter, (unsigned long long)CHUNK);
+					base = __shfl_sync(0xffffffffu, base, 0);
+					wcur = (long long)base;
+					wend = wcur + CHUNK < n_jobs ? wcur + CHUNK : n_jobs;
+					if (wcur >= n_jobs) { exhausted = true; wend = wcur; }
+				}
+				const long long avail = wend - wcur;
+				const int rank = __popc(need & ((1u << lane) - 1u));
+				if (state == IDLE && !got && (long long)rank < avail) { jb = jobs[wcur + rank]; got = true; }
+				const int served = (long long)__popc(need) < avail ? __popc(need) : (int)avail;
+				wcur += served;
+				need = __ballot_sync(0xffffffffu, state == IDLE && !got);
 			}
+			if (state == IDLE && !got && exhausted) state = DONE;
 			const unsigned fetched = __ballot_sync(0xffffffffu, got);
 			if (__popc(fetched) >= 8) {
 				// many lanes start together (e.g. at launch, or equal-length jobs): each builds its own state
@@ -116,8 +131,12 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 	if (blocks > need) blocks = need;
 	e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
 	if (e != cudaSuccess) return e;
+	// chunk of consecutive jobs a warp claims at once: large enough to keep a warp's jobs alike, small enough that every
+	// warp gets many chunks (load balance at the end of the launch)
+	long long chunk = n_jobs / (blocks * 16);
+	chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : (chunk / 32) * 32);
 	ksw_fast_kernel<KEYED><<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
-	                                                           KSW_FAST_QUADS(qmax), counter, res, cells);
+	                                                           KSW_FAST_QUADS(qmax), (int)chunk, counter, res, cells);
 	return cudaGetLastError();
 }
 

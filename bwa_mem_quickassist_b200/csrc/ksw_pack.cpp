@@ -178,9 +178,11 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 				qc = 1;
 				while (qc + 1 < KSW_FAST_CLASSES && j.qlen > KSW_FAST_CLASS_QMAX[qc]) ++qc;
 			}
-			const uint32_t tl = 127u - ((uint32_t)std::min(j.tlen, 2032) >> 4);   // 7 bits
-			const uint32_t hb = 63u - ((uint32_t)std::min(h0, 504) >> 3);         // 6 bits
-			const uint16_t ky = (uint16_t)((fast ? (qc << 13) : 0x8000u) | (tl << 6) | hb);
+			// rows first (long jobs at the front keep the tail of a launch short), then the carried-in score, which sets
+			// the band width; a warp claims chunks of consecutive jobs, so its lanes agree on both
+			const uint32_t tl = 63u - ((uint32_t)std::min(j.tlen, 1008) >> 4);    // 6 bits
+			const uint32_t hb = 127u - ((uint32_t)std::min(h0, 508) >> 2);        // 7 bits
+			const uint16_t ky = (uint16_t)((fast ? (qc << 13) : 0x8000u) | (tl << 7) | hb);
 			const uint32_t units = (ksw_words2(j.qlen) + ksw_words2(j.tlen) + 3) >> 2;
 			key[k] = ky; plan.units_of[k] = units;
 			cnt[t][ky]++; usum[t][ky] += units;
