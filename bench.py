@@ -272,9 +272,12 @@ def main():
         ok = all((res_cpu[f] == res_gpu[f][:ns]).all() for f in B.RES_DT.names)
         ok_cells = bool((ocells == cells_job[:ns].astype(np.int64)).all())
         parity = {"sample_jobs": ns, "bit_exact": bool(ok), "cells_match_oracle": ok_cells, "e2e_equals_resident": bool(same)}
+        n1 = min(ns, 100_000)                                    # and one core, as BASELINE.md 3.1(a) asks
+        _, _, dt1 = cpu_reference(K.make_cfg(), jobs[:n1], qpool, tpool, 1)
         cpu = {"value": float(ocells.sum()) / dt / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"first {ns} jobs of the batch, {threads} host threads, one pass",
-               "ext_per_s": ns / dt}
+               "ext_per_s": ns / dt,
+               "one_core": {"value": float(ocells[:n1].sum()) / dt1 / 1e9, "unit": UNIT, "ext_per_s": n1 / dt1, "sample": f"first {n1} jobs, 1 thread"}}
 
     if rank == 0:
         peaks = {}
