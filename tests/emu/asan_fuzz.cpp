@@ -1,0 +1,86 @@
+// tests/emu/asan_fuzz.cpp — TEST INFRASTRUCTURE.  The packer and the fast kernel's per-lane source compiled for the
+// CPU with AddressSanitizer + UBSan, every shared-memory array allocated at exactly the size the launcher gives the
+// kernel, random jobs checked against the oracle.  (compute-sanitizer is not available on the GPU pool; this finds
+// out-of-bounds accesses and undefined shifts in the same source on the host.)
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_pack.h"
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_fast_core.h"
+
+extern "C" int ksw_oracle_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                                  int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
+                                  int *qle, int *tle, int *gtle, int *gscore, int *max_off, int64_t *cells, int32_t *rows);
+
+int main(int argc, char **argv)
+{
+	const int n = argc > 1 ? atoi(argv[1]) : 20000;
+	const unsigned seed = argc > 2 ? (unsigned)atoi(argv[2]) : 1u;
+	std::mt19937 rng(seed);
+	auto U = [&](int lo, int hi) { return (int)(rng() % (unsigned)(hi - lo + 1)) + lo; };
+	ksw_b200_cfg_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	const int a = U(1, 3), b = U(1, 6);
+	for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) cfg.mat[i * 5 + j] = (int8_t)((i < 4 && j < 4) ? (i == j ? a : -b) : -1);
+	cfg.m = 5; cfg.o_del = U(0, 8); cfg.e_del = U(1, 3); cfg.o_ins = U(0, 8); cfg.e_ins = U(1, 3);
+	cfg.zdrop = U(0, 3) ? U(5, 150) : -1; cfg.end_bonus = U(0, 10);
+	std::vector<uint8_t> qpool, tpool;
+	std::vector<ksw_b200_job_t> jobs(n);
+	for (int k = 0; k < n; ++k) {
+		const int ql = U(1, 3) == 1 ? U(1, 12) : U(1, 300), tl = U(0, 2 * ql + 40);
+		jobs[k].q_off = qpool.size(); jobs[k].t_off = tpool.size(); jobs[k].qlen = ql; jobs[k].tlen = tl;
+		jobs[k].h0 = U(0, 4) ? U(0, 260) : 0; jobs[k].w = U(0, 3) ? 100 : U(1, 60);
+		std::vector<uint8_t> t(tl), q(ql);
+		for (auto &x : t) x = (uint8_t)U(0, 3);
+		const int shift = U(-3, 3), err = U(0, 30);
+		for (int j = 0; j < ql; ++j) {
+			const int p = j + shift;
+			q[j] = (p >= 0 && p < tl && U(0, 99) >= err) ? t[p] : (uint8_t)U(0, 3);
+			if (U(0, 199) == 0) q[j] = 4;
+		}
+		if (U(0, 29) == 0) for (auto &x : t) if (U(0, 19) == 0) x = 4;
+		qpool.insert(qpool.end(), q.begin(), q.end());
+		tpool.insert(tpool.end(), t.begin(), t.end());
+	}
+	qpool.push_back(0); tpool.push_back(0);
+	KswPool tp(2);
+	KswPackPlan plan;
+	std::string err;
+	if (ksw_pack_plan(&cfg, n, jobs.data(), KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1], &tp, plan, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+	std::vector<DevJob> dj(n);
+	std::vector<uint32_t> pool(plan.pool_bytes / 4), nmask;       // exact sizes: ASan sees any overrun
+	ksw_pack_fill(plan, &cfg, jobs.data(), qpool.data(), tpool.data(), dj.data(), pool.data(), nmask, &tp);
+	KswParams P; ksw_params_from_cfg(&cfg, P);
+	KswFastConst K; ksw_fast_make_const(P, K);
+	ksw_u2 mrow[5]; for (int t = 0; t < 5; ++t) mrow[t] = ksw_fast_matrow(P, t);
+	KswFastEdge edge[5]; for (int r = 0; r < 5; ++r) ksw_fast_edge_entry(r, edge[r]);
+	int bad = 0;
+	for (int64_t p = 0; p < plan.n_fast; ++p) {
+		const DevJob &jb = dj[p];
+		const int nq = KSW_FAST_QUADS(jb.qlen);
+		std::vector<ksw_u4> hq(nq);                               // exactly what ksw_fast_smem_bytes() reserves per lane
+		std::vector<uint32_t> sq(nq);
+		KswFastMem<1> M{hq.data(), sq.data(), edge};
+		KswFastLane L;
+		ksw_fast_setup_quads<1>(hq.data(), sq.data(), 0, 0, 1, K, jb.seq_off, jb.qlen, jb.h0, jb.flags, jb.nmask_off, pool.data(),
+		                        nmask.empty() ? nullptr : nmask.data());
+		ksw_fast_init_lane(L, jb, pool.data(), nmask.empty() ? nullptr : nmask.data());
+		if (p < plan.fast_class_n[0]) { while (!ksw_fast_row<1, true>(L, M, K, mrow)) {} }
+		else { while (!ksw_fast_row<1, false>(L, M, K, mrow)) {} }
+		DevRes r; ksw_fast_result(L, r);
+		const ksw_b200_job_t &j = jobs[jb.idx];
+		int qle, tle, gtle, gscore, max_off;
+		const int sc = ksw_oracle_extend2(j.qlen, qpool.data() + j.q_off, j.tlen, tpool.data() + j.t_off, 5, cfg.mat, cfg.o_del, cfg.e_del,
+		                                  cfg.o_ins, cfg.e_ins, j.w, cfg.end_bonus, cfg.zdrop, j.h0, &qle, &tle, &gtle, &gscore, &max_off, 0, 0);
+		if (sc != r.score || qle != r.qle || tle != r.tle || gtle != r.gtle || gscore != r.gscore || max_off != r.max_off) {
+			if (bad++ < 5) fprintf(stderr, "mismatch job %u: qlen %d tlen %d h0 %d w %d\n", jb.idx, j.qlen, j.tlen, j.h0, j.w);
+		}
+	}
+	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %d mismatches\n", n, (long long)plan.n_fast,
+	       (long long)plan.fast_class_n[0], bad);
+	return bad ? 1 : 0;
+}

@@ -108,3 +108,14 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c")):
                 s = open(os.path.join(dp, f)).read()
                 assert "libksw_oracle" not in s and "ksw_oracle_" not in s and "libksw_ref" not in s, f
+
+
+def test_lane_source_under_address_and_ub_sanitizers(oracle_built):
+    """compute-sanitizer is closed on the GPU pool, so the packer and the kernel's per-lane source run under ASan + UBSan on
+    the host with every array at exactly the size the launcher reserves (tests/emu/asan_fuzz.cpp)."""
+    import subprocess
+    emu = os.path.join(K.ROOT, "tests", "emu")
+    subprocess.run(["make", "-C", emu, "asan_fuzz", "--no-print-directory"], check=True, stdout=subprocess.DEVNULL)
+    for seed in (11, 12):
+        out = subprocess.run([os.path.join(emu, "asan_fuzz"), "4000", str(seed)], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "0 mismatches" in out.stdout, out.stdout + out.stderr[-2000:]
