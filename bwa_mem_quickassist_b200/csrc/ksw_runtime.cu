@@ -422,15 +422,9 @@ void ksw_b200_batch_free(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b)
 	if (b) { batch_release_buffers(b); delete b; }
 }
 
-// One-shot batched entry.  The batch is cut into chunks of ctx->chunk_jobs jobs (caller order); chunk c+1 is
-// packed on the host threads while chunk c is being copied / computed on the GPU (two slots, two streams).
-int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
-                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
+static int extend_batch_pipelined(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                                  const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
 {
-	if (!ctx || !cfg || n < 0) return 1;
-	if (n == 0) return 0;
-	if (!jobs || !res) return 1;
-	CU(cudaSetDevice(ctx->device));
 	const double t_begin = now_ms();
 	double t_plan = 0, t_fill = 0, t_wait = 0;
 	int64_t h2d = 0;
@@ -461,6 +455,23 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		fprintf(stderr, "[ksw_b200] extend_batch n=%lld chunk=%lld: total %.2f ms (plan %.2f, fill %.2f, wait-gpu %.2f)\n",
 		        (long long)n, (long long)chunk, now_ms() - t_begin, t_plan, t_fill, t_wait);
 	return 0;
+}
+
+// One-shot batched entry.  The batch is cut into chunks of ctx->chunk_jobs jobs (caller order); chunk c+1 is
+// packed on the host threads while chunk c is being copied / computed on the GPU (two slots, two streams).
+int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
+{
+	if (!ctx || !cfg || n < 0) return 1;
+	if (n == 0) return 0;
+	if (!jobs || !res) return 1;
+	CU(cudaSetDevice(ctx->device));
+	const int rc = extend_batch_pipelined(ctx, cfg, n, jobs, qpool, tpool, res);
+	if (rc) {
+		// leave the context reusable: nothing may stay in flight or marked busy after a failed call
+		for (Slot &s : ctx->slot) { cudaStreamSynchronize(s.stream); s.busy = false; }
+	}
+	return rc;
 }
 
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes)

@@ -93,6 +93,18 @@ def test_empty_and_single(gpu_ctx, oracle_built):
     assert gpu_ctx.extend_batch(empty.cfg, empty.jobs, empty.qpool, empty.tpool).shape[0] == 0
 
 
+def test_usage_errors_are_reported_and_context_stays_usable(gpu_ctx, oracle_built):
+    import bwa_mem_quickassist_b200 as B
+    b = K.gen_fuzz(50, seed=51)
+    bad = b.jobs.copy(); bad["qlen"][7] = 0                      # the reference would write out of bounds (ksw.c:394)
+    with pytest.raises(B.KswB200Error, match="qlen < 1"):
+        gpu_ctx.extend_batch(b.cfg, bad, b.qpool, b.tpool)
+    cfg6 = K.make_cfg(); cfg6.m = 6                               # no reference caller passes anything but 5
+    with pytest.raises(B.KswB200Error, match="m == 5"):
+        gpu_ctx.extend_batch(cfg6, b.jobs, b.qpool, b.tpool)
+    _check(gpu_ctx, b)                                            # the context still works
+
+
 def test_scalar_dropins(gpu_ctx, oracle_built):
     import bwa_mem_quickassist_b200 as B
     b = K.gen_fuzz(40, seed=21)
