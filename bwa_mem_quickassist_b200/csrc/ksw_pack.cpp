@@ -193,7 +193,11 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 		krange[2 * t] = klo; krange[2 * t + 1] = khi;
 		for (int c = 0; c <= KSW_FAST_CLASSES; ++c) qmax_cls[t * (KSW_FAST_CLASSES + 1) + c] = qm[c];
 	});
-	if (bad) { err = "ksw_b200: job with qlen < 1 or tlen < 0"; return 2; }
+	if (bad) {
+		plan.key_lo = 0; plan.key_hi = NKEY - 1;       // the histograms are dirty: have the next call clear all of them
+		err = "ksw_b200: job with qlen < 1 or tlen < 0";
+		return 2;
+	}
 
 	// exclusive prefix over (key, thread): start position / start pool offset of every (key, thread) run
 	// (only the key range that occurs is walked; class boundaries are picked up on the way)
@@ -215,7 +219,7 @@ int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jo
 		}
 	}
 	for (int c = 0; c <= KSW_FAST_CLASSES + 1; ++c) if (below[c] < 0) below[c] = (int64_t)pos;
-	if (off > 0xffffffffull) { err = "ksw_b200: packed pool exceeds 64 GiB"; return 2; }
+	if (off > 0xffffffffull) { plan.key_lo = 0; plan.key_hi = NKEY - 1; err = "ksw_b200: packed pool exceeds 64 GiB"; return 2; }
 	// keys: class c spans [c<<13, (c+1)<<13) (0x6000-0x7fff unused), the generic block starts at 0x8000
 	{
 		plan.n_fast = below[KSW_FAST_CLASSES + 1];

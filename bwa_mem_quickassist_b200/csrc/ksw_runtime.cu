@@ -474,6 +474,38 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 	return rc;
 }
 
+// Multi-GPU form: jobs are independent, so the batch is cut into n_ctx contiguous ranges of (nearly)
+// equal DP cells (sum of qlen*tlen); range r runs on ctxs[r] (one host thread per context / GPU, no exchange step) and
+// writes its results straight into res.  Returns the first non-zero code of any shard.
+int ksw_b200_extend_batch_multi(int n_ctx, ksw_b200_ctx_t **ctxs, const ksw_b200_cfg_t *cfg, int64_t n,
+                                const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
+{
+	if (n_ctx < 1 || !ctxs || !cfg || n < 0) return 1;
+	if (n_ctx == 1) return ksw_b200_extend_batch(ctxs[0], cfg, n, jobs, qpool, tpool, res);
+	std::vector<int64_t> cut(n_ctx + 1, n);
+	{
+		double total = 0;
+		for (int64_t k = 0; k < n; ++k) total += (double)jobs[k].qlen * (double)std::max(jobs[k].tlen, 1);
+		double acc = 0;
+		int r = 1;
+		cut[0] = 0;
+		for (int64_t k = 0; k < n && r < n_ctx; ++k) {
+			acc += (double)jobs[k].qlen * (double)std::max(jobs[k].tlen, 1);
+			while (r < n_ctx && acc >= total * r / n_ctx) cut[r++] = k + 1;
+		}
+	}
+	std::vector<int> rc(n_ctx, 0);
+	std::vector<std::thread> th;
+	for (int r = 0; r < n_ctx; ++r)
+		th.emplace_back([&, r] {
+			const int64_t b = cut[r], e = cut[r + 1];
+			if (e > b) rc[r] = ksw_b200_extend_batch(ctxs[r], cfg, e - b, jobs + b, qpool, tpool, res + b);
+		});
+	for (auto &t : th) t.join();
+	for (int r = 0; r < n_ctx; ++r) if (rc[r]) return rc[r];
+	return 0;
+}
+
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes)
 {
 	if (!ctx) return 1;

@@ -83,6 +83,7 @@ def load_library():
     lib.ksw_b200_ctx_launch_count.restype = i64
     lib.ksw_b200_ctx_sync.argtypes = [vp]
     lib.ksw_b200_extend_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.ksw_b200_extend_batch_multi.argtypes = [i32, vp, vp, i64, vp, vp, vp, vp]
     lib.ksw_b200_batch_upload.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(vp)]
     lib.ksw_b200_batch_run.argtypes = [vp, vp]
     lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
@@ -216,6 +217,19 @@ class KswB200:
         ops, ms = C.c_double(0), C.c_float(0)
         self._check(self.lib.ksw_b200_dpx_peak(self.ctx, which, C.byref(ops), C.byref(ms)), "ksw_b200_dpx_peak")
         return ops.value, ms.value
+
+
+def extend_batch_multi(ctxs, cfg: Cfg, jobs, qpool, tpool) -> np.ndarray:
+    """ksw_b200_extend_batch_multi over a list of KswB200 contexts (one per GPU)."""
+    lib = load_library()
+    jobs, qpool, tpool = KswB200._norm(jobs, qpool, tpool)
+    res = np.zeros(jobs.shape[0], dtype=RES_DT)
+    arr = (C.c_void_p * len(ctxs))(*[c.ctx for c in ctxs])
+    rc = lib.ksw_b200_extend_batch_multi(len(ctxs), arr, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool), _p(tpool), _p(res))
+    if rc != 0:
+        raise KswB200Error(f"ksw_b200_extend_batch_multi failed ({rc}): " + "; ".join(
+            lib.ksw_b200_strerror(c.ctx).decode() for c in ctxs))
+    return res
 
 
 def ksw_extend2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0):

@@ -91,6 +91,12 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
                           const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
                           ksw_b200_res_t *res);
 
+/* Multi-GPU form: the batch is cut into n_ctx contiguous ranges of (nearly) equal DP cells (sum of qlen*tlen), range r
+ * runs on ctxs[r] (normally one context per GPU) on its own host thread; no exchange step, results land in res. */
+int ksw_b200_extend_batch_multi(int n_ctx, ksw_b200_ctx_t **ctxs, const ksw_b200_cfg_t *cfg, int64_t n,
+                                const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
+                                ksw_b200_res_t *res);
+
 /* bytes the last ksw_b200_extend_batch call copied host->device and device->host */
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

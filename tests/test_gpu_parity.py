@@ -105,6 +105,18 @@ def test_usage_errors_are_reported_and_context_stays_usable(gpu_ctx, oracle_buil
     _check(gpu_ctx, b)                                            # the context still works
 
 
+def test_multi_context_sharding(oracle_built):
+    # one context per visible GPU (two contexts on the same GPU when only one is visible): same results as one context
+    import bwa_mem_quickassist_b200 as B
+    n_gpu = max(1, B.load_library().ksw_b200_device_count())
+    ctxs = [B.KswB200(d % n_gpu) for d in range(max(2, min(n_gpu, 8)))]
+    b = K.gen_fuzz(20000, seed=61, max_q=400)
+    got = B.extend_batch_multi(ctxs, b.cfg, b.jobs, b.qpool, b.tpool)
+    assert K.first_mismatch(K.run_oracle(b), got.view(K.RES_DT)) is None
+    for c in ctxs:
+        c.close()
+
+
 def test_scalar_dropins(gpu_ctx, oracle_built):
     import bwa_mem_quickassist_b200 as B
     b = K.gen_fuzz(40, seed=21)
