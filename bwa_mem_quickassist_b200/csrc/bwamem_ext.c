@@ -53,6 +53,25 @@ typedef struct {
 	ksw_b200_res_t left, right;
 } ext_rec_t;
 
+/* rounds mode (SURVEY.md 7.3-3 strategy B): the timeline of a read = its chains and the regions that other code
+ * (mem_chain2aln_short in the reference flow) inserted between them, in order */
+typedef struct {
+	int32_t chain;                     /* >= 0: a registered chain; -1: a fixed region */
+	b200_alnreg_t reg;
+} item_rec_t;
+
+typedef struct {
+	size_t item, item_end;             /* current / one-past-last timeline item of the read */
+	int32_t k;                         /* position in the sorted seed order of the current chain; -1: chain not started */
+	int32_t phase;                     /* 0: decide on seed k, 1: left result pending, 2: right result pending */
+	int32_t attempt;                   /* band try (0 or 1) */
+	int32_t aw0, aw1, sc0;
+	size_t cur;                        /* index of the region under construction in av */
+	uint64_t *order;                   /* sorted seeds of the current chain */
+	ksw_b200_res_t res;                /* the result that just arrived */
+	b200_alnreg_v av;
+} read_state_t;
+
 struct b200_ext_plan {
 	b200_ext_opt_t opt;
 	int64_t l_pac;
@@ -65,8 +84,11 @@ struct b200_ext_plan {
 	/* scratch of run() */
 	VEC(ksw_b200_job_t) jobs;
 	VEC(ksw_b200_res_t) res;
-	VEC(uint32_t) owner;               /* job -> ext record */
-	int64_t st_seeds, st_left, st_right, st_retry;
+	VEC(uint32_t) owner;               /* job -> ext record (speculative mode) / read (rounds mode) */
+	VEC(item_rec_t) items;             /* rounds mode */
+	VEC(size_t) read_item0;            /* first timeline item of every read (+ sentinel) */
+	VEC(read_state_t) rstate;
+	int64_t st_seeds, st_left, st_right, st_retry, st_rounds;
 };
 
 /* ---- small pieces of the reference logic ---------------------------------------------- */
@@ -123,6 +145,12 @@ void b200_ext_plan_destroy(b200_ext_plan_t *p)
 	if (!p) return;
 	free(p->reads.a); free(p->chains.a); free(p->seeds.a); free(p->ext.a);
 	free(p->qpool.a); free(p->tpool.a); free(p->jobs.a); free(p->res.a); free(p->owner.a);
+	free(p->items.a); free(p->read_item0.a);
+	if (p->rstate.a) {
+		size_t r;
+		for (r = 0; r < p->rstate.n; ++r) { free(p->rstate.a[r].order); free(p->rstate.a[r].av.a); }
+		free(p->rstate.a);
+	}
 	free(p);
 }
 
@@ -130,7 +158,13 @@ void b200_ext_plan_reset(b200_ext_plan_t *p)
 {
 	p->reads.n = p->chains.n = p->seeds.n = p->ext.n = 0;
 	p->qpool.n = p->tpool.n = 0;
-	p->st_seeds = p->st_left = p->st_right = p->st_retry = 0;
+	p->items.n = p->read_item0.n = 0;
+	{
+		size_t r;
+		for (r = 0; r < p->rstate.n; ++r) { free(p->rstate.a[r].order); free(p->rstate.a[r].av.a); }
+		p->rstate.n = 0;
+	}
+	p->st_seeds = p->st_left = p->st_right = p->st_retry = p->st_rounds = 0;
 }
 
 int b200_ext_plan_add_read(b200_ext_plan_t *p, int l_query, const uint8_t *query)
@@ -146,6 +180,7 @@ int b200_ext_plan_add_read(b200_ext_plan_t *p, int l_query, const uint8_t *query
 	for (i = 0; i < l_query; ++i) p->qpool.a[p->qpool.n + i] = query[l_query - 1 - i];
 	p->qpool.n += (size_t)l_query;
 	vec_push(p->reads, r);
+	vec_push(p->read_item0, p->items.n);
 	return (int)p->reads.n - 1;
 }
 
@@ -198,6 +233,13 @@ int b200_ext_plan_add_chain(b200_ext_plan_t *p, int read, const b200_chain_t *c)
 	}
 	vec_push(p->chains, ch);
 	p->st_seeds += c->n;
+	{
+		item_rec_t it;
+		memset(&it, 0, sizeof(it));
+		it.chain = (int32_t)p->chains.n - 1;
+		assert(read == (int)p->reads.n - 1);                    /* the timeline of a read is built before the next read */
+		vec_push(p->items, it);
+	}
 	return (int)p->chains.n - 1;
 }
 
@@ -334,6 +376,103 @@ static b200_alnreg_t *av_push(b200_alnreg_v *av)                /* kv_pushp, kve
 	return &av->a[av->n++];
 }
 
+/* bwamem.c:769-799: 1 if seed order[k] needs no extension (it lies inside, and near the diagonal of, a region found
+ * earlier, and no longer overlapping seed of the chain sits on another diagonal) */
+static int seed_is_covered(const b200_ext_opt_t *o, const b200_alnreg_v *av, const b200_seed_t *seeds, int n,
+                           const uint64_t *order, int k)
+{
+	const b200_seed_t *s = &seeds[(uint32_t)order[k]];
+	size_t i;
+	int j;
+	for (i = 0; i < av->n; ++i) {
+		const b200_alnreg_t *r = &av->a[i];
+		int64_t rd;
+		int qd, w, g;
+		if (s->rbeg < r->rb || s->rbeg + s->len > r->re || s->qbeg < r->qb || s->qbeg + s->len > r->qe) continue;
+		qd = s->qbeg - r->qb; rd = s->rbeg - r->rb;
+		g = max_gap_for(o, qd < rd ? qd : (int)rd);
+		w = g < o->w ? g : o->w;
+		if (qd - rd < w && rd - qd < w) break;
+		qd = r->qe - (s->qbeg + s->len); rd = r->re - (s->rbeg + s->len);
+		g = max_gap_for(o, qd < rd ? qd : (int)rd);
+		w = g < o->w ? g : o->w;
+		if (qd - rd < w && rd - qd < w) break;
+	}
+	if (i == av->n) return 0;
+	for (j = k + 1; j < n; ++j) {
+		const b200_seed_t *t;
+		if (order[j] == 0) continue;
+		t = &seeds[(uint32_t)order[j]];
+		if (t->len < s->len * .95) continue;
+		if (s->qbeg <= t->qbeg && s->qbeg + s->len - t->qbeg >= s->len >> 2 && t->qbeg - s->qbeg != t->rbeg - s->rbeg) return 0;
+		if (t->qbeg <= s->qbeg && t->qbeg + t->len - s->qbeg >= s->len >> 2 && s->qbeg - t->qbeg != s->rbeg - t->rbeg) return 0;
+	}
+	return 1;
+}
+
+static void region_begin(const b200_ext_opt_t *o, b200_alnreg_t *a)       /* bwamem.c:805-808 */
+{
+	memset(a, 0, sizeof(*a));
+	a->w = o->w;
+	a->score = a->truesc = -1;
+}
+
+static void region_left(const b200_ext_opt_t *o, b200_alnreg_t *a, const b200_seed_t *s, const ksw_b200_res_t *L)
+{
+	if (L) {                                                     /* bwamem.c:830-837 */
+		a->score = L->score;
+		if (L->gscore <= 0 || L->gscore <= a->score - o->pen_clip5) {   /* local end */
+			a->qb = s->qbeg - L->qle; a->rb = s->rbeg - L->tle;
+			a->truesc = a->score;
+		} else {                                                 /* reaches the query start */
+			a->qb = 0; a->rb = s->rbeg - L->gtle;
+			a->truesc = L->gscore;
+		}
+	} else {                                                     /* bwamem.c:839 */
+		a->score = a->truesc = s->len * o->a; a->qb = 0; a->rb = s->rbeg;
+	}
+}
+
+static void region_right(const b200_ext_opt_t *o, b200_alnreg_t *a, const b200_seed_t *s, const ksw_b200_res_t *R,
+                         int l_query, int64_t rmax0)
+{
+	if (R) {                                                     /* bwamem.c:858-865 */
+		const int sc0 = a->score, qe = s->qbeg + s->len;
+		const int64_t re = s->rbeg + s->len - rmax0;
+		a->score = R->score;
+		if (R->gscore <= 0 || R->gscore <= a->score - o->pen_clip3) {
+			a->qe = qe + R->qle; a->re = rmax0 + re + R->tle;
+			a->truesc += a->score - sc0;
+		} else {
+			a->qe = l_query; a->re = rmax0 + re + R->gtle;
+			a->truesc += R->gscore - sc0;
+		}
+	} else {                                                     /* bwamem.c:867 */
+		a->qe = l_query; a->re = s->rbeg + s->len;
+	}
+}
+
+static void region_end(b200_alnreg_t *a, const b200_seed_t *seeds, int n, int aw0, int aw1)   /* bwamem.c:870-875 */
+{
+	int j;
+	a->seedcov = 0;
+	for (j = 0; j < n; ++j) {
+		const b200_seed_t *t = &seeds[j];
+		if (t->qbeg >= a->qb && t->qbeg + t->len <= a->qe && t->rbeg >= a->rb && t->rbeg + t->len <= a->re)
+			a->seedcov += t->len;
+	}
+	a->w = aw0 > aw1 ? aw0 : aw1;
+}
+
+static uint64_t *sorted_seed_order(const b200_seed_t *seeds, int n)       /* bwamem.c:760-763 */
+{
+	uint64_t *order = malloc((size_t)(n > 0 ? n : 1) * 8);
+	int k;
+	for (k = 0; k < n; ++k) order[k] = (uint64_t)seeds[k].len << 32 | (uint32_t)k;
+	qsort(order, (size_t)n, 8, cmp_u64);
+	return order;
+}
+
 void b200_ext_replay_chain(const b200_ext_plan_t *p, int chain, b200_alnreg_v *av)
 {
 	const b200_ext_opt_t *o = &p->opt;
@@ -342,97 +481,179 @@ void b200_ext_replay_chain(const b200_ext_plan_t *p, int chain, b200_alnreg_v *a
 	const ext_rec_t *ext;
 	uint64_t *order;
 	int l_query, k, n;
-	size_t i;
 	if (chain < 0) return;
 	ch = &p->chains.a[chain];
 	seeds = p->seeds.a + ch->seed0;
 	ext = p->ext.a + ch->seed0;
 	n = ch->n;
 	l_query = p->reads.a[ch->read].l_query;
-	/* longest seed first; equal lengths in index order (bwamem.c:760-763) */
-	order = malloc((size_t)n * 8);
-	for (k = 0; k < n; ++k) order[k] = (uint64_t)seeds[k].len << 32 | (uint32_t)k;
-	qsort(order, (size_t)n, 8, cmp_u64);
-
+	order = sorted_seed_order(seeds, n);                          /* longest seed first; equal lengths in index order */
 	for (k = n - 1; k >= 0; --k) {
 		const int si = (int)(uint32_t)order[k];
 		const b200_seed_t *s = &seeds[si];
 		const ext_rec_t *x = &ext[si];
 		b200_alnreg_t *a;
-		int aw0 = o->w, aw1 = o->w, j;
-		/* is the seed inside, and near the diagonal of, a region found earlier? (bwamem.c:769-784) */
-		for (i = 0; i < av->n; ++i) {
-			const b200_alnreg_t *r = &av->a[i];
-			int64_t rd;
-			int qd, w, g;
-			if (s->rbeg < r->rb || s->rbeg + s->len > r->re || s->qbeg < r->qb || s->qbeg + s->len > r->qe) continue;
-			qd = s->qbeg - r->qb; rd = s->rbeg - r->rb;
-			g = max_gap_for(o, qd < rd ? qd : (int)rd);
-			w = g < o->w ? g : o->w;
-			if (qd - rd < w && rd - qd < w) break;
-			qd = r->qe - (s->qbeg + s->len); rd = r->re - (s->rbeg + s->len);
-			g = max_gap_for(o, qd < rd ? qd : (int)rd);
-			w = g < o->w ? g : o->w;
-			if (qd - rd < w && rd - qd < w) break;
-		}
-		if (i < av->n) {
-			/* contained: extend anyway only if a longer, overlapping seed lies on another diagonal (bwamem.c:785-799) */
-			for (j = k + 1; j < n; ++j) {
-				const b200_seed_t *t;
-				if (order[j] == 0) continue;
-				t = &seeds[(uint32_t)order[j]];
-				if (t->len < s->len * .95) continue;
-				if (s->qbeg <= t->qbeg && s->qbeg + s->len - t->qbeg >= s->len >> 2 && t->qbeg - s->qbeg != t->rbeg - s->rbeg) break;
-				if (t->qbeg <= s->qbeg && t->qbeg + t->len - s->qbeg >= s->len >> 2 && s->qbeg - t->qbeg != s->rbeg - t->rbeg) break;
-			}
-			if (j == n) { order[k] = 0; continue; }              /* skipped: marked like srt[k] = 0 */
-		}
-
+		if (seed_is_covered(o, av, seeds, n, order, k)) { order[k] = 0; continue; }   /* skipped: marked like srt[k] = 0 */
 		a = av_push(av);
-		memset(a, 0, sizeof(*a));
-		a->w = o->w;
-		a->score = a->truesc = -1;
-		if (x->has_left) {                                       /* bwamem.c:810-838 */
-			const ksw_b200_res_t *L = &x->left;
-			aw0 = x->aw_left;
-			a->score = L->score;
-			if (L->gscore <= 0 || L->gscore <= a->score - o->pen_clip5) {   /* local end */
-				a->qb = s->qbeg - L->qle; a->rb = s->rbeg - L->tle;
-				a->truesc = a->score;
-			} else {                                             /* reaches the query start */
-				a->qb = 0; a->rb = s->rbeg - L->gtle;
-				a->truesc = L->gscore;
-			}
-		} else {
-			a->score = a->truesc = s->len * o->a; a->qb = 0; a->rb = s->rbeg;
-		}
-		if (x->has_right) {                                      /* bwamem.c:841-867 */
-			const ksw_b200_res_t *R = &x->right;
-			const int sc0 = a->score, qe = s->qbeg + s->len;
-			const int64_t re = s->rbeg + s->len - ch->rmax0;
-			aw1 = x->aw_right;
-			a->score = R->score;
-			if (R->gscore <= 0 || R->gscore <= a->score - o->pen_clip3) {
-				a->qe = qe + R->qle; a->re = ch->rmax0 + re + R->tle;
-				a->truesc += a->score - sc0;
-			} else {
-				a->qe = l_query; a->re = ch->rmax0 + re + R->gtle;
-				a->truesc += R->gscore - sc0;
-			}
-		} else {
-			a->qe = l_query; a->re = s->rbeg + s->len;
-		}
-		/* seeds fully inside the new region (bwamem.c:870-874) */
-		a->seedcov = 0;
-		for (j = 0; j < n; ++j) {
-			const b200_seed_t *t = &seeds[j];
-			if (t->qbeg >= a->qb && t->qbeg + t->len <= a->qe && t->rbeg >= a->rb && t->rbeg + t->len <= a->re)
-				a->seedcov += t->len;
-		}
-		a->w = aw0 > aw1 ? aw0 : aw1;
+		region_begin(o, a);
+		region_left(o, a, s, x->has_left ? &x->left : 0);
+		region_right(o, a, s, x->has_right ? &x->right : 0, l_query, ch->rmax0);
+		region_end(a, seeds, n, x->has_left ? x->aw_left : o->w, x->has_right ? x->aw_right : o->w);
 	}
 	free(order);
 }
+
+/* ---- rounds mode: exact, minimal-work scheduling (SURVEY.md 7.3-3 strategy B) ------------------------------------ *
+ * Every read walks its own timeline exactly like the reference's sequential code and stops whenever it needs a DP
+ * result; one round = one batched GPU call with the pending job of every read that is still active (left and right
+ * jobs mixed; the band clamp of each job is computed here with its own end bonus).  Only the seeds the reference would
+ * extend are extended.                                                                                                  */
+
+int b200_ext_plan_add_region(b200_ext_plan_t *p, int read, const b200_alnreg_t *reg)
+{
+	item_rec_t it;
+	assert(read == (int)p->reads.n - 1);
+	it.chain = -1; it.reg = *reg;
+	vec_push(p->items, it);
+	return 0;
+}
+
+/* advances read r until it needs a job (returns 1 and fills *j) or its timeline is finished (returns 0) */
+static int read_advance(b200_ext_plan_t *p, read_state_t *st, ksw_b200_job_t *j)
+{
+	const b200_ext_opt_t *o = &p->opt;
+	for (;;) {
+		const item_rec_t *it;
+		const chain_rec_t *ch;
+		const b200_seed_t *seeds, *s;
+		b200_alnreg_t *a;
+		int n;
+		if (st->item >= st->item_end) return 0;
+		it = &p->items.a[st->item];
+		if (it->chain < 0) { *av_push(&st->av) = it->reg; ++st->item; continue; }
+		ch = &p->chains.a[it->chain];
+		seeds = p->seeds.a + ch->seed0; n = ch->n;
+		if (!st->order) { st->order = sorted_seed_order(seeds, n); st->k = n - 1; }        /* entering the chain */
+		if (st->k < 0) { free(st->order); st->order = 0; ++st->item; continue; }           /* all its seeds are done */
+		s = &seeds[(uint32_t)st->order[st->k]];
+		if (st->phase == 0) {
+			if (seed_is_covered(o, &st->av, seeds, n, st->order, st->k)) {
+				st->order[st->k] = 0;                                  /* skipped: marked like srt[k] = 0 */
+				--st->k;
+				continue;
+			}
+			st->cur = st->av.n;
+			a = av_push(&st->av);
+			region_begin(o, a);
+			st->aw0 = st->aw1 = o->w; st->attempt = 0;
+			if (s->qbeg) {                                            /* left extension needed */
+				left_job(p, ch, s, o->w, j);
+				j->w = ksw_b200_clamp_w(j->qlen, o->mat, o->o_del, o->e_del, o->o_ins, o->e_ins, o->w, o->pen_clip5);
+				st->phase = 1;
+				return 1;
+			}
+			region_left(o, a, s, 0);
+			st->phase = 3;                                            /* fall through to the right side */
+		}
+		a = &st->av.a[st->cur];
+		if (st->phase == 1) {                                         /* a left result arrived */
+			const int w = o->w << st->attempt;
+			st->aw0 = w;
+			if (st->attempt + 1 < B200_MAX_BAND_TRY && st->res.max_off >= (w >> 1) + (w >> 2)) {   /* bwamem.c:828 */
+				++st->attempt;
+				left_job(p, ch, s, 0, j);
+				j->w = ksw_b200_clamp_w(j->qlen, o->mat, o->o_del, o->e_del, o->o_ins, o->e_ins, o->w << st->attempt, o->pen_clip5);
+				++p->st_retry;
+				return 1;
+			}
+			region_left(o, a, s, &st->res);
+			st->phase = 3;
+		}
+		if (st->phase == 3) {                                         /* start the right side */
+			st->attempt = 0;
+			if (s->qbeg + s->len != p->reads.a[ch->read].l_query) {
+				st->sc0 = a->score;
+				right_job(p, ch, s, st->sc0, 0, j);
+				j->w = ksw_b200_clamp_w(j->qlen, o->mat, o->o_del, o->e_del, o->o_ins, o->e_ins, o->w, o->pen_clip3);
+				st->phase = 2;
+				return 1;
+			}
+			region_right(o, a, s, 0, p->reads.a[ch->read].l_query, ch->rmax0);
+			st->phase = 4;
+		}
+		if (st->phase == 2) {                                         /* a right result arrived */
+			const int w = o->w << st->attempt;
+			st->aw1 = w;
+			if (st->attempt + 1 < B200_MAX_BAND_TRY &&
+			    !(st->res.score == st->sc0 || st->res.max_off < (w >> 1) + (w >> 2))) {               /* bwamem.c:856 */
+				++st->attempt;
+				right_job(p, ch, s, st->sc0, 0, j);
+				j->w = ksw_b200_clamp_w(j->qlen, o->mat, o->o_del, o->e_del, o->o_ins, o->e_ins, o->w << st->attempt, o->pen_clip3);
+				++p->st_retry;
+				return 1;
+			}
+			region_right(o, a, s, &st->res, p->reads.a[ch->read].l_query, ch->rmax0);
+			st->phase = 4;
+		}
+		/* phase 4: the region is complete */
+		region_end(a, seeds, n, st->aw0, st->aw1);
+		st->phase = 0;
+		--st->k;
+	}
+}
+
+int b200_ext_plan_run_rounds(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx)
+{
+	const b200_ext_opt_t *o = &p->opt;
+	ksw_b200_cfg_t cfg;
+	size_t r, n_reads = p->reads.n, k;
+	int rc;
+	/* the packer clamps again with cfg.end_bonus; with the larger of the two bonuses that second clamp is a no-op */
+	cfg_from_opt(o, o->pen_clip5 > o->pen_clip3 ? o->pen_clip5 : o->pen_clip3, &cfg);
+	vec_push(p->read_item0, p->items.n);                           /* sentinel */
+	vec_reserve(p->rstate, n_reads + 1);
+	p->rstate.n = n_reads;
+	for (r = 0; r < n_reads; ++r) {
+		read_state_t *st = &p->rstate.a[r];
+		memset(st, 0, sizeof(*st));
+		st->item = p->read_item0.a[r]; st->item_end = p->read_item0.a[r + 1];
+		st->order = 0;
+	}
+	p->read_item0.n -= 1;
+	/* round 0 asks every read; later rounds only the reads whose job was in the previous round */
+	p->jobs.n = p->owner.n = 0;
+	for (r = 0; r < n_reads; ++r) {
+		ksw_b200_job_t j;
+		if (read_advance(p, &p->rstate.a[r], &j)) { vec_push(p->jobs, j); vec_push(p->owner, (uint32_t)r); }
+	}
+	while (p->jobs.n) {
+		size_t n_jobs = p->jobs.n, w = 0;
+		dump_jobs(p, &cfg);
+		vec_reserve(p->res, n_jobs);
+		rc = ksw_b200_extend_batch(ctx, &cfg, (int64_t)n_jobs, p->jobs.a, p->qpool.a, p->tpool.a, p->res.a);
+		if (rc) return rc;
+		++p->st_rounds;
+		for (k = 0; k < n_jobs; ++k) {
+			read_state_t *st = &p->rstate.a[p->owner.a[k]];
+			ksw_b200_job_t j;
+			if (st->phase == 1) ++p->st_left; else ++p->st_right;
+			st->res = p->res.a[k];
+			if (read_advance(p, st, &j)) { p->jobs.a[w] = j; p->owner.a[w] = p->owner.a[k]; ++w; }
+		}
+		p->jobs.n = p->owner.n = w;
+	}
+	return 0;
+}
+
+/* hands the regions of a read (rounds mode) to the caller, who frees them with free() */
+void b200_ext_plan_take_regions(b200_ext_plan_t *p, int read, b200_alnreg_v *out)
+{
+	read_state_t *st = &p->rstate.a[read];
+	*out = st->av;
+	st->av.n = st->av.m = 0; st->av.a = 0;
+}
+
+int64_t b200_ext_plan_rounds(const b200_ext_plan_t *p) { return p->st_rounds; }
 
 void b200_ext_plan_stats(const b200_ext_plan_t *p, int64_t *n_seeds, int64_t *n_left, int64_t *n_right, int64_t *n_retry)
 {
@@ -500,6 +721,43 @@ int b200_chain2aln_flat(ksw_b200_ctx_t *ctx, const b200_ext_opt_t *opt, int64_t 
 	}
 	*n_out = n;
 	free(handle);
+	b200_ext_plan_destroy(p);
+	return rc;
+}
+
+/* b200_chain2aln_flat with the rounds scheduler; n_jobs_out (may be NULL) = DP jobs actually run */
+int b200_chain2aln_flat_rounds(ksw_b200_ctx_t *ctx, const b200_ext_opt_t *opt, int64_t l_pac, const uint8_t *pac,
+                               int n_reads, const int64_t *read_off, const int32_t *read_len, const uint8_t *qpool,
+                               int n_chains, const int32_t *chain_read, const int64_t *chain_seed0, const int32_t *chain_nseeds,
+                               const b200_seed_t *seeds, int64_t out_cap, b200_alnreg_t *out, int32_t *out_read, int64_t *n_out,
+                               int64_t *n_jobs_out)
+{
+	b200_ext_plan_t *p = b200_ext_plan_create(opt, l_pac, pac);
+	int r, c = 0, rc;
+	int64_t n = 0;
+	if (!p) return 1;
+	for (r = 0; r < n_reads; ++r) {
+		const int rd = b200_ext_plan_add_read(p, read_len[r], qpool + read_off[r]);
+		for (; c < n_chains && chain_read[c] == r; ++c) {
+			b200_chain_t ch;
+			ch.n = ch.m = chain_nseeds[c]; ch.pos = 0;
+			ch.seeds = (b200_seed_t *)(seeds + chain_seed0[c]);
+			b200_ext_plan_add_chain(p, rd, &ch);
+		}
+	}
+	rc = b200_ext_plan_run_rounds(p, ctx);
+	for (r = 0; rc == 0 && r < n_reads; ++r) {
+		b200_alnreg_v av;
+		size_t k;
+		b200_ext_plan_take_regions(p, r, &av);
+		for (k = 0; k < av.n; ++k) {
+			if (n >= out_cap) { rc = -1; break; }
+			out[n] = av.a[k]; out_read[n] = r; ++n;
+		}
+		free(av.a);
+	}
+	*n_out = n;
+	if (n_jobs_out) *n_jobs_out = p->st_left + p->st_right;     /* retries are counted on the side they belong to */
 	b200_ext_plan_destroy(p);
 	return rc;
 }

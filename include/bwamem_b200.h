@@ -90,6 +90,17 @@ int b200_ext_plan_run(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx);
 /* same effect on *av as mem_chain2aln(opt, l_pac, pac, l_query, query, c, av) for the registered chain */
 void b200_ext_replay_chain(const b200_ext_plan_t *p, int chain, b200_alnreg_v *av);
 
+/* ---- rounds mode: exact, minimal-work scheduling (strategy B) ----
+ * Instead of extending every seed and replaying, every read walks its timeline (its chains, and the regions other code
+ * inserted between them — mem_chain2aln_short in the reference flow — registered with b200_ext_plan_add_region in
+ * order) like the reference's sequential code and stops whenever it needs a DP result; one round = one batched GPU
+ * call with the pending job of every active read.  Only the seeds the reference would extend are extended.
+ * Usage: add_read, then add_chain / add_region in order, for every read; run_rounds; take_regions per read. */
+int b200_ext_plan_add_region(b200_ext_plan_t *p, int read, const b200_alnreg_t *reg);
+int b200_ext_plan_run_rounds(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx);
+void b200_ext_plan_take_regions(b200_ext_plan_t *p, int read, b200_alnreg_v *out);   /* caller frees out->a with free() */
+int64_t b200_ext_plan_rounds(const b200_ext_plan_t *p);                                /* GPU rounds of the last run_rounds */
+
 /* counters of the last run: seeds registered, left / right jobs computed, band retries */
 void b200_ext_plan_stats(const b200_ext_plan_t *p, int64_t *n_seeds, int64_t *n_left, int64_t *n_right, int64_t *n_retry);
 
@@ -112,6 +123,13 @@ int b200_chain2aln_flat(ksw_b200_ctx_t *ctx, const b200_ext_opt_t *opt, int64_t 
                         int n_reads, const int64_t *read_off, const int32_t *read_len, const uint8_t *qpool,
                         int n_chains, const int32_t *chain_read, const int64_t *chain_seed0, const int32_t *chain_nseeds,
                         const b200_seed_t *seeds, int64_t out_cap, b200_alnreg_t *out, int32_t *out_read, int64_t *n_out);
+
+/* the same with the rounds scheduler; *n_jobs_out (may be NULL) = DP jobs actually run */
+int b200_chain2aln_flat_rounds(ksw_b200_ctx_t *ctx, const b200_ext_opt_t *opt, int64_t l_pac, const uint8_t *pac,
+                               int n_reads, const int64_t *read_off, const int32_t *read_len, const uint8_t *qpool,
+                               int n_chains, const int32_t *chain_read, const int64_t *chain_seed0, const int32_t *chain_nseeds,
+                               const b200_seed_t *seeds, int64_t out_cap, b200_alnreg_t *out, int32_t *out_read, int64_t *n_out,
+                               int64_t *n_jobs_out);
 
 /* the reference's reference-slice fetch (bns_get_seq, bntseq.c:355-376) as the driver uses it; returns the
  * number of bases written (0 when [beg,end) bridges the forward/reverse boundary) */

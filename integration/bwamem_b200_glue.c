@@ -11,6 +11,7 @@
  *     for every read of the batch: encode, mem_chain, mem_chain_flt       (host, unchanged: bwamem.c:1093-1097)
  *       for every chain: mem_chain2aln_short (host, unchanged); if it falls through, register the chain
  *     b200_ext_plan_run: pass L, pass R (+ band retries) on the GPU        (replaces the ksw_extend2 calls)
+ *       [or, with KSW_B200_SCHED=rounds, b200_ext_plan_run_rounds: only the seeds the reference extends, in rounds]
  *     for every read, chains in order: push the short-path region or replay mem_chain2aln from the cached DP
  *     mem_sort_and_dedup, mem_test_and_remove_exact                        (host, unchanged: bwamem.c:1111-1117)
  *
@@ -86,6 +87,15 @@ __attribute__((constructor)) static void b200_warmup(int argc, char **argv)
 
 typedef struct { int handle; int short_ok; mem_alnreg_t short_reg; } b200_chain_state_t;
 
+/* KSW_B200_SCHED=rounds selects the exact minimal-work scheduler (only the seeds the reference extends are extended, in
+ * as many GPU rounds as the longest per-read dependency chain); the default extends every seed in two passes and replays */
+static int b200_use_rounds(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("KSW_B200_SCHED"); v = (e && strcmp(e, "rounds") == 0) ? 1 : 0; }
+	return v;
+}
+
 static void worker1_b200(void *data, int start, int batch_size, int tid)
 {
 	worker_t *w = (worker_t *)data;
@@ -98,6 +108,7 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 	double t0 = realtime(), t1, ts = 0, tp = 0;
 	b200_add_time(&b200_t_init, t0 - tinit);
 
+	const int rounds = b200_use_rounds();
 	b200_ext_plan_reset(t->plan);
 	for (b = 0; b < batch_size; ++b) {
 		bseq1_t *s = &w->seqs[start + b];
@@ -116,14 +127,16 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 			kv_init(tmp);
 			ret = mem_chain2aln_short(opt, w->bns->l_pac, w->pac, s->l_seq, (uint8_t *)s->seq, &chn[b].a[i], &tmp);
 			cst[b][i].handle = -1;
-			if (ret == 0) { cst[b][i].short_ok = 1; cst[b][i].short_reg = tmp.a[0]; }
-			else if (ret > 0) cst[b][i].handle = b200_ext_plan_add_chain(t->plan, rd, (const b200_chain_t *)&chn[b].a[i]);
+			if (ret == 0) {
+				cst[b][i].short_ok = 1; cst[b][i].short_reg = tmp.a[0];
+				if (rounds) b200_ext_plan_add_region(t->plan, rd, (const b200_alnreg_t *)&tmp.a[0]);   /* keeps its place in the read's timeline */
+			} else if (ret > 0) cst[b][i].handle = b200_ext_plan_add_chain(t->plan, rd, (const b200_chain_t *)&chn[b].a[i]);
 			free(tmp.a);
 		}
 	}
 	tp = realtime() - t0 - ts;
 	t1 = realtime();
-	rc = b200_ext_plan_run(t->plan, t->ctx);
+	rc = rounds ? b200_ext_plan_run_rounds(t->plan, t->ctx) : b200_ext_plan_run(t->plan, t->ctx);
 	if (rc != 0) err_fatal(__func__, "GPU extension pass failed (%d): %s", rc, ksw_b200_strerror(t->ctx));
 	b200_add_time(&b200_t_seed, ts); b200_add_time(&b200_t_plan, tp); b200_add_time(&b200_t_gpu, realtime() - t1);
 	t1 = realtime();
@@ -131,9 +144,12 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 		bseq1_t *s = &w->seqs[start + b];
 		mem_alnreg_v regs;
 		kv_init(regs);
+		if (rounds) b200_ext_plan_take_regions(t->plan, b, (b200_alnreg_v *)&regs);     /* read handles are 0..batch_size-1 */
 		for (i = 0; i < (int)chn[b].n; ++i) {
-			if (cst[b][i].short_ok) kv_push(mem_alnreg_t, regs, cst[b][i].short_reg);
-			else b200_ext_replay_chain(t->plan, cst[b][i].handle, (b200_alnreg_v *)&regs);
+			if (!rounds) {
+				if (cst[b][i].short_ok) kv_push(mem_alnreg_t, regs, cst[b][i].short_reg);
+				else b200_ext_replay_chain(t->plan, cst[b][i].handle, (b200_alnreg_v *)&regs);
+			}
 			free(chn[b].a[i].seeds);
 		}
 		free(chn[b].a); free(cst[b]);

@@ -550,3 +550,30 @@ def gen_boundaries(seed: int = 99, cfg: Cfg | None = None) -> Batch:
                 qs.append(qq); ts.append(t); h0s.append(h0); ws.append(100)
                 qs.append(qq); ts.append(t[:ql]); h0s.append(h0); ws.append(1000)
     return _pools_from_lists(qs, ts, np.array(h0s), np.array(ws), cfg)
+
+
+# ------------------------------------------------------------------ host-side driver against an oracle-backed stub (no GPU)
+EXT_EMU_SO = os.path.join(EMU_DIR, "libext_emu.so")
+
+
+def ext_emu_lib():
+    if "extemu" not in _libs:
+        subprocess.run(["make", "-C", EMU_DIR, "libext_emu.so", "--no-print-directory"], check=True, stdout=subprocess.DEVNULL)
+        _libs["extemu"] = C.CDLL(EXT_EMU_SO)
+    return _libs["extemu"]
+
+
+def run_chain_driver(lib, cs: ChainSet, ctx=None, rounds: bool = False):
+    """b200_chain2aln_flat / _flat_rounds of `lib` (the product library with a GPU context, or the stub-backed test
+    build with ctx=None).  Returns (regions, region_read, n_jobs) — n_jobs only in rounds mode."""
+    if rounds:
+        fn = lib.b200_chain2aln_flat_rounds
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] + _FLAT_TAIL + [C.c_void_p]
+        regs, rr, nj = _run_chain_flat(fn, cs, extra_head=[ctx], want_calls=True)
+        return regs, rr, nj
+    fn = lib.b200_chain2aln_flat
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] + _FLAT_TAIL
+    regs, rr = _run_chain_flat(fn, cs, extra_head=[ctx])
+    return regs, rr, None

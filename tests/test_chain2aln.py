@@ -27,6 +27,21 @@ def test_oracle_chain2aln_matches_reference_on_fresh_sets(oracle_built):
         assert K.regs_equal(K.run_chain_oracle(cs)[:2], K.run_chain_ref(cs)), seed
 
 
+def test_host_driver_both_schedulers_against_golden_cpu(oracle_built):
+    """bwamem_ext.c (speculate-and-replay, and the rounds scheduler) linked against an oracle-backed stub of the GPU
+    entry: the host logic is checked on the CPU against the regions of the reference's own mem_chain2aln."""
+    lib = K.ext_emu_lib()
+    for name, (cs, want) in K.load_chain_golden().items():
+        spec = K.run_chain_driver(lib, cs)
+        assert K.regs_equal(spec[:2], want), ("speculative", name)
+        jobs_before = C.c_int64.in_dll(lib, "ext_stub_jobs").value
+        rnd = K.run_chain_driver(lib, cs, rounds=True)
+        assert K.regs_equal(rnd[:2], want), ("rounds", name)
+        # the rounds scheduler runs exactly the DP calls the sequential reference makes
+        assert rnd[2] == K.run_chain_oracle(cs)[2], name
+        assert C.c_int64.in_dll(lib, "ext_stub_jobs").value - jobs_before == rnd[2]
+
+
 def test_ref_slice_known_answers():
     import bwa_mem_quickassist_b200 as B
     lib = B.load_library()
@@ -56,4 +71,7 @@ def test_batched_driver_matches_golden_and_oracle(gpu_ctx, oracle_built):
     for seed, kw in ((31, {}), (32, dict(opt=K.make_ext_opt(w=10), indel=0.012, max_indel=16)),
                      (33, dict(sub=0.05, indel=0.02, max_indel=12, read_lens=(250,))), (34, dict(n_frac=0.05))):
         cs = K.gen_chains(600, seed=seed, **kw)
-        assert K.regs_equal(K.run_chain_gpu(gpu_ctx, cs), K.run_chain_oracle(cs)[:2]), seed
+        want = K.run_chain_oracle(cs)
+        assert K.regs_equal(K.run_chain_gpu(gpu_ctx, cs), want[:2]), seed
+        rnd = K.run_chain_driver(gpu_ctx.lib, cs, ctx=gpu_ctx.ctx, rounds=True)       # strategy B on the GPU
+        assert K.regs_equal(rnd[:2], want[:2]) and rnd[2] == want[2], seed

@@ -66,6 +66,11 @@ def test_pe150_byte_identical(tmp_path):
     S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4, extra=["-b", "3000"])
     ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
     assert ok, why
+    # the rounds scheduler (strategy B: only the seeds the reference extends) must give the same SAM
+    env = dict(os.environ, KSW_B200_SCHED="rounds")
+    S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_rounds.sam"), threads=4, extra=["-b", "3000"], env=env)
+    ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_rounds.sam"))
+    assert ok, ("rounds", why)
 
 
 @pytest.mark.gpu
@@ -87,3 +92,7 @@ def test_pe250_high_indel_byte_identical(tmp_path):
     S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4)
     ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
     assert ok, why
+    env = dict(os.environ, KSW_B200_SCHED="rounds")
+    S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_rounds.sam"), threads=4, env=env)
+    ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_rounds.sam"))
+    assert ok, ("rounds", why)
