@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 4)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--sched", default="speculate", choices=["speculate", "rounds"], help="KSW_B200_SCHED of the B200-bound build")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     sc = a.scale
@@ -53,14 +54,15 @@ def main():
                 S.write_reads_fast(reads, g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
                 n_reads = c["n"]
             t_stock, e_stock = timed(S.BWA_STOCK, fa, reads, os.path.join(d, "stock.sam"), a.threads)
-            t_b200, e_b200 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)])
+            env = dict(os.environ, KSW_B200_SCHED=a.sched) if a.sched == "rounds" else None
+            t_b200, e_b200 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)], env=env)
             ok, why = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200.sam"))
             cs, cb = chunk_times(e_stock), chunk_times(e_b200)
             # steady state = chunks after the first (the first B200 chunk pays CUDA context creation, which a real run
             # hides behind loading a GB-sized index)
             ss = sum(r for r, _ in cs[1:]) / max(sum(t for _, t in cs[1:]), 1e-9) if len(cs) > 1 else None
             sb = sum(r for r, _ in cb[1:]) / max(sum(t for _, t in cb[1:]), 1e-9) if len(cb) > 1 else None
-            row = {"config": name, "reads": n_reads, "threads": a.threads, "stock_wall_s": round(t_stock, 3), "b200_wall_s": round(t_b200, 3),
+            row = {"config": name, "sched": a.sched, "reads": n_reads, "threads": a.threads, "stock_wall_s": round(t_stock, 3), "b200_wall_s": round(t_b200, 3),
                    "stock_reads_per_s": round(n_reads / t_stock), "b200_reads_per_s": round(n_reads / t_b200),
                    "stock_chunks": cs, "b200_chunks": cb,
                    "stock_steady_reads_per_s": round(ss) if ss else None, "b200_steady_reads_per_s": round(sb) if sb else None,
