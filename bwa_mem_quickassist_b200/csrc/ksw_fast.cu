@@ -8,6 +8,7 @@
 // so lanes only wait for each other inside one DP row, never for a whole job.  Jobs arrive binned
 // (ksw_pack.cpp) so that neighbouring lanes sweep bands of similar width.
 #include <cuda_runtime.h>
+#include <atomic>
 #include "ksw_dev.cuh"
 #include "ksw_fast_core.h"
 #include "ksw_launch.h"
@@ -120,8 +121,21 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
                                  DevRes *res, uint32_t *cells, cudaStream_t st)
 {
 	const size_t smem = ksw_fast_smem_bytes(qmax);
-	cudaError_t e = cudaFuncSetAttribute(ksw_fast_kernel<KEYED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	// The dynamic shared-memory ceiling of the kernel is raised ONCE per device to the opt-in maximum and never lowered:
+	// several host threads (one context each) launch this kernel concurrently with different sizes, and a per-launch
+	// cudaFuncSetAttribute would let one thread shrink the ceiling under another thread's larger launch.
+	static std::atomic<unsigned long long> raised[2] = {{0ull}, {0ull}};     // bit d: done for device d (KEYED / not)
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
 	if (e != cudaSuccess) return e;
+	if (dev < 0 || dev >= 64 || !((raised[KEYED ? 1 : 0].load() >> dev) & 1ull)) {
+		int optin = 0;
+		e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(ksw_fast_kernel<KEYED>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+		if (e != cudaSuccess) return e;
+		if (dev >= 0 && dev < 64) raised[KEYED ? 1 : 0].fetch_or(1ull << dev);
+	}
 	int per_sm = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_fast_kernel<KEYED>, T, smem);
 	if (e != cudaSuccess) return e;

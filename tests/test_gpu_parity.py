@@ -117,6 +117,33 @@ def test_multi_context_sharding(oracle_built):
         c.close()
 
 
+def test_concurrent_contexts_with_different_query_lengths(oracle_built):
+    # regression: host threads (one context each) launching the fast kernel with different shared-memory sizes at the same
+    # time must not disturb each other (the dynamic shared-memory ceiling is a per-device kernel attribute)
+    import threading
+    import bwa_mem_quickassist_b200 as B
+    batches = [K.gen_fuzz(1500, seed=70 + i, max_q=mq, h0_max=80) for i, mq in enumerate((20, 60, 120, 250, 500, 30, 400, 100))]
+    wants = [K.run_oracle(b) for b in batches]
+    errs = []
+
+    def work(i):
+        try:
+            ctx = B.KswB200(0, pack_threads=1)
+            for _ in range(25):
+                got = ctx.extend_batch(batches[i].cfg, batches[i].jobs, batches[i].qpool, batches[i].tpool)
+                mm = K.first_mismatch(wants[i], got.view(K.RES_DT))
+                if mm is not None:
+                    errs.append((i, mm)); break
+            ctx.close()
+        except Exception as e:          # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(batches))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:3]
+
+
 def test_scalar_dropins(gpu_ctx, oracle_built):
     import bwa_mem_quickassist_b200 as B
     b = K.gen_fuzz(40, seed=21)
