@@ -2,9 +2,10 @@
 //
 // HBM layout of one packed batch (built by ksw_pack.cpp, consumed by the kernels):
 //
-//   d_jobs : DevJob[n]      32 B each, in *binned* order (fast class first, then generic;
-//                           inside a class sorted so that the 32 jobs of a warp have similar
-//                           row counts and band widths)
+//   d_jobs : DevJob[n]      32 B each, in the CALLER's order (the host packer only streams)
+//   d_order: uint32[n]      the *binned* order, built on the device (ksw_bin.cu): fast classes first, then
+//                           generic; inside a class sorted by (rows, carried-in score) so that the jobs a
+//                           warp draws together sweep bands of similar width and length
 //   d_pool : uint32[]       per job, 16-byte aligned:  query 2-bit words | target 2-bit words
 //                           base k of a sequence sits in word k/16 at bits 2*(k%16)
 //   d_npool: uint32[]       only for the (rare) jobs whose query or target holds an N (code 4):
@@ -29,7 +30,7 @@ struct DevJob {
 	int32_t  qlen, tlen;
 	int32_t  h0;        // already max(h0,0)              (ksw.c:384)
 	int32_t  w;         // already clamped by the reference rule (ksw.c:398-406), done on the host
-	uint32_t flags;     // bit0: query N-mask present, bit1: target N-mask present
+	uint32_t flags;     // bit0: query N-mask present, bit1: target N-mask present, bits 8-11: kernel class (KSW_CLASS_*)
 	uint32_t nmask_off; // word offset of the job's N masks in d_npool (valid iff flags != 0)
 };
 static_assert(sizeof(DevJob) == 32, "DevJob must be 32 bytes");
@@ -47,6 +48,10 @@ struct KswParams {          // passed by value as a kernel parameter (constant b
 };
 
 #define KSW_FAST_QUADS(qlen) (((qlen) >> 2) + 1)   /* 4-column quads of the fast kernel that cover columns 0..qlen */
+
+#define KSW_CLASS_SHIFT 8
+#define KSW_CLASS_MASK 0xfu
+#define KSW_CLASS_GENERIC 4u          /* classes 0..3: fast kernel (0 = keyed), 4: generic int32 kernel */
 
 #define KSW_FLAG_QN 1u
 #define KSW_FLAG_TN 2u

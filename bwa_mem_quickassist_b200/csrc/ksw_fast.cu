@@ -4,9 +4,9 @@
 // column each lane is at), DPX s16x2 arithmetic (see ksw_fast_core.h for the per-lane logic).
 //
 // Scheduling: persistent CTAs (SM count x CTAs that fit by shared memory); each lane pulls its
-// next job from a global counter (warp-aggregated atomicAdd) as soon as its previous job ends,
-// so lanes only wait for each other inside one DP row, never for a whole job.  Jobs arrive binned
-// (ksw_pack.cpp) so that neighbouring lanes sweep bands of similar width.
+// next job as soon as its previous job ends, so lanes only wait for each other inside one DP row, never for a
+// whole job.  Jobs are taken in the binned order built on the device (ksw_bin.cu), so that the lanes of a warp
+// sweep bands of similar width.
 #include <cuda_runtime.h>
 #include <atomic>
 #include "ksw_dev.cuh"
@@ -21,7 +21,8 @@ template <bool KEYED>
 __global__ void __launch_bounds__(T, 12)
 ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
                 const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap, const int chunk,
-                unsigned long long *__restrict__ counter, DevRes *__restrict__ res, uint32_t *__restrict__ cells)
+                unsigned long long *__restrict__ counter, const uint32_t *__restrict__ order,
+                DevRes *__restrict__ res, uint32_t *__restrict__ cells)
 {
 	extern __shared__ uint4 smem[];
 	const int lane = threadIdx.x;
@@ -69,7 +70,7 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 				}
 				const long long avail = wend - wcur;
 				const int rank = __popc(need & ((1u << lane) - 1u));
-				if (state == IDLE && !got && (long long)rank < avail) { jb = jobs[wcur + rank]; got = true; }
+				if (state == IDLE && !got && (long long)rank < avail) { jb = jobs[order[wcur + rank]]; got = true; }
 				const int served = (long long)__popc(need) < avail ? __popc(need) : (int)avail;
 				wcur += served;
 				need = __ballot_sync(0xffffffffu, state == IDLE && !got);
@@ -118,7 +119,7 @@ size_t ksw_fast_smem_bytes(int qmax)
 template <bool KEYED>
 static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                  const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
-                                 DevRes *res, uint32_t *cells, cudaStream_t st)
+                                 const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st)
 {
 	const size_t smem = ksw_fast_smem_bytes(qmax);
 	// The dynamic shared-memory ceiling of the kernel is raised ONCE per device to the opt-in maximum and never lowered:
@@ -150,15 +151,15 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 	long long chunk = n_jobs / (blocks * 16);
 	chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : (chunk / 32) * 32);
 	ksw_fast_kernel<KEYED><<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
-	                                                           KSW_FAST_QUADS(qmax), (int)chunk, counter, res, cells);
+	                                                           KSW_FAST_QUADS(qmax), (int)chunk, counter, order, res, cells);
 	return cudaGetLastError();
 }
 
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter,
-                            DevRes *res, uint32_t *cells, cudaStream_t st)
+                            const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st)
 {
 	if (n_jobs <= 0) return cudaSuccess;
-	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, res, cells, st)
-	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, res, cells, st);
+	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st)
+	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st);
 }

@@ -23,7 +23,8 @@ __device__ __forceinline__ int seq_code(const uint32_t *w2, const uint32_t *nmas
 // warp, which sweep similar columns at the same time, touch neighbouring addresses.
 __global__ void __launch_bounds__(128)
 ksw_generic_kernel(const DevJob *__restrict__ jobs, int64_t n_jobs, const uint32_t *__restrict__ pool,
-                   const uint32_t *__restrict__ npool, KswParams P, int2 *__restrict__ eh, uint8_t *__restrict__ qc, DevRes *__restrict__ res,
+                   const uint32_t *__restrict__ npool, KswParams P, int2 *__restrict__ eh, uint8_t *__restrict__ qc,
+                   const uint32_t *__restrict__ order, DevRes *__restrict__ res,
                    uint32_t *__restrict__ cells)
 {
 	const int64_t n_threads = (int64_t)gridDim.x * blockDim.x;
@@ -31,7 +32,7 @@ ksw_generic_kernel(const DevJob *__restrict__ jobs, int64_t n_jobs, const uint32
 	const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
 
 	for (int64_t k = g; k < n_jobs; k += n_threads) {
-		const DevJob jb = jobs[k];
+		const DevJob jb = jobs[order[k]];
 		const int qlen = jb.qlen, tlen = jb.tlen, h0 = jb.h0, w = jb.w;
 		const uint32_t *q2 = pool + (size_t)jb.seq_off * 4;
 		const uint32_t *t2 = q2 + ksw_words2(qlen);
@@ -142,10 +143,10 @@ dpx_peak_kernel(unsigned *out, int iters, unsigned seed)
 
 cudaError_t ksw_launch_generic(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                const KswParams &P,
-                               int2 *eh, uint8_t *qc, int n_blocks, DevRes *res, uint32_t *cells, cudaStream_t st)
+                               int2 *eh, uint8_t *qc, int n_blocks, const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st)
 {
 	if (n_jobs <= 0) return cudaSuccess;
-	ksw_generic_kernel<<<n_blocks, KSW_GENERIC_THREADS, 0, st>>>(jobs, n_jobs, pool, npool, P, eh, qc, res, cells);
+	ksw_generic_kernel<<<n_blocks, KSW_GENERIC_THREADS, 0, st>>>(jobs, n_jobs, pool, npool, P, eh, qc, order, res, cells);
 	return cudaGetLastError();
 }
 

@@ -9,16 +9,21 @@
 // generic int32 kernel: eh/qc are scratch slabs of (qmax+1) * n_blocks*KSW_GENERIC_THREADS entries
 cudaError_t ksw_launch_generic(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                const KswParams &P,
-                               int2 *eh, uint8_t *qc, int n_blocks, DevRes *res, uint32_t *cells, cudaStream_t st);
+                               int2 *eh, uint8_t *qc, int n_blocks, const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st);
 
 // DPX issue-rate probe; each thread issues iters*32 DPX instructions
 cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iters, cudaStream_t st);
 
 #define KSW_FAST_THREADS 32
 
-// fast s16x2 kernel over jobs[0..n_jobs) whose qlen <= qmax; keyed: every job satisfies the class-0 bounds of
+// fast s16x2 kernel over the jobs jobs[order[0..n_jobs)] whose qlen <= qmax; keyed: every job satisfies the class-0 bounds of
 // ksw_pack.h; counter: one device uint64 scratch word
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
-                            const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter,
+                            const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter, const uint32_t *order,
                             DevRes *res, uint32_t *cells, cudaStream_t st);
 size_t ksw_fast_smem_bytes(int qmax);
+
+// device-side binning (ksw_bin.cu): fills order[0..n) with the job indices sorted by the bin key
+size_t ksw_bin_temp_bytes(int64_t n);
+cudaError_t ksw_launch_bin(const DevJob *jobs, int64_t n, uint16_t *keys_in, uint16_t *keys_out, uint32_t *vals_in,
+                           uint32_t *order, void *temp, size_t temp_bytes, cudaStream_t st);

@@ -33,34 +33,27 @@ private:
 static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {124, 128, 256, 512};
 #define KSW_FAST_KEYED_MAXSCORE 511
 
-struct KswPackPlan {
-	int64_t n = 0, n_fast = 0, n_generic = 0;
-	// the fast jobs come first, grouped in KSW_FAST_CLASSES query-length classes (one launch each,
-	// so a few long queries do not shrink everybody's occupancy); then the generic jobs
-	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0, 0};
-	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0, 0};
-	size_t pool_bytes = 0;             // bytes of the 2-bit pool (multiple of 16)
-	int qmax_generic = 0;
-	int maxsc = 0;
-	// per caller index k (so that the fill pass streams the caller's buffers sequentially):
-	std::vector<uint32_t> pos_of;      // binned position of job k
-	std::vector<uint32_t> off_of;      // pool offset of job k in 16-byte units
-	std::vector<uint32_t> units_of;    // 16-byte units job k occupies
-	// scratch kept between calls (a plan object is meant to be reused: fresh pages are expensive)
-	std::vector<uint16_t> key;
-	std::vector<std::vector<uint32_t>> cnt;
-	std::vector<std::vector<uint64_t>> usum;
-	int key_lo = 0, key_hi = -1;       // range of keys the scratch histograms currently hold (to re-zero lazily)
+// What the launcher needs to know about a packed batch.  Classes 0..KSW_FAST_CLASSES-1 are the fast kernel's,
+// class KSW_FAST_CLASSES is the generic kernel's.
+struct KswPackStats {
+	int64_t n = 0;
+	int64_t class_n[KSW_FAST_CLASSES + 1] = {0, 0, 0, 0, 0};
+	int class_qmax[KSW_FAST_CLASSES + 1] = {0, 0, 0, 0, 0};
+	size_t pool_bytes = 0;                 // bytes of the 2-bit pool (multiple of 16)
+	std::vector<uint64_t> range_base;      // scratch: pool offset (16-byte units) at which each host thread's range starts
 };
 
-// fast_qmax: largest qlen the fast kernel accepts (0 = fast kernel disabled: everything is generic)
-int ksw_pack_plan(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs, int fast_qmax,
-                  KswPool *pool, KswPackPlan &plan, std::string &err);
+// Pass 1 (lengths only): classes, per-class counts / longest query, pool size.  fast_qmax: largest qlen the fast kernel
+// accepts (0 = fast kernel disabled: everything is generic).
+int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs, int fast_qmax, KswPool *tp,
+                   KswPackStats &st, std::string &err);
 
-// fills dj[0..n) and pool[0..pool_bytes/4); N masks of the rare jobs that have them are appended to nmask
-int ksw_pack_fill(const KswPackPlan &plan, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs,
-                  const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
-                  std::vector<uint32_t> &nmask, KswPool *tp);
+// Pass 2: streams the caller's byte-coded sequences once, in the caller's order: dj[k] describes jobs[k] (idx = k), its
+// sequences are 2-bit packed at consecutive pool offsets.  Binning (the order in which the kernels take the jobs) is
+// done on the device.  N masks of the rare jobs that have them are appended to nmask.
+int ksw_pack_stream(const KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs, int fast_qmax,
+                    const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
+                    std::vector<uint32_t> &nmask, KswPool *tp);
 
 void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P);
 

@@ -1,5 +1,5 @@
 // ksw_runtime.cu — host side of the C ABI declared in include/ksw_b200.h:
-// contexts, H2D/D2H staging on per-context streams, kernel dispatch, the chunked
+// contexts, H2D/D2H staging on per-context streams, device-side binning and kernel dispatch, the chunked
 // pack/copy/compute pipeline of the one-shot batched entry, and the scalar
 // ksw_extend/ksw_extend2 wrappers.  (The packer itself is ksw_pack.cpp.)
 //
@@ -65,6 +65,7 @@ struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs
 	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0, 0};
 	KswParams P;
 	DevBuf d_jobs, d_pool, d_npool, d_res, d_cells;
+	DevBuf d_order, d_keys, d_vals, d_sort_tmp;                 // device-side binning (ksw_bin.cu)
 	size_t pool_bytes = 0, npool_bytes = 0;
 	int qmax_generic = 0;
 };
@@ -75,7 +76,7 @@ namespace {
 struct Slot {
 	cudaStream_t stream = nullptr;
 	PinnedBuf h_jobs, h_pool, h_npool, h_res;
-	KswPackPlan plan;
+	KswPackStats stats;
 	std::vector<uint32_t> nmask;
 	ksw_b200_batch batch;
 	DevBuf d_eh, d_qc, d_counter;          // scratch of the generic kernel / job counters of the fast kernel
@@ -132,21 +133,24 @@ int fast_qmax_enabled()
 void batch_release_buffers(ksw_b200_batch *b)
 {
 	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release(); b->d_cells.release();
+	b->d_order.release(); b->d_keys.release(); b->d_vals.release(); b->d_sort_tmp.release();
 }
 
-// pack jobs[0..n) into the slot's pinned staging and start the H2D copies into `b` on the slot's stream
+// pack jobs[0..n) into the slot's pinned staging, start the H2D copies into `b` on the slot's stream and enqueue the
+// device-side binning behind them
 int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
                     const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch *b, double *t_plan, double *t_fill)
 {
 	std::string err;
 	const double t0 = now_ms();
-	int rc = ksw_pack_plan(cfg, n, jobs, fast_qmax_enabled(), pool_of(ctx), s.plan, err);
+	KswPool *tp = pool_of(ctx);
+	int rc = ksw_pack_sizes(cfg, n, jobs, fast_qmax_enabled(), tp, s.stats, err);
 	if (rc) return fail(ctx, rc, err);
-	const KswPackPlan &pl = s.plan;
+	const KswPackStats &st = s.stats;
 	const double t1 = now_ms();
 	CU(s.h_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
-	CU(s.h_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
-	rc = ksw_pack_fill(pl, cfg, jobs, qpool, tpool, (DevJob *)s.h_jobs.p, (uint32_t *)s.h_pool.p, s.nmask, pool_of(ctx));
+	CU(s.h_pool.reserve(std::max<size_t>(st.pool_bytes, 16)));
+	rc = ksw_pack_stream(st, cfg, jobs, fast_qmax_enabled(), qpool, tpool, (DevJob *)s.h_jobs.p, (uint32_t *)s.h_pool.p, s.nmask, tp);
 	if (rc) return fail(ctx, rc, "ksw_b200: packing failed");
 	const size_t npool_bytes = s.nmask.size() * 4;
 	CU(s.h_npool.reserve(std::max<size_t>(npool_bytes, 16)));
@@ -155,25 +159,36 @@ int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64
 	if (t_plan) *t_plan += t1 - t0;
 	if (t_fill) *t_fill += t2 - t1;
 
-	b->n = n; b->n_fast = pl.n_fast; b->n_generic = pl.n_generic;
+	b->n = n; b->n_fast = 0;
 	for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
-		b->fast_class_n[c] = pl.fast_class_n[c];
-		b->fast_class_qmax[c] = pl.fast_class_qmax[c];
+		b->fast_class_n[c] = st.class_n[c];
+		b->fast_class_qmax[c] = st.class_qmax[c];
+		b->n_fast += st.class_n[c];
 	}
-	b->qmax_generic = pl.qmax_generic;
-	b->pool_bytes = pl.pool_bytes; b->npool_bytes = npool_bytes;
+	b->n_generic = st.class_n[KSW_FAST_CLASSES];
+	b->qmax_generic = st.class_qmax[KSW_FAST_CLASSES];
+	b->pool_bytes = st.pool_bytes; b->npool_bytes = npool_bytes;
 	ksw_params_from_cfg(cfg, b->P);
-	CU(b->d_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
-	CU(b->d_pool.reserve(std::max<size_t>(pl.pool_bytes, 16)));
+	const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+	const size_t tmp_bytes = ksw_bin_temp_bytes(n);
+	CU(b->d_jobs.reserve(sizeof(DevJob) * n1));
+	CU(b->d_pool.reserve(std::max<size_t>(st.pool_bytes, 16)));
 	CU(b->d_npool.reserve(std::max<size_t>(npool_bytes, 16)));
-	CU(b->d_res.reserve(sizeof(DevRes) * (size_t)std::max<int64_t>(n, 1)));
-	CU(b->d_cells.reserve(sizeof(uint32_t) * (size_t)std::max<int64_t>(n, 1)));
+	CU(b->d_res.reserve(sizeof(DevRes) * n1));
+	CU(b->d_cells.reserve(sizeof(uint32_t) * n1));
+	CU(b->d_order.reserve(sizeof(uint32_t) * n1));
+	CU(b->d_keys.reserve(sizeof(uint16_t) * 2 * n1));
+	CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
+	CU(b->d_sort_tmp.reserve(std::max<size_t>(tmp_bytes, 16)));
 	if (n > 0) {
 		CU(cudaMemcpyAsync(b->d_jobs.p, s.h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
-		if (pl.pool_bytes)
-			CU(cudaMemcpyAsync(b->d_pool.p, s.h_pool.p, pl.pool_bytes, cudaMemcpyHostToDevice, s.stream));
+		if (st.pool_bytes)
+			CU(cudaMemcpyAsync(b->d_pool.p, s.h_pool.p, st.pool_bytes, cudaMemcpyHostToDevice, s.stream));
 		if (npool_bytes)
 			CU(cudaMemcpyAsync(b->d_npool.p, s.h_npool.p, npool_bytes, cudaMemcpyHostToDevice, s.stream));
+		CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, n, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
+		                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, s.stream));
+		ctx->launches += 2;                                      // key kernel + the radix sort (counted as one more)
 	}
 	return 0;
 }
@@ -217,10 +232,10 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 			++e;
 		}
 		CU(s.d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
-		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p + first, n_grp, (const uint32_t *)b->d_pool.p,
+		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p, n_grp, (const uint32_t *)b->d_pool.p,
 		                   (const uint32_t *)b->d_npool.p, b->P, qmax, keyed, ctx->sm_count,
-		                   (unsigned long long *)s.d_counter.p + c, (DevRes *)b->d_res.p,
-		                   (uint32_t *)b->d_cells.p, s.stream));
+		                   (unsigned long long *)s.d_counter.p + c, (const uint32_t *)b->d_order.p + first,
+		                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, s.stream));
 		ctx->launches++;
 		first += n_grp;
 		c = e;
@@ -231,9 +246,10 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 		if (rc) return rc;
 		const int64_t need = (b->n_generic + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS;
 		if (need < n_blocks) n_blocks = (int)need;
-		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p + b->n_fast, b->n_generic, (const uint32_t *)b->d_pool.p,
+		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p, b->n_generic, (const uint32_t *)b->d_pool.p,
 		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)s.d_eh.p, (uint8_t *)s.d_qc.p,
-		                      n_blocks, (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, s.stream));
+		                      n_blocks, (const uint32_t *)b->d_order.p + b->n_fast, (DevRes *)b->d_res.p,
+		                      (uint32_t *)b->d_cells.p, s.stream));
 		ctx->launches++;
 	}
 	return 0;

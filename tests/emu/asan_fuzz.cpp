@@ -48,19 +48,24 @@ int main(int argc, char **argv)
 	}
 	qpool.push_back(0); tpool.push_back(0);
 	KswPool tp(2);
-	KswPackPlan plan;
+	KswPackStats st;
 	std::string err;
-	if (ksw_pack_plan(&cfg, n, jobs.data(), KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1], &tp, plan, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+	const int fast_qmax = KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1];
+	if (ksw_pack_sizes(&cfg, n, jobs.data(), fast_qmax, &tp, st, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
 	std::vector<DevJob> dj(n);
-	std::vector<uint32_t> pool(plan.pool_bytes / 4), nmask;       // exact sizes: ASan sees any overrun
-	ksw_pack_fill(plan, &cfg, jobs.data(), qpool.data(), tpool.data(), dj.data(), pool.data(), nmask, &tp);
+	std::vector<uint32_t> pool(st.pool_bytes / 4), nmask;          // exact sizes: ASan sees any overrun
+	ksw_pack_stream(st, &cfg, jobs.data(), fast_qmax, qpool.data(), tpool.data(), dj.data(), pool.data(), nmask, &tp);
 	KswParams P; ksw_params_from_cfg(&cfg, P);
 	KswFastConst K; ksw_fast_make_const(P, K);
 	ksw_u2 mrow[5]; for (int t = 0; t < 5; ++t) mrow[t] = ksw_fast_matrow(P, t);
 	KswFastEdge edge[5]; for (int r = 0; r < 5; ++r) ksw_fast_edge_entry(r, edge[r]);
 	int bad = 0;
-	for (int64_t p = 0; p < plan.n_fast; ++p) {
+	long long n_fast = 0, n_keyed = 0;
+	for (int64_t p = 0; p < n; ++p) {
 		const DevJob &jb = dj[p];
+		const uint32_t cls = (jb.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK;
+		if (cls >= KSW_CLASS_GENERIC) continue;
+		++n_fast; n_keyed += cls == 0;
 		const int nq = KSW_FAST_QUADS(jb.qlen);
 		std::vector<ksw_u4> hq(nq);                               // exactly what ksw_fast_smem_bytes() reserves per lane
 		std::vector<uint32_t> sq(nq);
@@ -69,7 +74,7 @@ int main(int argc, char **argv)
 		ksw_fast_setup_quads<1>(hq.data(), sq.data(), 0, 0, 1, K, jb.seq_off, jb.qlen, jb.h0, jb.flags, jb.nmask_off, pool.data(),
 		                        nmask.empty() ? nullptr : nmask.data());
 		ksw_fast_init_lane(L, jb, pool.data(), nmask.empty() ? nullptr : nmask.data());
-		if (p < plan.fast_class_n[0]) { while (!ksw_fast_row<1, true>(L, M, K, mrow)) {} }
+		if (cls == 0) { while (!ksw_fast_row<1, true>(L, M, K, mrow)) {} }
 		else { while (!ksw_fast_row<1, false>(L, M, K, mrow)) {} }
 		DevRes r; ksw_fast_result(L, r);
 		const ksw_b200_job_t &j = jobs[jb.idx];
@@ -80,7 +85,6 @@ int main(int argc, char **argv)
 			if (bad++ < 5) fprintf(stderr, "mismatch job %u: qlen %d tlen %d h0 %d w %d\n", jb.idx, j.qlen, j.tlen, j.h0, j.w);
 		}
 	}
-	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %d mismatches\n", n, (long long)plan.n_fast,
-	       (long long)plan.fast_class_n[0], bad);
+	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %d mismatches\n", n, n_fast, n_keyed, bad);
 	return bad ? 1 : 0;
 }

@@ -15,14 +15,15 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
                                   const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res,
                                   int64_t *n_fast_out, int threads, int64_t *n_keyed_out)
 {
-	KswPackPlan plan;
-	std::string err;
 	KswPool tp(threads);
-	int rc = ksw_pack_plan(cfg, n, jobs, KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1], &tp, plan, err);
+	KswPackStats st;
+	std::string err;
+	const int fast_qmax = KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1];
+	int rc = ksw_pack_sizes(cfg, n, jobs, fast_qmax, &tp, st, err);
 	if (rc) return rc;
 	std::vector<DevJob> dj(n ? n : 1);
-	std::vector<uint32_t> pool(plan.pool_bytes / 4 + 4), nmask;
-	rc = ksw_pack_fill(plan, cfg, jobs, qpool, tpool, dj.data(), pool.data(), nmask, &tp);
+	std::vector<uint32_t> pool(st.pool_bytes / 4 + 4), nmask;
+	rc = ksw_pack_stream(st, cfg, jobs, fast_qmax, qpool, tpool, dj.data(), pool.data(), nmask, &tp);
 	if (rc) return rc;
 	if (nmask.empty()) nmask.push_back(0);
 	KswParams P;
@@ -31,13 +32,17 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 	ksw_fast_make_const(P, K);
 	ksw_u2 mrow[5];
 	for (int t = 0; t < 5; ++t) mrow[t] = ksw_fast_matrow(P, t);
-	if (n_fast_out) *n_fast_out = plan.n_fast;
+	int64_t n_fast = 0;
+	for (int c = 0; c < KSW_FAST_CLASSES; ++c) n_fast += st.class_n[c];
+	if (n_fast_out) *n_fast_out = n_fast;
 	for (int64_t k = 0; k < n; ++k) res[k].score = INT_MIN;
 	KswFastEdge edge[5];
 	for (int r = 0; r < 5; ++r) ksw_fast_edge_entry(r, edge[r]);
-	for (int64_t p = 0; p < plan.n_fast; ++p) {
+	for (int64_t p = 0; p < n; ++p) {                             // any order: the binned order only matters for speed
 		const DevJob &jb = dj[p];
-		const bool keyed = p < plan.fast_class_n[0];
+		const uint32_t cls = (jb.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK;
+		if (cls >= KSW_CLASS_GENERIC) continue;
+		const bool keyed = cls == 0;
 		const int nq = KSW_FAST_QUADS(jb.qlen);
 		std::vector<ksw_u4> hq(nq + 1);
 		std::vector<uint32_t> sq(nq + 1);
@@ -52,6 +57,6 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 		ksw_fast_result(L, r);
 		memcpy(&res[jb.idx], &r, sizeof(r));
 	}
-	if (n_keyed_out) *n_keyed_out = plan.fast_class_n[0];
+	if (n_keyed_out) *n_keyed_out = st.class_n[0];
 	return 0;
 }
