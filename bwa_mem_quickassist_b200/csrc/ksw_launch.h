@@ -23,6 +23,13 @@ cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *
                             DevRes *res, uint32_t *cells, cudaStream_t st);
 size_t ksw_fast_smem_bytes(int qmax);
 
+// pair kernel (two jobs per lane, ksw_pair.cu) over the class-0 jobs jobs[order[0..n_jobs)]: qlen <= qmax <= 124, biased
+// scores < 512, no N in the query
+cudaError_t ksw_launch_pair(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
+                            const KswParams &P, int qmax, int sm_count, unsigned long long *counter, const uint32_t *order,
+                            DevRes *res, uint32_t *cells, cudaStream_t st);
+size_t ksw_pair_smem_bytes(int qmax, int n_warps);
+
 // device-side binning (ksw_bin.cu): fills order[0..n) with the job indices sorted by the bin key
 size_t ksw_bin_temp_bytes(int64_t n);
 cudaError_t ksw_launch_bin(const DevJob *jobs, int64_t n, uint16_t *keys_in, uint16_t *keys_out, uint32_t *vals_in,

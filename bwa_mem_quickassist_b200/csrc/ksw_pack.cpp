@@ -192,7 +192,7 @@ int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *j
 	return 0;
 }
 
-int ksw_pack_stream(const KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs, int fast_qmax,
+int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs, int fast_qmax,
                     const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
                     std::vector<uint32_t> &nmask, KswPool *tp)
 {
@@ -246,7 +246,17 @@ int ksw_pack_stream(const KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw
 		if (l.words.empty()) continue;
 		const size_t base = nmask.size();
 		nmask.insert(nmask.end(), l.words.begin(), l.words.end());
-		for (auto &w : l.where) dj[w.first].nmask_off = (uint32_t)(base + w.second);
+		for (auto &w : l.where) {
+			DevJob &d = dj[w.first];
+			d.nmask_off = (uint32_t)(base + w.second);
+			// class 0 is the pair kernel's (ksw_pair_core.h): its score look-up has no room for the query-N column of the
+			// matrix, so a class-0 job whose QUERY holds an N moves to class 1 (one job per lane, any base code)
+			if ((d.flags & KSW_FLAG_QN) && ((d.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u) {
+				d.flags = (d.flags & ~(KSW_CLASS_MASK << KSW_CLASS_SHIFT)) | (1u << KSW_CLASS_SHIFT);
+				st.class_n[0]--; st.class_n[1]++;
+				st.class_qmax[1] = std::max(st.class_qmax[1], d.qlen);
+			}
+		}
 	}
 	return 0;
 }

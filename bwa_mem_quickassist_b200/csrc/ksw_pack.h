@@ -50,8 +50,9 @@ int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *j
 
 // Pass 2: streams the caller's byte-coded sequences once, in the caller's order: dj[k] describes jobs[k] (idx = k), its
 // sequences are 2-bit packed at consecutive pool offsets.  Binning (the order in which the kernels take the jobs) is
-// done on the device.  N masks of the rare jobs that have them are appended to nmask.
-int ksw_pack_stream(const KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs, int fast_qmax,
+// done on the device.  N masks of the rare jobs that have them are appended to nmask.  Class-0 jobs whose query holds
+// an N are moved to class 1 here (st.class_n / st.class_qmax are adjusted; class_qmax[0] stays an upper bound).
+int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_job_t *jobs, int fast_qmax,
                     const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
                     std::vector<uint32_t> &nmask, KswPool *tp);
 

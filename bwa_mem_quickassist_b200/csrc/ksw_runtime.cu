@@ -130,6 +130,16 @@ int fast_qmax_enabled()
 	return v;
 }
 
+// KSW_B200_PAIR=1 sends class 0 to the pair kernel (two jobs per lane, ksw_pair.cu) instead of the one-job-per-lane
+// kernel.  Off by default: on config 2 the pair kernel needs 40 % fewer ALU-pipe instructions per cell but, with the
+// same shared memory per job, runs half as many warps per SM and ends up latency-bound (1.72 vs 2.03 TCUPS, DESIGN.md
+// §5.2).  Read per launch: the tests and the A/B bench flip it inside one process.
+bool pair_enabled()
+{
+	const char *s = getenv("KSW_B200_PAIR");
+	return s && *s && *s != '0';
+}
+
 void batch_release_buffers(ksw_b200_batch *b)
 {
 	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release(); b->d_cells.release();
@@ -146,7 +156,7 @@ int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64
 	KswPool *tp = pool_of(ctx);
 	int rc = ksw_pack_sizes(cfg, n, jobs, fast_qmax_enabled(), tp, s.stats, err);
 	if (rc) return fail(ctx, rc, err);
-	const KswPackStats &st = s.stats;
+	KswPackStats &st = s.stats;
 	const double t1 = now_ms();
 	CU(s.h_jobs.reserve(sizeof(DevJob) * (size_t)std::max<int64_t>(n, 1)));
 	CU(s.h_pool.reserve(std::max<size_t>(st.pool_bytes, 16)));
@@ -213,6 +223,22 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 {
 	int64_t first = 0;
 	int c = 0;
+	CU(s.d_counter.reserve(sizeof(unsigned long long) * (KSW_FAST_CLASSES + 1)));
+	if (b->fast_class_n[0] > 0 && pair_enabled()) {
+		// class 0 goes to the pair kernel (two jobs per lane), unless it is a small minority next to other fast classes:
+		// then one launch of the one-job-per-lane kernel over all of them fills the GPU better than two thin launches
+		bool others = false;
+		for (int x = 1; x < KSW_FAST_CLASSES; ++x) others |= b->fast_class_n[x] > 0;
+		if (!others || b->fast_class_n[0] >= (int64_t)ctx->sm_count * 6 * 64 * 2) {
+			CU(ksw_launch_pair((const DevJob *)b->d_jobs.p, b->fast_class_n[0], (const uint32_t *)b->d_pool.p,
+			                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[0], ctx->sm_count,
+			                   (unsigned long long *)s.d_counter.p + KSW_FAST_CLASSES, (const uint32_t *)b->d_order.p,
+			                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, s.stream));
+			ctx->launches++;
+			first = b->fast_class_n[0];
+			c = 1;
+		}
+	}
 	while (c < KSW_FAST_CLASSES) {
 		if (b->fast_class_n[c] <= 0) { ++c; continue; }
 		int64_t n_grp = b->fast_class_n[c];
@@ -231,7 +257,6 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 			keyed = false;
 			++e;
 		}
-		CU(s.d_counter.reserve(sizeof(unsigned long long) * KSW_FAST_CLASSES));
 		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p, n_grp, (const uint32_t *)b->d_pool.p,
 		                   (const uint32_t *)b->d_npool.p, b->P, qmax, keyed, ctx->sm_count,
 		                   (unsigned long long *)s.d_counter.p + c, (const uint32_t *)b->d_order.p + first,

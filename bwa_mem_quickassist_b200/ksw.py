@@ -54,7 +54,8 @@ def make_cfg(a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100, end_bonus=
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libksw_b200.so")
+    # KSW_B200_LIB: development override (A/B builds of the same library); the product is the in-tree libksw_b200.so
+    return os.environ.get("KSW_B200_LIB") or os.path.join(_HERE, "libksw_b200.so")
 
 
 _lib = None

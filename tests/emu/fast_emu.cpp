@@ -60,3 +60,83 @@ extern "C" int ksw_fast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 	if (n_keyed_out) *n_keyed_out = st.class_n[0];
 	return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The PAIR kernel's lane (ksw_pair_core.h: two jobs per lane) on the CPU: `lanes` emulated lanes, each with two job
+// slots that are refilled from the class-0 job list as soon as a job ends — the same life cycle as on the GPU, so
+// that jobs meet partners at every phase (fresh job next to a half-finished one, disjoint bands, one slot empty at
+// the end).  order: 0 = caller order, 1 = the device's binning key order.  Jobs outside class 0 keep score = INT32_MIN.
+#include <algorithm>
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_pair_core.h"
+
+extern "C" int ksw_pair_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                                  const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res,
+                                  uint32_t *cells_out, int lanes, int order, int64_t *n_pair_out, int64_t *steps_out)
+{
+	KswPool tp(2);
+	KswPackStats st;
+	std::string err;
+	const int fast_qmax = KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1];
+	int rc = ksw_pack_sizes(cfg, n, jobs, fast_qmax, &tp, st, err);
+	if (rc) return rc;
+	std::vector<DevJob> dj(n ? n : 1);
+	std::vector<uint32_t> pool(st.pool_bytes / 4 + 4), nmask;
+	rc = ksw_pack_stream(st, cfg, jobs, fast_qmax, qpool, tpool, dj.data(), pool.data(), nmask, &tp);
+	if (rc) return rc;
+	if (nmask.empty()) nmask.push_back(0);
+	KswParams P;
+	ksw_params_from_cfg(cfg, P);
+	KswFastConst K;
+	ksw_fast_make_const(P, K);
+	ksw_u2 mrow[5];
+	for (int t = 0; t < 5; ++t) mrow[t] = ksw_fast_matrow(P, t);
+	for (int64_t k = 0; k < n; ++k) res[k].score = INT_MIN;
+	std::vector<uint32_t> list;
+	int qmax = 1;
+	for (int64_t k = 0; k < n; ++k)
+		if (((dj[k].flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u) { list.push_back((uint32_t)k); qmax = std::max(qmax, dj[k].qlen); }
+	if ((int64_t)list.size() != st.class_n[0]) return 77;            // the packer's class counts must match the flags
+	if (order == 1)
+		std::stable_sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) {
+			auto key = [&](const DevJob &j) { return ((63u - ((uint32_t)std::min(j.tlen, 1008) >> 4)) << 7) | (127u - ((uint32_t)std::min(j.h0, 508) >> 2)); };
+			return key(dj[a]) < key(dj[b]);
+		});
+	if (n_pair_out) *n_pair_out = (int64_t)list.size();
+	const int np = KSW_PAIR_COLPAIRS(qmax);
+	size_t next = 0;
+	int64_t steps = 0;
+	for (int ln = 0; ln < lanes; ++ln) {
+		// lanes run one after the other here (they are independent); each takes every lanes-th slice of the list
+		std::vector<ksw_u4> he(np);
+		std::vector<uint32_t> sq(np);
+		for (auto &v : he) v.x = v.y = v.z = v.w = 0x5a5a5a5au;  // stale garbage, as on the GPU
+		for (auto &v : sq) v = 0xa5a5a5a5u;
+		KswPairMem<1> M{he.data(), sq.data()};
+		KswFastLane L[2];
+		unsigned run = 0;
+		const size_t end = ln + 1 == lanes ? list.size() : std::min(list.size(), next + (list.size() + lanes - 1) / lanes);
+		while (true) {
+			for (int X = 0; X < 2; ++X) {
+				if (((run >> X) & 1u) || next >= end) continue;
+				const DevJob &jb = dj[list[next++]];
+				ksw_pair_setup<1>(he.data(), sq.data(), 0, X, 0, 1, K, jb.seq_off, jb.qlen, jb.h0, pool.data());
+				ksw_fast_init_lane(L[X], jb, pool.data(), nmask.data());
+				run |= 1u << X;
+			}
+			if (!run) break;
+			const unsigned fin = ksw_pair_row<1>(L, run, M, K, mrow);
+			++steps;
+			for (int X = 0; X < 2; ++X) {
+				if (!((fin >> X) & 1u)) continue;
+				DevRes r;
+				ksw_fast_result(L[X], r);
+				memcpy(&res[L[X].idx], &r, sizeof(r));
+				if (cells_out) cells_out[L[X].idx] = L[X].cells;
+				run &= ~(1u << X);
+			}
+		}
+		next = end;
+	}
+	if (steps_out) *steps_out = steps;
+	return 0;
+}

@@ -296,8 +296,24 @@ def emu_lib():
         lib.ksw_fast_emu_batch.restype = C.c_int
         lib.ksw_fast_emu_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int, C.c_void_p]
+        lib.ksw_pair_emu_batch.restype = C.c_int
+        lib.ksw_pair_emu_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _libs["emu"] = lib
     return _libs["emu"]
+
+
+def run_pair_emu(b: Batch, lanes: int = 3, order: int = 0):
+    """Results of the product packer + the PAIR kernel's lane code (two jobs per lane) compiled for the CPU.
+    Jobs outside class 0 come back with score == INT32_MIN.  Returns (res, cells, n_pair, lane_rows)."""
+    res = np.zeros(b.n, dtype=RES_DT)
+    cells = np.zeros(b.n, dtype=np.uint32)
+    npair = C.c_int64(0)
+    steps = C.c_int64(0)
+    rc = emu_lib().ksw_pair_emu_batch(C.byref(b.cfg), b.n, _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), _ptr(res),
+                                      _ptr(cells), lanes, order, C.byref(npair), C.byref(steps))
+    assert rc == 0, rc
+    return res, cells, int(npair.value), int(steps.value)
 
 
 def run_emu(b: Batch, threads: int = 4):

@@ -194,3 +194,37 @@ def test_size_independent_properties_full_rows(gpu_ctx, oracle_built):
     r2 = gpu_ctx.extend_batch(cfg, jobs[perm], t.reshape(-1), t.reshape(-1))
     for f in K.RES_DT.names:
         assert (r2[f] == r[f][perm]).all()
+
+
+# ------------------------------------------------------------------ the pair kernel (two jobs per lane), opt-in
+@pytest.fixture()
+def pair_kernel_on():
+    """KSW_B200_PAIR is read per launch: class 0 (qlen <= 124, scores < 512, no N in the query) goes to ksw_pair_kernel."""
+    os.environ["KSW_B200_PAIR"] = "1"
+    yield
+    os.environ.pop("KSW_B200_PAIR", None)
+
+
+def test_pair_kernel_config2_and_cells(gpu_ctx, oracle_built, pair_kernel_on):
+    b = K.gen_config2(150000, seed=61)
+    _, cells = K.run_oracle(b, want_cells=True)
+    _check(gpu_ctx, b, expect_fast=True)
+    rb = gpu_ctx.upload(b.cfg, b.jobs, b.qpool, b.tpool)
+    gpu_ctx.run(rb)
+    got = gpu_ctx.download_cells(rb)
+    rb.free()
+    assert (got.astype(np.int64) == cells).all()
+
+
+def test_pair_kernel_fuzz_and_adversarial(gpu_ctx, oracle_built, pair_kernel_on):
+    _check(gpu_ctx, K.gen_adversarial())
+    _check(gpu_ctx, K.gen_boundaries())
+    _check(gpu_ctx, K.gen_fuzz(30000, seed=62, max_q=124, h0_max=120))                  # mostly class 0, N in queries and targets
+    _check(gpu_ctx, K.gen_fuzz(20000, seed=63, max_q=300))                                # class 0 next to the other classes
+    _check(gpu_ctx, K.gen_fuzz(15000, seed=64, max_q=124, w_choices=(1, 3, 20, 300), h0_max=40,
+                               cfg=K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3, zdrop=15, end_bonus=2)))
+    _check(gpu_ctx, K.gen_fuzz(15000, seed=65, max_q=124, cfg=K.make_cfg(zdrop=-1)))
+    _check(gpu_ctx, K.gen_fuzz(3, seed=66, max_q=60, n_frac=0.0))                         # fewer jobs than one lane's two slots x 32
+    for name, (b, want) in K.load_golden().items():
+        got = gpu_ctx.extend_batch(b.cfg, b.jobs, b.qpool, b.tpool)
+        assert K.first_mismatch(want, got.view(K.RES_DT)) is None, name
