@@ -25,20 +25,26 @@
 //
 // The two jobs of a lane keep their own row counter, band [lo,hi), best cell, z-drop state ... (KswFastLane each);
 // they share only the column sweep.  Row r of the lane = row iA of job A and row iB of job B, swept over the UNION
-// of the two bands in absolute column numbers:
+// of the two bands in absolute column numbers, two columns (one 128-bit shared-memory word) at a time:
 //
-//      prologue  [min lo, ..)   only the job with the smaller lo is inside its band    -> masked column steps
-//      main      [max lo, min hi)   both inside (empty if the bands are disjoint)      -> plain steps, 2 columns each
-//      epilogue  [.., max hi)   only the job with the larger hi is inside its band     -> masked column steps
+//      masked pairs   up to the first column pair that lies inside BOTH bands
+//      plain pairs    while both jobs are inside their bands (empty if the bands are disjoint)
+//      masked pairs   from the first pair that is not inside both bands to the end of the union
 //
-// A masked step forces the inputs of the job that is outside its band to (H = -8192, E = 0): left of its band it then
-// computes h = 0 and keeps F = 0, exactly the state the reference starts the band with; right of its band it only sees
-// its own decaying F (< its row maximum), which can change neither (m, mj) nor any cell that is read later.  What such
-// "phantom" cells store is harmless: row r+1 of a job reads eh[j] only for lo <= j <= hi of row r, the real cells write
-// eh[lo..hi-1], and eh[hi] = (h1, 0) (ksw.c:446) is written explicitly after the sweep with two 16-bit stores.  The
-// zero detector ignores phantoms (a false zero would only cost the slow trim path, never exactness).
+// A masked pair forces the inputs of a job that is outside its band at a column to (H = -8192, E = 0): left of its
+// band it then computes h = 0 and keeps F = 0, exactly the state the reference starts the band with; right of its
+// band it only sees its own decaying F (< its row maximum), which can change neither (m, mj) nor any cell that is read
+// later.  What such "phantom" cells store is harmless: row r+1 of a job reads eh[j] only for lo <= j <= hi of row r,
+// the real cells write eh[lo..hi-1] (and eh[hi].h when column hi is swept), and the three slots the reference writes
+// outside its inner loop — eh[lo].h = first-column value (ksw.c:429), eh[hi] = (h1, 0) (ksw.c:446) — are written
+// after the sweep with 16-bit stores.  The zero detector ignores phantoms (a false zero would only cost the slow trim
+// path, never exactness).
 // Jobs whose query contains an N are not paired (a PRMT reaches 4 score bytes per job): the packer routes them to
 // the one-job-per-lane kernel.  A target N simply selects row 4 of the matrix.
+//
+// Status: bit-exact (tests/test_pair_lane.py on the CPU, tests/test_gpu_parity.py on the GPU) but NOT the default:
+// shared memory per job is the same as in the one-job-per-lane kernel, so an SM holds half as many warps (7 instead
+// of 13 for 101 bp queries) and the kernel is latency-bound — see DESIGN.md §5.2 for the measurements.
 #pragma once
 #include <stdint.h>
 #include "ksw_dev.cuh"
@@ -118,13 +124,8 @@ static KSW_HD ksw_u4 ksw_pair_cells(KswPairRowRegs &R, const KswFastConst &K, co
 	ksw_u4 o;
 	o.x = R.Hc;
 	o.z = h0;
-#ifdef KSW_PAIR_E2
-	o.y = addmax2(v.y, ksw_pk2(-K.e_del), addmax2(h0, ksw_pk2(-K.B), K.Bpk));
-	o.w = addmax2(v.w, ksw_pk2(-K.e_del), addmax2(h1, ksw_pk2(-K.B), K.Bpk));
-#else
 	o.y = max3_2(v.y - K.ed32, h0 - K.oed32, K.Bpk);           // every half is >= B = oe_del: the 32-bit subtractions cannot borrow
 	o.w = max3_2(v.w - K.ed32, h1 - K.oed32, K.Bpk);
-#endif
 	R.Hc = h1;
 	R.m = maxu2(R.m, maxu2(h0 * 128u + colpk, h1 * 128u + (colpk + 0x10001u)));
 	R.zmin = min3_2(R.zmin, h0 | z0, h1 | z1);
@@ -259,12 +260,8 @@ static KSW_HD unsigned ksw_pair_row(KswFastLane *L, const unsigned run, const Ks
 		ksw_u4 vn = M.he[M0 * T];                                   // software prefetch, one column pair ahead
 		uint32_t swn = M.sq[M0 * T];
 		uint32_t colpk = (uint32_t)(M0 << 1) * 0x10001u;
-#ifndef KSW_PAIR_UNROLL
-#define KSW_PAIR_UNROLL 4
-#endif
 #ifdef __CUDACC__
-		constexpr int kUnroll = KSW_PAIR_UNROLL;
-#pragma unroll kUnroll
+#pragma unroll 4
 #endif
 		for (int p = M0; p < M1; ++p) {
 			const ksw_u4 v = vn;
