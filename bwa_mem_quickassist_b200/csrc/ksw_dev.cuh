@@ -40,6 +40,20 @@ struct DevRes {
 };
 static_assert(sizeof(DevRes) == 24, "DevRes must be 24 bytes");
 
+// banded global alignment with backtrace (ksw_global.cu): sequences travel as byte codes, query then target
+struct DevGJob {
+	uint64_t seq_off;   // byte offset of the job's query in the chunk's sequence buffer (the target follows it)
+	int32_t  qlen, tlen, w;
+	uint32_t idx;       // index of this job in the chunk
+};
+static_assert(sizeof(DevGJob) == 24, "DevGJob must be 24 bytes");
+
+struct DevGRes {
+	int32_t   score, n_cigar;
+	long long cigar_off;  // first of the job's n_cigar operations in the chunk's CIGAR pool
+};
+static_assert(sizeof(DevGRes) == 16, "DevGRes must be 16 bytes");
+
 struct KswParams {          // passed by value as a kernel parameter (constant bank)
 	int8_t  mat[25];
 	int8_t  pad[3];

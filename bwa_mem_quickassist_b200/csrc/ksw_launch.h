@@ -11,6 +11,12 @@ cudaError_t ksw_launch_generic(const DevJob *jobs, int64_t n_jobs, const uint32_
                                const KswParams &P,
                                int2 *eh, uint8_t *qc, int n_blocks, const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st);
 
+// banded global alignment + backtrace (ksw_global.cu), one job per thread: eh/qc as for the generic kernel, z = direction
+// matrix slab of zcap cells per thread; cigar_pool must hold the sum of (qlen + tlen) operations in the worst case
+cudaError_t ksw_launch_global(const DevGJob *jobs, int64_t n_jobs, const uint8_t *seq, const KswParams &P, int2 *eh,
+                              uint8_t *qc, uint8_t *z, long long zcap, int n_blocks, unsigned long long *pool_used,
+                              uint32_t *cigar_pool, DevGRes *res, cudaStream_t st);
+
 // DPX issue-rate probe; each thread issues iters*32 DPX instructions
 cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iters, cudaStream_t st);
 

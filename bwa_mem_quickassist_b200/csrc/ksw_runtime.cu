@@ -98,6 +98,10 @@ struct ksw_b200_ctx {
 	int64_t launches = 0;
 	int64_t last_h2d = 0, last_d2h = 0;    // bytes moved by the last ksw_b200_extend_batch call
 	Slot slot[2];                           // slot[0] also serves upload / run / download of resident batches
+	// banded global alignment (ksw_b200_global_batch): staging, device buffers, the CIGAR pool handed to the caller
+	PinnedBuf g_hjobs, g_hseq, g_hres, g_hcig;
+	DevBuf g_djobs, g_dseq, g_dres, g_dcig, g_dused, g_deh, g_dqc, g_dz;
+	std::vector<uint32_t> g_cigar;
 };
 
 namespace {
@@ -354,6 +358,9 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 	}
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	ctx->g_hjobs.release(); ctx->g_hseq.release(); ctx->g_hres.release(); ctx->g_hcig.release();
+	ctx->g_djobs.release(); ctx->g_dseq.release(); ctx->g_dres.release(); ctx->g_dcig.release(); ctx->g_dused.release();
+	ctx->g_deh.release(); ctx->g_dqc.release(); ctx->g_dz.release();
 	delete ctx->pool;
 	delete ctx;
 }
@@ -586,6 +593,98 @@ int ksw_b200_clamp_w(int qlen, const int8_t *mat, int o_del, int e_del, int o_in
 	return ksw_clamp_w(qlen, ksw_mat_max(mat), o_del, e_del, o_ins, e_ins, w, end_bonus);
 }
 
+// ---- banded global alignment with backtrace (ksw_global.cu).  Synchronous, chunk by chunk on slot 0's stream: a chunk
+// is bounded by its sequence bytes, its worst-case CIGAR pool and the direction-matrix slab.
+int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
+                          const uint32_t **cigar_pool, int64_t *n_cigar_total)
+{
+	if (!ctx || !cfg || n < 0 || (n > 0 && (!jobs || !res))) return fail(ctx, 1, "ksw_b200_global_batch: bad argument");
+	if (cfg->m != 5) return fail(ctx, 2, "ksw_b200: only m == 5 is supported (every reference caller passes 5)");
+	CU(cudaSetDevice(ctx->device));
+	Slot &s = ctx->slot[0];
+	ctx->g_cigar.clear();
+	KswParams P;
+	ksw_params_from_cfg(cfg, P);
+	const int64_t max_chunk_jobs = 1 << 18;
+	const size_t max_seq = (size_t)256 << 20, max_ops = (size_t)128 << 20, z_budget = (size_t)8 << 30;
+	int64_t first = 0;
+	while (first < n) {
+		// chunk [first, last): as many jobs as the budgets allow (at least one)
+		int64_t last = first;
+		size_t seq_bytes = 0, ops = 0;
+		int qmax = 0;
+		long long zmax = 0;
+		while (last < n && last - first < max_chunk_jobs) {
+			const ksw_b200_gjob_t &j = jobs[last];
+			if (j.qlen < 0 || j.tlen < 0 || j.w < 0) return fail(ctx, 2, "ksw_b200_global_batch: job with qlen < 0, tlen < 0 or w < 0");
+			const size_t sb = (size_t)j.qlen + (size_t)j.tlen, so = sb + 2;
+			if (last > first && (seq_bytes + sb > max_seq || ops + so > max_ops)) break;
+			seq_bytes += sb; ops += so;
+			qmax = std::max(qmax, j.qlen);
+			const long long n_col = std::min<long long>(j.qlen, 2LL * j.w + 1);
+			zmax = std::max(zmax, n_col * j.tlen);
+			++last;
+		}
+		const int64_t m = last - first;
+		const long long zcap = zmax + qmax + 2;
+		// threads: bounded by the direction-matrix slab; every thread owns one column set and one z slab
+		size_t threads = (size_t)ctx->sm_count * 8 * KSW_GENERIC_THREADS;
+		while (threads > KSW_GENERIC_THREADS && threads * (size_t)zcap > z_budget) threads >>= 1;
+		threads = std::min<size_t>(threads, (size_t)((m + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS) * KSW_GENERIC_THREADS);
+		const int n_blocks = (int)(threads / KSW_GENERIC_THREADS);
+		CU(ctx->g_hjobs.reserve(sizeof(DevGJob) * (size_t)m));
+		CU(ctx->g_hseq.reserve(std::max<size_t>(seq_bytes, 16)));
+		CU(ctx->g_hres.reserve(sizeof(DevGRes) * (size_t)m));
+		CU(ctx->g_djobs.reserve(sizeof(DevGJob) * (size_t)m));
+		CU(ctx->g_dseq.reserve(std::max<size_t>(seq_bytes, 16)));
+		CU(ctx->g_dres.reserve(sizeof(DevGRes) * (size_t)m));
+		CU(ctx->g_dcig.reserve(sizeof(uint32_t) * ops));
+		CU(ctx->g_dused.reserve(sizeof(unsigned long long)));
+		CU(ctx->g_deh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
+		CU(ctx->g_dqc.reserve(threads * (size_t)(qmax + 1)));
+		CU(ctx->g_dz.reserve(threads * (size_t)zcap));
+		DevGJob *hj = (DevGJob *)ctx->g_hjobs.p;
+		uint8_t *hs = (uint8_t *)ctx->g_hseq.p;
+		size_t off = 0;
+		for (int64_t k = 0; k < m; ++k) {
+			const ksw_b200_gjob_t &j = jobs[first + k];
+			hj[k].seq_off = off; hj[k].qlen = j.qlen; hj[k].tlen = j.tlen; hj[k].w = j.w; hj[k].idx = (uint32_t)k;
+			if (j.qlen) memcpy(hs + off, qpool + j.q_off, (size_t)j.qlen);
+			if (j.tlen) memcpy(hs + off + j.qlen, tpool + j.t_off, (size_t)j.tlen);
+			off += (size_t)j.qlen + (size_t)j.tlen;
+		}
+		CU(cudaMemcpyAsync(ctx->g_djobs.p, hj, sizeof(DevGJob) * (size_t)m, cudaMemcpyHostToDevice, s.stream));
+		if (seq_bytes) CU(cudaMemcpyAsync(ctx->g_dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemsetAsync(ctx->g_dused.p, 0, sizeof(unsigned long long), s.stream));
+		CU(ksw_launch_global((const DevGJob *)ctx->g_djobs.p, m, (const uint8_t *)ctx->g_dseq.p, P, (int2 *)ctx->g_deh.p,
+		                     (uint8_t *)ctx->g_dqc.p, (uint8_t *)ctx->g_dz.p, zcap, n_blocks,
+		                     (unsigned long long *)ctx->g_dused.p, (uint32_t *)ctx->g_dcig.p, (DevGRes *)ctx->g_dres.p, s.stream));
+		ctx->launches++;
+		unsigned long long used = 0;
+		CU(cudaMemcpyAsync(ctx->g_hres.p, ctx->g_dres.p, sizeof(DevGRes) * (size_t)m, cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaMemcpyAsync(&used, ctx->g_dused.p, sizeof(used), cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+		const size_t base = ctx->g_cigar.size();
+		if (used) {
+			CU(ctx->g_hcig.reserve(sizeof(uint32_t) * (size_t)used));
+			CU(cudaMemcpyAsync(ctx->g_hcig.p, ctx->g_dcig.p, sizeof(uint32_t) * (size_t)used, cudaMemcpyDeviceToHost, s.stream));
+			CU(cudaStreamSynchronize(s.stream));
+			ctx->g_cigar.insert(ctx->g_cigar.end(), (const uint32_t *)ctx->g_hcig.p, (const uint32_t *)ctx->g_hcig.p + used);
+		}
+		const DevGRes *hr = (const DevGRes *)ctx->g_hres.p;
+		for (int64_t k = 0; k < m; ++k) {
+			res[first + k].score = hr[k].score;
+			res[first + k].n_cigar = hr[k].n_cigar;
+			res[first + k].cigar_off = (int64_t)base + hr[k].cigar_off;
+		}
+		first = last;
+	}
+	if (cigar_pool) *cigar_pool = ctx->g_cigar.data();
+	if (n_cigar_total) *n_cigar_total = (int64_t)ctx->g_cigar.size();
+	return 0;
+}
+
 // ---- scalar drop-ins (ksw.h:107-108).  One lazily created context per host thread.
 static ksw_b200_ctx *scalar_ctx()
 {
@@ -636,6 +735,42 @@ int ksw_extend(int qlen, const uint8_t *query, int tlen, const uint8_t *target, 
 {
 	return ksw_extend2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, end_bonus, zdrop, h0,
 	                   qle, tle, gtle, gscore, max_off);
+}
+
+// ksw.h:83-84.  As in the reference the CIGAR is only produced when both out-pointers are given, *n_cigar_ is zeroed
+// first (ksw.c:507), and the array is malloc'd for the caller.
+int ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar_, uint32_t **cigar_)
+{
+	ksw_b200_ctx *ctx = scalar_ctx();
+	ksw_b200_cfg_t cfg;
+	memcpy(cfg.mat, mat, 25);
+	cfg.m = m; cfg.o_del = o_del; cfg.e_del = e_del; cfg.o_ins = o_ins; cfg.e_ins = e_ins;
+	cfg.zdrop = 0; cfg.end_bonus = 0;
+	ksw_b200_gjob_t job;
+	job.q_off = 0; job.t_off = 0; job.qlen = qlen; job.tlen = tlen; job.w = w; job.reserved = 0;
+	ksw_b200_gres_t r;
+	const uint32_t *pool = nullptr;
+	int64_t total = 0;
+	if (n_cigar_) *n_cigar_ = 0;
+	int rc = ksw_b200_global_batch(ctx, &cfg, 1, &job, query, target, &r, &pool, &total);
+	if (rc) {
+		fprintf(stderr, "[ksw_b200] fatal: ksw_global2 failed on the GPU (%d): %s\n", rc, ksw_b200_strerror(ctx));
+		abort();
+	}
+	if (n_cigar_ && cigar_) {
+		uint32_t *c = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)std::max(r.n_cigar, 1));
+		if (!c) { fprintf(stderr, "[ksw_b200] fatal: out of memory\n"); abort(); }
+		for (int k = 0; k < r.n_cigar; ++k) c[k] = pool[r.cigar_off + k];
+		*n_cigar_ = r.n_cigar; *cigar_ = c;
+	}
+	return r.score;
+}
+
+int ksw_global(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+               int gapo, int gape, int w, int *n_cigar_, uint32_t **cigar_)
+{
+	return ksw_global2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, n_cigar_, cigar_);
 }
 
 } // extern "C"

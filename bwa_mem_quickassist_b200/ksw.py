@@ -17,6 +17,10 @@ JOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen",
                    ("h0", "<i4"), ("w", "<i4")])            # ksw_b200_job_t
 RES_DT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
                    ("gscore", "<i4"), ("max_off", "<i4")])  # ksw_b200_res_t
+# banded global alignment with backtrace
+GJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"),
+                    ("reserved", "<i4")])                   # ksw_b200_gjob_t
+GRES_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])   # ksw_b200_gres_t
 
 
 class KswB200Error(RuntimeError):
@@ -99,6 +103,9 @@ def load_library():
     scalar = [i32, vp, i32, vp, i32, vp]
     lib.ksw_extend.argtypes = scalar + [i32] * 6 + [C.POINTER(i32)] * 5
     lib.ksw_extend2.argtypes = scalar + [i32] * 8 + [C.POINTER(i32)] * 5
+    lib.ksw_b200_global_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(i64)]
+    lib.ksw_global.argtypes = scalar + [i32] * 3 + [C.POINTER(i32), C.POINTER(C.POINTER(C.c_uint32))]
+    lib.ksw_global2.argtypes = scalar + [i32] * 5 + [C.POINTER(i32), C.POINTER(C.POINTER(C.c_uint32))]
     _lib = lib
     return lib
 
@@ -176,6 +183,21 @@ class KswB200:
                                                    _p(tpool), _p(res)), "ksw_b200_extend_batch")
         return res
 
+    def global_batch(self, cfg: Cfg, jobs, qpool, tpool):
+        """ksw_b200_global_batch: banded global alignment + backtrace of every job (GJOB_DT).  Returns
+        (res[GRES_DT], cigar_pool[uint32]); job k's CIGAR is cigar_pool[res[k].cigar_off : +res[k].n_cigar],
+        one operation per word, len << 4 | op (0 = M, 1 = I, 2 = D) as in the reference."""
+        jobs = np.ascontiguousarray(jobs, dtype=GJOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        tpool = np.ascontiguousarray(tpool, dtype=np.uint8)
+        res = np.zeros(jobs.shape[0], dtype=GRES_DT)
+        pool = C.POINTER(C.c_uint32)()
+        total = C.c_int64(0)
+        self._check(self.lib.ksw_b200_global_batch(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool), _p(tpool),
+                                                   _p(res), C.byref(pool), C.byref(total)), "ksw_b200_global_batch")
+        cig = np.ctypeslib.as_array(pool, shape=(total.value,)).copy() if total.value else np.zeros(0, np.uint32)
+        return res, cig
+
     def upload(self, cfg: Cfg, jobs, qpool, tpool) -> ResidentBatch:
         jobs, qpool, tpool = self._norm(jobs, qpool, tpool)
         h = C.c_void_p()
@@ -249,3 +271,20 @@ def ksw_extend2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w
 def ksw_extend(qlen, query, tlen, target, m, mat, gapo, gape, w, end_bonus, zdrop, h0):
     """Scalar drop-in (ksw.h:107)."""
     return ksw_extend2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, end_bonus, zdrop, h0)
+
+
+def ksw_global2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w):
+    """Scalar drop-in with the reference's argument order (ksw.h:84).  Returns (score, cigar[uint32]); the array the
+    library malloc'd for the caller is freed here with libc free(), exactly what a C caller has to do."""
+    lib = load_library()
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    t = np.ascontiguousarray(target, dtype=np.uint8)
+    mt = np.ascontiguousarray(mat, dtype=np.int8)
+    n = C.c_int(0)
+    cig = C.POINTER(C.c_uint32)()
+    sc = lib.ksw_global2(qlen, _p(q), tlen, _p(t), m, _p(mt), o_del, e_del, o_ins, e_ins, w, C.byref(n), C.byref(cig))
+    out = np.array([cig[k] for k in range(n.value)], dtype=np.uint32)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(C.cast(cig, C.c_void_p))
+    return sc, out

@@ -118,6 +118,36 @@ int ksw_b200_batch_info(const ksw_b200_batch_t *b, int64_t *n_fast, int64_t *n_g
 void ksw_b200_batch_free(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);
 int ksw_b200_ctx_sync(ksw_b200_ctx_t *ctx);
 
+/* ---- banded global alignment with backtrace (CIGAR generation) ---------------- */
+/* SURVEY.md §8(f) rank 2.  Replaces a loop of ksw_global2 calls (bwa-0.7.8/ksw.c:501-584; the call site is
+ * bwa_gen_cigar2, bwa.c:132, reached from mem_reg2aln, bwamem.c:1196).  Scalar signatures unchanged (ksw.h:83-84):
+ * *cigar_ is malloc'd and owned by the caller, one uint32 per operation, len<<4|op with op 0=M 1=I 2=D. */
+int ksw_global(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+               int gapo, int gape, int w, int *n_cigar, uint32_t **cigar);
+int ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t **cigar);
+
+typedef struct {
+	uint64_t q_off, t_off;     /* byte offsets of query / target (codes 0..4) in the pools */
+	int32_t  qlen, tlen;       /* >= 0 */
+	int32_t  w;                /* band width, >= 0; as in the reference the result is only defined if the band holds
+	                            * the end cell, |tlen - qlen| <= w (bwa_gen_cigar2 guarantees it, bwa.c:124-126) */
+	int32_t  reserved;
+} ksw_b200_gjob_t;
+
+typedef struct {
+	int32_t score;             /* return value of ksw_global2 */
+	int32_t n_cigar;           /* number of CIGAR operations */
+	int64_t cigar_off;         /* index of the first one in the pool returned by the call */
+} ksw_b200_gres_t;
+
+/* cfg: mat, m (= 5), o_del, e_del, o_ins, e_ins are used; zdrop and end_bonus are ignored.  res[0..n) in the caller's
+ * order; *cigar_pool points to memory owned by ctx, valid until the next ksw_b200_global_batch call on this ctx or its
+ * destruction; *n_cigar_total = number of operations in it. */
+int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
+                          const uint32_t **cigar_pool, int64_t *n_cigar_total);
+
 /* ---- measurement helper ------------------------------------------------------ */
 /* Issue-rate microbenchmark of the DPX family used by the kernels (VIADDMNMX.S16x2[.RELU],
  * VIMNMX.S16x2): returns warp-level lane-operations per second sustained by the whole GPU

@@ -55,3 +55,51 @@ int ksw_ref_extend_batch(const ref_cfg_t *cfg, int64_t n, const ref_job_t *jobs,
 	free(tid); free(args);
 	return 0;
 }
+
+/* ---- the same for the reference's ksw_global2 (bwa-0.7.8/ksw.c:501, prototype ksw.h:84) ---- */
+int ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t **cigar);
+
+typedef struct { uint64_t q_off, t_off; int32_t qlen, tlen, w, reserved; } ref_gjob_t;
+typedef struct { int32_t score, n_cigar; int64_t cigar_off; } ref_gres_t;
+typedef struct {
+	const ref_cfg_t *cfg; const ref_gjob_t *jobs; const uint8_t *qpool, *tpool;
+	ref_gres_t *res; uint32_t *cigar; int64_t n, begin, stride;
+} garg_t;
+
+static void *gworker(void *p)
+{
+	garg_t *a = (garg_t *)p;
+	const ref_cfg_t *c = a->cfg;
+	int64_t k;
+	for (k = a->begin; k < a->n; k += a->stride) {
+		const ref_gjob_t *j = &a->jobs[k];
+		int nc = 0, x;
+		uint32_t *cig = 0;
+		a->res[k].score = ksw_global2(j->qlen, a->qpool + j->q_off, j->tlen, a->tpool + j->t_off, c->m, c->mat,
+		                              c->o_del, c->e_del, c->o_ins, c->e_ins, j->w, &nc, &cig);
+		a->res[k].n_cigar = nc;
+		for (x = 0; x < nc; ++x) a->cigar[a->res[k].cigar_off + x] = cig[x];   /* copy out, then give the array back */
+		free(cig);
+	}
+	return 0;
+}
+
+/* res[k].cigar_off must be preset by the caller to a slot with room for qlen + tlen + 2 operations */
+int ksw_ref_global_batch(const ref_cfg_t *cfg, int64_t n, const ref_gjob_t *jobs, const uint8_t *qpool,
+                         const uint8_t *tpool, ref_gres_t *res, uint32_t *cigar, int n_threads)
+{
+	int t;
+	pthread_t *tid; garg_t *args;
+	if (n_threads < 1) n_threads = 1;
+	tid = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
+	args = (garg_t *)malloc(sizeof(garg_t) * n_threads);
+	for (t = 0; t < n_threads; ++t) {
+		garg_t a = { cfg, jobs, qpool, tpool, res, cigar, n, t, n_threads };
+		args[t] = a;
+		pthread_create(&tid[t], 0, gworker, &args[t]);
+	}
+	for (t = 0; t < n_threads; ++t) pthread_join(tid[t], 0);
+	free(tid); free(args);
+	return 0;
+}

@@ -1,5 +1,6 @@
-"""Generates tests/golden/ksw_extend_golden.npz from the REFERENCE's own ksw_extend2
-(oracle/_ref/libksw_ref.so = bwa-0.7.8/ksw.c compiled unmodified by oracle/Makefile).
+"""Generates tests/golden/ksw_extend_golden.npz from the REFERENCE's own ksw_extend2, ksw_global_golden.npz from its
+ksw_global2 (oracle/_ref/libksw_ref.so = bwa-0.7.8/ksw.c compiled unmodified by oracle/Makefile) and
+chain2aln_golden.npz from its mem_chain2aln (oracle/_ref/libbwa_ref.so).
 
 Run in the build container (where /root/reference is mounted):  python tests/golden/make_golden.py
 The reference ships no known-answer vectors for this path, so these outputs of the
@@ -37,6 +38,30 @@ def main():
         out[f"{name}.res"] = res
         print(name, b.n, "jobs")
     path = os.path.join(HERE, "ksw_extend_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+    # banded global alignment with backtrace: scores and CIGARs from the reference's own ksw_global2
+    gsets = {
+        "default": K.gen_global(1500, seed=201),
+        "asym": K.gen_global(800, seed=202, cfg=K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3)),
+        "cheap_gaps": K.gen_global(800, seed=203, cfg=K.make_cfg(a=1, b=1, o_del=1, e_del=2, o_ins=2, e_ins=1)),
+        "short": K.gen_global(600, seed=204, max_q=12, w_extra=(0, 1, 2)),
+    }
+    out = {}
+    for name, b in gsets.items():
+        res, pool = K.run_global_ref(b, threads=4)
+        cig = np.concatenate([pool[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])] for r in res])
+        dense = res.copy()
+        dense["cigar_off"] = np.concatenate([[0], np.cumsum(res["n_cigar"].astype(np.int64))[:-1]])
+        out[f"{name}.jobs"] = b.jobs
+        out[f"{name}.qpool"] = b.qpool
+        out[f"{name}.tpool"] = b.tpool
+        out[f"{name}.cfg"] = np.frombuffer(bytes(b.cfg), dtype=np.uint8).copy()
+        out[f"{name}.res"] = dense
+        out[f"{name}.cigar"] = cig.astype(np.uint32)
+        print("global", name, b.n, "jobs", len(cig), "operations")
+    path = os.path.join(HERE, "ksw_global_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 

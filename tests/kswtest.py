@@ -25,6 +25,10 @@ JOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen",
 RES_DT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
                    ("gscore", "<i4"), ("max_off", "<i4")])
 assert JOB_DT.itemsize == 32 and RES_DT.itemsize == 24
+# banded global alignment with backtrace (ksw_global2): job / result records shared by oracle, reference shim and product
+GJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"), ("reserved", "<i4")])
+GRES_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])
+assert GJOB_DT.itemsize == 32 and GRES_DT.itemsize == 16
 
 
 class Cfg(C.Structure):
@@ -78,6 +82,9 @@ def oracle_lib():
         lib.ksw_oracle_extend_batch.restype = C.c_int
         lib.ksw_oracle_extend_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_int]
+        lib.ksw_oracle_global_batch.restype = C.c_int
+        lib.ksw_oracle_global_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_int]
         lib.ksw_oracle_clamp_w.restype = C.c_int
         lib.ksw_oracle_clamp_w.argtypes = [C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6
         _libs["oracle"] = lib
@@ -93,6 +100,9 @@ def ref_lib():
         lib = C.CDLL(REF_SO)
         lib.ksw_ref_extend_batch.restype = C.c_int
         lib.ksw_ref_extend_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int]
+        lib.ksw_ref_global_batch.restype = C.c_int
+        lib.ksw_ref_global_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int]
         _libs["ref"] = lib
     return _libs["ref"]
@@ -281,6 +291,20 @@ def load_golden():
         cfg = Cfg.from_buffer_copy(z[f"{nm}.cfg"].tobytes())
         b = Batch(cfg, z[f"{nm}.jobs"].astype(JOB_DT), z[f"{nm}.qpool"], z[f"{nm}.tpool"])
         out[nm] = (b, z[f"{nm}.res"].astype(RES_DT))
+    return out
+
+
+GLOBAL_GOLDEN = os.path.join(ROOT, "tests", "golden", "ksw_global_golden.npz")
+
+
+def load_global_golden():
+    """{name: (GBatch, (res, cigar pool))} from the committed fixture made from the compiled reference's ksw_global2."""
+    z = np.load(GLOBAL_GOLDEN)
+    out = {}
+    for nm in sorted({k.split(".")[0] for k in z.files}):
+        cfg = Cfg.from_buffer_copy(z[f"{nm}.cfg"].tobytes())
+        b = GBatch(cfg, z[f"{nm}.jobs"].astype(GJOB_DT), z[f"{nm}.qpool"], z[f"{nm}.tpool"])
+        out[nm] = (b, (z[f"{nm}.res"].astype(GRES_DT), z[f"{nm}.cigar"]))
     return out
 
 
@@ -593,3 +617,89 @@ def run_chain_driver(lib, cs: ChainSet, ctx=None, rounds: bool = False):
     fn.argtypes = [C.c_void_p] + _FLAT_TAIL
     regs, rr = _run_chain_flat(fn, cs, extra_head=[ctx])
     return regs, rr, None
+
+
+# ------------------------------------------------------------------ banded global alignment with backtrace (ksw_global2)
+@dataclass
+class GBatch:
+    cfg: Cfg
+    jobs: np.ndarray      # GJOB_DT
+    qpool: np.ndarray
+    tpool: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return int(self.jobs.shape[0])
+
+
+def _run_global(fn, b: GBatch, threads: int):
+    res = np.zeros(b.n, dtype=GRES_DT)
+    cap = b.jobs["qlen"].astype(np.int64) + b.jobs["tlen"] + 2
+    res["cigar_off"] = np.concatenate([[0], np.cumsum(cap)[:-1]]) if b.n else 0
+    pool = np.zeros(int(cap.sum()) + 1, dtype=np.uint32)
+    rc = fn(C.byref(b.cfg), b.n, _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), _ptr(res), _ptr(pool), threads)
+    assert rc == 0
+    return res, pool
+
+
+def run_global_oracle(b: GBatch, threads: int = 8):
+    """(res[GRES_DT], cigar pool) from the CPU restatement oracle/ksw_global_oracle.c."""
+    return _run_global(oracle_lib().ksw_oracle_global_batch, b, threads)
+
+
+def run_global_ref(b: GBatch, threads: int = 8):
+    """The same from the reference's own ksw_global2 (oracle/_ref/libksw_ref.so)."""
+    return _run_global(ref_lib().ksw_ref_global_batch, b, threads)
+
+
+def cigars(res: np.ndarray, pool: np.ndarray):
+    """Per-job CIGARs as a list of tuples of uint32 operations."""
+    return [tuple(int(x) for x in pool[int(r["cigar_off"]):int(r["cigar_off"]) + int(r["n_cigar"])]) for r in res]
+
+
+def global_mismatch(a, b):
+    """First job whose (score, CIGAR) differs between two (res, pool) results, or None."""
+    (ra, pa), (rb, pb) = a, b
+    bad = np.flatnonzero((ra["score"] != rb["score"]) | (ra["n_cigar"] != rb["n_cigar"]))
+    if bad.size:
+        k = int(bad[0])
+        return k, (int(ra["score"][k]), int(ra["n_cigar"][k])), (int(rb["score"][k]), int(rb["n_cigar"][k]))
+    ca, cb = cigars(ra, pa), cigars(rb, pb)
+    for k, (x, y) in enumerate(zip(ca, cb)):
+        if x != y:
+            return k, x, y
+    return None
+
+
+def gen_global(n: int, seed: int, cfg: Cfg | None = None, max_q: int = 250, n_frac: float = 0.01,
+               w_extra=(0, 1, 3, 10, 50), indel=(0.0, 0.005, 0.03), sub=(0.0, 0.01, 0.05, 0.2)) -> GBatch:
+    """Jobs of the shape bwa_gen_cigar2 produces (bwa.c:118-132): the target is the reference window of an alignment,
+    the query the read segment; the band always holds the end cell: w >= |tlen - qlen| (the reference reads
+    direction cells it never wrote otherwise).  Includes unrelated pairs, N, qlen/tlen of 1, and w = 0."""
+    rng = np.random.default_rng(seed)
+    cfg = cfg or make_cfg()
+    qs, ts, ws = [], [], []
+    for _ in range(n):
+        ql = int(rng.integers(1, max_q + 1))
+        mode = rng.random()
+        if mode < 0.85:
+            q = rng.integers(0, 4, ql).astype(np.uint8)
+            t = mutate(rng, q, float(rng.choice(sub)), float(rng.choice(indel)), max_indel=int(rng.choice([1, 3, 10])))
+            if len(t) == 0:
+                t = q[:1].copy()
+        else:
+            q = rng.integers(0, 4, ql).astype(np.uint8)
+            t = rng.integers(0, 4, int(rng.integers(1, ql + 30))).astype(np.uint8)
+        if rng.random() < 0.2:
+            q = np.where(rng.random(len(q)) < n_frac, 4, q).astype(np.uint8)
+        if rng.random() < 0.1:
+            t = np.where(rng.random(len(t)) < n_frac, 4, t).astype(np.uint8)
+        qs.append(q); ts.append(t)
+        ws.append(abs(len(t) - len(q)) + int(rng.choice(np.array(w_extra))))
+    jobs = np.zeros(n, dtype=GJOB_DT)
+    qlen = np.array([len(x) for x in qs], dtype=np.int64)
+    tlen = np.array([len(x) for x in ts], dtype=np.int64)
+    jobs["q_off"] = np.concatenate([[0], np.cumsum(qlen)[:-1]]) if n else 0
+    jobs["t_off"] = np.concatenate([[0], np.cumsum(tlen)[:-1]]) if n else 0
+    jobs["qlen"], jobs["tlen"], jobs["w"] = qlen, tlen, ws
+    return GBatch(cfg, jobs, np.ascontiguousarray(np.concatenate(qs)), np.ascontiguousarray(np.concatenate(ts)))
