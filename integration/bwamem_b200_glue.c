@@ -15,7 +15,16 @@
  *     for every read, chains in order: push the short-path region or replay mem_chain2aln from the cached DP
  *     mem_sort_and_dedup, mem_test_and_remove_exact                        (host, unchanged: bwamem.c:1111-1117)
  *
- * Everything else (seeding, chaining, pairing, mate rescue, CIGAR, SAM text) is the reference's own code,
+ *     CIGAR look-ahead: for every region of the batch, the global alignments that mem_reg2aln will
+ *       ask for in pass 2 (bwamem.c:1187-1200 via bwa_gen_cigar2, bwa.c:118-132; up to three bands per region) are
+ *       computed now in batches on the GPU (ksw_b200_global_batch) and stored in a table keyed by the EXACT inputs
+ *       of ksw_global2 (query bytes, reference-window bytes, band).
+ *   pass 2 (worker2) is the reference's own code; only the ksw_global2 call inside the reference's bwa_gen_cigar2 is
+ *   redirected (bwa.c is compiled with -Dksw_global2=b200_global2_hook, nothing is edited) to b200_global2_hook below:
+ *   table hit -> the stored score + CIGAR; miss (mate-rescued regions, bwa_fix_xref2) -> one GPU call for that job.
+ *   Because the key is the complete input of the DP, a wrong prediction can only cost a miss, never a wrong CIGAR.
+ *
+ * Everything else (seeding, chaining, pairing, mate rescue, MD/NM, SAM text) is the reference's own code,
  * so the SAM must be byte-identical to stock `bwa mem` apart from @PG.  One extension context per worker
  * thread; worker t uses GPU (t mod #GPUs), so read batches shard over the GPUs of the box with no exchange.
  * `-b` stays the batch knob; the default of 1 read per batch (bwamem.c:68) would mean one GPU round trip per
@@ -83,6 +92,233 @@ __attribute__((constructor)) static void b200_warmup(int argc, char **argv)
 	pthread_t th;
 	if (argc >= 2 && strcmp(argv[1], "mem") == 0 && !getenv("KSW_B200_NO_WARMUP"))
 		if (pthread_create(&th, 0, b200_warmup_thread, 0) == 0) pthread_detach(th);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * CIGAR look-ahead table.  Entries are written in pass 1 (several worker threads: lock-free push onto bucket lists,
+ * storage from per-worker arenas) and only read in pass 2; the table is emptied at the start of every chunk of reads. */
+typedef struct b200_cig_entry {
+	struct b200_cig_entry *next;
+	uint64_t hash;
+	int32_t qlen, tlen, w, score, n_cigar;
+	/* followed by: uint32_t cigar[n_cigar]; uint8_t query[qlen]; uint8_t target[tlen] */
+} b200_cig_entry_t;
+
+#define B200_CIG_BUCKETS (1u << 21)
+#define B200_ARENA_BLOCK ((size_t)4 << 20)
+typedef struct { char **blk; int n_blk, m_blk, cur; size_t used; } b200_arena_t;
+static b200_cig_entry_t **b200_cig_table;
+static b200_arena_t b200_cig_arena[B200_MAX_WORKERS];
+static long long b200_cig_hits, b200_cig_misses, b200_cig_jobs;
+static double b200_t_cigar;
+
+static int b200_cigar_on(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("KSW_B200_CIGAR"); v = (e && e[0] == '0') ? 0 : 1; }
+	return v;
+}
+
+static void *b200_arena_alloc(b200_arena_t *a, size_t n)
+{
+	n = (n + 15) & ~(size_t)15;
+	if (n > B200_ARENA_BLOCK) err_fatal(__func__, "entry of %ld bytes", (long)n);
+	if (a->n_blk == 0 || a->used + n > B200_ARENA_BLOCK) {
+		if (a->n_blk && a->cur + 1 < a->n_blk) ++a->cur;
+		else {
+			if (a->n_blk == a->m_blk) { a->m_blk = a->m_blk ? a->m_blk << 1 : 16; a->blk = (char **)realloc(a->blk, sizeof(char *) * a->m_blk); }
+			a->blk[a->n_blk] = (char *)malloc(B200_ARENA_BLOCK);
+			a->cur = a->n_blk++;
+		}
+		a->used = 0;
+	}
+	a->used += n;
+	return a->blk[a->cur] + a->used - n;
+}
+
+static void b200_cig_reset(void)                         /* single-threaded: called between chunks */
+{
+	int t;
+	if (!b200_cig_table) b200_cig_table = (b200_cig_entry_t **)calloc(B200_CIG_BUCKETS, sizeof(void *));
+	else memset(b200_cig_table, 0, sizeof(void *) * B200_CIG_BUCKETS);
+	for (t = 0; t < B200_MAX_WORKERS; ++t) { b200_cig_arena[t].cur = 0; b200_cig_arena[t].used = 0; }   /* blocks are kept and reused */
+}
+
+static uint64_t b200_cig_hash(int qlen, const uint8_t *q, int tlen, const uint8_t *t, int w)
+{
+	uint64_t h = 1469598103934665603ull ^ ((uint64_t)(uint32_t)qlen << 32 | (uint32_t)tlen) ^ ((uint64_t)(uint32_t)w * 0x9E3779B97F4A7C15ull);
+	int i;
+	for (i = 0; i < qlen; ++i) h = (h ^ q[i]) * 1099511628211ull;
+	for (i = 0; i < tlen; ++i) h = (h ^ t[i]) * 1099511628211ull;
+	return h;
+}
+
+static void b200_cig_insert(int tid, int qlen, const uint8_t *q, int tlen, const uint8_t *t, int w, int score, int n_cigar, const uint32_t *cigar)
+{
+	b200_cig_entry_t *e = (b200_cig_entry_t *)b200_arena_alloc(&b200_cig_arena[tid], sizeof(b200_cig_entry_t) + 4 * (size_t)n_cigar + qlen + tlen);
+	uint32_t *c = (uint32_t *)(e + 1);
+	uint8_t *p = (uint8_t *)(c + n_cigar);
+	b200_cig_entry_t **slot;
+	e->hash = b200_cig_hash(qlen, q, tlen, t, w);
+	e->qlen = qlen; e->tlen = tlen; e->w = w; e->score = score; e->n_cigar = n_cigar;
+	memcpy(c, cigar, 4 * (size_t)n_cigar); memcpy(p, q, qlen); memcpy(p + qlen, t, tlen);
+	slot = &b200_cig_table[e->hash & (B200_CIG_BUCKETS - 1)];
+	do { e->next = *(b200_cig_entry_t * volatile *)slot; } while (!__sync_bool_compare_and_swap(slot, e->next, e));
+}
+
+/* What the reference's bwa_gen_cigar2 calls instead of ksw_global2 (bwa.c:132) in this build.  Same contract: returns
+ * the score; the CIGAR array is malloc'd for the caller (who grows it with kputw to append MD, bwa.c:136). */
+int b200_global2_hook(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                      int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar_, uint32_t **cigar_)
+{
+	static __thread ksw_b200_ctx_t *ctx;                 /* only for misses */
+	ksw_b200_cfg_t cfg;
+	ksw_b200_gjob_t job;
+	ksw_b200_gres_t r;
+	const uint32_t *pool = 0;
+	int64_t total = 0;
+	int k;
+	if (!b200_cigar_on()) return ksw_global2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w, n_cigar_, cigar_);
+	if (b200_cig_table) {
+		const uint64_t h = b200_cig_hash(qlen, query, tlen, target, w);
+		const b200_cig_entry_t *e;
+		for (e = b200_cig_table[h & (B200_CIG_BUCKETS - 1)]; e; e = e->next) {
+			const uint32_t *c = (const uint32_t *)(e + 1);
+			const uint8_t *p = (const uint8_t *)(c + e->n_cigar);
+			if (e->hash != h || e->qlen != qlen || e->tlen != tlen || e->w != w) continue;
+			if (memcmp(p, query, qlen) != 0 || memcmp(p + qlen, target, tlen) != 0) continue;
+			__sync_fetch_and_add(&b200_cig_hits, 1);
+			if (n_cigar_) *n_cigar_ = 0;
+			if (n_cigar_ && cigar_) {
+				uint32_t *out = (uint32_t *)malloc(4 * (size_t)(e->n_cigar > 0 ? e->n_cigar : 1));
+				memcpy(out, c, 4 * (size_t)e->n_cigar);
+				*n_cigar_ = e->n_cigar; *cigar_ = out;
+			}
+			return e->score;
+		}
+	}
+	/* miss: one job on the GPU (there is no CPU fallback in this mode) */
+	__sync_fetch_and_add(&b200_cig_misses, 1);
+	if (!ctx) {
+		if (b200_n_gpus < 0) b200_n_gpus = ksw_b200_device_count();
+		if (b200_n_gpus < 1 || ksw_b200_ctx_create(0, &ctx) != 0) err_fatal(__func__, "no usable CUDA device");
+	}
+	memcpy(cfg.mat, mat, 25);
+	cfg.m = m; cfg.o_del = o_del; cfg.e_del = e_del; cfg.o_ins = o_ins; cfg.e_ins = e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
+	job.q_off = 0; job.t_off = 0; job.qlen = qlen; job.tlen = tlen; job.w = w; job.reserved = 0;
+	if (ksw_b200_global_batch(ctx, &cfg, 1, &job, query, target, &r, &pool, &total) != 0)
+		err_fatal(__func__, "GPU global alignment failed: %s", ksw_b200_strerror(ctx));
+	if (n_cigar_) *n_cigar_ = 0;
+	if (n_cigar_ && cigar_) {
+		uint32_t *out = (uint32_t *)malloc(4 * (size_t)(r.n_cigar > 0 ? r.n_cigar : 1));
+		for (k = 0; k < r.n_cigar; ++k) out[k] = pool[r.cigar_off + k];
+		*n_cigar_ = r.n_cigar; *cigar_ = out;
+	}
+	return r.score;
+}
+
+/* The jobs pass 2 will ask for, per region, predicted exactly the way mem_reg2aln + bwa_gen_cigar2 derive them. */
+typedef struct { int64_t rb, re; int qb, qe, w2, truesc, last_sc, read; } b200_cig_meta_t;
+typedef struct {
+	ksw_b200_gjob_t *jobs; b200_cig_meta_t *meta; int64_t n, m;
+	uint8_t *q, *t; size_t nq, mq, nt, mt;
+} b200_cig_batch_t;
+
+static void b200_cig_push(b200_cig_batch_t *B, const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const uint8_t *read,
+                          const b200_cig_meta_t *mt)
+{
+	/* bwa_gen_cigar2's prelude (bwa.c:95-126): window, strand reversal, band */
+	const int l_query = mt->qe - mt->qb;
+	int64_t rlen;
+	uint8_t *rseq;
+	int i, w, max_gap, max_ins, max_del, min_w;
+	if (l_query <= 0 || mt->rb >= mt->re || (mt->rb < bns->l_pac && mt->re > bns->l_pac)) return;
+	rseq = bns_get_seq(bns->l_pac, pac, mt->rb, mt->re, &rlen);
+	if (mt->re - mt->rb != rlen) { free(rseq); return; }
+	if (l_query == mt->re - mt->rb && mt->w2 == 0) { free(rseq); return; }          /* no DP in the reference either (bwa.c:110) */
+	max_ins = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_ins) / opt->e_ins + 1.);
+	max_del = (int)((double)(((l_query + 1) >> 1) * opt->mat[0] - opt->o_del) / opt->e_del + 1.);
+	max_gap = max_ins > max_del ? max_ins : max_del;
+	max_gap = max_gap > 1 ? max_gap : 1;
+	w = (max_gap + abs((int)rlen - l_query) + 1) >> 1;
+	w = w < mt->w2 ? w : mt->w2;
+	min_w = abs((int)rlen - l_query) + 3;
+	w = w > min_w ? w : min_w;
+	if (B->n == B->m) {
+		B->m = B->m ? B->m << 1 : 4096;
+		B->jobs = (ksw_b200_gjob_t *)realloc(B->jobs, sizeof(ksw_b200_gjob_t) * B->m);
+		B->meta = (b200_cig_meta_t *)realloc(B->meta, sizeof(b200_cig_meta_t) * B->m);
+	}
+	if (B->nq + l_query > B->mq) { B->mq = (B->mq ? B->mq << 1 : 1 << 20) + l_query; B->q = (uint8_t *)realloc(B->q, B->mq); }
+	if (B->nt + rlen > B->mt) { B->mt = (B->mt ? B->mt << 1 : 1 << 20) + rlen; B->t = (uint8_t *)realloc(B->t, B->mt); }
+	if (mt->rb >= bns->l_pac) {                      /* reverse both (bwa.c:103-108): indels end up left-aligned */
+		for (i = 0; i < l_query; ++i) B->q[B->nq + i] = read[mt->qb + l_query - 1 - i];
+		for (i = 0; i < rlen; ++i) B->t[B->nt + i] = rseq[rlen - 1 - i];
+	} else {
+		memcpy(B->q + B->nq, read + mt->qb, l_query);
+		memcpy(B->t + B->nt, rseq, rlen);
+	}
+	B->jobs[B->n].q_off = B->nq; B->jobs[B->n].t_off = B->nt;
+	B->jobs[B->n].qlen = l_query; B->jobs[B->n].tlen = (int)rlen; B->jobs[B->n].w = w; B->jobs[B->n].reserved = 0;
+	B->meta[B->n] = *mt;
+	B->nq += l_query; B->nt += rlen; ++B->n;
+	free(rseq);
+}
+
+static void b200_cig_lookahead(b200_thread_t *t, int tid, worker_t *w, int start, int batch_size)
+{
+	const mem_opt_t *opt = w->opt;
+	b200_cig_batch_t cur, nxt;
+	ksw_b200_cfg_t cfg;
+	ksw_b200_gres_t *res = 0;
+	int64_t m_res = 0;
+	int b, round;
+	size_t k;
+	memset(&cur, 0, sizeof(cur)); memset(&nxt, 0, sizeof(nxt));
+	memcpy(cfg.mat, opt->mat, 25);
+	cfg.m = 5; cfg.o_del = opt->o_del; cfg.e_del = opt->e_del; cfg.o_ins = opt->o_ins; cfg.e_ins = opt->e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
+	for (b = 0; b < batch_size; ++b) {
+		bseq1_t *s = &w->seqs[start + b];
+		const mem_alnreg_v *regs = &w->regs[start + b];
+		for (k = 0; k < regs->n; ++k) {
+			const mem_alnreg_t *ar = &regs->a[k];
+			b200_cig_meta_t mt;
+			int tmp, w2;
+			if (ar->rb < 0 || ar->re < 0 || ar->score < opt->T) continue;     /* never printed (bwamem.c:1015, bwamem_pair.c) */
+			mt.qb = ar->qb; mt.qe = ar->qe; mt.rb = ar->rb; mt.re = ar->re;
+			/* mem_reg2aln, bwamem.c:1183-1191 */
+			if (bwa_fix_xref2(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->w, w->bns, w->pac, (uint8_t *)s->seq,
+			                  &mt.qb, &mt.qe, &mt.rb, &mt.re) < 0) continue;
+			tmp = infer_bw(mt.qe - mt.qb, mt.re - mt.rb, ar->truesc, opt->a, opt->o_del, opt->e_del);
+			w2 = infer_bw(mt.qe - mt.qb, mt.re - mt.rb, ar->truesc, opt->a, opt->o_ins, opt->e_ins);
+			w2 = w2 > tmp ? w2 : tmp;
+			if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+			mt.w2 = w2; mt.truesc = ar->truesc; mt.last_sc = -(1 << 30); mt.read = start + b;
+			b200_cig_push(&cur, opt, w->bns, w->pac, (const uint8_t *)s->seq, &mt);
+		}
+	}
+	for (round = 0; round < 3 && cur.n > 0; ++round) {                           /* the do-while of bwamem.c:1194-1200 */
+		const uint32_t *pool = 0;
+		int64_t total = 0, j;
+		if (cur.n > m_res) { m_res = cur.n; res = (ksw_b200_gres_t *)realloc(res, sizeof(ksw_b200_gres_t) * m_res); }
+		if (ksw_b200_global_batch(t->ctx, &cfg, cur.n, cur.jobs, cur.q, cur.t, res, &pool, &total) != 0)
+			err_fatal(__func__, "GPU global alignment failed: %s", ksw_b200_strerror(t->ctx));
+		__sync_fetch_and_add(&b200_cig_jobs, cur.n);
+		nxt.n = 0; nxt.nq = 0; nxt.nt = 0;
+		for (j = 0; j < cur.n; ++j) {
+			const ksw_b200_gjob_t *g = &cur.jobs[j];
+			b200_cig_meta_t mt = cur.meta[j];
+			b200_cig_insert(tid, g->qlen, cur.q + g->q_off, g->tlen, cur.t + g->t_off, g->w, res[j].score, res[j].n_cigar, pool + res[j].cigar_off);
+			if (res[j].score == mt.last_sc) continue;                             /* bwamem.c:1198 */
+			mt.last_sc = res[j].score; mt.w2 <<= 1;
+			if (round + 1 < 3 && res[j].score < mt.truesc - opt->a)
+				b200_cig_push(&nxt, opt, w->bns, w->pac, (const uint8_t *)w->seqs[mt.read].seq, &mt);
+		}
+		{ b200_cig_batch_t x = cur; cur = nxt; nxt = x; }
+	}
+	free(cur.jobs); free(cur.meta); free(cur.q); free(cur.t);
+	free(nxt.jobs); free(nxt.meta); free(nxt.q); free(nxt.t);
+	free(res);
 }
 
 typedef struct { int handle; int short_ok; mem_alnreg_t short_reg; } b200_chain_state_t;
@@ -159,6 +395,11 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 	}
 	free(chn); free(cst);
 	b200_add_time(&b200_t_replay, realtime() - t1);
+	if (b200_cigar_on()) {
+		t1 = realtime();
+		b200_cig_lookahead(t, tid, w, start, batch_size);
+		b200_add_time(&b200_t_cigar, realtime() - t1);
+	}
 }
 
 void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed,
@@ -180,6 +421,7 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	w.opt = opt; w.bwt = bwt; w.bns = bns; w.pac = pac;
 	w.seqs = seqs; w.regs = regs; w.n_processed = n_processed;
 	w.pes = &pes[0];
+	if (b200_cigar_on()) b200_cig_reset();
 	kt_for_batch(opt->n_threads, worker1_b200, &w, n, batch);                       /* pass 1: extension on the GPU */
 	t_pass1 = realtime() - rtime;
 	if (opt->flag & MEM_F_PE) {
@@ -190,6 +432,8 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 	free(regs);
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec (extension on B200; thread-seconds so far: "
-		        "init %.2f, seed+chain %.2f, plan %.2f, gpu passes %.2f, replay %.2f; pass1 %.3f s real)\n", __func__, n,
-		        cputime() - ctime, realtime() - rtime, b200_t_init, b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, t_pass1);
+		        "init %.2f, seed+chain %.2f, plan %.2f, gpu passes %.2f, replay %.2f, cigar look-ahead %.2f; pass1 %.3f s real; "
+		        "global alignments so far: %lld computed ahead, %lld hits, %lld misses)\n", __func__, n,
+		        cputime() - ctime, realtime() - rtime, b200_t_init, b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, b200_t_cigar,
+		        t_pass1, b200_cig_jobs, b200_cig_hits, b200_cig_misses);
 }

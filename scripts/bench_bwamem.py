@@ -25,6 +25,16 @@ def chunk_times(err):
     return out
 
 
+def cigar_stats(err):
+    """(computed ahead, hits, misses) of the CIGAR look-ahead, from the glue's last chunk line."""
+    import re
+    m = None
+    for ln in err.splitlines():
+        x = re.search(r"global alignments so far: (\d+) computed ahead, (\d+) hits, (\d+) misses", ln)
+        m = x or m
+    return [int(v) for v in m.groups()] if m else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
@@ -57,6 +67,12 @@ def main():
             env = dict(os.environ, KSW_B200_SCHED=a.sched) if a.sched == "rounds" else None
             t_b200, e_b200 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)], env=env)
             ok, why = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200.sam"))
+            # the same build with the CIGAR look-ahead off (pass 2 entirely on the host, as before): isolates its effect
+            env0 = dict(env or os.environ, KSW_B200_CIGAR="0")
+            t_b200_0, e_b200_0 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200_0.sam"), a.threads, extra=["-b", str(a.batch)], env=env0)
+            ok0, _ = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200_0.sam"))
+            cb0 = chunk_times(e_b200_0)
+            sb0 = sum(r for r, _ in cb0[1:]) / max(sum(t for _, t in cb0[1:]), 1e-9) if len(cb0) > 1 else None
             cs, cb = chunk_times(e_stock), chunk_times(e_b200)
             # steady state = chunks after the first (the first B200 chunk pays CUDA context creation, which a real run
             # hides behind loading a GB-sized index)
@@ -66,7 +82,10 @@ def main():
                    "stock_reads_per_s": round(n_reads / t_stock), "b200_reads_per_s": round(n_reads / t_b200),
                    "stock_chunks": cs, "b200_chunks": cb,
                    "stock_steady_reads_per_s": round(ss) if ss else None, "b200_steady_reads_per_s": round(sb) if sb else None,
-                   "sam_identical_minus_PG": bool(ok)}
+                   "sam_identical_minus_PG": bool(ok),
+                   "cigar_lookahead": {"computed_ahead_hits_misses": cigar_stats(e_b200),
+                                       "off_wall_s": round(t_b200_0, 3), "off_steady_reads_per_s": round(sb0) if sb0 else None,
+                                       "off_sam_identical_minus_PG": bool(ok0)}}
             print(json.dumps(row), flush=True)
             rows.append(row)
     if a.out:
