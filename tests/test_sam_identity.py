@@ -2,6 +2,7 @@
 @PG line").  CPU: the harness itself (fork == stock, as SURVEY.md §0 found).  GPU: `bwa mem` with pass 1 bound to the
 B200 library (integration/bwamem_b200_glue.c) against stock 0.7.8, same -t, SE and PE, several -b / -t."""
 import os
+import re
 
 import pytest
 
@@ -71,6 +72,17 @@ def test_pe150_byte_identical(tmp_path):
     S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_rounds.sam"), threads=4, extra=["-b", "3000"], env=env)
     ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_rounds.sam"))
     assert ok, ("rounds", why)
+    # the CIGAR look-ahead (GPU ksw_global2 behind the reference's bwa_gen_cigar2) must have served pass 2 ...
+    err = S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_again.sam"), threads=4, extra=["-b", "3000"])
+    m = re.findall(r"global alignments so far: (\d+) computed ahead, (\d+) hits, (\d+) misses", err)
+    assert m, err[-500:]
+    ahead, hits, misses = (int(x) for x in m[-1])
+    assert ahead > 10000 and hits >= ahead * 0.9 and misses < ahead * 0.01, m[-1]    # (most 150 bp alignments need no DP at all: bwa.c:110)
+    # ... and switching it off (pass 2 entirely on the host, as in the reference) must give the same SAM
+    env = dict(os.environ, KSW_B200_CIGAR="0")
+    S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_nocig.sam"), threads=4, extra=["-b", "3000"], env=env)
+    ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_nocig.sam"))
+    assert ok, ("cigar look-ahead off", why)
 
 
 @pytest.mark.gpu
