@@ -160,11 +160,33 @@ def run_reference_arm(a):
         "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, torch.distributed
+    notices), at the C level as well, so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+    written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     a = parse()
+    capture_stdout()
     if a.impl == "reference":
         run_reference_arm(a)
         return
@@ -173,6 +195,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines ("NCCL version ...") go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist_
         torch.cuda.set_device(local)
@@ -316,7 +340,7 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -58,6 +58,8 @@ double now_ms()
 
 } // namespace
 
+#define KSW_N_SLOTS 3
+
 // ------------------------------------------------------------------ opaque types
 struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
 	int64_t n = 0, n_fast = 0, n_generic = 0;
@@ -97,7 +99,11 @@ struct ksw_b200_ctx {
 	int trace = 0;
 	int64_t launches = 0;
 	int64_t last_h2d = 0, last_d2h = 0;    // bytes moved by the last ksw_b200_extend_batch call
-	Slot slot[2];                           // slot[0] also serves upload / run / download of resident batches
+	// Pipeline slots of the one-shot entry; slot[0] also serves upload / run / download of resident batches.  Three, not
+	// two: a slot is reusable only after its chunk's results are back, and pack (3 ms) + H2D (2.5 ms) of the next chunk
+	// for that slot take longer than the other slot's kernel (3.7 ms per 2^20 config-2 jobs), so with two slots the GPU
+	// idled 2.4 ms per chunk.
+	Slot slot[KSW_N_SLOTS];
 	// banded global alignment (ksw_b200_global_batch): staging, device buffers, the CIGAR pool handed to the caller
 	PinnedBuf g_hjobs, g_hseq, g_hres, g_hcig;
 	DevBuf g_djobs, g_dseq, g_dres, g_dcig, g_dused, g_deh, g_dqc, g_dz;
@@ -328,7 +334,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	ksw_b200_ctx *ctx = new ksw_b200_ctx();
 	ctx->device = device;
 	cudaError_t e = cudaSetDevice(device);
-	for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
+	for (int i = 0; i < KSW_N_SLOTS && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -478,7 +484,7 @@ static int extend_batch_pipelined(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg
 	int64_t h2d = 0;
 	const int64_t chunk = ctx->chunk_jobs;
 	int which = 0;
-	for (int64_t first = 0; first < n; first += chunk, which ^= 1) {
+	for (int64_t first = 0; first < n; first += chunk, which = (which + 1) % KSW_N_SLOTS) {
 		const int64_t nc = std::min(chunk, n - first);
 		Slot &s = ctx->slot[which];
 		int rc = retire_slot(ctx, s, res, &t_wait);              // its staging and device buffers are about to be reused
@@ -492,9 +498,9 @@ static int extend_batch_pipelined(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg
 		s.busy = true; s.first = first; s.n = nc;
 		h2d += (int64_t)(sizeof(DevJob) * (size_t)nc + s.batch.pool_bytes + s.batch.npool_bytes);
 	}
-	// retire in submission order
-	for (int k = 0; k < 2; ++k) {
-		int rc = retire_slot(ctx, ctx->slot[which ^ k], res, &t_wait);
+	// retire in submission order (the oldest chunk in flight sits in the slot that would be used next)
+	for (int k = 0; k < KSW_N_SLOTS; ++k) {
+		int rc = retire_slot(ctx, ctx->slot[(which + k) % KSW_N_SLOTS], res, &t_wait);
 		if (rc) return rc;
 	}
 	ctx->last_h2d = h2d;
@@ -506,7 +512,7 @@ static int extend_batch_pipelined(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg
 }
 
 // One-shot batched entry.  The batch is cut into chunks of ctx->chunk_jobs jobs (caller order); chunk c+1 is
-// packed on the host threads while chunk c is being copied / computed on the GPU (two slots, two streams).
+// packed on the host threads while chunks c and c-1 are being copied / computed on the GPU (three slots, three streams).
 int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
                           const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
 {
