@@ -1,7 +1,7 @@
 // ksw_bin.cu — binning on the device.  The host packer only streams (DevJob[k] describes the caller's job k); here
 // a key is computed per job and (key, k) pairs are radix-sorted (cub::DeviceRadixSort, 16-bit keys), which yields the
 // order in which the extension kernels take the jobs:
-//     key = generic bit | fast class | 63 - rows/16 | 127 - h0/4
+//     key = generic bit | fast class | 63 - rows/16 | 127 - f(h0)   (f exact below 96, then in steps of 16)
 // fast classes first (one contiguous range per class, so a launch is a sub-range), then the generic jobs; inside a
 // class long jobs first (short tail at the end of a launch), then by carried-in score, which sets the band width.
 // A warp claims chunks of consecutive entries of this order, so the jobs it works on at any moment are alike.
@@ -20,7 +20,10 @@ ksw_bin_keys_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__re
 	const DevJob jb = jobs[k];
 	const uint32_t cls = (jb.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK;
 	const uint32_t tl = 63u - ((uint32_t)min(jb.tlen, 1008) >> 4);      // 6 bits
-	const uint32_t hb = 127u - ((uint32_t)min(jb.h0, 508) >> 2);        // 7 bits
+	// carried-in score: exact below 96 (seed scores and most left-extension scores), 16 per step above — it sets the
+	// band a job starts with, and the jobs of a warp finish their rows together only if their bands are alike
+	const uint32_t h0 = (uint32_t)jb.h0;
+	const uint32_t hb = 127u - (h0 < 96u ? h0 : 96u + min((h0 - 96u) >> 4, 31u));   // 7 bits
 	keys[k] = (uint16_t)((cls >= KSW_CLASS_GENERIC ? 0x8000u : (cls << 13)) | (tl << 7) | hb);
 	vals[k] = (uint32_t)k;
 }
