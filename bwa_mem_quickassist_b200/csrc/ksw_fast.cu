@@ -9,6 +9,7 @@
 // sweep bands of similar width.
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstdlib>
 #include "ksw_dev.cuh"
 #include "ksw_fast_core.h"
 #include "ksw_launch.h"
@@ -46,7 +47,7 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 	enum { IDLE = 0, RUN = 1, DONE = 2 };
 	int state = IDLE;
 
-	// Job supply: the warp takes CHUNK (32..256, chosen by the launcher: >= 16 chunks per warp) consecutive jobs of the binned list at a time (one atomicAdd per chunk) and its
+	// Job supply: the warp takes CHUNK (32 by default, see the launcher) consecutive jobs of the binned list at a time (one atomicAdd per chunk) and its
 	// lanes draw from that chunk, so the 32 jobs a warp works on at any moment are neighbours in the binned order
 	// (similar band width and length) even after the lanes have drifted apart in time.
 	const long long CHUNK = chunk;
@@ -146,10 +147,11 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 	if (blocks > need) blocks = need;
 	e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
 	if (e != cudaSuccess) return e;
-	// chunk of consecutive jobs a warp claims at once: large enough to keep a warp's jobs alike, small enough that every
-	// warp gets many chunks (load balance at the end of the launch)
-	long long chunk = n_jobs / (blocks * 16);
-	chunk = chunk < 32 ? 32 : (chunk > 256 ? 256 : (chunk / 32) * 32);
+	// consecutive jobs of the binned list a warp claims at once (one atomicAdd per claim).  Measured on config 2 with the
+	// exact-h0 binning key: 32 -> 14.33 ms, 128 -> 14.47, 256 -> 14.68, 1024 -> 15.65 per 4 M jobs: neighbours in the
+	// binned order are alike anyway, so the smallest claim (best load balance) wins.
+	long long chunk = 32;
+	if (const char *ev = getenv("KSW_B200_FAST_CHUNK")) chunk = atoi(ev) > 0 ? atoi(ev) : chunk;      // tuning knob
 	ksw_fast_kernel<KEYED><<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
 	                                                           KSW_FAST_QUADS(qmax), (int)chunk, counter, order, res, cells);
 	return cudaGetLastError();

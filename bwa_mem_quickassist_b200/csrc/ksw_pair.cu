@@ -146,10 +146,8 @@ cudaError_t ksw_launch_pair(const DevJob *jobs, int64_t n_jobs, const uint32_t *
 	const size_t smem = ksw_pair_smem_bytes(qmax, n_warps);
 	e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
 	if (e != cudaSuccess) return e;
-	// chunk of consecutive jobs a warp claims at once: large enough to keep a warp's 64 jobs alike, small enough that
-	// every warp gets many chunks (load balance at the end of the launch)
-	long long chunk = n_jobs / (blocks * n_warps * 16);
-	chunk = chunk < 64 ? 64 : (chunk > 512 ? 512 : (chunk / 64) * 64);
+	// consecutive jobs a warp claims at once: one round of its 64 slots (see ksw_fast.cu: small claims balance best)
+	long long chunk = 64;
 	ksw_pair_kernel<<<(unsigned)blocks, T * n_warps, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P, KSW_PAIR_COLPAIRS(qmax),
 	                                                    (int)chunk, counter, order, res, cells);
 	return cudaGetLastError();
