@@ -142,6 +142,7 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_fast_kernel<KEYED>, T, smem);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	if (const char *ev = getenv("KSW_B200_FAST_CTAS")) per_sm = atoi(ev) > 0 && atoi(ev) < per_sm ? atoi(ev) : per_sm;   // tuning knob
 	long long blocks = (long long)sm_count * per_sm;
 	const long long need = (n_jobs + T - 1) / T;
 	if (blocks > need) blocks = need;
