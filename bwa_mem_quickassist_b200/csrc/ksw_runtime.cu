@@ -635,7 +635,9 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		const int64_t m = last - first;
 		const long long zcap = zmax + qmax + 2;
 		// threads: bounded by the direction-matrix slab; every thread owns one column set and one z slab
-		size_t threads = (size_t)ctx->sm_count * 8 * KSW_GENERIC_THREADS;
+		int bps = 4;                                        // blocks per SM: 4 keeps the H/E slabs of a 150 bp batch inside L2
+		if (const char *ev = getenv("KSW_B200_GLOBAL_BPS")) bps = std::max(1, atoi(ev));     // tuning knob
+		size_t threads = (size_t)ctx->sm_count * bps * KSW_GENERIC_THREADS;
 		while (threads > KSW_GENERIC_THREADS && threads * (size_t)zcap > z_budget) threads >>= 1;
 		threads = std::min<size_t>(threads, (size_t)((m + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS) * KSW_GENERIC_THREADS);
 		const int n_blocks = (int)(threads / KSW_GENERIC_THREADS);
