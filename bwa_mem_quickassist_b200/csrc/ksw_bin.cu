@@ -1,7 +1,7 @@
 // ksw_bin.cu — binning on the device.  The host packer only streams (DevJob[k] describes the caller's job k); here
 // a key is computed per job and (key, k) pairs are radix-sorted (cub::DeviceRadixSort, 16-bit keys), which yields the
 // order in which the extension kernels take the jobs:
-//     key = generic bit | fast class | 63 - rows/16 | 127 - f(h0)   (f exact below 96, then in steps of 16)
+//     key = generic bit | fast class | 63 - g(qlen) | 127 - f(h0)   (f exact below 96, then in steps of 16)
 // fast classes first (one contiguous range per class, so a launch is a sub-range), then the generic jobs; inside a
 // class long jobs first (short tail at the end of a launch), then by carried-in score, which sets the band width.
 // A warp claims chunks of consecutive entries of this order, so the jobs it works on at any moment are alike.
@@ -19,7 +19,11 @@ ksw_bin_keys_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__re
 	if (k >= n) return;
 	const DevJob jb = jobs[k];
 	const uint32_t cls = (jb.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK;
-	const uint32_t tl = 63u - ((uint32_t)min(jb.tlen, 1008) >> 4);      // 6 bits
+	// query length (6 bits; steps of 2 / 2 / 4 / 8 columns for the four classes): the band of a row is capped by it, and
+	// the lanes of a warp wait for the widest band in every row.  (It replaced the row count tlen/16: how long a job
+	// lasts does not matter, a lane draws its next job as soon as it is done.  Real bwa mem mix, PE150: lanes busy in
+	// the interior loop 62 % -> see DESIGN.md §7.)
+	const uint32_t tl = 63u - min((uint32_t)jb.qlen >> (cls >= 3u ? 3 : (cls == 2u ? 2 : 1)), 63u);
 	// carried-in score: exact below 96 (seed scores and most left-extension scores), 16 per step above — it sets the
 	// band a job starts with, and the jobs of a warp finish their rows together only if their bands are alike
 	const uint32_t h0 = (uint32_t)jb.h0;

@@ -75,15 +75,38 @@ static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bn
 	return t;
 }
 
-/* CUDA context creation costs seconds on a large GPU; start it while `bwa mem` is still loading the index.
- * (glibc passes argc/argv to constructors.) */
+/* CUDA context creation costs seconds on a large GPU, and so does the first launch of every kernel; start both while
+ * `bwa mem` is still loading the index and parsing the first chunk of reads.  (glibc passes argc/argv to constructors.) */
 static void *b200_warmup_thread(void *arg)
 {
 	int d, n = ksw_b200_device_count();
 	(void)arg;
 	for (d = 0; d < n; ++d) {
 		ksw_b200_ctx_t *c = 0;
-		if (ksw_b200_ctx_create(d, &c) == 0) ksw_b200_ctx_destroy(c);
+		if (ksw_b200_ctx_create(d, &c) != 0) continue;
+		{
+			/* one job per kernel (keyed, unkeyed, generic; binning; global alignment): with lazy module loading the first
+			 * launch of every kernel costs tens of milliseconds, and 16 workers would queue up behind it in their first batch */
+			static const int qlens[3] = {20, 200, 600};
+			uint8_t seq[600];
+			ksw_b200_cfg_t cfg;
+			ksw_b200_job_t jobs[3];
+			ksw_b200_res_t res[3];
+			ksw_b200_gjob_t gj;
+			ksw_b200_gres_t gr;
+			const uint32_t *pool;
+			int64_t total;
+			int i;
+			for (i = 0; i < 600; ++i) seq[i] = (uint8_t)((i * 7 + i / 5) & 3);
+			memset(&cfg, 0, sizeof(cfg));
+			bwa_fill_scmat(1, 4, cfg.mat);
+			cfg.m = 5; cfg.o_del = cfg.o_ins = 6; cfg.e_del = cfg.e_ins = 1; cfg.zdrop = 100; cfg.end_bonus = 5;
+			for (i = 0; i < 3; ++i) { jobs[i].q_off = 0; jobs[i].t_off = 0; jobs[i].qlen = qlens[i]; jobs[i].tlen = qlens[i]; jobs[i].h0 = 19; jobs[i].w = 100; }
+			ksw_b200_extend_batch(c, &cfg, 3, jobs, seq, seq, res);
+			gj.q_off = gj.t_off = 0; gj.qlen = gj.tlen = 100; gj.w = 10; gj.reserved = 0;
+			ksw_b200_global_batch(c, &cfg, 1, &gj, seq, seq, &gr, &pool, &total);
+		}
+		ksw_b200_ctx_destroy(c);
 	}
 	return 0;
 }

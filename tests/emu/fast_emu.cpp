@@ -98,7 +98,7 @@ extern "C" int ksw_pair_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 	if ((int64_t)list.size() != st.class_n[0]) return 77;            // the packer's class counts must match the flags
 	if (order == 1)
 		std::stable_sort(list.begin(), list.end(), [&](uint32_t a, uint32_t b) {
-			auto key = [&](const DevJob &j) { return ((63u - ((uint32_t)std::min(j.tlen, 1008) >> 4)) << 7) | (127u - ((uint32_t)j.h0 < 96u ? (uint32_t)j.h0 : 96u + std::min(((uint32_t)j.h0 - 96u) >> 4, 31u))); };
+			auto key = [&](const DevJob &j) { return ((63u - std::min((uint32_t)j.qlen >> 1, 63u)) << 7) | (127u - ((uint32_t)j.h0 < 96u ? (uint32_t)j.h0 : 96u + std::min(((uint32_t)j.h0 - 96u) >> 4, 31u))); };
 			return key(dj[a]) < key(dj[b]);
 		});
 	if (n_pair_out) *n_pair_out = (int64_t)list.size();
