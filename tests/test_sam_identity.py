@@ -53,6 +53,11 @@ def test_se100_config1_byte_identical(tmp_path):
         S.bwa_mem(S.BWA_B200, fa, [fq], out, threads=thr, extra=extra)
         ok, why = S.sam_equal(str(tmp_path / ("stock.sam" if thr == 4 else "stock_t.sam")), out)
         assert ok, (tag, why)
+    # the opt-in pair kernel (two jobs per lane) must give the same SAM
+    out = str(tmp_path / "b200_pair.sam")
+    S.bwa_mem(S.BWA_B200, fa, [fq], out, threads=4, extra=["-b", "20000"], env=dict(os.environ, KSW_B200_PAIR="1"))
+    ok, why = S.sam_equal(str(tmp_path / "stock.sam"), out)
+    assert ok, ("pair kernel", why)
 
 
 @pytest.mark.gpu
