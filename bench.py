@@ -330,13 +330,13 @@ def main():
             "gpu_launches": int(kernel_launches),
             "roofline": {"bound": "dpx_issue", "achieved": per_gpu_gcups, "peak": peak_gcups, "unit": "GCUPS/GPU",
                          "frac": per_gpu_gcups / peak_gcups,
-                         # DRAM bytes per launch: ncu --set full of the same kernel on 400 k jobs measured 103.8 B/job
-                         # (profiles/r1_ncu_fast_kernel_summary.txt: 40.69 MB read + 0.83 MB write), scaled to this launch
-                         "traffic": 103.8 * n, "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum, 400k-job capture, per job x jobs",
+                         # DRAM bytes per launch: ncu --set full of the same kernel on 400 k jobs measured 105.5 B/job
+                         # (profiles/r1_ncu_fast_kernel_summary.txt: 40.80 MB read + 1.39 MB write), scaled to this launch
+                         "traffic": 105.5 * n, "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum, 400k-job capture, per job x jobs",
                          "peak_source": f"live DPX probe: {lane_ops / 1e12:.2f} T lane-ops/s x 2 cells / 8 issue slots "
                                         "(SURVEY.md 8d); not in MEASURED_PEAKS.json"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes * a.steps / t_dev / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes * a.steps / t_dev / 1e9 / hbm_peak, "traffic": 103.8 * n,
+                             "frac": alg_bytes * a.steps / t_dev / 1e9 / hbm_peak, "traffic": 105.5 * n,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
         }
