@@ -105,3 +105,31 @@ def test_gpu_global_empty_batch_and_scalar_dropin(gpu_ctx, oracle_built):
         sc, got = B.ksw_global2(int(j["qlen"]), q, int(j["tlen"]), t, 5, K.cfg_mat(b.cfg), b.cfg.o_del, b.cfg.e_del,
                                 b.cfg.o_ins, b.cfg.e_ins, int(j["w"]))
         assert sc == int(want_res["score"][k]) and tuple(int(x) for x in got) == cig
+
+
+def _degenerate_batch():
+    """Empty query or empty target, single bases, w = 0 on equal lengths: the band still holds the end cell."""
+    rng = np.random.default_rng(9)
+    shapes = [(0, 0, 0), (0, 5, 5), (5, 0, 5), (1, 1, 0), (1, 1, 3), (7, 7, 0), (1, 9, 8), (9, 1, 8), (3, 3, 50), (0, 1, 1), (1, 0, 1)]
+    qs, ts = [], []
+    jobs = np.zeros(len(shapes), dtype=K.GJOB_DT)
+    qo = to = 0
+    for k, (ql, tl, w) in enumerate(shapes):
+        qs.append(rng.integers(0, 4, ql).astype(np.uint8)); ts.append(rng.integers(0, 4, tl).astype(np.uint8))
+        jobs[k] = (qo, to, ql, tl, w, 0)
+        qo += ql; to += tl
+    return K.GBatch(K.make_cfg(), jobs, np.concatenate(qs + [np.zeros(1, np.uint8)]), np.concatenate(ts + [np.zeros(1, np.uint8)]))
+
+
+def test_global_degenerate_shapes_oracle_vs_reference(oracle_built):
+    if not K.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    b = _degenerate_batch()
+    assert K.global_mismatch(K.run_global_oracle(b, threads=1), K.run_global_ref(b, threads=1)) is None
+
+
+@pytest.mark.gpu
+def test_gpu_global_degenerate_shapes(gpu_ctx, oracle_built):
+    b = _degenerate_batch()
+    mm = K.global_mismatch(gpu_ctx.global_batch(b.cfg, b.jobs, b.qpool, b.tpool), K.run_global_oracle(b, threads=1))
+    assert mm is None, mm
