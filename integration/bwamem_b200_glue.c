@@ -194,7 +194,11 @@ static void b200_cig_insert(int tid, int qlen, const uint8_t *q, int tlen, const
 int b200_global2_hook(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
                       int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar_, uint32_t **cigar_)
 {
-	static __thread ksw_b200_ctx_t *ctx;                 /* only for misses */
+	/* only for misses, which are rare: one context for the whole process behind a mutex (kt_for starts fresh threads for
+	 * every chunk, so thread-local contexts would pile up) */
+	static ksw_b200_ctx_t *ctx;
+	static pthread_mutex_t miss_mu = PTHREAD_MUTEX_INITIALIZER;
+	int score;
 	ksw_b200_cfg_t cfg;
 	ksw_b200_gjob_t job;
 	ksw_b200_gres_t r;
@@ -222,6 +226,7 @@ int b200_global2_hook(int qlen, const uint8_t *query, int tlen, const uint8_t *t
 	}
 	/* miss: one job on the GPU (there is no CPU fallback in this mode) */
 	__sync_fetch_and_add(&b200_cig_misses, 1);
+	pthread_mutex_lock(&miss_mu);
 	if (!ctx) {
 		if (b200_n_gpus < 0) b200_n_gpus = ksw_b200_device_count();
 		if (b200_n_gpus < 1 || ksw_b200_ctx_create(0, &ctx) != 0) err_fatal(__func__, "no usable CUDA device");
@@ -237,7 +242,9 @@ int b200_global2_hook(int qlen, const uint8_t *query, int tlen, const uint8_t *t
 		for (k = 0; k < r.n_cigar; ++k) out[k] = pool[r.cigar_off + k];
 		*n_cigar_ = r.n_cigar; *cigar_ = out;
 	}
-	return r.score;
+	score = r.score;
+	pthread_mutex_unlock(&miss_mu);
+	return score;
 }
 
 /* The jobs pass 2 will ask for, per region, predicted exactly the way mem_reg2aln + bwa_gen_cigar2 derive them. */
