@@ -135,12 +135,16 @@ static b200_arena_t b200_cig_arena[B200_MAX_WORKERS];
 static long long b200_cig_hits, b200_cig_misses, b200_cig_jobs;
 static double b200_t_cigar;
 
-static int b200_cigar_on(void)
+/* KSW_B200_CIGAR: unset/1 = look-ahead in pass 1 + table (default); 0 = off, pass 2 entirely the reference's (its own
+ * ksw_global2); 2 = no look-ahead but the redirected call stays: every look-up misses and goes to the GPU one job at a
+ * time (slow; it exists to test the miss path) */
+static int b200_cigar_mode(void)
 {
 	static int v = -1;
-	if (v < 0) { const char *e = getenv("KSW_B200_CIGAR"); v = (e && e[0] == '0') ? 0 : 1; }
+	if (v < 0) { const char *e = getenv("KSW_B200_CIGAR"); v = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }
 	return v;
 }
+static int b200_cigar_on(void) { return b200_cigar_mode() != 0; }
 
 static void *b200_arena_alloc(b200_arena_t *a, size_t n)
 {
@@ -425,7 +429,7 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 	}
 	free(chn); free(cst);
 	b200_add_time(&b200_t_replay, realtime() - t1);
-	if (b200_cigar_on()) {
+	if (b200_cigar_mode() == 1) {
 		t1 = realtime();
 		b200_cig_lookahead(t, tid, w, start, batch_size);
 		b200_add_time(&b200_t_cigar, realtime() - t1);

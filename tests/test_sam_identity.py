@@ -53,6 +53,16 @@ def test_se100_config1_byte_identical(tmp_path):
         S.bwa_mem(S.BWA_B200, fa, [fq], out, threads=thr, extra=extra)
         ok, why = S.sam_equal(str(tmp_path / ("stock.sam" if thr == 4 else "stock_t.sam")), out)
         assert ok, (tag, why)
+    # every CIGAR through the miss path of the redirected ksw_global2 call (one GPU job per look-up): same SAM
+    fq_small = str(tmp_path / "small.fq")
+    with open(fq, "rb") as src, open(fq_small, "wb") as dst:
+        dst.writelines(src.readlines()[:4 * 3000])
+    S.bwa_mem(S.BWA_STOCK, fa, [fq_small], str(tmp_path / "stock_small.sam"), threads=4)
+    err = S.bwa_mem(S.BWA_B200, fa, [fq_small], str(tmp_path / "b200_miss.sam"), threads=4, env=dict(os.environ, KSW_B200_CIGAR="2"))
+    ok, why = S.sam_equal(str(tmp_path / "stock_small.sam"), str(tmp_path / "b200_miss.sam"))
+    assert ok, ("miss path", why)
+    m = re.findall(r"global alignments so far: (\d+) computed ahead, (\d+) hits, (\d+) misses", err)
+    assert m and int(m[-1][0]) == 0 and int(m[-1][1]) == 0 and int(m[-1][2]) > 300, m
     # the opt-in pair kernel (two jobs per lane) must give the same SAM
     out = str(tmp_path / "b200_pair.sam")
     S.bwa_mem(S.BWA_B200, fa, [fq], out, threads=4, extra=["-b", "20000"], env=dict(os.environ, KSW_B200_PAIR="1"))
