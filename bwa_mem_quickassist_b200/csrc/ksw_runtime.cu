@@ -654,13 +654,26 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		CU(ctx->g_dz.reserve(threads * (size_t)zcap));
 		DevGJob *hj = (DevGJob *)ctx->g_hjobs.p;
 		uint8_t *hs = (uint8_t *)ctx->g_hseq.p;
-		size_t off = 0;
-		for (int64_t k = 0; k < m; ++k) {
-			const ksw_b200_gjob_t &j = jobs[first + k];
-			hj[k].seq_off = off; hj[k].qlen = j.qlen; hj[k].tlen = j.tlen; hj[k].w = j.w; hj[k].idx = (uint32_t)k;
-			if (j.qlen) memcpy(hs + off, qpool + j.q_off, (size_t)j.qlen);
-			if (j.tlen) memcpy(hs + off + j.qlen, tpool + j.t_off, (size_t)j.tlen);
-			off += (size_t)j.qlen + (size_t)j.tlen;
+		{
+			// records (a running offset: serial, cheap), then the sequence bytes on the pack threads
+			size_t off = 0;
+			for (int64_t k = 0; k < m; ++k) {
+				const ksw_b200_gjob_t &j = jobs[first + k];
+				hj[k].seq_off = off; hj[k].qlen = j.qlen; hj[k].tlen = j.tlen; hj[k].w = j.w; hj[k].idx = (uint32_t)k;
+				off += (size_t)j.qlen + (size_t)j.tlen;
+			}
+			KswPool *tp = pool_of(ctx);
+			const int T = (int)std::max<int64_t>(1, std::min<int64_t>(tp->size(), m / 4096));
+			const int64_t per = (m + T - 1) / T;
+			auto body = [&](int t) {
+				const int64_t b = std::min<int64_t>(m, t * per), e = std::min<int64_t>(m, b + per);
+				for (int64_t k = b; k < e; ++k) {
+					const ksw_b200_gjob_t &j = jobs[first + k];
+					if (j.qlen) memcpy(hs + hj[k].seq_off, qpool + j.q_off, (size_t)j.qlen);
+					if (j.tlen) memcpy(hs + hj[k].seq_off + j.qlen, tpool + j.t_off, (size_t)j.tlen);
+				}
+			};
+			if (T == 1) body(0); else tp->run(T, body);
 		}
 		CU(cudaMemcpyAsync(ctx->g_djobs.p, hj, sizeof(DevGJob) * (size_t)m, cudaMemcpyHostToDevice, s.stream));
 		if (seq_bytes) CU(cudaMemcpyAsync(ctx->g_dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, s.stream));
