@@ -14,6 +14,9 @@
  *     follows the fork's own, unused, accelerator sketch ext_param_t /
  *     ext_res_t (bwamem.c:553-577) but is per *side*, because the right
  *     extension's h0 is the left extension's score (bwamem.c:842,854).
+ *   - ksw_global / ksw_global2 (ksw.h:83-84, the CIGAR generator behind
+ *     bwa_gen_cigar2, bwa.c:132) and their batched form ksw_b200_global_batch:
+ *     banded global alignment with backtrace, SURVEY.md §8(f) rank 2.
  *
  * Plain C types only; no CUDA or torch types cross this boundary.
  * All functions return 0 on success and a non-zero code on a CUDA/usage error
