@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--sched", default="speculate", choices=["speculate", "rounds"], help="KSW_B200_SCHED of the B200-bound build")
     ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="substring of the config name to run alone (e.g. PE150)")
+    ap.add_argument("--genome", type=int, default=0, help="override the genome length of the selected configs (bp)")
     a = ap.parse_args()
     sc = a.scale
     cfgs = [
@@ -49,6 +51,10 @@ def main():
         ("config3-shape PE150 (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(1_500_000 * sc), L=150, sub=0.01, indel=0.001, imax=1)),
         ("config4-shape PE250 high-indel (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(600_000 * sc), L=250, sub=0.03, indel=0.002, imax=12)),
     ]
+    if a.only:
+        cfgs = [(n, c) for n, c in cfgs if a.only in n]
+    if a.genome:
+        cfgs = [(n.replace("10 Mbp", f"{a.genome / 1e6:.0f} Mbp"), dict(c, genome=a.genome)) for n, c in cfgs]
     rows = []
     with tempfile.TemporaryDirectory() as d:
         for name, c in cfgs:
