@@ -39,7 +39,7 @@ ksw_pair_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 	KswFastConst K;
 	ksw_fast_make_const(P, K);
 	const KswPairMem<T> M{he + lane, sq + lane};
-	KswFastLane L[2];
+	KswFastLane L[2] = {};                                          // (the row code reads both slots' scalars before it masks)
 	unsigned run = 0;                                               // bit X: slot X holds a running job
 	unsigned dead = 0;                                              // bit X: slot X will get no more jobs
 

@@ -112,7 +112,7 @@ extern "C" int ksw_pair_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 		for (auto &v : he) v.x = v.y = v.z = v.w = 0x5a5a5a5au;  // stale garbage, as on the GPU
 		for (auto &v : sq) v = 0xa5a5a5a5u;
 		KswPairMem<1> M{he.data(), sq.data()};
-		KswFastLane L[2];
+		KswFastLane L[2] = {};
 		unsigned run = 0;
 		const size_t end = ln + 1 == lanes ? list.size() : std::min(list.size(), next + (list.size() + lanes - 1) / lanes);
 		while (true) {
