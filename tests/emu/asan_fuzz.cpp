@@ -1,4 +1,4 @@
-// tests/emu/asan_fuzz.cpp — TEST INFRASTRUCTURE.  The packer and the fast kernel's per-lane source compiled for the
+// tests/emu/asan_fuzz.cpp — TEST INFRASTRUCTURE.  The packer and the per-lane sources of both s16x2 kernels (one job per lane, two jobs per lane) compiled for the
 // CPU with AddressSanitizer + UBSan, every shared-memory array allocated at exactly the size the launcher gives the
 // kernel, random jobs checked against the oracle.  (compute-sanitizer is not available on the GPU pool; this finds
 // out-of-bounds accesses and undefined shifts in the same source on the host.)
@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../bwa_mem_quickassist_b200/csrc/ksw_pack.h"
 #include "../../bwa_mem_quickassist_b200/csrc/ksw_fast_core.h"
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_pair_core.h"
 
 extern "C" int ksw_oracle_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
                                   int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
@@ -85,6 +86,45 @@ int main(int argc, char **argv)
 			if (bad++ < 5) fprintf(stderr, "mismatch job %u: qlen %d tlen %d h0 %d w %d\n", jb.idx, j.qlen, j.tlen, j.h0, j.w);
 		}
 	}
-	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %d mismatches\n", n, n_fast, n_keyed, bad);
+	// the pair kernel's lane (two jobs per lane) over the class-0 jobs, arrays at exactly the launcher's size
+	long long n_pair = 0;
+	{
+		std::vector<uint32_t> list;
+		int qmax = 1;
+		for (int64_t p = 0; p < n; ++p)
+			if (((dj[p].flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u) { list.push_back((uint32_t)p); qmax = std::max(qmax, dj[p].qlen); }
+		const int np = KSW_PAIR_COLPAIRS(qmax);                     // what ksw_pair_smem_bytes() reserves per lane
+		std::vector<ksw_u4> he(np);
+		std::vector<uint32_t> sq(np);
+		KswPairMem<1> PM{he.data(), sq.data()};
+		KswFastLane L[2] = {};
+		unsigned run = 0;
+		size_t next = 0;
+		while (true) {
+			for (int X = 0; X < 2; ++X) {
+				if (((run >> X) & 1u) || next >= list.size()) continue;
+				const DevJob &jb = dj[list[next++]];
+				ksw_pair_setup<1>(he.data(), sq.data(), 0, X, 0, 1, K, jb.seq_off, jb.qlen, jb.h0, pool.data());
+				ksw_fast_init_lane(L[X], jb, pool.data(), nmask.empty() ? nullptr : nmask.data());
+				run |= 1u << X;
+			}
+			if (!run) break;
+			const unsigned fin = ksw_pair_row<1>(L, run, PM, K, mrow);
+			for (int X = 0; X < 2; ++X) {
+				if (!((fin >> X) & 1u)) continue;
+				DevRes r; ksw_fast_result(L[X], r);
+				const ksw_b200_job_t &j = jobs[L[X].idx];
+				int qle, tle, gtle, gscore, max_off;
+				const int sc = ksw_oracle_extend2(j.qlen, qpool.data() + j.q_off, j.tlen, tpool.data() + j.t_off, 5, cfg.mat, cfg.o_del, cfg.e_del,
+				                                  cfg.o_ins, cfg.e_ins, j.w, cfg.end_bonus, cfg.zdrop, j.h0, &qle, &tle, &gtle, &gscore, &max_off, nullptr, nullptr);
+				if (sc != r.score || qle != r.qle || tle != r.tle || gtle != r.gtle || gscore != r.gscore || max_off != r.max_off) {
+					if (bad++ < 5) fprintf(stderr, "pair mismatch job %u: qlen %d tlen %d h0 %d w %d\n", L[X].idx, j.qlen, j.tlen, j.h0, j.w);
+				}
+				++n_pair;
+				run &= ~(1u << X);
+			}
+		}
+	}
+	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %lld through the pair lane, %d mismatches\n", n, n_fast, n_keyed, n_pair, bad);
 	return bad ? 1 : 0;
 }
