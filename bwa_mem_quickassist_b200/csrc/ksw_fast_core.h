@@ -6,26 +6,34 @@
 // One extension job per lane, semantics of bwa-0.7.8/ksw.c:379-476 row by row, but the cells of
 // a row are computed four columns at a time in two s16x2 registers with the DPX instructions:
 //
-//   quad q = columns 4q..4q+3 = pair A (lo half = c0, hi half = c1) and pair B (lo = c3, hi = c2).
-//   The B pair is stored half-swapped so that the serial F chain  c0 -> c1 -> c2 -> c3 -> c0'
-//   walks lo -> hi -> hi -> lo -> lo' and never needs a shift between pairs.
+//   quad q = columns c0..c3 = 4q..4q+3 = pair A (lo half = c0, hi half = c2) and pair B (lo = c1, hi = c3).
+//   With this interleaving the serial F chain c0 -> c1 -> c2 -> c3 -> c0' stays inside one half for two steps
+//   (lo: c0 -> c1 -> c2, hi: c2 -> c3 -> c0'), and the two moves between the halves are whole-half moves that
+//   integer multiply-adds do on the FMA pipe (x * 65536 + y, x >> 16 as a multiply-high), so the chain costs
+//   four DPX instructions per quad and no byte permutes on the ALU pipe.
 //
-//   per pair:  score  = PRMT(matrow, selector)                       1 ALU   (sign-extending byte lookup)
-//              h'     = VIADDMNMX.S16x2(Hdiag, score, E)             H(i-1,j-1)+S vs E(i,j)      ksw.c:430-431
-//              g      = VIADDMNMX.S16x2.RELU(h', -oe_ins, 0)
-//              F      : 2 x VIADDMNMX.S16x2 + 1 PRMT                 F(j+1) = max(F(j)-e_ins, g(j))   (*)
-//              h      = VIMNMX.S16x2(h', F)                                                      ksw.c:432
-//              E'     = VIMNMX3.S16x2(E - e_del, h - oe_del, 0): ONE ALU-pipe op; the two subtractions are plain
-//                       32-bit IADDs that the compiler places on the FMA pipe.  They are borrow-free because every
-//                       H/E/F value is kept with a constant bias B = o_del+e_del in both halves (B instead of 0 is
-//                       the floor of all the max() clamps)                                        ksw.c:436-439
-//              (m,mj) : KEYED jobs (qlen <= 124, scores < 512): key = h*128 + column (1 IMAD on the FMA pipe),
-//                       VIMNMX.U16x2 on the keys — the larger column wins ties, as in the reference;
-//                       other jobs: VIMNMX.S16x2 with predicate outputs + 2 predicated index moves   ksw.c:434-435
-//              zero?  : VIMNMX3.S16x2 min over the row (1 per quad)  feeds the band trim        ksw.c:463-466
-//   (*) the reference computes F(j+1) = max(F(j)-e_ins, max(H(j)-oe_ins,0)) with H = max(h',F);
-//       since o_ins >= 0 implies F-oe_ins <= F-e_ins this equals max(F(j)-e_ins, h'(j)-oe_ins, 0)
-//       in exact integer arithmetic (jobs with o_ins < 0 are routed to the generic kernel).
+//   per quad:  score   = PRMT(matrow, selector)                     2 ALU   (sign-extending byte lookup)
+//              h'      = VIADDMNMX.S16x2(Hdiag, score, E)           2 ALU   H(i-1,j-1)+S vs E(i,j)      ksw.c:430-431
+//              Fs      : 4 x VIADDMNMX.S16x2 + 2 IMAD               4 ALU   Fs(j+1) = max(Fs(j)-e_ins, h'(j))   (*)
+//              h       = VIADDMNMX.S16x2(Fs, -oe_ins, h')           2 ALU                               ksw.c:432
+//              E'      = VIMNMX3.S16x2(E - e_del, h - oe_del, 0)    2 ALU   the two subtractions are plain 32-bit IADDs
+//                        that the compiler places on the FMA pipe.  They are borrow-free because every H/E/F
+//                        value is kept with a constant bias B = o_del+e_del in both halves (B instead of 0 is
+//                        the floor of all the max() clamps)                                     ksw.c:436-439
+//              (m,mj)  : KEYED jobs (qlen <= 124, scores < 512): key = h*128 + column relative to the current quad
+//                        (1 IMAD per pair on the FMA pipe), m = VIADDMNMX.U16x2(m, -4, keyA), m = VIMNMX.U16x2(m, keyB)
+//                        — the running maximum is moved back by four columns per quad instead of the column counters
+//                        being moved forward; the larger column wins ties, as in the reference;
+//                        other jobs: VIMNMX.S16x2 with predicate outputs + 2 predicated index moves   ksw.c:434-435
+//              zero?   : VIMNMX3.S16x2 min over the row (1 per quad)  feeds the band trim        ksw.c:463-466
+//              store   : eh[j].h = H(i,j-1) is pair A' = (H(c0-1), H(c1)) = one funnel shift of (previous hB, hB), and
+//                        pair B' = (H(c0), H(c2)) = hA as it is
+//   (*) Fs = F + oe_ins, WITHOUT the reference's floor at 0: the reference computes
+//       F(j+1) = max(F(j)-e_ins, max(H(j)-oe_ins,0)) with H = max(h',F).  Since o_ins >= 0 implies F-oe_ins <= F-e_ins,
+//       that equals max(F(j)-e_ins, h'(j)-oe_ins, 0).  Dropping the floor gives F~ <= F with max(F~,0) = F by induction
+//       (if F~(j) < 0 = F(j) then F~(j)-e_ins < 0, so max(F~(j+1),0) = max(h'(j)-oe_ins,0) = F(j+1)), and F is only ever
+//       used through max(h', F) with h' >= E >= 0, so H and E are unchanged; F~ >= min h' - oe_ins is bounded below.
+//       (jobs with o_ins < 0 are routed to the generic kernel).
 //
 // Band edges that are not multiples of four are handled by "phantom" columns: their inputs are
 // forced to (H = -8192, E = 0) so that they produce h = 0 on the left of the band and a decaying F
@@ -52,6 +60,7 @@ __device__ __forceinline__ uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) 
 __device__ __forceinline__ uint32_t addmax2_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 __device__ __forceinline__ uint32_t maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+__device__ __forceinline__ uint32_t addmaxu2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); }
 __device__ __forceinline__ uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo) { return __vibmax_s16x2(a, b, &ge_hi, &ge_lo); }
@@ -81,6 +90,11 @@ KSW_EMU uint32_t maxu2(uint32_t a, uint32_t b)
 {
 	const uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
 	return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+}
+KSW_EMU uint32_t addmaxu2(uint32_t a, uint32_t b, uint32_t c)   // max(a + b, c) per unsigned half, the sum wraps mod 2^16
+{
+	const uint32_t sl = (a + b) & 0xffffu, sh = ((a >> 16) + (b >> 16)) & 0xffffu, cl = c & 0xffffu, ch = c >> 16;
+	return (sl > cl ? sl : cl) | ((sh > ch ? sh : ch) << 16);
 }
 KSW_EMU uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -112,12 +126,22 @@ KSW_EMU uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)   // PTX prmt.b32, gen
 } // namespace kswdpx
 
 // ----------------------------------------------------------------------------- lane state
+#define KSW_KEY_RA 0x00020000u      /* columns of pair A relative to its quad: lo 0, hi 2 */
+#define KSW_KEY_RB 0x00030001u      /* pair B: lo 1, hi 3 */
+#define KSW_KEY_DEC 0xfffcfffcu     /* -4 in both halves: the running key maximum moves back one quad */
+#define KSW_KEY_INIT 0x00800080u    /* 4 * 32 quads: never wraps below 0 and never beats a real key (>= 128 * B, B >= 1) */
+
 struct KswFastConst {
 	uint32_t neg_ei, neg_oei;                    // both halves: -e_ins, -(o_ins+e_ins)
+	uint32_t neg_2ei;                            // both halves: -2*e_ins
 	uint32_t ed32, oed32;                        // both halves: e_del, o_del+e_del (subtracted with 32-bit IADDs)
 	uint32_t Bpk;                                // both halves: the bias B = o_del+e_del carried by every H/E/F value
 	int32_t B;
 	int32_t o_del, e_del, e_ins, oe_ins, zdrop;
+	// KEYED arg-max: columns of pair A / pair B relative to their quad (lo 0, hi 2 / lo 1, hi 3).  Held in registers
+	// the compiler cannot fold (built from a kernel-parameter byte that is always 0), so that key = h*128 + column
+	// stays one multiply-add on the FMA pipe instead of a shift-add with an immediate on the ALU pipe.
+	uint32_t keyRA, keyRB;
 };
 
 struct KswFastLane {
@@ -139,10 +163,11 @@ static KSW_HD uint32_t ksw_pk2(int v) { return ((uint32_t)v & 0xffffu) | ((uint3
 
 static KSW_HD void ksw_fast_make_const(const KswParams &P, KswFastConst &K)
 {
-	K.neg_ei = ksw_pk2(-P.e_ins); K.neg_oei = ksw_pk2(-(P.o_ins + P.e_ins));
+	K.neg_ei = ksw_pk2(-P.e_ins); K.neg_oei = ksw_pk2(-(P.o_ins + P.e_ins)); K.neg_2ei = ksw_pk2(-2 * P.e_ins);
 	K.ed32 = ksw_pk2(P.e_del); K.oed32 = ksw_pk2(P.o_del + P.e_del);
 	K.B = P.o_del + P.e_del; K.Bpk = ksw_pk2(K.B);
 	K.o_del = P.o_del; K.e_del = P.e_del; K.e_ins = P.e_ins; K.oe_ins = P.o_ins + P.e_ins; K.zdrop = P.zdrop;
+	K.keyRA = KSW_KEY_RA + (uint32_t)(uint8_t)P.pad[0]; K.keyRB = KSW_KEY_RB + (uint32_t)(uint8_t)P.pad[0];
 }
 
 // row t of the scoring matrix as PRMT source bytes: x = mat[t][0..3], y = mat[t][4] (upper bytes 0)
@@ -155,11 +180,11 @@ static KSW_HD ksw_u2 ksw_fast_matrow(const KswParams &P, int t)
 	return r;
 }
 
-// halfword index of column c's H inside its quad's uint4 {HA, EA, HB, EB}; E is at +2
-static KSW_HD int ksw_fast_hslot(int c) { const int k = c & 3; return k < 2 ? k : 7 - k; }
+// halfword index of column c's H inside its quad's uint4 {HA, EA, HB, EB} (A: lo c0, hi c2; B: lo c1, hi c3); E is at +2
+static KSW_HD int ksw_fast_hslot(int c) { const int k = c & 3; return (k >> 1) + ((k & 1) << 2); }
 
 // Edge look-up table (one copy per CTA in shared memory), indexed by r = a column position inside a quad, 0..4:
-//   ge / lt   : halfword masks of the quad's columns >= r / < r in the (A: lo c0, hi c1; B: lo c3, hi c2) layout
+//   ge / lt   : halfword masks of the quad's columns >= r / < r in the (A: lo c0, hi c2; B: lo c1, hi c3) layout
 //   only      : halfword mask of column r alone (all-zero for r == 4)
 //   sel_left  : PRMT selector that extracts H of column r-1 from (hA, hB) into the low half, zero-extended
 struct KswFastEdge {
@@ -169,9 +194,9 @@ struct KswFastEdge {
 
 static KSW_HD void ksw_fast_edge_entry(int r, KswFastEdge &e)
 {
-	// column k of a quad: k=0 -> A.lo, 1 -> A.hi, 2 -> B.hi, 3 -> B.lo
-	const uint32_t colA[4] = {0x0000ffffu, 0xffff0000u, 0u, 0u};
-	const uint32_t colB[4] = {0u, 0u, 0xffff0000u, 0x0000ffffu};
+	// column k of a quad: k=0 -> A.lo, 1 -> B.lo, 2 -> A.hi, 3 -> B.hi
+	const uint32_t colA[4] = {0x0000ffffu, 0u, 0xffff0000u, 0u};
+	const uint32_t colB[4] = {0u, 0x0000ffffu, 0u, 0xffff0000u};
 	e.geA = e.geB = e.ltA = e.ltB = 0u;
 	for (int k = 0; k < 4; ++k) {
 		if (k >= r) { e.geA |= colA[k]; e.geB |= colB[k]; }
@@ -179,9 +204,9 @@ static KSW_HD void ksw_fast_edge_entry(int r, KswFastEdge &e)
 	}
 	e.onlyA = r < 4 ? colA[r] : 0u;
 	e.onlyB = r < 4 ? colB[r] : 0u;
-	// bytes of (hA, hB): 0,1 = A.lo  2,3 = A.hi  4,5 = B.lo  6,7 = B.hi; the upper result bytes replicate the sign
-	// (always 0: H >= 0), i.e. selector nibbles {lo, hi, 8|hi, 8|hi}
-	const uint32_t sel[4] = {0x9910u, 0xbb32u, 0xff76u, 0xdd54u};
+	// bytes of (hA, hB): 0,1 = A.lo (c0)  2,3 = A.hi (c2)  4,5 = B.lo (c1)  6,7 = B.hi (c3); the upper result bytes
+	// replicate the sign (always 0: H >= 0), i.e. selector nibbles {lo, hi, 8|hi, 8|hi}
+	const uint32_t sel[4] = {0x9910u, 0xdd54u, 0xbb32u, 0xff76u};
 	e.sel_left = r >= 1 ? sel[r - 1] : sel[0];
 	e.pad = 0u;
 }
@@ -244,35 +269,42 @@ static KSW_HD void ksw_fast_setup_quads(ksw_u4 *hq, uint32_t *sq, const int owne
 			sb[k] = code | ((8u | code) << 4);                                // byte lookup + sign replicate
 		}
 		ksw_u4 v4;
-		v4.x = (uint32_t)hv[0] | ((uint32_t)hv[1] << 16);   // pair A: lo c0, hi c1
+		v4.x = (uint32_t)hv[0] | ((uint32_t)hv[2] << 16);   // pair A: lo c0, hi c2
 		v4.y = K.Bpk;                                       // E = 0 (+ bias)
-		v4.z = (uint32_t)hv[3] | ((uint32_t)hv[2] << 16);   // pair B: lo c3, hi c2
+		v4.z = (uint32_t)hv[1] | ((uint32_t)hv[3] << 16);   // pair B: lo c1, hi c3
 		v4.w = K.Bpk;
 		hq[q * T + owner] = v4;
-		sq[q * T + owner] = (sb[0] | (sb[1] << 8)) | ((sb[3] | (sb[2] << 8)) << 16);
+		sq[q * T + owner] = (sb[0] | (sb[2] << 8)) | ((sb[1] | (sb[3] << 8)) << 16);
 	}
 }
 
 // ----------------------------------------------------------------------------- one row
 struct KswFastRowRegs {       // registers carried along a row
-	uint32_t X;               // F entering the next column (lo half at quad entry)
-	uint32_t Hc;              // lo half = H(i, c0-1): carry for the shifted H store
-	uint32_t m, zmin;         // running max (keys if KEYED) / running min of the row, per half
+	uint32_t X;               // lo half = Fs entering the quad's first column, hi half = 0
+	uint32_t Hc;              // hi half = H(i, c0-1): carry for the shifted H store (the previous quad's hB)
+	uint32_t m, zmin;         // running max (keys relative to the current quad if KEYED) / running min of the row, per half
 	int mjl, mjh;             // !KEYED: last column where the lo / hi half reached its running max
-	uint32_t colA, colB;      // KEYED: packed column numbers of the current quad's pairs
 	uint32_t hA, hB;          // H of the last processed quad
 };
 
 #if defined(__CUDA_ARCH__)
 static __device__ __forceinline__ uint32_t ksw_hi16_of(uint32_t w) { return __umulhi(w, 0x10000u); }   // FMA pipe, not ALU
+// (a.lo << 16) + b: moves a's low half into the high half on the FMA pipe; b's high half must be 0
+static __device__ __forceinline__ uint32_t ksw_lo_to_hi_add(uint32_t a, uint32_t b)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(d) : "r"(a), "r"(b));
+	return d;
+}
 #else
 static inline uint32_t ksw_hi16_of(uint32_t w) { return w >> 16; }
+static inline uint32_t ksw_lo_to_hi_add(uint32_t a, uint32_t b) { return (a << 16) + b; }
 #endif
 
 // One quad (4 cells).  EDGE: 0 = interior quad, 1 = a quad at the band edge: its out-of-band ("phantom")
 // columns are masked with keepA/keepB, the reference's edge writes are folded into its store.
 template <int T, bool KEYED, bool EDGE>
-static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, const KswFastConst &K, const ksw_u2 mr,
+static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, ksw_u4 *dst, const KswFastConst &K, const ksw_u2 mr,
                                  const int q, ksw_u4 v, const uint32_t sw, const uint32_t keepA, const uint32_t keepB,
                                  const uint32_t firstA, const uint32_t firstB, const uint32_t left0pk,
                                  const uint32_t endA, const uint32_t endB)
@@ -285,43 +317,55 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 		v.z = (v.z & keepB) | (KSW_NEGPK & ~keepB); v.w = (v.w & keepB) | (K.Bpk & ~keepB);
 	}
 	const uint32_t scA = prmt(mr.x, mr.y, sw), scB = prmt(mr.x, mr.y, ksw_hi16_of(sw));
-	const uint32_t hpA = addmax2(v.x, scA, v.y), hpB = addmax2(v.z, scB, v.w);
-	// max(h' - oe_ins, 0), with the bias: the floor is B
-	const uint32_t gA = addmax2(hpA, K.neg_oei, K.Bpk), gB = addmax2(hpB, K.neg_oei, K.Bpk);
-	// F chain: c0 (A.lo) -> c1 (A.hi) -> c2 (B.hi) -> c3 (B.lo) -> next quad
-	const uint32_t t1 = addmax2(R.X, K.neg_ei, gA);        // lo = F(c1)
-	const uint32_t FA = prmt(R.X, t1, 0x5410u);            // (F(c0), F(c1))
-	const uint32_t t2 = addmax2(FA, K.neg_ei, gA);         // hi = F(c2)
-	const uint32_t t3 = addmax2(t2, K.neg_ei, gB);         // hi = F(c3)
-	const uint32_t FB = prmt(t2, t3, 0x3276u);             // (lo = F(c3), hi = F(c2))
-	R.X = addmax2(FB, K.neg_ei, gB);                       // lo = F(c0 of the next quad)
-	const uint32_t hA = max2(hpA, FA), hB = max2(hpB, FB);
+	const uint32_t hpA = addmax2(v.x, scA, v.y), hpB = addmax2(v.z, scB, v.w);   // (h'(c0), h'(c2)), (h'(c1), h'(c3))
+	// F chain on Fs = F + oe_ins (no floor, see the header): lo half c0 -> c1 -> c2, hi half c2 -> c3 -> c0'
+#ifdef KSW_V_CHAIN2
+	// two columns per chain step: G = (max(h'(c0)-e, h'(c1)), max(h'(c2)-e, h'(c3))) is off the chain, and
+	// Fs(c+2) = max(Fs(c) - 2e, G) — the serial part of a quad is two DPX instructions and the two half moves
+	const uint32_t G = addmax2(hpA, K.neg_ei, hpB);
+	const uint32_t u2 = addmax2(R.X, K.neg_2ei, G);        // lo = Fs(c2)
+	const uint32_t FA = ksw_lo_to_hi_add(u2, R.X);         // (Fs(c0), Fs(c2))
+	const uint32_t u4 = addmax2(FA, K.neg_2ei, G);         // hi = Fs(c0 of the next quad)
+	const uint32_t FB = addmax2(FA, K.neg_ei, hpA);        // (Fs(c1), Fs(c3))
+	R.X = ksw_hi16_of(u4);
+#else
+	const uint32_t u1 = addmax2(R.X, K.neg_ei, hpA);       // lo = Fs(c1)
+	const uint32_t u2 = addmax2(u1, K.neg_ei, hpB);        // lo = Fs(c2)
+	const uint32_t FA = ksw_lo_to_hi_add(u2, R.X);         // (Fs(c0), Fs(c2))
+	const uint32_t FB = addmax2(FA, K.neg_ei, hpA);        // (Fs(c1), Fs(c3))
+	const uint32_t u4 = addmax2(FB, K.neg_ei, hpB);        // hi = Fs(c0 of the next quad)
+	R.X = ksw_hi16_of(u4);
+#endif
+	const uint32_t hA = addmax2(FA, K.neg_oei, hpA), hB = addmax2(FB, K.neg_oei, hpB);   // max(F, h')
 	// E(i+1,j) = max(E - e_del, H - oe_del, 0); every half is >= B >= oe_del, so the 32-bit subtractions cannot borrow
 	uint32_t eA = max3_2(v.y - K.ed32, hA - K.oed32, K.Bpk);
 	uint32_t eB = max3_2(v.w - K.ed32, hB - K.oed32, K.Bpk);
 	// row maximum, ties to the last column (ksw.c:434)
 	if (KEYED) {
-		R.m = maxu2(R.m, hA * 128u + R.colA);
-		R.m = maxu2(R.m, hB * 128u + R.colB);
-		R.colA += 0x00040004u; R.colB += 0x00040004u;
+		R.m = addmaxu2(R.m, KSW_KEY_DEC, hA * 128u + K.keyRA);
+		R.m = maxu2(R.m, hB * 128u + K.keyRB);
 	} else {
 		// per half (each half sees its columns in rising order)
 		const int c0 = q << 2;
 		bool ph, pl;
 		R.m = bmax2(hA, R.m, ph, pl);
 		if (pl) R.mjl = c0;
-		if (ph) R.mjh = c0 + 1;
-		R.m = bmax2(hB, R.m, ph, pl);
 		if (ph) R.mjh = c0 + 2;
-		if (pl) R.mjl = c0 + 3;
+		R.m = bmax2(hB, R.m, ph, pl);
+		if (pl) R.mjl = c0 + 1;
+		if (ph) R.mjh = c0 + 3;
 	}
 	// zero detector over the in-band cells
 	if (EDGE) R.zmin = min3_2(R.zmin, hA | (~keepA & 0x7fff7fffu), hB | (~keepB & 0x7fff7fffu));
 	else R.zmin = min3_2(R.zmin, hA, hB);
 	// store: eh[j].h = H(i, j-1), eh[j].e = E(i+1, j)
 	ksw_u4 o;
-	o.x = prmt(R.Hc, hA, 0x5410u);                         // (H(c0-1), H(c0))
-	o.z = prmt(hA, hB, 0x3276u);                           // (lo: H(c2) for column c3, hi: H(c1) for column c2)
+#ifdef KSW_V_STORE_IMAD
+	o.x = ksw_lo_to_hi_add(hB, ksw_hi16_of(R.Hc));         // (H(c0-1), H(c1)) for columns c0, c2: two FMA-pipe moves
+#else
+	o.x = prmt(R.Hc, hB, 0x5432u);                         // (H(c0-1), H(c1)) for columns c0, c2
+#endif
+	o.z = hA;                                              // (H(c0), H(c2)) for columns c1, c3
 	if (EDGE) {
 		// eh[beg].h = first-column value (ksw.c:429) where this quad holds column lo; eh[end].e = 0 (ksw.c:446)
 		// where it holds column hi (eh[end].h = h1 is what the shifted store writes there anyway)
@@ -330,8 +374,8 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, const KswFastMem<T> &M, cons
 		eA = (eA & ~endA) | (K.Bpk & endA); eB = (eB & ~endB) | (K.Bpk & endB);
 	}
 	o.y = eA; o.w = eB;
-	M.hq[q * T] = o;
-	R.Hc = hB;                                             // lo half = H(c3)
+	*dst = o;
+	R.Hc = hB;                                             // hi half = H(c3)
 	R.hA = hA; R.hB = hB;
 }
 
@@ -382,7 +426,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		if ((nx << 4) < L.tlen) L.tw_next = L.t2[nx];
 	}
 	int t = (int)((L.tw >> ((i & 15) << 1)) & 3u);
-	if (L.tn && ((L.tn[i >> 5] >> (i & 31)) & 1u)) t = 4;
+	if (!KEYED && L.tn && ((L.tn[i >> 5] >> (i & 31)) & 1u)) t = 4;      // keyed jobs are N-free (ksw_pack.cpp)
 	const ksw_u2 mr = mrow[t];
 
 	int left0 = L.h0 - (K.o_del + K.e_del * (i + 1));          // first-column value, used even when lo>0 (ksw.c:415-416)
@@ -406,36 +450,42 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 	const KswFastEdge eL = M.edge[lo & 3], eR = M.edge[hi_rel];
 	const uint32_t left0pk = (uint32_t)(left0 + K.B) * 0x10001u;
 	KswFastRowRegs R;
-	R.X = K.Bpk; R.Hc = 0; R.m = 0; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
-	if (KEYED) {
-		const uint32_t c0 = (uint32_t)(q0 << 2);
-		R.colA = (c0 | ((c0 + 1u) << 16));
-		R.colB = ((c0 + 3u) | ((c0 + 2u) << 16));
-	} else { R.colA = R.colB = 0; }
-	ksw_u4 v = M.hq[q0 * T];
-	uint32_t sw = M.sq[q0 * T];
+	R.X = (uint32_t)(K.B + K.oe_ins);                          // F = 0 entering the band (ksw.c:417), as Fs, high half clear
+	R.Hc = 0; R.m = KEYED ? KSW_KEY_INIT : 0u; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
+	ksw_u4 *ph = M.hq + q0 * T;                                // running pointers: the loop needs no index arithmetic
+	const uint32_t *ps = M.sq + q0 * T;
+	ksw_u4 v = *ph;
+	uint32_t sw = *ps;
 	if (q1 == q0) {
-		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, v, sw, eL.geA & eR.ltA, eL.geB & eR.ltB, eL.onlyA, eL.onlyB, left0pk, eR.onlyA, eR.onlyB);
+		ksw_fast_quad<T, KEYED, true>(R, ph, K, mr, q0, v, sw, eL.geA & eR.ltA, eL.geB & eR.ltB, eL.onlyA, eL.onlyB, left0pk, eR.onlyA, eR.onlyB);
 	} else {
-		ksw_u4 vn = M.hq[(q0 + 1) * T];                        // software prefetch, one quad ahead
-		uint32_t swn = M.sq[(q0 + 1) * T];
-		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q0, v, sw, eL.geA, eL.geB, eL.onlyA, eL.onlyB, left0pk, 0u, 0u);
+		ksw_u4 vn = ph[T];                                     // software prefetch, one quad ahead
+		uint32_t swn = ps[T];
+		ksw_fast_quad<T, KEYED, true>(R, ph, K, mr, q0, v, sw, eL.geA, eL.geB, eL.onlyA, eL.onlyB, left0pk, 0u, 0u);
+		ksw_u4 *const pl = M.hq + q1 * T;
+		int q = q0 + 1;
+		ph += T; ps += T;
 #ifdef __CUDACC__
+#ifdef KSW_V_UNROLL4
+#pragma unroll 4
+#else
 #pragma unroll 2
 #endif
-		for (int q = q0 + 1; q < q1; ++q) {
+#endif
+		for (; ph != pl; ph += T, ps += T, ++q) {
 			v = vn; sw = swn;
-			vn = M.hq[(q + 1) * T]; swn = M.sq[(q + 1) * T];
-			ksw_fast_quad<T, KEYED, false>(R, M, K, mr, q, v, sw, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+			vn = ph[T]; swn = ps[T];
+			ksw_fast_quad<T, KEYED, false>(R, ph, K, mr, q, v, sw, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
 		}
-		ksw_fast_quad<T, KEYED, true>(R, M, K, mr, q1, vn, swn, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
+		ksw_fast_quad<T, KEYED, true>(R, pl, K, mr, q1, vn, swn, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
 	}
 	// H(i, hi-1): the reference's h1 after the loop
 	const int left_b = (int)prmt(R.hA, R.hB, eR.sel_left);     // still biased
 	const int left = left_b - K.B;
 	if (hi_rel == 4) {
 		// column hi opens the next quad: eh[end].h = h1, eh[end].e = 0 (ksw.c:446); the other half-words of that
-		// 64-bit slot belong to column hi+1, which is rewritten before it is read again
+		// 64-bit slot belong to column hi+2, which is rewritten before it is read again (the band end grows by at most
+		// one column per row, and every row writes eh[end])
 		ksw_u2 *p = reinterpret_cast<ksw_u2 *>(&M.hq[(q1 + 1) * T]);
 		ksw_u2 w2; w2.x = (uint32_t)left_b; w2.y = K.Bpk;
 		*p = w2;
@@ -447,7 +497,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 	int rmax, rarg;
 	if (KEYED) {
 		const uint32_t k_lo = R.m & 0xffffu, k_hi = R.m >> 16;
-		const uint32_t kmax = k_lo > k_hi ? k_lo : k_hi;
+		const uint32_t kmax = (k_lo > k_hi ? k_lo : k_hi) + (uint32_t)(q1 << 2);   // keys are relative to the last quad
 		rmax = (int)(kmax >> 7) - K.B; rarg = (int)(kmax & 127u);
 	} else {
 		const int m_lo = (int)(int16_t)(R.m & 0xffffu), m_hi = (int)(int16_t)(R.m >> 16);

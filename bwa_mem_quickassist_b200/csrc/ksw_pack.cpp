@@ -267,9 +267,10 @@ int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_
 		for (auto &w : l.where) {
 			DevJob &d = dj[w.first];
 			d.nmask_off = (uint32_t)(base + w.second);
-			// class 0 is the pair kernel's (ksw_pair_core.h): its score look-up has no room for the query-N column of the
-			// matrix, so a class-0 job whose QUERY holds an N moves to class 1 (one job per lane, any base code)
-			if ((d.flags & KSW_FLAG_QN) && ((d.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u) {
+			// class 0 is N-free: the pair kernel's score look-up (ksw_pair_core.h) has no room for the query-N column of
+			// the matrix, and the keyed one-job-per-lane kernel skips the N-mask look-ups of both sequences.  A class-0 job
+			// that holds an N moves to class 1 (one job per lane, any base code)
+			if (((d.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u) {
 				d.flags = (d.flags & ~(KSW_CLASS_MASK << KSW_CLASS_SHIFT)) | (1u << KSW_CLASS_SHIFT);
 				st.class_n[0]--; st.class_n[1]++;
 				st.class_qmax[1] = std::max(st.class_qmax[1], d.qlen);

@@ -1,12 +1,19 @@
-"""Profile target: one upload of N config-2 jobs, then a few launches of the fast kernel."""
-import sys, os
-sys.path[:0] = [os.path.join(os.path.dirname(__file__), "..", "tests"), os.path.join(os.path.dirname(__file__), "..")]
-import kswtest as K
+#!/usr/bin/env python
+"""Development helper (GPU box): uploads N config-2 jobs and launches the resident kernels a few times — the process
+ncu attaches to (ncu -k regex:ksw_fast --launch-skip 1 --launch-count 1 --set full ...).
+   python scripts/prof_fast.py [jobs] [launches]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import numpy as np
 import bwa_mem_quickassist_b200 as B
+from bwa_mem_quickassist_b200.synth import config2_jobs
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+it = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+jobs, qpool, tpool = config2_jobs(n, seed=12345)
 ctx = B.KswB200(0)
-b = K.gen_config2(n, seed=1)
-rb = ctx.upload(b.cfg, b.jobs, b.qpool, b.tpool)
-ms = ctx.run_timed(rb, reps)
-print("ms", ms)
+rb = ctx.upload(B.make_cfg(), jobs, qpool, tpool)
+ms = ctx.run_timed(rb, it)
+cells = ctx.download_cells(rb).astype(np.int64).sum()
+print(f"{n} jobs, {cells} visited cells, ms per launch {ms}, {cells / ms[1:].mean() / 1e6:.1f} GCUPS")
