@@ -52,9 +52,9 @@ def test_pair_lane_never_takes_a_query_with_n(oracle_built):
     sel, _ = _check(b)
     has_qn = np.array([(b.qpool[int(j["q_off"]):int(j["q_off"]) + int(j["qlen"])] == 4).any() for j in b.jobs])
     assert has_qn.any() and not (sel & has_qn).any()
-    # a target N is fine (row 4 of the matrix)
+    # class 0 is N-free altogether (the keyed one-job-per-lane kernel skips the target's N mask): no target N either
     has_tn = np.array([(b.tpool[int(j["t_off"]):int(j["t_off"]) + int(j["tlen"])] == 4).any() for j in b.jobs])
-    assert (sel & has_tn).any()
+    assert has_tn.any() and not (sel & has_tn).any()
 
 
 def test_pair_lane_adversarial_and_boundaries(oracle_built):
