@@ -1,0 +1,58 @@
+// ksw_class.h — per-job decisions shared by the host packer (ksw_pack.cpp) and the device packer (ksw_devpack.cu):
+// the reference's band clamp (ksw.c:398-406) and the routing of a job to a kernel class.  One source, compiled for
+// both sides, so that a batch packed on the GPU is routed exactly like the same batch packed on the host.
+#pragma once
+#include <stdint.h>
+#include "ksw_dev.cuh"
+
+// Fast-kernel job classes (one launch each): class 0 = "keyed" jobs (qlen <= 124 and every score < 512, so the
+// row arg-max can be tracked as h*128+column in 16 bits, and no N in either sequence); classes 1..3 by query length.
+#define KSW_FAST_CLASSES 4
+#define KSW_FAST_KEYED_MAXSCORE 511
+static KSW_HD int ksw_fast_class_qmax(int c) { return c == 0 ? 124 : (c == 1 ? 128 : (c == 2 ? 256 : 512)); }
+
+// what the routing needs to know about the scoring of a batch
+struct KswScoring {
+	int32_t maxsc, minsc;              // largest (floored at 0, like ksw.c:399) / smallest matrix entry
+	int32_t o_del, e_del, o_ins, e_ins, end_bonus;
+	int32_t fast_qmax;                 // largest qlen the fast kernel accepts (0: fast kernel disabled)
+};
+
+// the reference's band clamp (ksw.c:398-406), evaluated with the identical C expression (IEEE double division on
+// both the host and the device)
+static KSW_HD int ksw_clamp_w_expr(int qlen, int maxsc, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus)
+{
+	int max_ins = (int)((double)(qlen * maxsc + end_bonus - o_ins) / e_ins + 1.);
+	max_ins = max_ins > 1 ? max_ins : 1;
+	w = w < max_ins ? w : max_ins;
+	int max_del = (int)((double)(qlen * maxsc + end_bonus - o_del) / e_del + 1.);
+	max_del = max_del > 1 ? max_del : 1;
+	w = w < max_del ? w : max_del;
+	return w;
+}
+
+// A job may take the fast s16x2 kernel iff every value its DP can hold stays far inside int16
+// and its columns fit the kernel's shared-memory budget; everything else goes to the generic
+// int32 kernel (still on the GPU).
+static KSW_HD bool ksw_fast_eligible(const KswScoring &S, int qlen, int h0)
+{
+	if (qlen > S.fast_qmax) return false;
+	if (S.o_ins < 0 || S.o_del < 0 || S.e_ins < 1 || S.e_del < 1) return false;
+	if (S.o_ins + S.e_ins > 4000 || S.o_del + S.e_del > 4000) return false;
+	if (S.minsc < -120 || S.maxsc > 120) return false;
+	if ((long long)h0 + (long long)qlen * S.maxsc > 20000) return false;
+	return true;
+}
+
+// kernel class of a job before its sequences have been looked at (a class-0 job that holds an N moves to class 1)
+static KSW_HD uint32_t ksw_job_class(const KswScoring &S, int qlen, int h0)
+{
+	if (!ksw_fast_eligible(S, qlen, h0)) return KSW_CLASS_GENERIC;
+	if (qlen <= ksw_fast_class_qmax(0) && (long long)h0 + (long long)qlen * S.maxsc + S.o_del + S.e_del <= KSW_FAST_KEYED_MAXSCORE) return 0;
+	uint32_t qc = 1;
+	while (qc + 1 < KSW_FAST_CLASSES && qlen > ksw_fast_class_qmax((int)qc)) ++qc;
+	return qc;
+}
+
+// 16-byte units of a job's packed sequences in the 2-bit pool: query words | target words, padded
+static KSW_HD uint32_t ksw_job_units(int qlen, int tlen) { return (ksw_words2(qlen) + ksw_words2(tlen) + 3) >> 2; }

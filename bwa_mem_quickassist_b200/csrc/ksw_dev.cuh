@@ -54,6 +54,19 @@ struct DevGRes {
 };
 static_assert(sizeof(DevGRes) == 16, "DevGRes must be 16 bytes");
 
+// chunk totals written by the device packer's prep kernel (ksw_devpack.cu) and read back by the host before it sizes
+// the chunk's 2-bit pool; nmask_used is the pack kernel's allocation cursor in the N side pool
+struct DevPackStats {
+	unsigned long long units;          // 16-byte units of the 2-bit pool
+	unsigned long long nmask_words;    // words of the N side pool if every job held an N in both sequences (capacity)
+	unsigned long long q_hi, t_hi;     // one past the last query / target byte any job of the chunk reads
+	unsigned long long q_lo_inv, t_lo_inv;   // ~(first query / target byte any job reads): a maximum, so that 0 initialises it
+	unsigned int class_n[5];           // jobs per kernel class before the N demotion (class 0 -> 1)
+	int class_qmax[5];                 // longest query per class, before the N demotion
+	unsigned int bad;                  // a job with qlen < 1 or tlen < 0
+	unsigned int nmask_used;
+};
+
 struct KswParams {          // passed by value as a kernel parameter (constant bank)
 	int8_t  mat[25];
 	int8_t  pad[3];

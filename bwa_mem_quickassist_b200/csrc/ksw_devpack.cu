@@ -1,0 +1,241 @@
+// ksw_devpack.cu — packing on the device.  When the caller's job / sequence / result arrays are page-locked, the host
+// does not touch the sequences at all: the raw job records (ksw_b200_job_t, 32 B) and the raw byte-coded sequences are
+// copied to HBM as they are (a few large cudaMemcpyAsync calls per chunk), and three small kernels turn them into what
+// the extension kernels read (ksw_dev.cuh):
+//
+//   ksw_prep_kernel   one thread per job: band clamp (ksw.c:398-406, same double expression as the host), kernel class,
+//                     DevJob record, size of the job's 2-bit sequences; chunk totals for the host (DevPackStats)
+//   (cub scan)        exclusive sum of the sizes = each job's offset in the 2-bit pool
+//   ksw_pack_kernel   one warp per job: 16 bases -> one 32-bit word per lane (base k in word k/16 at bits 2(k%16)),
+//                     N masks for the rare jobs that hold an N (allocated with one atomicAdd per such job); a class-0
+//                     job that holds an N moves to class 1, exactly as in the host packer (ksw_pack.cpp)
+//   ksw_range_kernel  after the binning sort: first entry of each kernel class in the binned order, read by the
+//                     extension kernels from device memory (the host never learns the post-demotion class sizes)
+//
+// Same routing source as the host packer (ksw_class.h), so a batch packed here runs through the same kernels in the
+// same classes as the same batch packed on the host; tests compare the two paths bit for bit.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include "../../include/ksw_b200.h"
+#include "ksw_class.h"
+#include "ksw_dev.cuh"
+#include "ksw_launch.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+ksw_prep_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const KswScoring S, DevJob *__restrict__ jobs,
+                uint32_t *__restrict__ units, DevPackStats *__restrict__ stats)
+{
+	__shared__ unsigned long long s_units, s_nmask, s_qhi, s_thi, s_qlo, s_tlo;
+	__shared__ unsigned s_cn[KSW_FAST_CLASSES + 1];
+	__shared__ int s_qm[KSW_FAST_CLASSES + 1];
+	__shared__ unsigned s_bad;
+	if (threadIdx.x == 0) { s_units = 0; s_nmask = 0; s_qhi = 0; s_thi = 0; s_qlo = 0; s_tlo = 0; s_bad = 0; }
+	if (threadIdx.x <= KSW_FAST_CLASSES) { s_cn[threadIdx.x] = 0; s_qm[threadIdx.x] = 0; }
+	__syncthreads();
+	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long my_units = 0, my_nmask = 0, my_qhi = 0, my_thi = 0, my_qlo = 0, my_tlo = 0;   // *_lo hold ~offset
+	if (k < n) {
+		const ksw_b200_job_t j = raw[k];
+		DevJob d;
+		d.seq_off = 0; d.idx = (uint32_t)k; d.qlen = j.qlen; d.tlen = j.tlen;
+		d.h0 = j.h0 < 0 ? 0 : j.h0;                                                    // ksw.c:384
+		d.nmask_off = 0;
+		if (j.qlen < 1 || j.tlen < 0) {
+			s_bad = 1;                                                                  // benign race: any writer wins
+			d.qlen = 1; d.tlen = 0; d.w = 0; d.flags = KSW_CLASS_GENERIC << KSW_CLASS_SHIFT;
+			units[k] = 0;
+		} else {
+			d.w = ksw_clamp_w_expr(j.qlen, S.maxsc, S.o_del, S.e_del, S.o_ins, S.e_ins, j.w, S.end_bonus);
+			const uint32_t c = ksw_job_class(S, j.qlen, d.h0);
+			d.flags = c << KSW_CLASS_SHIFT;
+			const uint32_t u = ksw_job_units(j.qlen, j.tlen);
+			units[k] = u;
+			my_units = u;
+			my_nmask = ksw_words1(j.qlen) + ksw_words1(j.tlen);
+			my_qhi = j.q_off + (unsigned long long)j.qlen;
+			my_thi = j.t_off + (unsigned long long)j.tlen;
+			my_qlo = ~(unsigned long long)j.q_off;
+			if (j.tlen > 0) my_tlo = ~(unsigned long long)j.t_off;
+			atomicAdd(&s_cn[c], 1u);
+			atomicMax(&s_qm[c], j.qlen);
+		}
+		jobs[k] = d;
+	}
+	// warp-level sums / maxima, then one shared atomic per warp and one global atomic per block
+	for (int o = 16; o > 0; o >>= 1) {
+		my_units += __shfl_down_sync(0xffffffffu, my_units, o);
+		my_nmask += __shfl_down_sync(0xffffffffu, my_nmask, o);
+		const unsigned long long a = __shfl_down_sync(0xffffffffu, my_qhi, o), b = __shfl_down_sync(0xffffffffu, my_thi, o);
+		my_qhi = my_qhi > a ? my_qhi : a;
+		my_thi = my_thi > b ? my_thi : b;
+		const unsigned long long c = __shfl_down_sync(0xffffffffu, my_qlo, o), d = __shfl_down_sync(0xffffffffu, my_tlo, o);
+		my_qlo = my_qlo > c ? my_qlo : c;
+		my_tlo = my_tlo > d ? my_tlo : d;
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&s_units, my_units); atomicAdd(&s_nmask, my_nmask);
+		atomicMax(&s_qhi, my_qhi); atomicMax(&s_thi, my_thi);
+		atomicMax(&s_qlo, my_qlo); atomicMax(&s_tlo, my_tlo);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		atomicAdd(&stats->units, s_units); atomicAdd(&stats->nmask_words, s_nmask);
+		atomicMax(&stats->q_hi, s_qhi); atomicMax(&stats->t_hi, s_thi);
+		atomicMax(&stats->q_lo_inv, s_qlo); atomicMax(&stats->t_lo_inv, s_tlo);
+		if (s_bad) atomicOr(&stats->bad, 1u);
+	}
+	if (threadIdx.x <= KSW_FAST_CLASSES && s_cn[threadIdx.x]) {
+		atomicAdd(&stats->class_n[threadIdx.x], s_cn[threadIdx.x]);
+		atomicMax(&stats->class_qmax[threadIdx.x], s_qm[threadIdx.x]);
+	}
+}
+
+// 16 byte codes starting at s (only the first `lim` exist) -> one 2-bit word; *n_bits gets bit x set where code x > 3.
+// A full group of 16 is read as five aligned 32-bit words and funnel-shifted into place (the job slices start wherever
+// the caller put them); that touches up to 3 bytes before s and 7 after s+16, inside the buffer's alignment / slack.
+__device__ __forceinline__ uint32_t squeeze16_dev(const uint8_t *__restrict__ s, int lim, uint32_t *n_bits)
+{
+	uint32_t word = 0, nb = 0;
+	if (lim >= 16) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+		const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8u;
+		uint32_t x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3], x4 = sh ? w[4] : 0u;
+		uint32_t v[4] = {__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh)};
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			// bytes > 3 are N: flagged and stored as 0
+			const uint32_t hi = v[q] & 0xfcfcfcfcu;
+			if (hi) {
+#pragma unroll
+				for (int b = 0; b < 4; ++b)
+					if ((hi >> (8 * b)) & 0xffu) { nb |= 1u << (4 * q + b); v[q] &= ~(0xffu << (8 * b)); }
+			}
+			const uint32_t x = v[q];                                                   // four codes 0..3, one per byte
+			word |= ((x & 3u) | ((x >> 6) & 0xcu) | ((x >> 12) & 0x30u) | ((x >> 18) & 0xc0u)) << (8 * q);
+		}
+	} else {
+		for (int x = 0; x < lim; ++x) {
+			const uint32_t c = s[x];
+			if (c > 3u) nb |= 1u << x;
+			else word |= c << (2 * x);
+		}
+	}
+	*n_bits = nb;
+	return word;
+}
+
+#define KSW_PACK_WARPS 8
+
+__global__ void __launch_bounds__(KSW_PACK_WARPS * 32)
+ksw_pack_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const uint8_t *__restrict__ qraw, const uint8_t *__restrict__ traw,
+                const uint32_t *__restrict__ offs, DevJob *__restrict__ jobs, uint32_t *__restrict__ pool,
+                uint32_t *__restrict__ npool, DevPackStats *__restrict__ stats)
+{
+	const int lane = threadIdx.x & 31;
+	const long long k = (long long)blockIdx.x * KSW_PACK_WARPS + (threadIdx.x >> 5);
+	if (k >= n) return;
+	const ksw_b200_job_t j = raw[k];
+	if (j.qlen < 1 || j.tlen < 0) return;                                              // reported by the prep kernel
+	const uint32_t qw = ksw_words2(j.qlen), tw = ksw_words2(j.tlen), total = ksw_job_units(j.qlen, j.tlen) * 4u;
+	const uint32_t off = offs[k];
+	uint32_t *out = pool + (size_t)off * 4;
+	const uint8_t *q = qraw + j.q_off, *t = traw + j.t_off;
+	bool qn = false, tn = false;
+	for (uint32_t wi = lane; wi < total; wi += 32) {
+		uint32_t word = 0, nb = 0;
+		if (wi < qw) { word = squeeze16_dev(q + 16 * wi, j.qlen - 16 * (int)wi, &nb); qn |= nb != 0; }
+		else if (wi < qw + tw) { word = squeeze16_dev(t + 16 * (wi - qw), j.tlen - 16 * (int)(wi - qw), &nb); tn |= nb != 0; }
+		out[wi] = word;
+	}
+	qn = __any_sync(0xffffffffu, qn);
+	tn = __any_sync(0xffffffffu, tn);
+	if (!qn && !tn) {
+		if (lane == 0) jobs[k].seq_off = off;
+		return;
+	}
+	// rare: the job holds an N.  Masks (1 bit per base) go to the side pool: [query mask words][target mask words]
+	const uint32_t qmw = ksw_words1(j.qlen), tmw = ksw_words1(j.tlen);
+	uint32_t base = 0;
+	if (lane == 0) base = atomicAdd(&stats->nmask_used, (qn ? qmw : 0u) + (tn ? tmw : 0u));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	uint32_t at = base;
+	if (qn) {
+		for (uint32_t mi = lane; mi < qmw; mi += 32) {
+			uint32_t m = 0;
+			const int lim = j.qlen - 32 * (int)mi < 32 ? j.qlen - 32 * (int)mi : 32;
+			for (int x = 0; x < lim; ++x) if (q[32 * mi + x] > 3) m |= 1u << x;
+			npool[at + mi] = m;
+		}
+		at += qmw;
+	}
+	if (tn) {
+		for (uint32_t mi = lane; mi < tmw; mi += 32) {
+			uint32_t m = 0;
+			const int lim = j.tlen - 32 * (int)mi < 32 ? j.tlen - 32 * (int)mi : 32;
+			for (int x = 0; x < lim; ++x) if (t[32 * mi + x] > 3) m |= 1u << x;
+			npool[at + mi] = m;
+		}
+	}
+	if (lane == 0) {
+		DevJob d = jobs[k];
+		d.seq_off = off;
+		d.nmask_off = base;
+		d.flags |= (qn ? KSW_FLAG_QN : 0u) | (tn ? KSW_FLAG_TN : 0u);
+		if (((d.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u)                      // class 0 is N-free (ksw_pack.cpp)
+			d.flags = (d.flags & ~(KSW_CLASS_MASK << KSW_CLASS_SHIFT)) | (1u << KSW_CLASS_SHIFT);
+		jobs[k] = d;
+	}
+}
+
+// sorted_keys: the binning keys in ascending order (ksw_bin.cu): class c occupies [range[c], range[c+1])
+__global__ void ksw_range_kernel(const uint16_t *__restrict__ sorted_keys, long long n, uint32_t *__restrict__ range)
+{
+	const int c = threadIdx.x;                                                          // 0 .. KSW_FAST_CLASSES + 1
+	if (c > KSW_FAST_CLASSES + 1) return;
+	if (c == KSW_FAST_CLASSES + 1) { range[c] = (uint32_t)n; return; }
+	const uint32_t lowest = c >= (int)KSW_CLASS_GENERIC ? 0x8000u : ((uint32_t)c << 13);  // smallest key of class c
+	long long lo = 0, hi = n;
+	while (lo < hi) {
+		const long long mid = (lo + hi) >> 1;
+		if ((uint32_t)sorted_keys[mid] < lowest) lo = mid + 1; else hi = mid;
+	}
+	range[c] = (uint32_t)lo;
+}
+
+} // namespace
+
+size_t ksw_devpack_scan_temp_bytes(int64_t n)
+{
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n > 0 ? n : 1));
+	return bytes;
+}
+
+cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *units,
+                            uint32_t *offs, void *temp, size_t temp_bytes, DevPackStats *stats, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(DevPackStats), st);
+	if (e != cudaSuccess) return e;
+	ksw_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const ksw_b200_job_t *)raw_jobs, (long long)n, S, jobs, units, stats);
+	e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, (const uint32_t *)units, offs, (int)n, st);
+}
+
+cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *traw, const uint32_t *offs,
+                            DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	ksw_pack_kernel<<<(unsigned)((n + KSW_PACK_WARPS - 1) / KSW_PACK_WARPS), KSW_PACK_WARPS * 32, 0, st>>>(
+	    (const ksw_b200_job_t *)raw_jobs, (long long)n, qraw, traw, offs, jobs, pool, npool, stats);
+	return cudaGetLastError();
+}
+
+cudaError_t ksw_launch_ranges(const uint16_t *sorted_keys, int64_t n, uint32_t *range, cudaStream_t st)
+{
+	ksw_range_kernel<<<1, 32, 0, st>>>(sorted_keys, (long long)n, range);
+	return cudaGetLastError();
+}

@@ -23,8 +23,15 @@ __global__ void __launch_bounds__(T, 12)
 ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_t *__restrict__ pool,
                 const uint32_t *__restrict__ npool, const KswParams P, const int nq_cap, const int chunk,
                 unsigned long long *__restrict__ counter, const uint32_t *__restrict__ order,
-                DevRes *__restrict__ res, uint32_t *__restrict__ cells)
+                DevRes *__restrict__ res, uint32_t *__restrict__ cells, const uint32_t *__restrict__ drange, const int c_lo, const int c_hi)
 {
+	// device-packed batches (ksw_devpack.cu): the launch covers the kernel classes [c_lo, c_hi) of the binned order,
+	// whose bounds only the device knows (n_jobs is then the host's upper bound, used for the grid size)
+	if (drange) {
+		const uint32_t f = drange[c_lo];
+		n_jobs = (long long)drange[c_hi] - (long long)f;
+		order += f;
+	}
 	extern __shared__ uint4 smem[];
 	const int lane = threadIdx.x;
 	uint4 *hq = smem;
@@ -120,7 +127,8 @@ size_t ksw_fast_smem_bytes(int qmax)
 template <bool KEYED>
 static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                  const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
-                                 const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st)
+                                 const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st,
+                                 const uint32_t *drange, int c_lo, int c_hi)
 {
 	const size_t smem = ksw_fast_smem_bytes(qmax);
 	// The dynamic shared-memory ceiling of the kernel is raised ONCE per device to the opt-in maximum and never lowered:
@@ -154,15 +162,17 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 	long long chunk = 32;
 	if (const char *ev = getenv("KSW_B200_FAST_CHUNK")) chunk = atoi(ev) > 0 ? atoi(ev) : chunk;      // tuning knob
 	ksw_fast_kernel<KEYED><<<(unsigned)blocks, T, smem, st>>>(jobs, (long long)n_jobs, pool, npool, P,
-	                                                           KSW_FAST_QUADS(qmax), (int)chunk, counter, order, res, cells);
+	                                                           KSW_FAST_QUADS(qmax), (int)chunk, counter, order, res, cells,
+	                                                           drange, c_lo, c_hi);
 	return cudaGetLastError();
 }
 
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter,
-                            const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st)
+                            const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st,
+                            const uint32_t *drange, int c_lo, int c_hi)
 {
 	if (n_jobs <= 0) return cudaSuccess;
-	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st)
-	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st);
+	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st, drange, c_lo, c_hi)
+	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st, drange, c_lo, c_hi);
 }

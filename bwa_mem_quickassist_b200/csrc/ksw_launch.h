@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "ksw_dev.cuh"
+#include "ksw_class.h"
 
 #define KSW_GENERIC_THREADS 128
 
@@ -23,10 +24,12 @@ cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iter
 #define KSW_FAST_THREADS 32
 
 // fast s16x2 kernel over the jobs jobs[order[0..n_jobs)] whose qlen <= qmax; keyed: every job satisfies the class-0 bounds of
-// ksw_pack.h; counter: one device uint64 scratch word
+// ksw_class.h; counter: one device uint64 scratch word.  drange != nullptr (device-packed batches): the launch covers
+// order[drange[c_lo] .. drange[c_hi]) instead, n_jobs is only the host's upper bound of that count
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter, const uint32_t *order,
-                            DevRes *res, uint32_t *cells, cudaStream_t st);
+                            DevRes *res, uint32_t *cells, cudaStream_t st,
+                            const uint32_t *drange = nullptr, int c_lo = 0, int c_hi = 0);
 size_t ksw_fast_smem_bytes(int qmax);
 
 // pair kernel (two jobs per lane, ksw_pair.cu) over the class-0 jobs jobs[order[0..n_jobs)]: qlen <= qmax <= 124, biased
@@ -40,3 +43,13 @@ size_t ksw_pair_smem_bytes(int qmax, int n_warps);
 size_t ksw_bin_temp_bytes(int64_t n);
 cudaError_t ksw_launch_bin(const DevJob *jobs, int64_t n, uint16_t *keys_in, uint16_t *keys_out, uint32_t *vals_in,
                            uint32_t *order, void *temp, size_t temp_bytes, cudaStream_t st);
+
+// device-side packing (ksw_devpack.cu): raw ksw_b200_job_t records + raw byte-coded sequences in HBM -> DevJob[] + 2-bit pool
+size_t ksw_devpack_scan_temp_bytes(int64_t n);
+// prep: DevJob records (seq_off left 0), sizes, their exclusive sum (offs), chunk totals (stats; zeroed first)
+cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *units,
+                            uint32_t *offs, void *temp, size_t temp_bytes, DevPackStats *stats, cudaStream_t st);
+cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *traw, const uint32_t *offs,
+                            DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st);
+// range[c] = first entry of kernel class c in the binned order (c = 0..KSW_FAST_CLASSES+1; the last one is n)
+cudaError_t ksw_launch_ranges(const uint16_t *sorted_keys, int64_t n, uint32_t *range, cudaStream_t st);

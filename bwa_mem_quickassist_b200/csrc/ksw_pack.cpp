@@ -102,19 +102,6 @@ inline bool pack2(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
 	return has_n;
 }
 
-// A job may take the fast s16x2 kernel iff every value its DP can hold stays far inside int16
-// and its columns fit the kernel's shared-memory budget; everything else goes to the generic
-// int32 kernel (still on the GPU).
-bool fast_eligible(const ksw_b200_cfg_t *cfg, int fast_qmax, int maxsc, int minsc, int qlen, int h0)
-{
-	if (qlen > fast_qmax) return false;
-	if (cfg->o_ins < 0 || cfg->o_del < 0 || cfg->e_ins < 1 || cfg->e_del < 1) return false;
-	if (cfg->o_ins + cfg->e_ins > 4000 || cfg->o_del + cfg->e_del > 4000) return false;
-	if (minsc < -120 || maxsc > 120) return false;
-	if ((int64_t)h0 + (int64_t)qlen * maxsc > 20000) return false;
-	return true;
-}
-
 } // namespace
 
 int ksw_mat_max(const int8_t *mat)
@@ -126,13 +113,16 @@ int ksw_mat_max(const int8_t *mat)
 
 int ksw_clamp_w(int qlen, int maxsc, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus)
 {
-	int max_ins = (int)((double)(qlen * maxsc + end_bonus - o_ins) / e_ins + 1.);
-	max_ins = max_ins > 1 ? max_ins : 1;
-	w = w < max_ins ? w : max_ins;
-	int max_del = (int)((double)(qlen * maxsc + end_bonus - o_del) / e_del + 1.);
-	max_del = max_del > 1 ? max_del : 1;
-	w = w < max_del ? w : max_del;
-	return w;
+	return ksw_clamp_w_expr(qlen, maxsc, o_del, e_del, o_ins, e_ins, w, end_bonus);
+}
+
+void ksw_scoring_from_cfg(const ksw_b200_cfg_t *cfg, int fast_qmax, KswScoring &S)
+{
+	S.maxsc = ksw_mat_max(cfg->mat);
+	S.minsc = 0;
+	for (int i = 0; i < 25; ++i) S.minsc = std::min<int>(S.minsc, cfg->mat[i]);
+	S.o_del = cfg->o_del; S.e_del = cfg->e_del; S.o_ins = cfg->o_ins; S.e_ins = cfg->e_ins;
+	S.end_bonus = cfg->end_bonus; S.fast_qmax = fast_qmax;
 }
 
 void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P)
@@ -148,15 +138,6 @@ namespace {
 // the same contiguous split of [0,n) in both passes
 inline int pack_ranges(KswPool *tp, int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>(tp ? tp->size() : 1, (n + 16383) / 16384)); }
 
-inline uint32_t job_class(const ksw_b200_cfg_t *cfg, int fast_qmax, int maxsc, int minsc, int qlen, int h0)
-{
-	if (!fast_eligible(cfg, fast_qmax, maxsc, minsc, qlen, h0)) return KSW_CLASS_GENERIC;
-	if (qlen <= KSW_FAST_CLASS_QMAX[0] && (int64_t)h0 + (int64_t)qlen * maxsc + cfg->o_del + cfg->e_del <= KSW_FAST_KEYED_MAXSCORE) return 0;
-	uint32_t qc = 1;
-	while (qc + 1 < KSW_FAST_CLASSES && qlen > KSW_FAST_CLASS_QMAX[qc]) ++qc;
-	return qc;
-}
-
 template <class F>
 void run_ranges(KswPool *tp, int T, F &&fn) { if (T == 1) fn(0); else tp->run(T, fn); }
 
@@ -167,9 +148,8 @@ int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *j
 {
 	if (cfg->m != 5) { err = "ksw_b200: only m == 5 is supported (every reference caller passes 5)"; return 2; }
 	if (n > 0x7fffffffLL) { err = "ksw_b200: more than 2^31-1 jobs in one batch"; return 2; }
-	const int maxsc = ksw_mat_max(cfg->mat);
-	int minsc = 0;
-	for (int i = 0; i < 25; ++i) minsc = std::min<int>(minsc, cfg->mat[i]);
+	KswScoring S;
+	ksw_scoring_from_cfg(cfg, fast_qmax, S);
 	const int T = pack_ranges(tp, n);
 	const int64_t per = (n + T - 1) / T;
 	struct Local { int64_t cn[KSW_FAST_CLASSES + 1]; int qm[KSW_FAST_CLASSES + 1]; uint64_t units; int bad; char pad[64]; };
@@ -181,9 +161,9 @@ int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *j
 		for (int64_t k = b; k < e; ++k) {
 			const ksw_b200_job_t &j = jobs[k];
 			if (j.qlen < 1 || j.tlen < 0) { l.bad = 1; continue; }
-			const uint32_t c = job_class(cfg, fast_qmax, maxsc, minsc, j.qlen, j.h0 < 0 ? 0 : j.h0);
+			const uint32_t c = ksw_job_class(S, j.qlen, j.h0 < 0 ? 0 : j.h0);
 			l.cn[c]++; l.qm[c] = std::max(l.qm[c], j.qlen);
-			l.units += (ksw_words2(j.qlen) + ksw_words2(j.tlen) + 3) >> 2;
+			l.units += ksw_job_units(j.qlen, j.tlen);
 		}
 		loc[t] = l;
 	});
@@ -208,9 +188,9 @@ int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_
                     std::vector<uint32_t> &nmask, KswPool *tp)
 {
 	const int64_t n = st.n;
-	const int maxsc = ksw_mat_max(cfg->mat);
-	int minsc = 0;
-	for (int i = 0; i < 25; ++i) minsc = std::min<int>(minsc, cfg->mat[i]);
+	KswScoring S;
+	ksw_scoring_from_cfg(cfg, fast_qmax, S);
+	const int maxsc = S.maxsc;
 	const int T = pack_ranges(tp, n);
 	const int64_t per = (n + T - 1) / T;
 	struct NList { std::vector<uint32_t> words; std::vector<std::pair<int64_t, uint32_t>> where; };
@@ -232,7 +212,7 @@ int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_
 				last_qlen = j.qlen; last_w = j.w;
 			}
 			d.w = last_weff;
-			d.flags = job_class(cfg, fast_qmax, maxsc, minsc, j.qlen, d.h0) << KSW_CLASS_SHIFT;
+			d.flags = ksw_job_class(S, j.qlen, d.h0) << KSW_CLASS_SHIFT;
 			d.nmask_off = 0;
 			const uint32_t qw = ksw_words2(j.qlen), tw = ksw_words2(j.tlen), units = (qw + tw + 3) >> 2;
 			const uint32_t qmw = ksw_words1(j.qlen), tmw = ksw_words1(j.tlen);

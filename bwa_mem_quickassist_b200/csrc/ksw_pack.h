@@ -27,11 +27,8 @@ private:
 	int n_;
 };
 
-// Fast-kernel job classes (one launch each): class 0 = "keyed" jobs (qlen <= 124 and every score < 512, so the
-// row arg-max can be tracked as h*128+column in 16 bits); classes 1..3 by query length.
-#define KSW_FAST_CLASSES 4
+#include "ksw_class.h"               // job classes, band clamp: shared with the device packer
 static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {124, 128, 256, 512};
-#define KSW_FAST_KEYED_MAXSCORE 511
 
 // What the launcher needs to know about a packed batch.  Classes 0..KSW_FAST_CLASSES-1 are the fast kernel's,
 // class KSW_FAST_CLASSES is the generic kernel's.
@@ -57,6 +54,7 @@ int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_
                     std::vector<uint32_t> &nmask, KswPool *tp);
 
 void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P);
+void ksw_scoring_from_cfg(const ksw_b200_cfg_t *cfg, int fast_qmax, KswScoring &S);
 
 // the reference's band clamp (ksw.c:398-406), evaluated with the identical C expression
 int ksw_clamp_w(int qlen, int maxsc, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus);

@@ -7,7 +7,10 @@
 // from a kernel launch.  If CUDA is unusable the calls fail loudly.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,7 +61,7 @@ double now_ms()
 
 } // namespace
 
-#define KSW_N_SLOTS 3
+#define KSW_N_SLOTS 4
 
 // ------------------------------------------------------------------ opaque types
 struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
@@ -70,6 +73,10 @@ struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs
 	DevBuf d_order, d_keys, d_vals, d_sort_tmp;                 // device-side binning (ksw_bin.cu)
 	size_t pool_bytes = 0, npool_bytes = 0;
 	int qmax_generic = 0;
+	// device-packed batches (ksw_devpack.cu): the class sizes above are the host's view BEFORE class-0 jobs that hold an
+	// N moved to class 1; the kernels read the true class bounds of the binned order from d_range
+	bool dev_ranges = false;
+	DevBuf d_range;
 };
 
 namespace {
@@ -84,6 +91,20 @@ struct Slot {
 	DevBuf d_eh, d_qc, d_counter;          // scratch of the generic kernel / job counters of the fast kernel
 	bool busy = false;                     // results of a chunk are in flight into h_res
 	int64_t first = 0, n = 0;              // caller range of that chunk
+	// device-side packing (pinned callers): raw job records, sizes / offsets of the 2-bit slices, chunk totals
+	DevBuf d_rawjobs, d_units, d_offs, d_scan_tmp, d_stats;
+	PinnedBuf h_stats;
+	cudaEvent_t ev_jobs = nullptr, ev_stats = nullptr, ev_up = nullptr, ev_ext = nullptr, ev_done = nullptr;
+	bool host_packed = false;              // pinned-caller pipeline: this chunk was packed on the host threads
+};
+
+struct AsyncReq {
+	ksw_b200_cfg_t cfg;
+	int64_t n = 0;
+	const ksw_b200_job_t *jobs = nullptr;
+	const uint8_t *qpool = nullptr, *tpool = nullptr;
+	size_t qbytes = 0, tbytes = 0;
+	ksw_b200_res_t *res = nullptr;
 };
 
 } // namespace
@@ -97,13 +118,27 @@ struct ksw_b200_ctx {
 	KswPool *pool = nullptr;               // (re)created lazily with pack_threads workers
 	int64_t chunk_jobs = 1 << 20;
 	int trace = 0;
-	int64_t launches = 0;
+	std::atomic<long long> launches{0};
 	int64_t last_h2d = 0, last_d2h = 0;    // bytes moved by the last ksw_b200_extend_batch call
+	std::mutex err_mu;                     // the two lanes of the pinned-caller pipeline may both report an error
 	// Pipeline slots of the one-shot entry; slot[0] also serves upload / run / download of resident batches.  Three, not
 	// two: a slot is reusable only after its chunk's results are back, and pack (3 ms) + H2D (2.5 ms) of the next chunk
 	// for that slot take longer than the other slot's kernel (3.7 ms per 2^20 config-2 jobs), so with two slots the GPU
 	// idled 2.4 ms per chunk.
 	Slot slot[KSW_N_SLOTS];
+	// pinned callers (ksw_b200_extend_batch_async): the raw byte-coded pools in HBM, the stream their uploads are
+	// ordered on, and the worker thread that feeds the pipeline while the caller goes on
+	DevBuf d_qraw, d_traw;
+	cudaStream_t up_stream = nullptr, main_stream = nullptr, down_stream = nullptr;
+	int hybrid = 1;                        // a second lane packs chunks on the host threads (KSW_B200_HYBRID=0: device packing only)
+	Slot hslot[2];                         // that lane's staging / device buffers (events only; it uses the shared streams)
+	double host_ms_per_job = 0, dev_ms_per_job = 0;   // measured pace of the two lanes (0 = not measured yet)
+	std::thread worker;
+	std::mutex mu;
+	std::condition_variable cv;
+	bool worker_started = false, req_pending = false, req_running = false, stop = false;
+	int async_rc = 0;
+	AsyncReq req;
 	// banded global alignment (ksw_b200_global_batch): staging, device buffers, the CIGAR pool handed to the caller
 	PinnedBuf g_hjobs, g_hseq, g_hres, g_hcig;
 	DevBuf g_djobs, g_dseq, g_dres, g_dcig, g_dused, g_deh, g_dqc, g_dz;
@@ -114,7 +149,10 @@ namespace {
 
 int fail(ksw_b200_ctx *ctx, int code, const std::string &msg)
 {
-	if (ctx) ctx->err = msg;
+	if (ctx) {
+		std::lock_guard<std::mutex> lk(ctx->err_mu);
+		ctx->err = msg;
+	}
 	return code;
 }
 #define CU(call)                                                                                   \
@@ -154,13 +192,17 @@ void batch_release_buffers(ksw_b200_batch *b)
 {
 	b->d_jobs.release(); b->d_pool.release(); b->d_npool.release(); b->d_res.release(); b->d_cells.release();
 	b->d_order.release(); b->d_keys.release(); b->d_vals.release(); b->d_sort_tmp.release();
+	b->d_range.release();
 }
 
 // pack jobs[0..n) into the slot's pinned staging, start the H2D copies into `b` on the slot's stream and enqueue the
 // device-side binning behind them
 int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
-                    const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch *b, double *t_plan, double *t_fill)
+                    const uint8_t *qpool, const uint8_t *tpool, ksw_b200_batch *b, double *t_plan, double *t_fill,
+                    cudaStream_t copy_st = nullptr, cudaStream_t comp_st = nullptr)
 {
+	if (!copy_st) copy_st = s.stream;
+	if (!comp_st) comp_st = s.stream;
 	std::string err;
 	const double t0 = now_ms();
 	KswPool *tp = pool_of(ctx);
@@ -188,6 +230,7 @@ int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64
 	b->n_generic = st.class_n[KSW_FAST_CLASSES];
 	b->qmax_generic = st.class_qmax[KSW_FAST_CLASSES];
 	b->pool_bytes = st.pool_bytes; b->npool_bytes = npool_bytes;
+	b->dev_ranges = false;                                       // packed on the host: the class sizes are exact
 	ksw_params_from_cfg(cfg, b->P);
 	const size_t n1 = (size_t)std::max<int64_t>(n, 1);
 	const size_t tmp_bytes = ksw_bin_temp_bytes(n);
@@ -201,13 +244,17 @@ int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64
 	CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
 	CU(b->d_sort_tmp.reserve(std::max<size_t>(tmp_bytes, 16)));
 	if (n > 0) {
-		CU(cudaMemcpyAsync(b->d_jobs.p, s.h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemcpyAsync(b->d_jobs.p, s.h_jobs.p, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, copy_st));
 		if (st.pool_bytes)
-			CU(cudaMemcpyAsync(b->d_pool.p, s.h_pool.p, st.pool_bytes, cudaMemcpyHostToDevice, s.stream));
+			CU(cudaMemcpyAsync(b->d_pool.p, s.h_pool.p, st.pool_bytes, cudaMemcpyHostToDevice, copy_st));
 		if (npool_bytes)
-			CU(cudaMemcpyAsync(b->d_npool.p, s.h_npool.p, npool_bytes, cudaMemcpyHostToDevice, s.stream));
+			CU(cudaMemcpyAsync(b->d_npool.p, s.h_npool.p, npool_bytes, cudaMemcpyHostToDevice, copy_st));
+		if (copy_st != comp_st) {
+			CU(cudaEventRecord(s.ev_up, copy_st));
+			CU(cudaStreamWaitEvent(comp_st, s.ev_up, 0));
+		}
 		CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, n, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
-		                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, s.stream));
+		                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, comp_st));
 		ctx->launches += 2;                                      // key kernel + the radix sort (counted as one more)
 	}
 	return 0;
@@ -228,49 +275,63 @@ int ensure_generic_scratch(ksw_b200_ctx *ctx, Slot &s, int qmax, int &n_blocks)
 
 // launches the kernels of batch b on slot s's stream: the fast classes (contiguous in the binned order) are grouped
 // into as few launches as is free — a class is folded into the next one when it is small or when the next class's
-// actual longest query needs (almost) the same shared memory — then the generic kernel
-int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
+// actual longest query needs (almost) the same shared memory — then the generic kernel.
+// Device-packed batches (b->dev_ranges): the class sizes are upper bounds (a class-0 job that holds an N has moved to
+// class 1 on the device), so class 1 counts as populated whenever class 0 is, and every launch takes its bounds from
+// b->d_range.
+int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t st = nullptr)
 {
+	if (!st) st = s.stream;
+	int64_t cn[KSW_FAST_CLASSES];
+	int cq[KSW_FAST_CLASSES];
+	for (int x = 0; x < KSW_FAST_CLASSES; ++x) { cn[x] = b->fast_class_n[x]; cq[x] = b->fast_class_qmax[x]; }
+	if (b->dev_ranges && cn[0] > 0) { cn[1] += cn[0]; cq[1] = std::max(cq[1], cq[0]); }
+	const uint32_t *drange = b->dev_ranges ? (const uint32_t *)b->d_range.p : nullptr;
 	int64_t first = 0;
 	int c = 0;
 	CU(s.d_counter.reserve(sizeof(unsigned long long) * (KSW_FAST_CLASSES + 1)));
-	if (b->fast_class_n[0] > 0 && pair_enabled()) {
+	if (cn[0] > 0 && pair_enabled() && !b->dev_ranges) {
 		// class 0 goes to the pair kernel (two jobs per lane), unless it is a small minority next to other fast classes:
 		// then one launch of the one-job-per-lane kernel over all of them fills the GPU better than two thin launches
 		bool others = false;
-		for (int x = 1; x < KSW_FAST_CLASSES; ++x) others |= b->fast_class_n[x] > 0;
-		if (!others || b->fast_class_n[0] >= (int64_t)ctx->sm_count * 6 * 64 * 2) {
-			CU(ksw_launch_pair((const DevJob *)b->d_jobs.p, b->fast_class_n[0], (const uint32_t *)b->d_pool.p,
-			                   (const uint32_t *)b->d_npool.p, b->P, b->fast_class_qmax[0], ctx->sm_count,
+		for (int x = 1; x < KSW_FAST_CLASSES; ++x) others |= cn[x] > 0;
+		if (!others || cn[0] >= (int64_t)ctx->sm_count * 6 * 64 * 2) {
+			CU(ksw_launch_pair((const DevJob *)b->d_jobs.p, cn[0], (const uint32_t *)b->d_pool.p,
+			                   (const uint32_t *)b->d_npool.p, b->P, cq[0], ctx->sm_count,
 			                   (unsigned long long *)s.d_counter.p + KSW_FAST_CLASSES, (const uint32_t *)b->d_order.p,
-			                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, s.stream));
+			                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, st));
 			ctx->launches++;
-			first = b->fast_class_n[0];
+			first = cn[0];
 			c = 1;
 		}
 	}
+	const int64_t thin = (int64_t)ctx->sm_count * 13 * 32 * 4;
 	while (c < KSW_FAST_CLASSES) {
-		if (b->fast_class_n[c] <= 0) { ++c; continue; }
-		int64_t n_grp = b->fast_class_n[c];
-		int qmax = b->fast_class_qmax[c];
+		if (cn[c] <= 0) { ++c; continue; }
+		int64_t n_grp = cn[c];
+		int qmax = cq[c];
 		bool keyed = c == 0;
 		int e = c + 1;
 		while (e < KSW_FAST_CLASSES) {
-			if (b->fast_class_n[e] <= 0) { ++e; continue; }
-			const bool small = n_grp < (int64_t)ctx->sm_count * 13 * 32 * 4 || b->fast_class_n[e] < (int64_t)ctx->sm_count * 13 * 32 * 4;
-			const bool same_smem = KSW_FAST_QUADS(b->fast_class_qmax[e]) <= KSW_FAST_QUADS(qmax) + KSW_FAST_QUADS(qmax) / 8;
+			if (cn[e] <= 0) { ++e; continue; }
+			// the folding test looks at the host's own counts: class 1's upper bound of a device-packed batch would
+			// never look small
+			const int64_t ne = b->fast_class_n[e];
+			const bool small = n_grp < thin || ne < thin;
+			const bool same_smem = KSW_FAST_QUADS(cq[e]) <= KSW_FAST_QUADS(qmax) + KSW_FAST_QUADS(qmax) / 8;
 			// never give up the keyed variant of a big class 0 for a small neighbour; fold class 0 only if it is small itself
-			if (keyed && n_grp >= (int64_t)ctx->sm_count * 13 * 32 * 4) break;
+			if (keyed && n_grp >= thin) break;
 			if (!(small || same_smem)) break;
-			n_grp += b->fast_class_n[e];
-			qmax = std::max(qmax, b->fast_class_qmax[e]);
+			n_grp += cn[e];
+			qmax = std::max(qmax, cq[e]);
 			keyed = false;
 			++e;
 		}
+		while (e < KSW_FAST_CLASSES && cn[e] <= 0) ++e;          // empty classes in between belong to the range too
 		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p, n_grp, (const uint32_t *)b->d_pool.p,
 		                   (const uint32_t *)b->d_npool.p, b->P, qmax, keyed, ctx->sm_count,
-		                   (unsigned long long *)s.d_counter.p + c, (const uint32_t *)b->d_order.p + first,
-		                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, s.stream));
+		                   (unsigned long long *)s.d_counter.p + c, (const uint32_t *)b->d_order.p + (drange ? 0 : first),
+		                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, st, drange, c, e));
 		ctx->launches++;
 		first += n_grp;
 		c = e;
@@ -284,7 +345,7 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b)
 		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p, b->n_generic, (const uint32_t *)b->d_pool.p,
 		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)s.d_eh.p, (uint8_t *)s.d_qc.p,
 		                      n_blocks, (const uint32_t *)b->d_order.p + b->n_fast, (DevRes *)b->d_res.p,
-		                      (uint32_t *)b->d_cells.p, s.stream));
+		                      (uint32_t *)b->d_cells.p, st));
 		ctx->launches++;
 	}
 	return 0;
@@ -334,12 +395,32 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	ksw_b200_ctx *ctx = new ksw_b200_ctx();
 	ctx->device = device;
 	cudaError_t e = cudaSetDevice(device);
-	for (int i = 0; i < KSW_N_SLOTS && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking);
+	for (int i = 0; i < KSW_N_SLOTS && e == cudaSuccess; ++i) {
+		Slot &s = ctx->slot[i];
+		e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+		cudaEvent_t *evs[5] = {&s.ev_jobs, &s.ev_stats, &s.ev_up, &s.ev_ext, &s.ev_done};
+		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+	}
+	for (Slot &s : ctx->hslot) {
+		cudaEvent_t *evs[3] = {&s.ev_up, &s.ev_ext, &s.ev_done};
+		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+	}
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
 	if (e != cudaSuccess) {
 		fprintf(stderr, "[ksw_b200] cannot create context on device %d: %s\n", device, cudaGetErrorString(e));
+		for (Slot &s : ctx->slot) {
+			if (s.stream) cudaStreamDestroy(s.stream);
+			for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
+		}
+		for (Slot &s : ctx->hslot) for (cudaEvent_t ev : {s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
+		for (cudaStream_t st : {ctx->up_stream, ctx->main_stream, ctx->down_stream}) if (st) cudaStreamDestroy(st);
+		if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+		if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 		delete ctx;
 		return 100 + (int)e;
 	}
@@ -347,6 +428,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	ctx->pack_threads = (int)std::max(1u, std::min(hw ? hw : 8u, 32u));
 	if (const char *s = getenv("KSW_B200_CHUNK")) ctx->chunk_jobs = std::max<int64_t>(1024, atoll(s));
 	if (const char *s = getenv("KSW_B200_TRACE")) ctx->trace = atoi(s);
+	if (const char *s = getenv("KSW_B200_HYBRID")) ctx->hybrid = atoi(s);
 	*out = ctx;
 	return 0;
 }
@@ -354,13 +436,33 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 {
 	if (!ctx) return;
+	if (ctx->worker_started) {
+		{
+			std::unique_lock<std::mutex> lk(ctx->mu);
+			ctx->cv.wait(lk, [&] { return !ctx->req_pending && !ctx->req_running; });   // a batch in flight finishes first
+			ctx->stop = true;
+		}
+		ctx->cv.notify_all();
+		ctx->worker.join();
+	}
 	cudaSetDevice(ctx->device);
 	for (Slot &s : ctx->slot) {
 		if (s.stream) cudaStreamSynchronize(s.stream);
 		batch_release_buffers(&s.batch);
 		s.h_jobs.release(); s.h_pool.release(); s.h_npool.release(); s.h_res.release();
 		s.d_eh.release(); s.d_qc.release(); s.d_counter.release();
+		s.d_rawjobs.release(); s.d_units.release(); s.d_offs.release(); s.d_scan_tmp.release(); s.d_stats.release();
+		s.h_stats.release();
+		for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
 		if (s.stream) cudaStreamDestroy(s.stream);
+	}
+	ctx->d_qraw.release(); ctx->d_traw.release();
+	for (cudaStream_t st : {ctx->up_stream, ctx->main_stream, ctx->down_stream}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+	for (Slot &s : ctx->hslot) {
+		batch_release_buffers(&s.batch);
+		s.h_jobs.release(); s.h_pool.release(); s.h_npool.release();
+		s.d_eh.release(); s.d_qc.release(); s.d_counter.release();
+		for (cudaEvent_t ev : {s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
 	}
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -387,7 +489,7 @@ int ksw_b200_ctx_set_chunk_jobs(ksw_b200_ctx_t *ctx, int64_t chunk_jobs)
 	return 0;
 }
 
-int64_t ksw_b200_ctx_launch_count(const ksw_b200_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+int64_t ksw_b200_ctx_launch_count(const ksw_b200_ctx_t *ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
 
 int ksw_b200_ctx_sync(ksw_b200_ctx_t *ctx)
 {
@@ -526,6 +628,362 @@ int ksw_b200_extend_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		for (Slot &s : ctx->slot) { cudaStreamSynchronize(s.stream); s.busy = false; }
 	}
 	return rc;
+}
+
+// ---- pinned callers (ksw_b200_extend_batch_async).  The host does not have to touch the sequences: the raw job
+// records and the raw byte-coded sequences go to HBM as they are, packing runs on the device (ksw_devpack.cu), results
+// are copied straight into the caller's array.  Three streams: `up` (all host->device copies), `main` (all kernels),
+// `down` (results).  Device lane, per chunk c (c' = the lane's next chunk):
+//     up:    job records of c' | the bytes of the two sequence pools chunk c reads and no earlier chunk brought
+//     main:  prep(c') + its totals D2H -> pack(c) -> bin(c) -> extension kernels(c)
+//     down:  results(c) into res
+// prep(c') sits BEFORE the kernels of chunk c: the extension kernels fill every SM's shared memory, so nothing launched
+// later runs beside them, and the host needs the totals of c' (pool sizes, which pool bytes to upload) while the
+// extension kernels of c are running, so that the uploads of c' overlap them.  The lane only ever waits for those
+// totals and for a free slot.
+// Host lane (hybrid): raw bytes are 2.4x the packed bytes, so with idle host threads the link is the bottleneck.  A
+// second lane therefore packs chunks on the host threads (ksw_pack.cpp) and sends only their packed form.  Both lanes
+// draw chunks from one counter, each at its own pace (the host lane stops early enough not to become the tail), so the
+// split follows the hardware: with 16 host threads per GPU about half of the chunks, with 4 hardly any.
+static bool is_pinned(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
+
+namespace {
+
+// byte ranges of a pool that are already in HBM (disjoint, sorted); add() returns the missing pieces of [lo, hi)
+struct Uploaded {
+	std::vector<std::pair<size_t, size_t>> iv;
+	void add(size_t lo, size_t hi, std::vector<std::pair<size_t, size_t>> &missing)
+	{
+		missing.clear();
+		if (lo >= hi) return;
+		size_t cur = lo;
+		for (const auto &x : iv) {
+			if (x.second <= cur) continue;
+			if (x.first >= hi) break;
+			if (x.first > cur) missing.emplace_back(cur, x.first);
+			cur = std::max(cur, x.second);
+			if (cur >= hi) break;
+		}
+		if (cur < hi) missing.emplace_back(cur, hi);
+		// merge [lo, hi) into the set
+		std::vector<std::pair<size_t, size_t>> out;
+		size_t a = lo, b = hi;
+		bool placed = false;
+		for (const auto &x : iv) {
+			if (x.second < a) out.push_back(x);
+			else if (x.first > b) { if (!placed) { out.emplace_back(a, b); placed = true; } out.push_back(x); }
+			else { a = std::min(a, x.first); b = std::max(b, x.second); }
+		}
+		if (!placed) out.emplace_back(a, b);
+		iv.swap(out);
+	}
+};
+
+struct DevpackShared {                    // what the two lanes of one call share
+	std::atomic<long long> next{0};       // next unclaimed chunk
+	std::atomic<int> rc{0};               // first error of either lane
+	long long n_chunks = 0;
+	std::atomic<long long> h2d{0}, host_chunks{0};
+};
+
+} // namespace
+
+// finishing touches both lanes share: extension kernels, results home, slot marked busy
+static int devpack_finish_chunk(ksw_b200_ctx_t *ctx, Slot &s, int64_t first, int64_t nc, ksw_b200_res_t *res)
+{
+	int rc = enqueue_kernels(ctx, s, &s.batch, ctx->main_stream);
+	if (rc) return rc;
+	CU(cudaEventRecord(s.ev_ext, ctx->main_stream));
+	CU(cudaStreamWaitEvent(ctx->down_stream, s.ev_ext, 0));
+	CU(cudaMemcpyAsync(res + first, s.batch.d_res.p, sizeof(DevRes) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->down_stream));
+	CU(cudaEventRecord(s.ev_done, ctx->down_stream));
+	s.busy = true; s.first = first; s.n = nc;
+	return 0;
+}
+
+static int devpack_wait_slot(ksw_b200_ctx_t *ctx, Slot &s)
+{
+	if (!s.busy) return 0;
+	CU(cudaEventSynchronize(s.ev_done));
+	s.busy = false;
+	return 0;
+}
+
+// the host lane: packs whole chunks on the pack threads while the device lane works on others
+static void devpack_host_lane(ksw_b200_ctx_t *ctx, DevpackShared *sh, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                              const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
+{
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return;
+	const int64_t chunk = ctx->chunk_jobs;
+	int k = 0;
+	for (;;) {
+		if (sh->rc.load()) break;
+		// take a chunk only if the device lane will still be busy when it is packed: never become the tail
+		const long long remaining = sh->n_chunks - sh->next.load();
+		long long need = 4;
+		if (ctx->host_ms_per_job > 0 && ctx->dev_ms_per_job > 0)
+			need = (long long)(ctx->host_ms_per_job / ctx->dev_ms_per_job) + 2;
+		if (remaining < need) break;
+		const long long ci = sh->next.fetch_add(1);
+		if (ci >= sh->n_chunks) break;
+		const int64_t first = ci * chunk, nc = std::min<int64_t>(chunk, n - first);
+		Slot &s = ctx->hslot[k++ & 1];
+		int rc = devpack_wait_slot(ctx, s);
+		const double t0 = now_ms();
+		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, nullptr, nullptr, ctx->up_stream, ctx->main_stream);
+		const double dt = now_ms() - t0;
+		if (!rc) rc = devpack_finish_chunk(ctx, s, first, nc, res);
+		if (rc) { int z = 0; sh->rc.compare_exchange_strong(z, rc); break; }
+		ctx->host_ms_per_job = ctx->host_ms_per_job <= 0 ? dt / (double)nc : 0.5 * ctx->host_ms_per_job + 0.5 * dt / (double)nc;
+		sh->h2d += (long long)(sizeof(DevJob) * (size_t)nc + s.batch.pool_bytes + s.batch.npool_bytes);
+		sh->host_chunks++;
+	}
+}
+
+static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                                const uint8_t *qpool, size_t qbytes, const uint8_t *tpool, size_t tbytes, ksw_b200_res_t *res)
+{
+	if (cfg->m != 5) return fail(ctx, 2, "ksw_b200: only m == 5 is supported (every reference caller passes 5)");
+	if (n > 0x7fffffffLL) return fail(ctx, 2, "ksw_b200: more than 2^31-1 jobs in one batch");
+	const double t_begin = now_ms();
+	double t_wait = 0;
+	KswScoring S;
+	ksw_scoring_from_cfg(cfg, fast_qmax_enabled(), S);
+	KswParams P;
+	ksw_params_from_cfg(cfg, P);
+	CU(ctx->d_qraw.reserve(qbytes + 64));
+	CU(ctx->d_traw.reserve(tbytes + 64));
+	cudaStream_t up = ctx->up_stream, mainst = ctx->main_stream;
+	const int64_t chunk = ctx->chunk_jobs;
+	DevpackShared sh;
+	sh.n_chunks = (n + chunk - 1) / chunk;
+	Uploaded q_up, t_up;
+	std::vector<std::pair<size_t, size_t>> missing;
+	std::thread host_lane;
+	if (ctx->hybrid && sh.n_chunks >= 4) {
+		pool_of(ctx);                                               // created here, used by the host lane only
+		host_lane = std::thread(devpack_host_lane, ctx, &sh, cfg, n, jobs, qpool, tpool, res);
+	}
+	auto claim = [&]() -> long long { const long long c = sh.next.fetch_add(1); return c < sh.n_chunks ? c : -1; };
+	// job records of chunk ci to the device (upload stream), then its prep kernel and its totals home (main stream)
+	auto start_chunk = [&](long long ci) -> int {
+		Slot &s = ctx->slot[ci % KSW_N_SLOTS];
+		const int64_t first = ci * chunk, nc = std::min(chunk, n - first);
+		const size_t n1 = (size_t)nc;
+		{
+			const double t0 = now_ms();
+			int rc = devpack_wait_slot(ctx, s);
+			t_wait += now_ms() - t0;
+			if (rc) return rc;
+		}
+		CU(s.d_rawjobs.reserve(sizeof(ksw_b200_job_t) * n1));
+		CU(s.d_units.reserve(sizeof(uint32_t) * n1));
+		CU(s.d_offs.reserve(sizeof(uint32_t) * n1));
+		CU(s.d_scan_tmp.reserve(std::max<size_t>(ksw_devpack_scan_temp_bytes(nc), 16)));
+		CU(s.d_stats.reserve(sizeof(DevPackStats)));
+		CU(s.h_stats.reserve(sizeof(DevPackStats)));
+		CU(s.batch.d_jobs.reserve(sizeof(DevJob) * n1));
+		CU(cudaMemcpyAsync(s.d_rawjobs.p, jobs + first, sizeof(ksw_b200_job_t) * n1, cudaMemcpyHostToDevice, up));
+		CU(cudaEventRecord(s.ev_jobs, up));
+		sh.h2d += (long long)(sizeof(ksw_b200_job_t) * n1);
+		CU(cudaStreamWaitEvent(mainst, s.ev_jobs, 0));
+		CU(ksw_launch_prep(s.d_rawjobs.p, nc, S, (DevJob *)s.batch.d_jobs.p, (uint32_t *)s.d_units.p, (uint32_t *)s.d_offs.p,
+		                   s.d_scan_tmp.p, s.d_scan_tmp.cap, (DevPackStats *)s.d_stats.p, mainst));
+		CU(cudaMemcpyAsync(s.h_stats.p, s.d_stats.p, sizeof(DevPackStats), cudaMemcpyDeviceToHost, mainst));
+		CU(cudaEventRecord(s.ev_stats, mainst));
+		ctx->launches += 2;                                        // prep kernel + the scan (counted as one more)
+		return 0;
+	};
+	auto device_lane = [&]() -> int {
+		long long cur = claim();
+		if (cur >= 0) { int rc = start_chunk(cur); if (rc) return rc; }
+		double t_last = now_ms();
+		while (cur >= 0) {
+			if (sh.rc.load()) return 0;
+			const int64_t first = cur * chunk, nc = std::min(chunk, n - first);
+			const size_t n1 = (size_t)nc;
+			Slot &s = ctx->slot[cur % KSW_N_SLOTS];
+			ksw_b200_batch *b = &s.batch;
+			{
+				const double t0 = now_ms();
+				CU(cudaEventSynchronize(s.ev_stats));
+				t_wait += now_ms() - t0;
+			}
+			const DevPackStats st = *(const DevPackStats *)s.h_stats.p;
+			if (st.bad) return fail(ctx, 2, "ksw_b200: job with qlen < 1 or tlen < 0");
+			if (st.q_hi > qbytes || st.t_hi > tbytes) return fail(ctx, 2, "ksw_b200: a job reads past the end of its sequence pool");
+			if (st.units > 0xffffffffull) return fail(ctx, 2, "ksw_b200: packed pool exceeds 64 GiB");
+			b->n = nc; b->n_fast = 0;
+			for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
+				b->fast_class_n[c] = st.class_n[c];
+				b->fast_class_qmax[c] = st.class_qmax[c];
+				b->n_fast += st.class_n[c];
+			}
+			b->n_generic = st.class_n[KSW_FAST_CLASSES];
+			b->qmax_generic = st.class_qmax[KSW_FAST_CLASSES];
+			b->pool_bytes = (size_t)st.units * 16; b->npool_bytes = (size_t)st.nmask_words * 4;
+			b->P = P;
+			b->dev_ranges = true;
+			CU(b->d_pool.reserve(std::max<size_t>(b->pool_bytes, 16)));
+			CU(b->d_npool.reserve(std::max<size_t>(b->npool_bytes, 16)));
+			CU(b->d_res.reserve(sizeof(DevRes) * n1));
+			CU(b->d_cells.reserve(sizeof(uint32_t) * n1));
+			CU(b->d_order.reserve(sizeof(uint32_t) * n1));
+			CU(b->d_keys.reserve(sizeof(uint16_t) * 2 * n1));
+			CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
+			CU(b->d_sort_tmp.reserve(std::max<size_t>(ksw_bin_temp_bytes(nc), 16)));
+			CU(b->d_range.reserve(sizeof(uint32_t) * (KSW_FAST_CLASSES + 2)));
+			// the lane's next chunk: its records travel ahead of this chunk's sequences, its prep kernel runs ahead of
+			// this chunk's kernels
+			const long long nxt = claim();
+			if (nxt >= 0) { int rc = start_chunk(nxt); if (rc) return rc; }
+			// the bytes of the two pools this chunk reads and no earlier chunk has brought over
+			q_up.add((size_t)~st.q_lo_inv, (size_t)st.q_hi, missing);
+			for (const auto &m : missing) {
+				CU(cudaMemcpyAsync((uint8_t *)ctx->d_qraw.p + m.first, qpool + m.first, m.second - m.first, cudaMemcpyHostToDevice, up));
+				sh.h2d += (long long)(m.second - m.first);
+			}
+			t_up.add((size_t)~st.t_lo_inv, (size_t)st.t_hi, missing);
+			for (const auto &m : missing) {
+				CU(cudaMemcpyAsync((uint8_t *)ctx->d_traw.p + m.first, tpool + m.first, m.second - m.first, cudaMemcpyHostToDevice, up));
+				sh.h2d += (long long)(m.second - m.first);
+			}
+			CU(cudaEventRecord(s.ev_up, up));
+			CU(cudaStreamWaitEvent(mainst, s.ev_up, 0));
+			CU(ksw_launch_pack(s.d_rawjobs.p, nc, (const uint8_t *)ctx->d_qraw.p, (const uint8_t *)ctx->d_traw.p, (const uint32_t *)s.d_offs.p,
+			                   (DevJob *)b->d_jobs.p, (uint32_t *)b->d_pool.p, (uint32_t *)b->d_npool.p, (DevPackStats *)s.d_stats.p, mainst));
+			CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, nc, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
+			                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, mainst));
+			CU(ksw_launch_ranges((const uint16_t *)b->d_keys.p + n1, nc, (uint32_t *)b->d_range.p, mainst));
+			ctx->launches += 4;                                    // pack, key kernel, radix sort (one more), ranges
+			int rc = devpack_finish_chunk(ctx, s, first, nc, res);
+			if (rc) return rc;
+			const double t = now_ms();
+			const double per = (t - t_last) / (double)nc;
+			ctx->dev_ms_per_job = ctx->dev_ms_per_job <= 0 ? per : 0.5 * ctx->dev_ms_per_job + 0.5 * per;
+			t_last = t;
+			cur = nxt;
+		}
+		return 0;
+	};
+	int rc = device_lane();
+	if (rc) { int z = 0; sh.rc.compare_exchange_strong(z, rc); }
+	if (host_lane.joinable()) host_lane.join();
+	if (sh.rc.load()) return sh.rc.load();
+	for (Slot &s : ctx->slot) { rc = devpack_wait_slot(ctx, s); if (rc) return rc; }
+	for (Slot &s : ctx->hslot) { rc = devpack_wait_slot(ctx, s); if (rc) return rc; }
+	ctx->last_h2d = (int64_t)sh.h2d.load();
+	ctx->last_d2h = (int64_t)(sizeof(DevRes) * (size_t)n + sizeof(DevPackStats) * (size_t)(sh.n_chunks - sh.host_chunks.load()));
+	if (ctx->trace)
+		fprintf(stderr, "[ksw_b200] extend_batch_async n=%lld chunk=%lld: total %.2f ms (device lane waited %.2f; host lane packed %lld of %lld chunks; "
+		                "pace %.2f / %.2f ns per job)\n", (long long)n, (long long)chunk, now_ms() - t_begin, t_wait,
+		        (long long)sh.host_chunks.load(), (long long)sh.n_chunks, ctx->dev_ms_per_job * 1e6, ctx->host_ms_per_job * 1e6);
+	return 0;
+}
+
+static int run_devpack(ksw_b200_ctx_t *ctx, const AsyncReq &r)
+{
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+	const int rc = extend_batch_devpack(ctx, &r.cfg, r.n, r.jobs, r.qpool, r.qbytes, r.tpool, r.tbytes, r.res);
+	if (rc) {
+		// leave the context reusable: nothing may stay in flight or marked busy after a failed call
+		for (cudaStream_t st : {ctx->up_stream, ctx->main_stream, ctx->down_stream}) cudaStreamSynchronize(st);
+		for (Slot &s : ctx->slot) { cudaStreamSynchronize(s.stream); s.busy = false; }
+		for (Slot &s : ctx->hslot) s.busy = false;
+	}
+	return rc;
+}
+
+static void worker_main(ksw_b200_ctx_t *ctx)
+{
+	for (;;) {
+		AsyncReq r;
+		{
+			std::unique_lock<std::mutex> lk(ctx->mu);
+			ctx->cv.wait(lk, [&] { return ctx->stop || ctx->req_pending; });
+			if (ctx->stop) return;
+			r = ctx->req;
+			ctx->req_pending = false; ctx->req_running = true;
+		}
+		const int rc = run_devpack(ctx, r);
+		{
+			std::unique_lock<std::mutex> lk(ctx->mu);
+			ctx->async_rc = rc;
+			ctx->req_running = false;
+		}
+		ctx->cv.notify_all();
+	}
+}
+
+void *ksw_b200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void ksw_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int ksw_b200_host_register(void *p, size_t bytes)
+{
+	if (!p || !bytes) return 1;
+	cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); return 100 + (int)e; }
+	return 0;
+}
+
+int ksw_b200_host_unregister(void *p)
+{
+	if (!p) return 1;
+	cudaError_t e = cudaHostUnregister(p);
+	if (e != cudaSuccess) { cudaGetLastError(); return 100 + (int)e; }
+	return 0;
+}
+
+// Asynchronous batched entry for page-locked caller buffers: returns as soon as the batch is handed to
+// the context's feeder thread; ksw_b200_wait returns when res[0..n) is complete.  One batch in flight per context.
+int ksw_b200_extend_batch_async(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                                const uint8_t *qpool, size_t qpool_bytes, const uint8_t *tpool, size_t tpool_bytes,
+                                ksw_b200_res_t *res)
+{
+	if (!ctx || !cfg || n < 0) return 1;
+	if (n > 0 && (!jobs || !res)) return 1;
+	{
+		std::unique_lock<std::mutex> lk(ctx->mu);
+		if (ctx->req_pending || ctx->req_running) return fail(ctx, 4, "ksw_b200_extend_batch_async: a batch is already in flight on this context (call ksw_b200_wait first)");
+	}
+	if (n > 0) {
+		CU(cudaSetDevice(ctx->device));
+		if (!is_pinned(jobs) || !is_pinned(res) || (qpool_bytes && !is_pinned(qpool)) || (tpool_bytes && !is_pinned(tpool)))
+			return fail(ctx, 3, "ksw_b200_extend_batch_async: jobs, qpool, tpool and res must be page-locked "
+			                    "(ksw_b200_host_alloc / ksw_b200_host_register); pageable callers use ksw_b200_extend_batch");
+	}
+	std::unique_lock<std::mutex> lk(ctx->mu);
+	if (!ctx->worker_started) {
+		ctx->worker = std::thread(worker_main, ctx);
+		ctx->worker_started = true;
+	}
+	ctx->req.cfg = *cfg; ctx->req.n = n; ctx->req.jobs = jobs; ctx->req.qpool = qpool; ctx->req.tpool = tpool;
+	ctx->req.qbytes = qpool_bytes; ctx->req.tbytes = tpool_bytes; ctx->req.res = res;
+	ctx->async_rc = 0;
+	ctx->req_pending = true;
+	lk.unlock();
+	ctx->cv.notify_all();
+	return 0;
+}
+
+int ksw_b200_wait(ksw_b200_ctx_t *ctx)
+{
+	if (!ctx) return 1;
+	std::unique_lock<std::mutex> lk(ctx->mu);
+	ctx->cv.wait(lk, [&] { return !ctx->req_pending && !ctx->req_running; });
+	return ctx->async_rc;
 }
 
 // Multi-GPU form: jobs are independent, so the batch is cut into n_ctx contiguous ranges of (nearly)

@@ -89,6 +89,14 @@ def load_library():
     lib.ksw_b200_ctx_sync.argtypes = [vp]
     lib.ksw_b200_extend_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.ksw_b200_extend_batch_multi.argtypes = [i32, vp, vp, i64, vp, vp, vp, vp]
+    lib.ksw_b200_host_alloc.argtypes = [C.c_size_t]
+    lib.ksw_b200_host_alloc.restype = vp
+    lib.ksw_b200_host_free.argtypes = [vp]
+    lib.ksw_b200_host_free.restype = None
+    lib.ksw_b200_host_register.argtypes = [vp, C.c_size_t]
+    lib.ksw_b200_host_unregister.argtypes = [vp]
+    lib.ksw_b200_extend_batch_async.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
+    lib.ksw_b200_wait.argtypes = [vp]
     lib.ksw_b200_batch_upload.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(vp)]
     lib.ksw_b200_batch_run.argtypes = [vp, vp]
     lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
@@ -112,6 +120,41 @@ def load_library():
 
 def _p(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """A page-locked host array from ksw_b200_host_alloc, viewed as numpy (`.a`); freed with close() or by the GC."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if not np.isscalar(shape) else int(shape)
+        self.nbytes = n * dtype.itemsize
+        self.ptr = self.lib.ksw_b200_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise KswB200Error(f"ksw_b200_host_alloc({self.nbytes}) failed")
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.a = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes).view(dtype).reshape(shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.a = None
+            self.lib.ksw_b200_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pinned_copy(a: np.ndarray) -> PinnedArray:
+    """`a` copied into page-locked memory (what a C caller would have filled in place)."""
+    a = np.ascontiguousarray(a)
+    p = PinnedArray(a.shape, a.dtype)
+    p.a[...] = a
+    return p
 
 
 class ResidentBatch:
@@ -182,6 +225,19 @@ class KswB200:
         self._check(self.lib.ksw_b200_extend_batch(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool),
                                                    _p(tpool), _p(res)), "ksw_b200_extend_batch")
         return res
+
+    def extend_batch_async(self, cfg: Cfg, jobs: np.ndarray, qpool: np.ndarray, tpool: np.ndarray, res: np.ndarray):
+        """ksw_b200_extend_batch_async: all four arrays must live in page-locked memory (PinnedArray.a or registered)
+        and stay alive until wait() returns.  Packing runs on the device; returns immediately."""
+        assert jobs.dtype == JOB_DT and res.dtype == RES_DT and qpool.dtype == np.uint8 and tpool.dtype == np.uint8
+        assert jobs.flags.c_contiguous and res.flags.c_contiguous and qpool.flags.c_contiguous and tpool.flags.c_contiguous
+        assert res.shape[0] == jobs.shape[0]
+        self._cfg_keepalive = cfg
+        self._check(self.lib.ksw_b200_extend_batch_async(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool), qpool.nbytes,
+                                                         _p(tpool), tpool.nbytes, _p(res)), "ksw_b200_extend_batch_async")
+
+    def wait(self):
+        self._check(self.lib.ksw_b200_wait(self.ctx), "ksw_b200_wait")
 
     def global_batch(self, cfg: Cfg, jobs, qpool, tpool):
         """ksw_b200_global_batch: banded global alignment + backtrace of every job (GJOB_DT).  Returns

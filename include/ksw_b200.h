@@ -100,7 +100,26 @@ int ksw_b200_extend_batch_multi(int n_ctx, ksw_b200_ctx_t **ctxs, const ksw_b200
                                 const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
                                 ksw_b200_res_t *res);
 
-/* bytes the last ksw_b200_extend_batch call copied host->device and device->host */
+/* ---- asynchronous batched entry for page-locked caller buffers (SURVEY.md 8(b) "batched entry to add") ---------- */
+/* The caller owns pinned job / sequence / result arrays (allocated with ksw_b200_host_alloc, or its own memory pinned
+ * with ksw_b200_host_register).  ksw_b200_extend_batch_async hands the batch to the context and returns at once; the
+ * host does not touch the sequences: raw job records and raw byte-coded sequences are copied to the GPU as they are
+ * (cudaMemcpyAsync, chunk by chunk, on the context's streams), 2-bit packing, binning and the extension kernels run
+ * on the device, and the results are copied straight into res.  ksw_b200_wait returns when res[0..n) is complete.
+ * One batch in flight per context; jobs, qpool, tpool and res must stay valid and unmodified until ksw_b200_wait
+ * returns; no other call on this context in between.  qpool_bytes / tpool_bytes: sizes of the two pools (every job
+ * must lie inside them).  Errors: 3 = a buffer is not page-locked, 4 = a batch is already in flight; CUDA and job
+ * errors are reported by ksw_b200_wait.  Results are bit-identical to ksw_b200_extend_batch. */
+void *ksw_b200_host_alloc(size_t bytes);
+void  ksw_b200_host_free(void *p);
+int   ksw_b200_host_register(void *p, size_t bytes);
+int   ksw_b200_host_unregister(void *p);
+int ksw_b200_extend_batch_async(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs,
+                                const uint8_t *qpool, size_t qpool_bytes, const uint8_t *tpool, size_t tpool_bytes,
+                                ksw_b200_res_t *res);
+int ksw_b200_wait(ksw_b200_ctx_t *ctx);
+
+/* bytes the last ksw_b200_extend_batch / ksw_b200_extend_batch_async call copied host->device and device->host */
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /* ---- split form: upload once, run many times (bench / two-pass drivers) ----- */
