@@ -9,9 +9,13 @@ batched extension over the whole batch.
 
   value   GCUPS over *visited* DP cells (sum over executed rows of end-beg, ksw.c:418-421; counted by
           the kernels themselves and cross-checked against the oracle on the CPU sample), inputs
-          already packed and resident in HBM, kernels timed with CUDA events on the launching stream.
-  e2e     the same metric through the C-ABI call a host program makes (ksw_b200_extend_batch with
-          HOST buffers): 2-bit packing, H2D from pinned staging, kernels, D2H, every step.
+          already packed and resident in HBM; a step = binning (key kernel + radix sort) + the extension
+          kernels, timed with CUDA events on the launching stream.
+  e2e     the same metric through the C-ABI call a host program makes with HOST buffers
+          (ksw_b200_extend_batch_async + ksw_b200_wait on page-locked job / sequence / result arrays):
+          raw H2D, 2-bit packing on the device (some chunks on idle host threads), binning, kernels,
+          D2H into the caller's result array, every step.  `e2e_pageable` is the same through
+          ksw_b200_extend_batch on ordinary (pageable) arrays: host packing into pinned staging.
   roofline      cell-update rate against the DPX issue peak measured live by the library's probe
                 kernel (peak_CUPS = lane-ops/s x 2 cells / 8 issue slots); the path is
                 integer-issue bound, so the HBM figure is reported beside it as a sanity line.
@@ -266,24 +270,43 @@ def main():
     kernel_launches = l1 - l0
     rb.free()
 
-    # ---- end to end through the C ABI with host buffers (pack + H2D + kernels + D2H inside)
+    # ---- end to end through the C ABI with host buffers (copies, packing, binning, kernels, results inside)
     ne = a.e2e_jobs or n
     ej, eq, et = (jobs, qpool, tpool) if ne == n else (jobs[:ne], qpool, tpool)
     e_cells = float(cells_job[:ne].astype(np.int64).sum())
-    res_e2e = np.zeros(ne, dtype=B.RES_DT)                         # caller-owned result array, reused every step
+    # (1) page-locked caller buffers, asynchronous entry: what a host program that owns its buffers would call
+    pj, pq, pt = B.pinned_copy(ej), B.pinned_copy(eq), B.pinned_copy(et)
+    pr = B.PinnedArray(ne, B.RES_DT)
     for _ in range(max(a.warmup, 1)):
-        ctx.extend_batch(cfg, ej, eq, et, out=res_e2e)
-    res_e2e[:] = 0                                                 # so that the check below sees only timed-step results
+        ctx.extend_batch_async(cfg, pj.a, pq.a, pt.a, pr.a); ctx.wait()
+    pr.a[:] = 0                                                    # so that the check below sees only timed-step results
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        ctx.extend_batch(cfg, ej, eq, et, out=res_e2e)
+        ctx.extend_batch_async(cfg, pj.a, pq.a, pt.a, pr.a)
+        ctx.wait()
     t_e2e = time.perf_counter() - t0
     barrier()
     t_e2e_max = max_over_ranks(t_e2e)
     h2d, d2h = ctx.last_transfer()
     e2e_value = sum_over_ranks(e_cells) * a.steps / t_e2e_max / 1e9
-    same = all((res_e2e[f] == res_gpu[f][:ne]).all() for f in B.RES_DT.names)
+    same = all((pr.a[f] == res_gpu[f][:ne]).all() for f in B.RES_DT.names)
+    # (2) pageable caller buffers, synchronous entry (host packing into the library's pinned staging)
+    res_e2e = np.zeros(ne, dtype=B.RES_DT)
+    ctx.extend_batch(cfg, ej, eq, et, out=res_e2e)
+    res_e2e[:] = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ctx.extend_batch(cfg, ej, eq, et, out=res_e2e)
+    t_pg = time.perf_counter() - t0
+    barrier()
+    t_pg_max = max_over_ranks(t_pg)
+    h2d_pg, d2h_pg = ctx.last_transfer()
+    pg_value = sum_over_ranks(e_cells) * a.steps / t_pg_max / 1e9
+    same = same and all((res_e2e[f] == res_gpu[f][:ne]).all() for f in B.RES_DT.names)
+    for p in (pj, pq, pt, pr):
+        p.close()
 
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) + bit-exact check of that sample
     cpu = None
@@ -326,17 +349,26 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ext_per_s": ne * world * a.steps / t_e2e_max, "jobs_per_step_per_gpu": ne,
                     "ms_per_step": 1e3 * t_e2e_max / a.steps,
-                    "what": "ksw_b200_extend_batch on host byte-code buffers: pack + H2D + kernels + D2H"},
+                    "what": "ksw_b200_extend_batch_async + ksw_b200_wait on page-locked host byte-code buffers: raw H2D + "
+                            "packing on the device (idle host threads pack some chunks) + binning + kernels + D2H into the caller's array"},
+            "e2e_pageable": {"value": pg_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_pg), "d2h_bytes_per_step": int(d2h_pg),
+                             "ms_per_step": 1e3 * t_pg_max / a.steps,
+                             "what": "ksw_b200_extend_batch on pageable host buffers: host packing into pinned staging + H2D + "
+                                     "binning + kernels + D2H + copy into the caller's array"},
             "gpu_launches": int(kernel_launches),
+            "value_includes": "per step: binning (key kernel + radix sort) + extension kernels, all on the GPU",
             "roofline": {"bound": "dpx_issue", "achieved": per_gpu_gcups, "peak": peak_gcups, "unit": "GCUPS/GPU",
                          "frac": per_gpu_gcups / peak_gcups,
-                         # DRAM bytes per launch: ncu --set full of the same kernel on 400 k jobs measured 105.5 B/job
-                         # (profiles/r1_ncu_fast_kernel_summary.txt: 40.80 MB read + 1.39 MB write), scaled to this launch
-                         "traffic": 105.5 * n, "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum, 400k-job capture, per job x jobs",
+                         # DRAM bytes per launch are not measurable from inside this run: the figure is the ncu --set full
+                         # capture of the same kernel build on 400 k jobs (profiles/r2_ncu_fast_kernel_summary.txt:
+                         # 40.79 MB read + 1.48 MB write = 105.7 B/job), scaled to this launch's job count
+                         "traffic": 105.7 * n,
+                         "traffic_source": "ncu capture of the same kernel (400k jobs, dram__bytes_read.sum+dram__bytes_write.sum = 105.7 B/job) "
+                                           "x this launch's jobs; not measured in this run",
                          "peak_source": f"live DPX probe: {lane_ops / 1e12:.2f} T lane-ops/s x 2 cells / 8 issue slots "
                                         "(SURVEY.md 8d); not in MEASURED_PEAKS.json"},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes * a.steps / t_dev / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": alg_bytes * a.steps / t_dev / 1e9 / hbm_peak, "traffic": 105.5 * n,
+                             "frac": alg_bytes * a.steps / t_dev / 1e9 / hbm_peak, "traffic": 105.7 * n,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
         }

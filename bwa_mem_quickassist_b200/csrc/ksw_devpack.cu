@@ -4,9 +4,8 @@
 // the extension kernels read (ksw_dev.cuh):
 //
 //   ksw_prep_kernel   one thread per job: band clamp (ksw.c:398-406, same double expression as the host), kernel class,
-//                     DevJob record, size of the job's 2-bit sequences; chunk totals for the host (DevPackStats)
-//   (cub scan)        exclusive sum of the sizes = each job's offset in the 2-bit pool
-//   ksw_pack_kernel   one warp per job: 16 bases -> one 32-bit word per lane (base k in word k/16 at bits 2(k%16)),
+//                     DevJob record, the job's slice of the 2-bit pool; chunk totals for the host (DevPackStats)
+//   ksw_pack_kernel   sixteen lanes per job: 16 bases -> one 32-bit word per lane (base k in word k/16 at bits 2(k%16)),
 //                     N masks for the rare jobs that hold an N (allocated with one atomicAdd per such job); a class-0
 //                     job that holds an N moves to class 1, exactly as in the host packer (ksw_pack.cpp)
 //   ksw_range_kernel  after the binning sort: first entry of each kernel class in the binned order, read by the
@@ -15,7 +14,6 @@
 // Same routing source as the host packer (ksw_class.h), so a batch packed here runs through the same kernels in the
 // same classes as the same batch packed on the host; tests compare the two paths bit for bit.
 #include <cuda_runtime.h>
-#include <cub/device/device_scan.cuh>
 #include "../../include/ksw_b200.h"
 #include "ksw_class.h"
 #include "ksw_dev.cuh"
@@ -23,19 +21,21 @@
 
 namespace {
 
+// No shared memory and no separate scan kernel: the kernel is launched while the extension kernels of the previous chunk
+// fill every SM's shared memory, and must still find room beside them (a block without shared memory fits into the
+// 1 KB that 13 extension CTAs leave free).  Offsets in the 2-bit pool come from a warp-level exclusive scan plus one
+// atomicAdd per warp on the chunk total, so the order of the jobs' slices in the pool follows the order in which the
+// warps get there — it has no meaning, every job finds its slice through DevJob::seq_off.
 __global__ void __launch_bounds__(256)
 ksw_prep_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const KswScoring S, DevJob *__restrict__ jobs,
-                uint32_t *__restrict__ units, DevPackStats *__restrict__ stats)
+                uint32_t *__restrict__ offs, DevPackStats *__restrict__ stats)
 {
-	__shared__ unsigned long long s_units, s_nmask, s_qhi, s_thi, s_qlo, s_tlo;
-	__shared__ unsigned s_cn[KSW_FAST_CLASSES + 1];
-	__shared__ int s_qm[KSW_FAST_CLASSES + 1];
-	__shared__ unsigned s_bad;
-	if (threadIdx.x == 0) { s_units = 0; s_nmask = 0; s_qhi = 0; s_thi = 0; s_qlo = 0; s_tlo = 0; s_bad = 0; }
-	if (threadIdx.x <= KSW_FAST_CLASSES) { s_cn[threadIdx.x] = 0; s_qm[threadIdx.x] = 0; }
-	__syncthreads();
 	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned long long my_units = 0, my_nmask = 0, my_qhi = 0, my_thi = 0, my_qlo = 0, my_tlo = 0;   // *_lo hold ~offset
+	const int lane = threadIdx.x & 31;
+	unsigned long long my_nmask = 0, my_qhi = 0, my_thi = 0, my_qlo = 0, my_tlo = 0;   // *_lo hold ~offset
+	uint32_t my_units = 0, cls = 0xffu;
+	int my_qlen = 0;
+	bool bad = false;
 	if (k < n) {
 		const ksw_b200_job_t j = raw[k];
 		DevJob d;
@@ -43,52 +43,53 @@ ksw_prep_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const KswSc
 		d.h0 = j.h0 < 0 ? 0 : j.h0;                                                    // ksw.c:384
 		d.nmask_off = 0;
 		if (j.qlen < 1 || j.tlen < 0) {
-			s_bad = 1;                                                                  // benign race: any writer wins
+			bad = true;
 			d.qlen = 1; d.tlen = 0; d.w = 0; d.flags = KSW_CLASS_GENERIC << KSW_CLASS_SHIFT;
-			units[k] = 0;
 		} else {
 			d.w = ksw_clamp_w_expr(j.qlen, S.maxsc, S.o_del, S.e_del, S.o_ins, S.e_ins, j.w, S.end_bonus);
-			const uint32_t c = ksw_job_class(S, j.qlen, d.h0);
-			d.flags = c << KSW_CLASS_SHIFT;
-			const uint32_t u = ksw_job_units(j.qlen, j.tlen);
-			units[k] = u;
-			my_units = u;
+			cls = ksw_job_class(S, j.qlen, d.h0);
+			d.flags = cls << KSW_CLASS_SHIFT;
+			my_units = ksw_job_units(j.qlen, j.tlen);
 			my_nmask = ksw_words1(j.qlen) + ksw_words1(j.tlen);
 			my_qhi = j.q_off + (unsigned long long)j.qlen;
 			my_thi = j.t_off + (unsigned long long)j.tlen;
 			my_qlo = ~(unsigned long long)j.q_off;
 			if (j.tlen > 0) my_tlo = ~(unsigned long long)j.t_off;
-			atomicAdd(&s_cn[c], 1u);
-			atomicMax(&s_qm[c], j.qlen);
+			my_qlen = j.qlen;
 		}
 		jobs[k] = d;
 	}
-	// warp-level sums / maxima, then one shared atomic per warp and one global atomic per block
+	// this job's slice: exclusive scan of the sizes inside the warp, one atomicAdd per warp
+	uint32_t incl = my_units;
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += v;
+	}
+	const uint32_t warp_units = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned long long base = 0;
+	if (lane == 0 && warp_units) base = atomicAdd(&stats->units, (unsigned long long)warp_units);
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (k < n) offs[k] = (uint32_t)(base + incl - my_units);       // the host rejects chunks whose total exceeds 32 bits
+	// chunk totals: warp-level reductions, then one global atomic per warp and quantity
 	for (int o = 16; o > 0; o >>= 1) {
-		my_units += __shfl_down_sync(0xffffffffu, my_units, o);
 		my_nmask += __shfl_down_sync(0xffffffffu, my_nmask, o);
 		const unsigned long long a = __shfl_down_sync(0xffffffffu, my_qhi, o), b = __shfl_down_sync(0xffffffffu, my_thi, o);
-		my_qhi = my_qhi > a ? my_qhi : a;
-		my_thi = my_thi > b ? my_thi : b;
 		const unsigned long long c = __shfl_down_sync(0xffffffffu, my_qlo, o), d = __shfl_down_sync(0xffffffffu, my_tlo, o);
-		my_qlo = my_qlo > c ? my_qlo : c;
-		my_tlo = my_tlo > d ? my_tlo : d;
+		my_qhi = my_qhi > a ? my_qhi : a; my_thi = my_thi > b ? my_thi : b;
+		my_qlo = my_qlo > c ? my_qlo : c; my_tlo = my_tlo > d ? my_tlo : d;
 	}
-	if ((threadIdx.x & 31) == 0) {
-		atomicAdd(&s_units, my_units); atomicAdd(&s_nmask, my_nmask);
-		atomicMax(&s_qhi, my_qhi); atomicMax(&s_thi, my_thi);
-		atomicMax(&s_qlo, my_qlo); atomicMax(&s_tlo, my_tlo);
+	if (lane == 0) {
+		if (my_nmask) atomicAdd(&stats->nmask_words, my_nmask);
+		atomicMax(&stats->q_hi, my_qhi); atomicMax(&stats->t_hi, my_thi);
+		atomicMax(&stats->q_lo_inv, my_qlo); atomicMax(&stats->t_lo_inv, my_tlo);
 	}
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		atomicAdd(&stats->units, s_units); atomicAdd(&stats->nmask_words, s_nmask);
-		atomicMax(&stats->q_hi, s_qhi); atomicMax(&stats->t_hi, s_thi);
-		atomicMax(&stats->q_lo_inv, s_qlo); atomicMax(&stats->t_lo_inv, s_tlo);
-		if (s_bad) atomicOr(&stats->bad, 1u);
-	}
-	if (threadIdx.x <= KSW_FAST_CLASSES && s_cn[threadIdx.x]) {
-		atomicAdd(&stats->class_n[threadIdx.x], s_cn[threadIdx.x]);
-		atomicMax(&stats->class_qmax[threadIdx.x], s_qm[threadIdx.x]);
+	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&stats->bad, 1u);
+	for (uint32_t c = 0; c <= KSW_FAST_CLASSES; ++c) {
+		const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+		if (!m) continue;
+		int q = cls == c ? my_qlen : 0;
+		for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_down_sync(0xffffffffu, q, o); q = q > v ? q : v; }
+		if (lane == 0) { atomicAdd(&stats->class_n[c], (unsigned)__popc(m)); atomicMax(&stats->class_qmax[c], q); }
 	}
 }
 
@@ -126,16 +127,18 @@ __device__ __forceinline__ uint32_t squeeze16_dev(const uint8_t *__restrict__ s,
 	return word;
 }
 
-#define KSW_PACK_WARPS 8
+#define KSW_PACK_THREADS 512
+#define KSW_PACK_LANES 16            /* lanes per job: a 101 x 101 bp job is 7 + 7 words (+ 2 of padding) */
 
-__global__ void __launch_bounds__(KSW_PACK_WARPS * 32)
+__global__ void __launch_bounds__(KSW_PACK_THREADS)
 ksw_pack_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const uint8_t *__restrict__ qraw, const uint8_t *__restrict__ traw,
                 const uint32_t *__restrict__ offs, DevJob *__restrict__ jobs, uint32_t *__restrict__ pool,
                 uint32_t *__restrict__ npool, DevPackStats *__restrict__ stats)
 {
-	const int lane = threadIdx.x & 31;
-	const long long k = (long long)blockIdx.x * KSW_PACK_WARPS + (threadIdx.x >> 5);
-	if (k >= n) return;
+	const int sub = threadIdx.x & (KSW_PACK_LANES - 1);                                 // lane inside the job's half-warp
+	const unsigned grp = 0xffffu << (threadIdx.x & 16);                                 // the half-warp's lanes
+	const long long k = ((long long)blockIdx.x * KSW_PACK_THREADS + threadIdx.x) / KSW_PACK_LANES;
+	if (k >= n) return;                                                                 // whole half-warps leave together
 	const ksw_b200_job_t j = raw[k];
 	if (j.qlen < 1 || j.tlen < 0) return;                                              // reported by the prep kernel
 	const uint32_t qw = ksw_words2(j.qlen), tw = ksw_words2(j.tlen), total = ksw_job_units(j.qlen, j.tlen) * 4u;
@@ -143,26 +146,26 @@ ksw_pack_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const uint8
 	uint32_t *out = pool + (size_t)off * 4;
 	const uint8_t *q = qraw + j.q_off, *t = traw + j.t_off;
 	bool qn = false, tn = false;
-	for (uint32_t wi = lane; wi < total; wi += 32) {
+	for (uint32_t wi = sub; wi < total; wi += KSW_PACK_LANES) {
 		uint32_t word = 0, nb = 0;
 		if (wi < qw) { word = squeeze16_dev(q + 16 * wi, j.qlen - 16 * (int)wi, &nb); qn |= nb != 0; }
 		else if (wi < qw + tw) { word = squeeze16_dev(t + 16 * (wi - qw), j.tlen - 16 * (int)(wi - qw), &nb); tn |= nb != 0; }
 		out[wi] = word;
 	}
-	qn = __any_sync(0xffffffffu, qn);
-	tn = __any_sync(0xffffffffu, tn);
+	const unsigned bq = __ballot_sync(grp, qn), bt = __ballot_sync(grp, tn);
+	qn = (bq & grp) != 0; tn = (bt & grp) != 0;
 	if (!qn && !tn) {
-		if (lane == 0) jobs[k].seq_off = off;
+		if (sub == 0) jobs[k].seq_off = off;
 		return;
 	}
 	// rare: the job holds an N.  Masks (1 bit per base) go to the side pool: [query mask words][target mask words]
 	const uint32_t qmw = ksw_words1(j.qlen), tmw = ksw_words1(j.tlen);
 	uint32_t base = 0;
-	if (lane == 0) base = atomicAdd(&stats->nmask_used, (qn ? qmw : 0u) + (tn ? tmw : 0u));
-	base = __shfl_sync(0xffffffffu, base, 0);
+	if (sub == 0) base = atomicAdd(&stats->nmask_used, (qn ? qmw : 0u) + (tn ? tmw : 0u));
+	base = __shfl_sync(grp, base, threadIdx.x & 16);
 	uint32_t at = base;
 	if (qn) {
-		for (uint32_t mi = lane; mi < qmw; mi += 32) {
+		for (uint32_t mi = sub; mi < qmw; mi += KSW_PACK_LANES) {
 			uint32_t m = 0;
 			const int lim = j.qlen - 32 * (int)mi < 32 ? j.qlen - 32 * (int)mi : 32;
 			for (int x = 0; x < lim; ++x) if (q[32 * mi + x] > 3) m |= 1u << x;
@@ -171,14 +174,14 @@ ksw_pack_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const uint8
 		at += qmw;
 	}
 	if (tn) {
-		for (uint32_t mi = lane; mi < tmw; mi += 32) {
+		for (uint32_t mi = sub; mi < tmw; mi += KSW_PACK_LANES) {
 			uint32_t m = 0;
 			const int lim = j.tlen - 32 * (int)mi < 32 ? j.tlen - 32 * (int)mi : 32;
 			for (int x = 0; x < lim; ++x) if (t[32 * mi + x] > 3) m |= 1u << x;
 			npool[at + mi] = m;
 		}
 	}
-	if (lane == 0) {
+	if (sub == 0) {
 		DevJob d = jobs[k];
 		d.seq_off = off;
 		d.nmask_off = base;
@@ -206,30 +209,22 @@ __global__ void ksw_range_kernel(const uint16_t *__restrict__ sorted_keys, long 
 
 } // namespace
 
-size_t ksw_devpack_scan_temp_bytes(int64_t n)
-{
-	size_t bytes = 0;
-	cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n > 0 ? n : 1));
-	return bytes;
-}
-
-cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *units,
-                            uint32_t *offs, void *temp, size_t temp_bytes, DevPackStats *stats, cudaStream_t st)
+cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *offs,
+                            DevPackStats *stats, cudaStream_t st)
 {
 	if (n <= 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(DevPackStats), st);
 	if (e != cudaSuccess) return e;
-	ksw_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const ksw_b200_job_t *)raw_jobs, (long long)n, S, jobs, units, stats);
-	e = cudaGetLastError();
-	if (e != cudaSuccess) return e;
-	return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, (const uint32_t *)units, offs, (int)n, st);
+	ksw_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const ksw_b200_job_t *)raw_jobs, (long long)n, S, jobs, offs, stats);
+	return cudaGetLastError();
 }
 
 cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *traw, const uint32_t *offs,
                             DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st)
 {
 	if (n <= 0) return cudaSuccess;
-	ksw_pack_kernel<<<(unsigned)((n + KSW_PACK_WARPS - 1) / KSW_PACK_WARPS), KSW_PACK_WARPS * 32, 0, st>>>(
+	const long long per_block = KSW_PACK_THREADS / KSW_PACK_LANES;
+	ksw_pack_kernel<<<(unsigned)((n + per_block - 1) / per_block), KSW_PACK_THREADS, 0, st>>>(
 	    (const ksw_b200_job_t *)raw_jobs, (long long)n, qraw, traw, offs, jobs, pool, npool, stats);
 	return cudaGetLastError();
 }

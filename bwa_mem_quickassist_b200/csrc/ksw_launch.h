@@ -45,10 +45,9 @@ cudaError_t ksw_launch_bin(const DevJob *jobs, int64_t n, uint16_t *keys_in, uin
                            uint32_t *order, void *temp, size_t temp_bytes, cudaStream_t st);
 
 // device-side packing (ksw_devpack.cu): raw ksw_b200_job_t records + raw byte-coded sequences in HBM -> DevJob[] + 2-bit pool
-size_t ksw_devpack_scan_temp_bytes(int64_t n);
-// prep: DevJob records (seq_off left 0), sizes, their exclusive sum (offs), chunk totals (stats; zeroed first)
-cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *units,
-                            uint32_t *offs, void *temp, size_t temp_bytes, DevPackStats *stats, cudaStream_t st);
+// prep: DevJob records (seq_off left 0), each job's offset in the 2-bit pool (offs), chunk totals (stats; zeroed first)
+cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *offs,
+                            DevPackStats *stats, cudaStream_t st);
 cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *traw, const uint32_t *offs,
                             DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st);
 // range[c] = first entry of kernel class c in the binned order (c = 0..KSW_FAST_CLASSES+1; the last one is n)

@@ -61,7 +61,8 @@ double now_ms()
 
 } // namespace
 
-#define KSW_N_SLOTS 4
+#define KSW_N_SLOTS 6
+#define KSW_N_HSLOTS 3
 
 // ------------------------------------------------------------------ opaque types
 struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
@@ -92,9 +93,9 @@ struct Slot {
 	bool busy = false;                     // results of a chunk are in flight into h_res
 	int64_t first = 0, n = 0;              // caller range of that chunk
 	// device-side packing (pinned callers): raw job records, sizes / offsets of the 2-bit slices, chunk totals
-	DevBuf d_rawjobs, d_units, d_offs, d_scan_tmp, d_stats;
+	DevBuf d_rawjobs, d_offs, d_stats;
 	PinnedBuf h_stats;
-	cudaEvent_t ev_jobs = nullptr, ev_stats = nullptr, ev_up = nullptr, ev_ext = nullptr, ev_done = nullptr;
+	cudaEvent_t ev_jobs = nullptr, ev_stats = nullptr, ev_up = nullptr, ev_packed = nullptr, ev_ext = nullptr, ev_done = nullptr;
 	bool host_packed = false;              // pinned-caller pipeline: this chunk was packed on the host threads
 };
 
@@ -117,6 +118,7 @@ struct ksw_b200_ctx {
 	int pack_threads = 8;
 	KswPool *pool = nullptr;               // (re)created lazily with pack_threads workers
 	int64_t chunk_jobs = 1 << 20;
+	int64_t async_chunk_jobs = 1 << 19;    // pinned-caller pipeline: shorter chunks, the two lanes share them one by one
 	int trace = 0;
 	std::atomic<long long> launches{0};
 	int64_t last_h2d = 0, last_d2h = 0;    // bytes moved by the last ksw_b200_extend_batch call
@@ -129,9 +131,9 @@ struct ksw_b200_ctx {
 	// pinned callers (ksw_b200_extend_batch_async): the raw byte-coded pools in HBM, the stream their uploads are
 	// ordered on, and the worker thread that feeds the pipeline while the caller goes on
 	DevBuf d_qraw, d_traw;
-	cudaStream_t up_stream = nullptr, main_stream = nullptr, down_stream = nullptr;
+	cudaStream_t up_stream = nullptr, pre_stream = nullptr, main_stream = nullptr, ext2_stream = nullptr, host_stream = nullptr, down_stream = nullptr, hdown_stream = nullptr;
 	int hybrid = 1;                        // a second lane packs chunks on the host threads (KSW_B200_HYBRID=0: device packing only)
-	Slot hslot[2];                         // that lane's staging / device buffers (events only; it uses the shared streams)
+	Slot hslot[KSW_N_HSLOTS];                         // that lane's staging / device buffers (events only; it uses the shared streams)
 	double host_ms_per_job = 0, dev_ms_per_job = 0;   // measured pace of the two lanes (0 = not measured yet)
 	std::thread worker;
 	std::mutex mu;
@@ -398,7 +400,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	for (int i = 0; i < KSW_N_SLOTS && e == cudaSuccess; ++i) {
 		Slot &s = ctx->slot[i];
 		e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
-		cudaEvent_t *evs[5] = {&s.ev_jobs, &s.ev_stats, &s.ev_up, &s.ev_ext, &s.ev_done};
+		cudaEvent_t *evs[6] = {&s.ev_jobs, &s.ev_stats, &s.ev_up, &s.ev_packed, &s.ev_ext, &s.ev_done};
 		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 	}
 	for (Slot &s : ctx->hslot) {
@@ -407,6 +409,10 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->hdown_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ext2_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
@@ -415,10 +421,10 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 		fprintf(stderr, "[ksw_b200] cannot create context on device %d: %s\n", device, cudaGetErrorString(e));
 		for (Slot &s : ctx->slot) {
 			if (s.stream) cudaStreamDestroy(s.stream);
-			for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
+			for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_packed, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
 		}
 		for (Slot &s : ctx->hslot) for (cudaEvent_t ev : {s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
-		for (cudaStream_t st : {ctx->up_stream, ctx->main_stream, ctx->down_stream}) if (st) cudaStreamDestroy(st);
+		for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) if (st) cudaStreamDestroy(st);
 		if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 		if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 		delete ctx;
@@ -426,7 +432,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	}
 	unsigned hw = std::thread::hardware_concurrency();
 	ctx->pack_threads = (int)std::max(1u, std::min(hw ? hw : 8u, 32u));
-	if (const char *s = getenv("KSW_B200_CHUNK")) ctx->chunk_jobs = std::max<int64_t>(1024, atoll(s));
+	if (const char *s = getenv("KSW_B200_CHUNK")) ctx->chunk_jobs = ctx->async_chunk_jobs = std::max<int64_t>(1024, atoll(s));
 	if (const char *s = getenv("KSW_B200_TRACE")) ctx->trace = atoi(s);
 	if (const char *s = getenv("KSW_B200_HYBRID")) ctx->hybrid = atoi(s);
 	*out = ctx;
@@ -451,13 +457,13 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 		batch_release_buffers(&s.batch);
 		s.h_jobs.release(); s.h_pool.release(); s.h_npool.release(); s.h_res.release();
 		s.d_eh.release(); s.d_qc.release(); s.d_counter.release();
-		s.d_rawjobs.release(); s.d_units.release(); s.d_offs.release(); s.d_scan_tmp.release(); s.d_stats.release();
+		s.d_rawjobs.release(); s.d_offs.release(); s.d_stats.release();
 		s.h_stats.release();
-		for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
+		for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_packed, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
 		if (s.stream) cudaStreamDestroy(s.stream);
 	}
 	ctx->d_qraw.release(); ctx->d_traw.release();
-	for (cudaStream_t st : {ctx->up_stream, ctx->main_stream, ctx->down_stream}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+	for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
 	for (Slot &s : ctx->hslot) {
 		batch_release_buffers(&s.batch);
 		s.h_jobs.release(); s.h_pool.release(); s.h_npool.release();
@@ -485,7 +491,7 @@ int ksw_b200_ctx_set_pack_threads(ksw_b200_ctx_t *ctx, int n_threads)
 int ksw_b200_ctx_set_chunk_jobs(ksw_b200_ctx_t *ctx, int64_t chunk_jobs)
 {
 	if (!ctx || chunk_jobs < 1) return 1;
-	ctx->chunk_jobs = chunk_jobs;
+	ctx->chunk_jobs = ctx->async_chunk_jobs = chunk_jobs;
 	return 0;
 }
 
@@ -529,8 +535,15 @@ int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters
 	if (!ctx || !b || iters < 1 || !ms) return 1;
 	CU(cudaSetDevice(ctx->device));
 	Slot &s = ctx->slot[0];
+	const size_t n1 = (size_t)std::max<int64_t>(b->n, 1);
 	for (int i = 0; i < iters; ++i) {
 		CU(cudaEventRecord(ctx->ev0, s.stream));
+		// a step is everything the GPU does for a packed batch: binning (key kernel + radix sort) and the extension kernels
+		if (b->n > 0 && !b->dev_ranges) {
+			CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, b->n, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
+			                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, s.stream));
+			ctx->launches += 2;
+		}
 		int rc = enqueue_kernels(ctx, s, b);
 		if (rc) return rc;
 		CU(cudaEventRecord(ctx->ev1, s.stream));
@@ -684,24 +697,39 @@ struct Uploaded {
 	}
 };
 
+struct ChunkTimes {                       // KSW_B200_TRACE >= 2: where each chunk's time went on the GPU
+	cudaEvent_t up = nullptr, k0 = nullptr, k1 = nullptr, done = nullptr;
+	int lane = 0;
+	double host_enq = 0;
+};
+
 struct DevpackShared {                    // what the two lanes of one call share
 	std::atomic<long long> next{0};       // next unclaimed chunk
 	std::atomic<int> rc{0};               // first error of either lane
 	long long n_chunks = 0;
+	std::vector<int64_t> start;           // chunk ci = jobs [start[ci], start[ci+1]); the first two chunks are short so
+	                                      // that the GPU gets something to do early
 	std::atomic<long long> h2d{0}, host_chunks{0};
+	std::vector<ChunkTimes> times;        // empty unless tracing
+	cudaEvent_t t0 = nullptr;
+	double host_t0 = 0;
 };
 
 } // namespace
 
 // finishing touches both lanes share: extension kernels, results home, slot marked busy
-static int devpack_finish_chunk(ksw_b200_ctx_t *ctx, Slot &s, int64_t first, int64_t nc, ksw_b200_res_t *res)
+static int devpack_finish_chunk(ksw_b200_ctx_t *ctx, Slot &s, int64_t first, int64_t nc, ksw_b200_res_t *res, cudaStream_t lane,
+                                cudaStream_t down, ChunkTimes *tm = nullptr)
 {
-	int rc = enqueue_kernels(ctx, s, &s.batch, ctx->main_stream);
+	if (tm) { cudaEventCreate(&tm->k0); cudaEventCreate(&tm->k1); cudaEventCreate(&tm->done); cudaEventRecord(tm->k0, lane); }
+	int rc = enqueue_kernels(ctx, s, &s.batch, lane);
 	if (rc) return rc;
-	CU(cudaEventRecord(s.ev_ext, ctx->main_stream));
-	CU(cudaStreamWaitEvent(ctx->down_stream, s.ev_ext, 0));
-	CU(cudaMemcpyAsync(res + first, s.batch.d_res.p, sizeof(DevRes) * (size_t)nc, cudaMemcpyDeviceToHost, ctx->down_stream));
-	CU(cudaEventRecord(s.ev_done, ctx->down_stream));
+	if (tm) cudaEventRecord(tm->k1, lane);
+	CU(cudaEventRecord(s.ev_ext, lane));
+	CU(cudaStreamWaitEvent(down, s.ev_ext, 0));
+	CU(cudaMemcpyAsync(res + first, s.batch.d_res.p, sizeof(DevRes) * (size_t)nc, cudaMemcpyDeviceToHost, down));
+	CU(cudaEventRecord(s.ev_done, down));
+	if (tm) cudaEventRecord(tm->done, down);
 	s.busy = true; s.first = first; s.n = nc;
 	return 0;
 }
@@ -719,7 +747,6 @@ static void devpack_host_lane(ksw_b200_ctx_t *ctx, DevpackShared *sh, const ksw_
                               const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
 {
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return;
-	const int64_t chunk = ctx->chunk_jobs;
 	int k = 0;
 	for (;;) {
 		if (sh->rc.load()) break;
@@ -727,17 +754,19 @@ static void devpack_host_lane(ksw_b200_ctx_t *ctx, DevpackShared *sh, const ksw_
 		const long long remaining = sh->n_chunks - sh->next.load();
 		long long need = 4;
 		if (ctx->host_ms_per_job > 0 && ctx->dev_ms_per_job > 0)
-			need = (long long)(ctx->host_ms_per_job / ctx->dev_ms_per_job) + 2;
+			need = (long long)(ctx->host_ms_per_job / ctx->dev_ms_per_job + 0.999) + 1;
 		if (remaining < need) break;
 		const long long ci = sh->next.fetch_add(1);
 		if (ci >= sh->n_chunks) break;
-		const int64_t first = ci * chunk, nc = std::min<int64_t>(chunk, n - first);
-		Slot &s = ctx->hslot[k++ & 1];
+		const int64_t first = sh->start[(size_t)ci], nc = sh->start[(size_t)ci + 1] - first;
+		Slot &s = ctx->hslot[k++ % KSW_N_HSLOTS];
 		int rc = devpack_wait_slot(ctx, s);
 		const double t0 = now_ms();
-		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, nullptr, nullptr, ctx->up_stream, ctx->main_stream);
+		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, nullptr, nullptr, ctx->up_stream, ctx->host_stream);
 		const double dt = now_ms() - t0;
-		if (!rc) rc = devpack_finish_chunk(ctx, s, first, nc, res);
+		ChunkTimes *tm = sh->times.empty() ? nullptr : &sh->times[(size_t)ci];
+		if (tm) { tm->lane = 1; tm->host_enq = now_ms() - sh->host_t0; cudaEventCreate(&tm->up); cudaEventRecord(tm->up, ctx->up_stream); }
+		if (!rc) rc = devpack_finish_chunk(ctx, s, first, nc, res, ctx->host_stream, ctx->hdown_stream, tm);
 		if (rc) { int z = 0; sh->rc.compare_exchange_strong(z, rc); break; }
 		ctx->host_ms_per_job = ctx->host_ms_per_job <= 0 ? dt / (double)nc : 0.5 * ctx->host_ms_per_job + 0.5 * dt / (double)nc;
 		sh->h2d += (long long)(sizeof(DevJob) * (size_t)nc + s.batch.pool_bytes + s.batch.npool_bytes);
@@ -758,12 +787,27 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 	ksw_params_from_cfg(cfg, P);
 	CU(ctx->d_qraw.reserve(qbytes + 64));
 	CU(ctx->d_traw.reserve(tbytes + 64));
-	cudaStream_t up = ctx->up_stream, mainst = ctx->main_stream;
-	const int64_t chunk = ctx->chunk_jobs;
+	cudaStream_t up = ctx->up_stream, pre = ctx->pre_stream;
+	const int64_t chunk = ctx->async_chunk_jobs;
 	DevpackShared sh;
-	sh.n_chunks = (n + chunk - 1) / chunk;
+	{
+		int64_t at = 0;
+		const int64_t lead[2] = {std::max<int64_t>(chunk / 4, 1024), std::max<int64_t>(chunk / 2, 1024)};
+		for (int i = 0; at < n; ++i) {
+			sh.start.push_back(at);
+			at += std::min<int64_t>(n - at, (i < 2 && n > 2 * chunk) ? lead[i] : chunk);
+		}
+		sh.start.push_back(n);
+		sh.n_chunks = (long long)sh.start.size() - 1;
+	}
 	Uploaded q_up, t_up;
 	std::vector<std::pair<size_t, size_t>> missing;
+	if (ctx->trace >= 2) {
+		sh.times.resize((size_t)sh.n_chunks);
+		sh.host_t0 = now_ms();
+		cudaEventCreate(&sh.t0);
+		cudaEventRecord(sh.t0, up);
+	}
 	std::thread host_lane;
 	if (ctx->hybrid && sh.n_chunks >= 4) {
 		pool_of(ctx);                                               // created here, used by the host lane only
@@ -771,9 +815,12 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 	}
 	auto claim = [&]() -> long long { const long long c = sh.next.fetch_add(1); return c < sh.n_chunks ? c : -1; };
 	// job records of chunk ci to the device (upload stream), then its prep kernel and its totals home (main stream)
+	std::vector<int> slot_of((size_t)sh.n_chunks, 0);              // the device lane's chunks take its slots in turn
+	long long dev_seq = 0;
 	auto start_chunk = [&](long long ci) -> int {
-		Slot &s = ctx->slot[ci % KSW_N_SLOTS];
-		const int64_t first = ci * chunk, nc = std::min(chunk, n - first);
+		slot_of[(size_t)ci] = (int)(dev_seq++ % KSW_N_SLOTS);
+		Slot &s = ctx->slot[slot_of[(size_t)ci]];
+		const int64_t first = sh.start[(size_t)ci], nc = sh.start[(size_t)ci + 1] - first;
 		const size_t n1 = (size_t)nc;
 		{
 			const double t0 = now_ms();
@@ -782,32 +829,33 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 			if (rc) return rc;
 		}
 		CU(s.d_rawjobs.reserve(sizeof(ksw_b200_job_t) * n1));
-		CU(s.d_units.reserve(sizeof(uint32_t) * n1));
 		CU(s.d_offs.reserve(sizeof(uint32_t) * n1));
-		CU(s.d_scan_tmp.reserve(std::max<size_t>(ksw_devpack_scan_temp_bytes(nc), 16)));
 		CU(s.d_stats.reserve(sizeof(DevPackStats)));
 		CU(s.h_stats.reserve(sizeof(DevPackStats)));
 		CU(s.batch.d_jobs.reserve(sizeof(DevJob) * n1));
 		CU(cudaMemcpyAsync(s.d_rawjobs.p, jobs + first, sizeof(ksw_b200_job_t) * n1, cudaMemcpyHostToDevice, up));
 		CU(cudaEventRecord(s.ev_jobs, up));
 		sh.h2d += (long long)(sizeof(ksw_b200_job_t) * n1);
-		CU(cudaStreamWaitEvent(mainst, s.ev_jobs, 0));
-		CU(ksw_launch_prep(s.d_rawjobs.p, nc, S, (DevJob *)s.batch.d_jobs.p, (uint32_t *)s.d_units.p, (uint32_t *)s.d_offs.p,
-		                   s.d_scan_tmp.p, s.d_scan_tmp.cap, (DevPackStats *)s.d_stats.p, mainst));
-		CU(cudaMemcpyAsync(s.h_stats.p, s.d_stats.p, sizeof(DevPackStats), cudaMemcpyDeviceToHost, mainst));
-		CU(cudaEventRecord(s.ev_stats, mainst));
-		ctx->launches += 2;                                        // prep kernel + the scan (counted as one more)
+		CU(cudaStreamWaitEvent(pre, s.ev_jobs, 0));
+		CU(ksw_launch_prep(s.d_rawjobs.p, nc, S, (DevJob *)s.batch.d_jobs.p, (uint32_t *)s.d_offs.p, (DevPackStats *)s.d_stats.p, pre));
+		CU(cudaMemcpyAsync(s.h_stats.p, s.d_stats.p, sizeof(DevPackStats), cudaMemcpyDeviceToHost, pre));
+		CU(cudaEventRecord(s.ev_stats, pre));
+		ctx->launches += 1;
 		return 0;
 	};
 	auto device_lane = [&]() -> int {
-		long long cur = claim();
-		if (cur >= 0) { int rc = start_chunk(cur); if (rc) return rc; }
-		double t_last = now_ms();
+		// the lane works two chunks ahead: while chunk `cur` is being uploaded and run, the records of the next two are
+		// already on the device and their prep kernels sit ahead of cur's kernels in the stream, so that the totals of
+		// chunk cur+1 are back before cur's upload ends and the link never waits for the host
+		long long cur = claim(), nxt = -1;
+		if (cur >= 0) { int rc = start_chunk(cur); if (rc) return rc; nxt = claim(); }
+		if (nxt >= 0) { int rc = start_chunk(nxt); if (rc) return rc; }
+		long long dev_jobs_done = 0, ext_seq = 0;
 		while (cur >= 0) {
 			if (sh.rc.load()) return 0;
-			const int64_t first = cur * chunk, nc = std::min(chunk, n - first);
+			const int64_t first = sh.start[(size_t)cur], nc = sh.start[(size_t)cur + 1] - first;
 			const size_t n1 = (size_t)nc;
-			Slot &s = ctx->slot[cur % KSW_N_SLOTS];
+			Slot &s = ctx->slot[slot_of[(size_t)cur]];
 			ksw_b200_batch *b = &s.batch;
 			{
 				const double t0 = now_ms();
@@ -838,10 +886,10 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 			CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
 			CU(b->d_sort_tmp.reserve(std::max<size_t>(ksw_bin_temp_bytes(nc), 16)));
 			CU(b->d_range.reserve(sizeof(uint32_t) * (KSW_FAST_CLASSES + 2)));
-			// the lane's next chunk: its records travel ahead of this chunk's sequences, its prep kernel runs ahead of
+			// the chunk after next: its records travel ahead of this chunk's sequences, its prep kernel runs ahead of
 			// this chunk's kernels
-			const long long nxt = claim();
-			if (nxt >= 0) { int rc = start_chunk(nxt); if (rc) return rc; }
+			const long long nxt2 = nxt >= 0 ? claim() : -1;
+			if (nxt2 >= 0) { int rc = start_chunk(nxt2); if (rc) return rc; }
 			// the bytes of the two pools this chunk reads and no earlier chunk has brought over
 			q_up.add((size_t)~st.q_lo_inv, (size_t)st.q_hi, missing);
 			for (const auto &m : missing) {
@@ -854,31 +902,54 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 				sh.h2d += (long long)(m.second - m.first);
 			}
 			CU(cudaEventRecord(s.ev_up, up));
-			CU(cudaStreamWaitEvent(mainst, s.ev_up, 0));
+			CU(cudaStreamWaitEvent(pre, s.ev_up, 0));
+			ChunkTimes *tm = sh.times.empty() ? nullptr : &sh.times[(size_t)cur];
+			if (tm) { tm->lane = 0; tm->host_enq = now_ms() - sh.host_t0; cudaEventCreate(&tm->up); cudaEventRecord(tm->up, up); }
+			// pack / key kernels need no shared memory and run beside the previous chunk's extension kernels; the sort
+			// does and runs when those end
 			CU(ksw_launch_pack(s.d_rawjobs.p, nc, (const uint8_t *)ctx->d_qraw.p, (const uint8_t *)ctx->d_traw.p, (const uint32_t *)s.d_offs.p,
-			                   (DevJob *)b->d_jobs.p, (uint32_t *)b->d_pool.p, (uint32_t *)b->d_npool.p, (DevPackStats *)s.d_stats.p, mainst));
+			                   (DevJob *)b->d_jobs.p, (uint32_t *)b->d_pool.p, (uint32_t *)b->d_npool.p, (DevPackStats *)s.d_stats.p, pre));
 			CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, nc, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
-			                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, mainst));
-			CU(ksw_launch_ranges((const uint16_t *)b->d_keys.p + n1, nc, (uint32_t *)b->d_range.p, mainst));
+			                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, pre));
+			CU(ksw_launch_ranges((const uint16_t *)b->d_keys.p + n1, nc, (uint32_t *)b->d_range.p, pre));
+			CU(cudaEventRecord(s.ev_packed, pre));
 			ctx->launches += 4;                                    // pack, key kernel, radix sort (one more), ranges
-			int rc = devpack_finish_chunk(ctx, s, first, nc, res);
+			// extension kernels of consecutive chunks alternate between two streams: the next launch fills the SMs as
+			// the warps of the previous one run out of jobs
+			cudaStream_t ext = (ext_seq++ & 1) ? ctx->ext2_stream : ctx->main_stream;
+			CU(cudaStreamWaitEvent(ext, s.ev_packed, 0));
+			int rc = devpack_finish_chunk(ctx, s, first, nc, res, ext, ctx->down_stream, tm);
 			if (rc) return rc;
-			const double t = now_ms();
-			const double per = (t - t_last) / (double)nc;
-			ctx->dev_ms_per_job = ctx->dev_ms_per_job <= 0 ? per : 0.5 * ctx->dev_ms_per_job + 0.5 * per;
-			t_last = t;
-			cur = nxt;
+			dev_jobs_done += nc;
+			ctx->dev_ms_per_job = (now_ms() - t_begin) / (double)dev_jobs_done;   // the lane's pace so far, throttled by the GPU
+			cur = nxt; nxt = nxt2;
 		}
 		return 0;
 	};
 	int rc = device_lane();
 	if (rc) { int z = 0; sh.rc.compare_exchange_strong(z, rc); }
 	if (host_lane.joinable()) host_lane.join();
+	// a host lane that sat a call out (its last measured pace looked too slow, e.g. a cold first call) gets another try
+	if (ctx->hybrid && sh.n_chunks >= 4 && sh.host_chunks.load() == 0) ctx->host_ms_per_job *= 0.5;
 	if (sh.rc.load()) return sh.rc.load();
 	for (Slot &s : ctx->slot) { rc = devpack_wait_slot(ctx, s); if (rc) return rc; }
 	for (Slot &s : ctx->hslot) { rc = devpack_wait_slot(ctx, s); if (rc) return rc; }
 	ctx->last_h2d = (int64_t)sh.h2d.load();
 	ctx->last_d2h = (int64_t)(sizeof(DevRes) * (size_t)n + sizeof(DevPackStats) * (size_t)(sh.n_chunks - sh.host_chunks.load()));
+	if (!sh.times.empty()) {
+		fprintf(stderr, "[ksw_b200] chunk lane host-enqueue | upload-done kernels-start kernels-end results-home  (ms since the call began)\n");
+		for (size_t c = 0; c < sh.times.size(); ++c) {
+			ChunkTimes &t = sh.times[c];
+			float a = 0, b0 = 0, b1 = 0, d = 0;
+			if (t.up) cudaEventElapsedTime(&a, sh.t0, t.up);
+			if (t.k0) cudaEventElapsedTime(&b0, sh.t0, t.k0);
+			if (t.k1) cudaEventElapsedTime(&b1, sh.t0, t.k1);
+			if (t.done) cudaEventElapsedTime(&d, sh.t0, t.done);
+			fprintf(stderr, "[ksw_b200] %3zu %s %7.2f | %7.2f %7.2f %7.2f %7.2f\n", c, t.lane ? "host" : "dev ", t.host_enq, a, b0, b1, d);
+			for (cudaEvent_t ev : {t.up, t.k0, t.k1, t.done}) if (ev) cudaEventDestroy(ev);
+		}
+		cudaEventDestroy(sh.t0);
+	}
 	if (ctx->trace)
 		fprintf(stderr, "[ksw_b200] extend_batch_async n=%lld chunk=%lld: total %.2f ms (device lane waited %.2f; host lane packed %lld of %lld chunks; "
 		                "pace %.2f / %.2f ns per job)\n", (long long)n, (long long)chunk, now_ms() - t_begin, t_wait,
@@ -893,7 +964,7 @@ static int run_devpack(ksw_b200_ctx_t *ctx, const AsyncReq &r)
 	const int rc = extend_batch_devpack(ctx, &r.cfg, r.n, r.jobs, r.qpool, r.qbytes, r.tpool, r.tbytes, r.res);
 	if (rc) {
 		// leave the context reusable: nothing may stay in flight or marked busy after a failed call
-		for (cudaStream_t st : {ctx->up_stream, ctx->main_stream, ctx->down_stream}) cudaStreamSynchronize(st);
+		for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) cudaStreamSynchronize(st);
 		for (Slot &s : ctx->slot) { cudaStreamSynchronize(s.stream); s.busy = false; }
 		for (Slot &s : ctx->hslot) s.busy = false;
 	}

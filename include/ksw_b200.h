@@ -128,7 +128,8 @@ int ksw_b200_batch_upload(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
                           ksw_b200_batch_t **out);
 /* enqueue the kernels for a resident batch on the ctx stream (asynchronous) */
 int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);
-/* run `iters` times, each bracketed by CUDA events on the ctx stream; ms[i] = device time of run i */
+/* run `iters` times, each bracketed by CUDA events on the ctx stream; ms[i] = device time of run i.  A run is everything
+ * the GPU does for a packed batch: the binning (key kernel + radix sort) and the extension kernels */
 int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms);
 /* wait for the stream and copy results (caller's job order) to host */
 int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_res_t *res);
