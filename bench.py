@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="jobs in the CPU baseline sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--real-mix-reads", type=int, default=200_000,
+                    help="reads per harvested real job mix (0 = skip the real_mix leg)")
     return ap.parse_args()
 
 
@@ -130,6 +132,39 @@ def visited_cells_oracle(cfg, jobs, qpool, tpool, threads):
     import kswtest as K
     _, cells = K.run_oracle(K.Batch(cfg, jobs, qpool, tpool), threads=threads, want_cells=True)
     return cells
+
+
+def real_mixes(ctx, peak_gcups, n_reads):
+    """Job mixes harvested from the B200-bound `bwa mem` on synthetic reads of the BASELINE shapes (every job of both
+    extension passes, bwa_mem_quickassist_b200/jobdump.py), replayed through the resident kernel path: GCUPS over
+    visited cells, fraction of the DPX peak, bit-exact flag against the oracle for every job."""
+    import kswtest as K
+    from bwa_mem_quickassist_b200 import jobdump
+    out = {}
+    for mix in ("se100", "pe150", "pe250hi"):
+        try:
+            t0 = time.perf_counter()
+            batches = jobdump.harvest(mix, n_reads if mix != "pe250hi" else max(n_reads // 2, 2), genome_len=2_000_000, seed=7)
+            cfg, jobs, qpool, tpool = jobdump.merge(batches)
+            t_h = time.perf_counter() - t0
+            rb = ctx.upload(cfg, jobs, qpool, tpool)
+            info = rb.info()
+            ms = ctx.run_timed(rb, 5)[1:]
+            cells = ctx.download_cells(rb).astype(np.int64)
+            got = ctx.download(rb)
+            rb.free()
+            want, ocells = K.run_oracle(K.Batch(cfg, jobs, qpool, tpool), threads=os.cpu_count() or 1, want_cells=True)
+            ok = all((want[f] == got[f]).all() for f in want.dtype.names) and bool((ocells == cells).all())
+            g = float(cells.sum()) / float(ms.mean()) / 1e6
+            out[mix] = {"jobs": int(len(jobs)), "reads": int(n_reads if mix != "pe250hi" else max(n_reads // 2, 2)),
+                        "mean_qlen": float(jobs["qlen"].mean()), "mean_tlen": float(jobs["tlen"].mean()),
+                        "visited_cells_per_job": float(cells.mean()), "ms": float(ms.mean()), "gcups": g,
+                        "ext_per_s": len(jobs) / float(ms.mean()) * 1e3, "frac_of_dpx_peak": g / peak_gcups,
+                        "fast_jobs": info["n_fast"], "generic_jobs": info["n_generic"], "bit_exact": bool(ok),
+                        "harvest_s": t_h}
+        except Exception as e:                                       # e.g. integration/_bin/bwa_b200 did not travel
+            out[mix] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def run_reference_arm(a):
@@ -326,6 +361,10 @@ def main():
                "ext_per_s": ns / dt,
                "one_core": {"value": float(ocells[:n1].sum()) / dt1 / 1e9, "unit": UNIT, "ext_per_s": n1 / dt1, "sample": f"first {n1} jobs, 1 thread"}}
 
+    mixes = None
+    if rank == 0 and world == 1 and a.real_mix_reads > 0:
+        mixes = real_mixes(ctx, peak_gcups, a.real_mix_reads)
+
     if rank == 0:
         peaks = {}
         try:
@@ -371,6 +410,7 @@ def main():
                              "frac": alg_bytes * a.steps / t_dev / 1e9 / hbm_peak, "traffic": 105.7 * n,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "cpu_baseline": cpu, "parity": parity, "clocks": clocks,
+            "real_mix": mixes,
         }
         emit(line)
     ctx.close()

@@ -9,30 +9,15 @@ import kswtest as K
 import bwa_mem_quickassist_b200 as B
 
 
+from bwa_mem_quickassist_b200 import jobdump
+
+
 def read_batches(path, limit):
-    out = []
-    with open(path, "rb") as f:
-        while len(out) < limit:
-            magic = f.read(4)
-            if len(magic) < 4:
-                break
-            assert magic == b"KSWJ"
-            cfg = K.Cfg.from_buffer_copy(f.read(C.sizeof(K.Cfg)))
-            n, nq, nt = struct.unpack("<3Q", f.read(24))
-            jobs = np.frombuffer(f.read(32 * n), dtype=K.JOB_DT).copy()
-            q = np.frombuffer(f.read(nq), dtype=np.uint8).copy()
-            t = np.frombuffer(f.read(nt), dtype=np.uint8).copy()
-            out.append(K.Batch(cfg, jobs, q, t))
-    return out
+    return [K.Batch(*b) for b in jobdump.read_batches(path, limit)]
 
 
 def merge(batches):
-    """one big batch per end_bonus class (passes of many worker batches concatenated)"""
-    jobs, qs, ts, qo, to = [], [], [], 0, 0
-    for b in batches:
-        j = b.jobs.copy(); j["q_off"] += qo; j["t_off"] += to
-        jobs.append(j); qs.append(b.qpool); ts.append(b.tpool); qo += len(b.qpool); to += len(b.tpool)
-    return K.Batch(batches[0].cfg, np.concatenate(jobs), np.concatenate(qs), np.concatenate(ts))
+    return K.Batch(*jobdump.merge([(b.cfg, b.jobs, b.qpool, b.tpool) for b in batches]))
 
 
 def main():

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 BWA_STOCK = os.path.join(REFDIR, "bwa_stock")
 BWA_FORK = os.path.join(REFDIR, "bwa_fork")
-BWA_B200 = os.path.join(REFDIR, "bwa_b200")
+BWA_B200 = os.path.join(ROOT, "integration", "_bin", "bwa_b200")
 ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 COMP = np.array([3, 2, 1, 0], dtype=np.uint8)
 

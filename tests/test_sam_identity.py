@@ -33,7 +33,7 @@ def test_harness_fork_equals_stock_cpu(small_se):
     assert len(S.sam_body(str(d / "stock.sam"))) > 3000
 
 
-need_b200 = pytest.mark.skipif(not S.have_binaries(S.BWA_STOCK, S.BWA_B200), reason="oracle/_ref/bwa_b200 not built")
+need_b200 = pytest.mark.skipif(not S.have_binaries(S.BWA_STOCK, S.BWA_B200), reason="integration/_bin/bwa_b200 not built")
 
 
 @pytest.mark.gpu
