@@ -153,7 +153,8 @@ def real_mixes(ctx, peak_gcups, n_reads):
             cells = ctx.download_cells(rb).astype(np.int64)
             got = ctx.download(rb)
             rb.free()
-            want, ocells = K.run_oracle(K.Batch(cfg, jobs, qpool, tpool), threads=os.cpu_count() or 1, want_cells=True)
+            kcfg = K.Cfg.from_buffer_copy(bytes(cfg))            # same layout, the checker's own ctypes class
+            want, ocells = K.run_oracle(K.Batch(kcfg, jobs, qpool, tpool), threads=os.cpu_count() or 1, want_cells=True)
             ok = all((want[f] == got[f]).all() for f in want.dtype.names) and bool((ocells == cells).all())
             g = float(cells.sum()) / float(ms.mean()) / 1e6
             out[mix] = {"jobs": int(len(jobs)), "reads": int(n_reads if mix != "pe250hi" else max(n_reads // 2, 2)),

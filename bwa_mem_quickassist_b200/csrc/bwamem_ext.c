@@ -286,6 +286,8 @@ static void right_job(const b200_ext_plan_t *p, const chain_rec_t *ch, const b20
  * [magic "KSWJ"][cfg][n][qpool bytes][tpool bytes][jobs][qpool][tpool] for offline replay (scripts/bench_jobs.py). */
 #include <stdio.h>
 #include <unistd.h>
+#include <pthread.h>
+static pthread_mutex_t dump_mu = PTHREAD_MUTEX_INITIALIZER;     /* the worker threads of one process share the file */
 static void dump_jobs(const b200_ext_plan_t *p, const ksw_b200_cfg_t *cfg)
 {
 	const char *pre = getenv("KSW_B200_DUMP");
@@ -294,8 +296,9 @@ static void dump_jobs(const b200_ext_plan_t *p, const ksw_b200_cfg_t *cfg)
 	uint64_t hdr[3];
 	if (!pre || !*pre) return;
 	snprintf(path, sizeof(path), "%s.%d.bin", pre, (int)getpid());
+	pthread_mutex_lock(&dump_mu);
 	f = fopen(path, "ab");
-	if (!f) return;
+	if (!f) { pthread_mutex_unlock(&dump_mu); return; }
 	hdr[0] = p->jobs.n; hdr[1] = p->qpool.n; hdr[2] = p->tpool.n;
 	fwrite("KSWJ", 1, 4, f);
 	fwrite(cfg, sizeof(*cfg), 1, f);
@@ -304,6 +307,7 @@ static void dump_jobs(const b200_ext_plan_t *p, const ksw_b200_cfg_t *cfg)
 	fwrite(p->qpool.a, 1, p->qpool.n, f);
 	fwrite(p->tpool.a, 1, p->tpool.n, f);
 	fclose(f);
+	pthread_mutex_unlock(&dump_mu);
 }
 
 static int run_jobs(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg)

@@ -761,9 +761,9 @@ static void devpack_host_lane(ksw_b200_ctx_t *ctx, DevpackShared *sh, const ksw_
 		const int64_t first = sh->start[(size_t)ci], nc = sh->start[(size_t)ci + 1] - first;
 		Slot &s = ctx->hslot[k++ % KSW_N_HSLOTS];
 		int rc = devpack_wait_slot(ctx, s);
-		const double t0 = now_ms();
-		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, nullptr, nullptr, ctx->up_stream, ctx->host_stream);
-		const double dt = now_ms() - t0;
+		double t_plan = 0, t_fill = 0;
+		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, &t_plan, &t_fill, ctx->up_stream, ctx->host_stream);
+		const double dt = t_plan + t_fill;                           // packing proper: buffer growth (first calls) is not the lane's pace
 		ChunkTimes *tm = sh->times.empty() ? nullptr : &sh->times[(size_t)ci];
 		if (tm) { tm->lane = 1; tm->host_enq = now_ms() - sh->host_t0; cudaEventCreate(&tm->up); cudaEventRecord(tm->up, ctx->up_stream); }
 		if (!rc) rc = devpack_finish_chunk(ctx, s, first, nc, res, ctx->host_stream, ctx->hdown_stream, tm);
@@ -811,6 +811,12 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 	std::thread host_lane;
 	if (ctx->hybrid && sh.n_chunks >= 4) {
 		pool_of(ctx);                                               // created here, used by the host lane only
+		// the lane's pinned staging is sized here, from the average job, so that its first chunk does not pay for it
+		const size_t per_job = (size_t)((qbytes + tbytes) / (size_t)n) / 4 + 24;
+		for (Slot &hs : ctx->hslot) {
+			CU(hs.h_jobs.reserve(sizeof(DevJob) * (size_t)chunk));
+			CU(hs.h_pool.reserve(per_job * (size_t)chunk));
+		}
 		host_lane = std::thread(devpack_host_lane, ctx, &sh, cfg, n, jobs, qpool, tpool, res);
 	}
 	auto claim = [&]() -> long long { const long long c = sh.next.fetch_add(1); return c < sh.n_chunks ? c : -1; };
