@@ -1,8 +1,8 @@
 // ksw_bin.cu — binning on the device.  The host packer only streams (DevJob[k] describes the caller's job k); here
 // a key is computed per job and (key, k) pairs are radix-sorted (cub::DeviceRadixSort, 16-bit keys), which yields the
 // order in which the extension kernels take the jobs:
-//     key = generic bit | fast class | 63 - g(qlen) | 127 - f(h0)   (f exact below 96, then in steps of 16)
-// fast classes first (one contiguous range per class, so a launch is a sub-range), then the generic jobs; inside a
+//     key = kernel class | 63 - g(qlen) | 127 - f(h0)   (f exact below 96, then in steps of 16)
+// fast classes first (one contiguous range per class, so a launch is a sub-range), then the int32 kernels' jobs; inside a
 // class long jobs first (short tail at the end of a launch), then by carried-in score, which sets the band width.
 // A warp claims chunks of consecutive entries of this order, so the jobs it works on at any moment are alike.
 #include <cuda_runtime.h>
@@ -28,7 +28,8 @@ ksw_bin_keys_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__re
 	// band a job starts with, and the jobs of a warp finish their rows together only if their bands are alike
 	const uint32_t h0 = (uint32_t)jb.h0;
 	const uint32_t hb = 127u - (h0 < 96u ? h0 : 96u + min((h0 - 96u) >> 4, 31u));   // 7 bits
-	keys[k] = (uint16_t)((cls >= KSW_CLASS_GENERIC ? 0x8000u : (cls << 13)) | (tl << 7) | hb);
+	// fast classes: cls << 13; warp-cooperative jobs 0x8000 | ..., thread-per-job jobs 0xC000 | ... (13 key bits below)
+	keys[k] = (uint16_t)((cls >= KSW_CLASS_GENERIC ? (cls == KSW_CLASS_WARP ? 0x8000u : 0xC000u) : (cls << 13)) | (tl << 7) | hb);
 	vals[k] = (uint32_t)k;
 }
 

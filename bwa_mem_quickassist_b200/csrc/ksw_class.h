@@ -16,6 +16,7 @@ struct KswScoring {
 	int32_t maxsc, minsc;              // largest (floored at 0, like ksw.c:399) / smallest matrix entry
 	int32_t o_del, e_del, o_ins, e_ins, end_bonus;
 	int32_t fast_qmax;                 // largest qlen the fast kernel accepts (0: fast kernel disabled)
+	int32_t warp_qmax;                 // largest qlen the warp-cooperative kernel accepts (0: disabled)
 };
 
 // the reference's band clamp (ksw.c:398-406), evaluated with the identical C expression (IEEE double division on
@@ -44,10 +45,24 @@ static KSW_HD bool ksw_fast_eligible(const KswScoring &S, int qlen, int h0)
 	return true;
 }
 
+// The warp-cooperative int32 kernel (ksw_warp.cu) takes what the s16x2 kernel cannot hold if the row is long enough to
+// occupy 32 lanes and the query's columns fit an SM's shared memory; its F scan relies on o_ins >= 0 like the fast
+// kernel's, and its offsets on scores far inside int32.
+#define KSW_WARP_MIN_QLEN 129
+#define KSW_WARP_MAX_QLEN 24000
+static KSW_HD bool ksw_warp_eligible(const KswScoring &S, int qlen, int h0)
+{
+	if (qlen < KSW_WARP_MIN_QLEN || qlen > S.warp_qmax) return false;
+	if (S.o_ins < 0 || S.e_ins < 0 || S.o_ins > (1 << 20) || S.e_ins > (1 << 20) || S.o_del > (1 << 20) || S.e_del > (1 << 20)) return false;
+	if (S.o_del < -(1 << 20) || S.e_del < -(1 << 20)) return false;
+	if ((long long)h0 + (long long)qlen * S.maxsc > (1ll << 27)) return false;
+	return true;
+}
+
 // kernel class of a job before its sequences have been looked at (a class-0 job that holds an N moves to class 1)
 static KSW_HD uint32_t ksw_job_class(const KswScoring &S, int qlen, int h0)
 {
-	if (!ksw_fast_eligible(S, qlen, h0)) return KSW_CLASS_GENERIC;
+	if (!ksw_fast_eligible(S, qlen, h0)) return ksw_warp_eligible(S, qlen, h0) ? KSW_CLASS_WARP : KSW_CLASS_THREAD;
 	if (qlen <= ksw_fast_class_qmax(0) && (long long)h0 + (long long)qlen * S.maxsc + S.o_del + S.e_del <= KSW_FAST_KEYED_MAXSCORE) return 0;
 	uint32_t qc = 1;
 	while (qc + 1 < KSW_FAST_CLASSES && qlen > ksw_fast_class_qmax((int)qc)) ++qc;

@@ -61,8 +61,8 @@ struct DevPackStats {
 	unsigned long long nmask_words;    // words of the N side pool if every job held an N in both sequences (capacity)
 	unsigned long long q_hi, t_hi;     // one past the last query / target byte any job of the chunk reads
 	unsigned long long q_lo_inv, t_lo_inv;   // ~(first query / target byte any job reads): a maximum, so that 0 initialises it
-	unsigned int class_n[5];           // jobs per kernel class before the N demotion (class 0 -> 1)
-	int class_qmax[5];                 // longest query per class, before the N demotion
+	unsigned int class_n[6];           // jobs per kernel class (KSW_N_CLASSES) before the N demotion (class 0 -> 1)
+	int class_qmax[6];                 // longest query per class, before the N demotion
 	unsigned int bad;                  // a job with qlen < 1 or tlen < 0
 	unsigned int nmask_used;
 };
@@ -78,7 +78,10 @@ struct KswParams {          // passed by value as a kernel parameter (constant b
 
 #define KSW_CLASS_SHIFT 8
 #define KSW_CLASS_MASK 0xfu
-#define KSW_CLASS_GENERIC 4u          /* classes 0..3: fast kernel (0 = keyed), 4: generic int32 kernel */
+#define KSW_CLASS_GENERIC 4u          /* classes 0..3: fast s16x2 kernel (0 = keyed); >= 4: the int32 kernels */
+#define KSW_CLASS_WARP 4u             /* one job per warp, columns in shared memory (ksw_warp.cu) */
+#define KSW_CLASS_THREAD 5u           /* one job per thread, columns in HBM (ksw_generic.cu): everything else */
+#define KSW_N_CLASSES 6
 
 #define KSW_FLAG_QN 1u
 #define KSW_FLAG_TN 2u

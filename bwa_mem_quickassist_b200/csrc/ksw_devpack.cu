@@ -44,7 +44,7 @@ ksw_prep_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const KswSc
 		d.nmask_off = 0;
 		if (j.qlen < 1 || j.tlen < 0) {
 			bad = true;
-			d.qlen = 1; d.tlen = 0; d.w = 0; d.flags = KSW_CLASS_GENERIC << KSW_CLASS_SHIFT;
+			d.qlen = 1; d.tlen = 0; d.w = 0; d.flags = KSW_CLASS_THREAD << KSW_CLASS_SHIFT;
 		} else {
 			d.w = ksw_clamp_w_expr(j.qlen, S.maxsc, S.o_del, S.e_del, S.o_ins, S.e_ins, j.w, S.end_bonus);
 			cls = ksw_job_class(S, j.qlen, d.h0);
@@ -84,7 +84,7 @@ ksw_prep_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const KswSc
 		atomicMax(&stats->q_lo_inv, my_qlo); atomicMax(&stats->t_lo_inv, my_tlo);
 	}
 	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&stats->bad, 1u);
-	for (uint32_t c = 0; c <= KSW_FAST_CLASSES; ++c) {
+	for (uint32_t c = 0; c < KSW_N_CLASSES; ++c) {
 		const unsigned m = __ballot_sync(0xffffffffu, cls == c);
 		if (!m) continue;
 		int q = cls == c ? my_qlen : 0;
@@ -195,10 +195,10 @@ ksw_pack_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const uint8
 // sorted_keys: the binning keys in ascending order (ksw_bin.cu): class c occupies [range[c], range[c+1])
 __global__ void ksw_range_kernel(const uint16_t *__restrict__ sorted_keys, long long n, uint32_t *__restrict__ range)
 {
-	const int c = threadIdx.x;                                                          // 0 .. KSW_FAST_CLASSES + 1
-	if (c > KSW_FAST_CLASSES + 1) return;
-	if (c == KSW_FAST_CLASSES + 1) { range[c] = (uint32_t)n; return; }
-	const uint32_t lowest = c >= (int)KSW_CLASS_GENERIC ? 0x8000u : ((uint32_t)c << 13);  // smallest key of class c
+	const int c = threadIdx.x;                                                          // 0 .. KSW_N_CLASSES
+	if (c > KSW_N_CLASSES) return;
+	if (c == KSW_N_CLASSES) { range[c] = (uint32_t)n; return; }
+	const uint32_t lowest = c >= (int)KSW_CLASS_GENERIC ? (c == (int)KSW_CLASS_WARP ? 0x8000u : 0xC000u) : ((uint32_t)c << 13);  // smallest key of class c
 	long long lo = 0, hi = n;
 	while (lo < hi) {
 		const long long mid = (lo + hi) >> 1;

@@ -18,6 +18,12 @@ cudaError_t ksw_launch_global(const DevGJob *jobs, int64_t n_jobs, const uint8_t
                               uint8_t *qc, uint8_t *z, long long zcap, int n_blocks, unsigned long long *pool_used,
                               uint32_t *cigar_pool, DevGRes *res, cudaStream_t st);
 
+// warp-cooperative int32 kernel (ksw_warp.cu) over the jobs jobs[order[0..n_jobs)]: one job per warp, qlen <= qmax
+cudaError_t ksw_launch_warp(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool, const KswParams &P,
+                            int qmax, int sm_count, unsigned long long *counter, const uint32_t *order, DevRes *res,
+                            uint32_t *cells, cudaStream_t st);
+size_t ksw_warp_smem_bytes(int qmax);
+
 // DPX issue-rate probe; each thread issues iters*32 DPX instructions
 cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iters, cudaStream_t st);
 
@@ -50,5 +56,5 @@ cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S
                             DevPackStats *stats, cudaStream_t st);
 cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *traw, const uint32_t *offs,
                             DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st);
-// range[c] = first entry of kernel class c in the binned order (c = 0..KSW_FAST_CLASSES+1; the last one is n)
+// range[c] = first entry of kernel class c in the binned order (c = 0..KSW_N_CLASSES; the last one is n)
 cudaError_t ksw_launch_ranges(const uint16_t *sorted_keys, int64_t n, uint32_t *range, cudaStream_t st);

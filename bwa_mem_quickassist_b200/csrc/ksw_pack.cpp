@@ -2,6 +2,7 @@
 #include "ksw_pack.h"
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -123,6 +124,9 @@ void ksw_scoring_from_cfg(const ksw_b200_cfg_t *cfg, int fast_qmax, KswScoring &
 	for (int i = 0; i < 25; ++i) S.minsc = std::min<int>(S.minsc, cfg->mat[i]);
 	S.o_del = cfg->o_del; S.e_del = cfg->e_del; S.o_ins = cfg->o_ins; S.e_ins = cfg->e_ins;
 	S.end_bonus = cfg->end_bonus; S.fast_qmax = fast_qmax;
+	// KSW_B200_DISABLE_WARP=1 (A/B switch): what the warp-cooperative kernel would take goes to the thread-per-job kernel
+	static const int warp_qmax = [] { const char *e = getenv("KSW_B200_DISABLE_WARP"); return (e && *e && *e != '0') ? 0 : KSW_WARP_MAX_QLEN; }();
+	S.warp_qmax = warp_qmax;
 }
 
 void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P)
@@ -152,7 +156,7 @@ int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *j
 	ksw_scoring_from_cfg(cfg, fast_qmax, S);
 	const int T = pack_ranges(tp, n);
 	const int64_t per = (n + T - 1) / T;
-	struct Local { int64_t cn[KSW_FAST_CLASSES + 1]; int qm[KSW_FAST_CLASSES + 1]; uint64_t units; int bad; char pad[64]; };
+	struct Local { int64_t cn[KSW_N_CLASSES]; int qm[KSW_N_CLASSES]; uint64_t units; int bad; char pad[64]; };
 	std::vector<Local> loc(T);
 	run_ranges(tp, T, [&](int t) {
 		Local l;
@@ -169,13 +173,13 @@ int ksw_pack_sizes(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *j
 	});
 	st.n = n;
 	st.range_base.assign(T + 1, 0);
-	for (int c = 0; c <= KSW_FAST_CLASSES; ++c) { st.class_n[c] = 0; st.class_qmax[c] = 0; }
+	for (int c = 0; c < KSW_N_CLASSES; ++c) { st.class_n[c] = 0; st.class_qmax[c] = 0; }
 	uint64_t off = 0;
 	for (int t = 0; t < T; ++t) {
 		if (loc[t].bad) { err = "ksw_b200: job with qlen < 1 or tlen < 0"; return 2; }
 		st.range_base[t] = off;
 		off += loc[t].units;
-		for (int c = 0; c <= KSW_FAST_CLASSES; ++c) { st.class_n[c] += loc[t].cn[c]; st.class_qmax[c] = std::max(st.class_qmax[c], loc[t].qm[c]); }
+		for (int c = 0; c < KSW_N_CLASSES; ++c) { st.class_n[c] += loc[t].cn[c]; st.class_qmax[c] = std::max(st.class_qmax[c], loc[t].qm[c]); }
 	}
 	st.range_base[T] = off;
 	if (off > 0xffffffffull) { err = "ksw_b200: packed pool exceeds 64 GiB"; return 2; }

@@ -31,11 +31,11 @@ private:
 static const int KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES] = {124, 128, 256, 512};
 
 // What the launcher needs to know about a packed batch.  Classes 0..KSW_FAST_CLASSES-1 are the fast kernel's,
-// class KSW_FAST_CLASSES is the generic kernel's.
+// KSW_CLASS_WARP the warp-cooperative int32 kernel's, KSW_CLASS_THREAD the thread-per-job generic kernel's.
 struct KswPackStats {
 	int64_t n = 0;
-	int64_t class_n[KSW_FAST_CLASSES + 1] = {0, 0, 0, 0, 0};
-	int class_qmax[KSW_FAST_CLASSES + 1] = {0, 0, 0, 0, 0};
+	int64_t class_n[KSW_N_CLASSES] = {0, 0, 0, 0, 0, 0};
+	int class_qmax[KSW_N_CLASSES] = {0, 0, 0, 0, 0, 0};
 	size_t pool_bytes = 0;                 // bytes of the 2-bit pool (multiple of 16)
 	std::vector<uint64_t> range_base;      // scratch: pool offset (16-byte units) at which each host thread's range starts
 };

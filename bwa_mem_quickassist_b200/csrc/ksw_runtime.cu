@@ -66,14 +66,14 @@ double now_ms()
 
 // ------------------------------------------------------------------ opaque types
 struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
-	int64_t n = 0, n_fast = 0, n_generic = 0;
+	int64_t n = 0, n_fast = 0, n_warp = 0, n_generic = 0;   // n_generic: the thread-per-job kernel's jobs
 	int64_t fast_class_n[KSW_FAST_CLASSES] = {0, 0, 0, 0};
 	int fast_class_qmax[KSW_FAST_CLASSES] = {0, 0, 0, 0};
 	KswParams P;
 	DevBuf d_jobs, d_pool, d_npool, d_res, d_cells;
 	DevBuf d_order, d_keys, d_vals, d_sort_tmp;                 // device-side binning (ksw_bin.cu)
 	size_t pool_bytes = 0, npool_bytes = 0;
-	int qmax_generic = 0;
+	int qmax_warp = 0, qmax_generic = 0;
 	// device-packed batches (ksw_devpack.cu): the class sizes above are the host's view BEFORE class-0 jobs that hold an
 	// N moved to class 1; the kernels read the true class bounds of the binned order from d_range
 	bool dev_ranges = false;
@@ -229,8 +229,9 @@ int pack_and_upload(ksw_b200_ctx *ctx, Slot &s, const ksw_b200_cfg_t *cfg, int64
 		b->fast_class_qmax[c] = st.class_qmax[c];
 		b->n_fast += st.class_n[c];
 	}
-	b->n_generic = st.class_n[KSW_FAST_CLASSES];
-	b->qmax_generic = st.class_qmax[KSW_FAST_CLASSES];
+	b->n_warp = st.class_n[KSW_CLASS_WARP]; b->qmax_warp = st.class_qmax[KSW_CLASS_WARP];
+	b->n_generic = st.class_n[KSW_CLASS_THREAD];
+	b->qmax_generic = st.class_qmax[KSW_CLASS_THREAD];
 	b->pool_bytes = st.pool_bytes; b->npool_bytes = npool_bytes;
 	b->dev_ranges = false;                                       // packed on the host: the class sizes are exact
 	ksw_params_from_cfg(cfg, b->P);
@@ -291,7 +292,7 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t 
 	const uint32_t *drange = b->dev_ranges ? (const uint32_t *)b->d_range.p : nullptr;
 	int64_t first = 0;
 	int c = 0;
-	CU(s.d_counter.reserve(sizeof(unsigned long long) * (KSW_FAST_CLASSES + 1)));
+	CU(s.d_counter.reserve(sizeof(unsigned long long) * (KSW_FAST_CLASSES + 2)));
 	if (cn[0] > 0 && pair_enabled() && !b->dev_ranges) {
 		// class 0 goes to the pair kernel (two jobs per lane), unless it is a small minority next to other fast classes:
 		// then one launch of the one-job-per-lane kernel over all of them fills the GPU better than two thin launches
@@ -338,6 +339,12 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t 
 		first += n_grp;
 		c = e;
 	}
+	if (b->n_warp > 0) {
+		CU(ksw_launch_warp((const DevJob *)b->d_jobs.p, b->n_warp, (const uint32_t *)b->d_pool.p, (const uint32_t *)b->d_npool.p,
+		                   b->P, b->qmax_warp, ctx->sm_count, (unsigned long long *)s.d_counter.p + KSW_FAST_CLASSES + 1,
+		                   (const uint32_t *)b->d_order.p + b->n_fast, (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, st));
+		ctx->launches++;
+	}
 	if (b->n_generic > 0) {
 		int n_blocks = 0;
 		int rc = ensure_generic_scratch(ctx, s, b->qmax_generic, n_blocks);
@@ -346,7 +353,7 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t 
 		if (need < n_blocks) n_blocks = (int)need;
 		CU(ksw_launch_generic((const DevJob *)b->d_jobs.p, b->n_generic, (const uint32_t *)b->d_pool.p,
 		                      (const uint32_t *)b->d_npool.p, b->P, (int2 *)s.d_eh.p, (uint8_t *)s.d_qc.p,
-		                      n_blocks, (const uint32_t *)b->d_order.p + b->n_fast, (DevRes *)b->d_res.p,
+		                      n_blocks, (const uint32_t *)b->d_order.p + b->n_fast + b->n_warp, (DevRes *)b->d_res.p,
 		                      (uint32_t *)b->d_cells.p, st));
 		ctx->launches++;
 	}
@@ -580,7 +587,7 @@ int ksw_b200_batch_info(const ksw_b200_batch_t *b, int64_t *n_fast, int64_t *n_g
 {
 	if (!b) return 1;
 	if (n_fast) *n_fast = b->n_fast;
-	if (n_generic) *n_generic = b->n_generic;
+	if (n_generic) *n_generic = b->n_warp + b->n_generic;       // everything outside the s16x2 kernel
 	if (packed_bytes) *packed_bytes = (int64_t)(b->pool_bytes + b->npool_bytes + sizeof(DevJob) * (size_t)b->n);
 	return 0;
 }
@@ -878,8 +885,9 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 				b->fast_class_qmax[c] = st.class_qmax[c];
 				b->n_fast += st.class_n[c];
 			}
-			b->n_generic = st.class_n[KSW_FAST_CLASSES];
-			b->qmax_generic = st.class_qmax[KSW_FAST_CLASSES];
+			b->n_warp = st.class_n[KSW_CLASS_WARP]; b->qmax_warp = st.class_qmax[KSW_CLASS_WARP];
+			b->n_generic = st.class_n[KSW_CLASS_THREAD];
+			b->qmax_generic = st.class_qmax[KSW_CLASS_THREAD];
 			b->pool_bytes = (size_t)st.units * 16; b->npool_bytes = (size_t)st.nmask_words * 4;
 			b->P = P;
 			b->dev_ranges = true;
@@ -891,7 +899,7 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 			CU(b->d_keys.reserve(sizeof(uint16_t) * 2 * n1));
 			CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
 			CU(b->d_sort_tmp.reserve(std::max<size_t>(ksw_bin_temp_bytes(nc), 16)));
-			CU(b->d_range.reserve(sizeof(uint32_t) * (KSW_FAST_CLASSES + 2)));
+			CU(b->d_range.reserve(sizeof(uint32_t) * (KSW_N_CLASSES + 1)));
 			// the chunk after next: its records travel ahead of this chunk's sequences, its prep kernel runs ahead of
 			// this chunk's kernels
 			const long long nxt2 = nxt >= 0 ? claim() : -1;

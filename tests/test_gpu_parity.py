@@ -228,3 +228,22 @@ def test_pair_kernel_fuzz_and_adversarial(gpu_ctx, oracle_built, pair_kernel_on)
     for name, (b, want) in K.load_golden().items():
         got = gpu_ctx.extend_batch(b.cfg, b.jobs, b.qpool, b.tpool)
         assert K.first_mismatch(want, got.view(K.RES_DT)) is None, name
+
+
+def test_warp_cooperative_kernel_long_queries(gpu_ctx, oracle_built):
+    """Queries longer than the s16x2 kernel's 512 columns and int16-unsafe jobs of 129+ columns run on the
+    warp-cooperative int32 kernel (ksw_warp.cu: one job per warp, F by a max-plus scan over the lanes)."""
+    b = K.gen_fuzz(1500, seed=41, max_q=3000, w_choices=(5, 50, 100, 400, 1500))
+    rb = gpu_ctx.upload(b.cfg, b.jobs, b.qpool, b.tpool)
+    info = rb.info()
+    rb.free()
+    assert info["n_generic"] > 300 and info["n_fast"] > 100, info        # both routes populated
+    _check(gpu_ctx, b)
+    # bwasw-style scoring (no z-drop), asymmetric gaps, and very long queries
+    _check(gpu_ctx, K.gen_fuzz(400, seed=42, max_q=2500, cfg=K.make_cfg(zdrop=-1, end_bonus=0), w_choices=(30, 200, 2500)))
+    _check(gpu_ctx, K.gen_fuzz(400, seed=43, max_q=2000, cfg=K.make_cfg(a=2, b=3, o_del=4, e_del=2, o_ins=7, e_ins=1, zdrop=30, end_bonus=9)))
+    _check(gpu_ctx, K.gen_fuzz(12, seed=44, max_q=20000, w_choices=(100, 3000), related=1.0))
+    # carried-in scores beyond int16 with medium queries: warp kernel (129+) and thread kernel (shorter) side by side
+    _check(gpu_ctx, K.gen_fuzz(1500, seed=45, max_q=400, h0_max=60000))
+    cfg = K.make_cfg(a=100, b=120, o_del=200, e_del=30, o_ins=250, e_ins=20, zdrop=3000, end_bonus=50)
+    _check(gpu_ctx, K.gen_fuzz(800, seed=46, cfg=cfg, max_q=700, h0_max=3000))
