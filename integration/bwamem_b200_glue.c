@@ -2,7 +2,7 @@
  * integration/bwamem_b200_glue.c — the reference-side binding: `bwa mem` with its seed-extension
  * pass running on the B200 library.
  *
- * How it is built (oracle/Makefile, target _ref/bwa_b200): this one file is compiled INSTEAD of the
+ * How it is built (integration/Makefile, target _bin/bwa_b200): this one file is compiled INSTEAD of the
  * reference's bwamem.c.  It textually includes the reference's bwamem.c where it lies (nothing is
  * copied) with the fork's mem_process_seqs renamed, and then defines mem_process_seqs again with pass 1
  * restructured as the fork's authors sketched it (bwamem.c:579 `mem_chain2aln_batched`, commented out):
@@ -48,6 +48,14 @@ typedef struct {
 #define B200_MAX_WORKERS 1024
 static b200_thread_t b200_workers[B200_MAX_WORKERS];
 static int b200_n_gpus = -1;
+/* GPUs the read batches shard over: all visible ones, or the first KSW_B200_GPUS of them */
+static int b200_gpu_count(void)
+{
+	int n = ksw_b200_device_count();
+	const char *e = getenv("KSW_B200_GPUS");
+	if (e && atoi(e) > 0 && atoi(e) < n) n = atoi(e);
+	return n;
+}
 /* wall-clock seconds summed over worker threads: seeding+chaining, planning, GPU passes, replay+dedup */
 static double b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, b200_t_init;
 static void b200_add_time(double *acc, double dt) { __sync_synchronize(); { static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER; pthread_mutex_lock(&mu); *acc += dt; pthread_mutex_unlock(&mu); } }
@@ -58,7 +66,7 @@ static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bn
 	if (tid < 0 || tid >= B200_MAX_WORKERS) err_fatal(__func__, "more than %d worker threads", B200_MAX_WORKERS);
 	t = &b200_workers[tid];
 	if (!t->ctx) {
-		if (b200_n_gpus < 0) b200_n_gpus = ksw_b200_device_count();
+		if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
 		if (b200_n_gpus < 1 || ksw_b200_ctx_create(tid % b200_n_gpus, &t->ctx) != 0)
 			err_fatal(__func__, "no usable CUDA device: the B200 extension path has no CPU fallback");
 		ksw_b200_ctx_set_pack_threads(t->ctx, 1);          /* the bwa worker threads are the parallelism */
@@ -232,7 +240,7 @@ int b200_global2_hook(int qlen, const uint8_t *query, int tlen, const uint8_t *t
 	__sync_fetch_and_add(&b200_cig_misses, 1);
 	pthread_mutex_lock(&miss_mu);
 	if (!ctx) {
-		if (b200_n_gpus < 0) b200_n_gpus = ksw_b200_device_count();
+		if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
 		if (b200_n_gpus < 1 || ksw_b200_ctx_create(0, &ctx) != 0) err_fatal(__func__, "no usable CUDA device");
 	}
 	memcpy(cfg.mat, mat, 25);

@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--only", default="", help="substring of the config name to run alone (e.g. PE150)")
     ap.add_argument("--genome", type=int, default=0, help="override the genome length of the selected configs (bp)")
+    ap.add_argument("--reads", type=int, default=0, help="override the number of reads (SE) / pairs (PE) of the selected configs")
+    ap.add_argument("--no-cigar-off", action="store_true", help="skip the extra run with the CIGAR look-ahead off")
+    ap.add_argument("--gpus", type=int, default=0, help="KSW_B200_GPUS of the B200-bound build (0 = all visible)")
     a = ap.parse_args()
     sc = a.scale
     cfgs = [
@@ -55,6 +58,8 @@ def main():
         cfgs = [(n, c) for n, c in cfgs if a.only in n]
     if a.genome:
         cfgs = [(n.replace("10 Mbp", f"{a.genome / 1e6:.0f} Mbp"), dict(c, genome=a.genome)) for n, c in cfgs]
+    if a.reads:
+        cfgs = [(n, dict(c, n=a.reads)) for n, c in cfgs]
     rows = []
     with tempfile.TemporaryDirectory() as d:
         for name, c in cfgs:
@@ -70,13 +75,18 @@ def main():
                 S.write_reads_fast(reads, g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
                 n_reads = c["n"]
             t_stock, e_stock = timed(S.BWA_STOCK, fa, reads, os.path.join(d, "stock.sam"), a.threads)
-            env = dict(os.environ, KSW_B200_SCHED=a.sched) if a.sched == "rounds" else None
+            env = dict(os.environ, KSW_B200_SCHED=a.sched) if a.sched == "rounds" else dict(os.environ)
+            if a.gpus:
+                env["KSW_B200_GPUS"] = str(a.gpus)
             t_b200, e_b200 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200.sam"), a.threads, extra=["-b", str(a.batch)], env=env)
             ok, why = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200.sam"))
             # the same build with the CIGAR look-ahead off (pass 2 entirely on the host, as before): isolates its effect
-            env0 = dict(env or os.environ, KSW_B200_CIGAR="0")
-            t_b200_0, e_b200_0 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200_0.sam"), a.threads, extra=["-b", str(a.batch)], env=env0)
-            ok0, _ = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200_0.sam"))
+            if a.no_cigar_off:
+                t_b200_0, e_b200_0, ok0 = 0.0, "", None
+            else:
+                env0 = dict(env or os.environ, KSW_B200_CIGAR="0")
+                t_b200_0, e_b200_0 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200_0.sam"), a.threads, extra=["-b", str(a.batch)], env=env0)
+                ok0, _ = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200_0.sam"))
             cb0 = chunk_times(e_b200_0)
             sb0 = sum(r for r, _ in cb0[1:]) / max(sum(t for _, t in cb0[1:]), 1e-9) if len(cb0) > 1 else None
             cs, cb = chunk_times(e_stock), chunk_times(e_b200)
@@ -91,7 +101,8 @@ def main():
                    "sam_identical_minus_PG": bool(ok),
                    "cigar_lookahead": {"computed_ahead_hits_misses": cigar_stats(e_b200),
                                        "off_wall_s": round(t_b200_0, 3), "off_steady_reads_per_s": round(sb0) if sb0 else None,
-                                       "off_sam_identical_minus_PG": bool(ok0)}}
+                                       "off_sam_identical_minus_PG": ok0},
+                   "n_gpus": a.gpus or "all visible", "genome_bp": c["genome"]}
             print(json.dumps(row), flush=True)
             rows.append(row)
     if a.out:

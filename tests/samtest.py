@@ -118,13 +118,23 @@ def sam_body(path):
 
 
 def sam_equal(a, b):
-    la, lb = sam_body(a), sam_body(b)
-    if la == lb:
-        return True, None
-    for i, (x, y) in enumerate(zip(la, lb)):
+    """Streams both files (multi-GB SAMs of the BASELINE-size runs must not be held in memory)."""
+    def body(path):
+        with open(path, "rb") as f:
+            for ln in f:
+                if not ln.startswith(b"@PG"):
+                    yield ln
+    ia, ib = body(a), body(b)
+    i = 0
+    while True:
+        x, y = next(ia, None), next(ib, None)
+        if x is None and y is None:
+            return True, None
         if x != y:
+            if x is None or y is None:
+                return False, (i, b"<length differs>", b"one file ends at line %d" % i)
             return False, (i, x[:300], y[:300])
-    return False, (min(len(la), len(lb)), b"<length differs>", f"{len(la)} vs {len(lb)}".encode())
+        i += 1
 
 
 # ------------------------------------------------------------------ vectorised read simulator (millions of reads in seconds)
