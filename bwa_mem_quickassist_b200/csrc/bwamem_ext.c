@@ -83,13 +83,20 @@ struct b200_ext_plan {
 	VEC(uint8_t) qpool, tpool;
 	/* scratch of run() */
 	VEC(ksw_b200_job_t) jobs;
+	VEC(ksw_b200_rjob_t) rjobs;         /* device-reference mode: what is actually submitted */
 	VEC(ksw_b200_res_t) res;
 	VEC(uint32_t) owner;               /* job -> ext record (speculative mode) / read (rounds mode) */
 	VEC(item_rec_t) items;             /* rounds mode */
 	VEC(size_t) read_item0;            /* first timeline item of every read (+ sentinel) */
 	VEC(read_state_t) rstate;
 	int64_t st_seeds, st_left, st_right, st_retry, st_rounds;
+	/* device-reference mode: the chain windows are not materialised here; a job's t_off holds the
+	 * doubled-space coordinate of its first target base (bit 63: the run goes downwards) and the GPU slices the resident
+	 * .pac (ksw_b200_extend_batch_ref) */
+	int ref_mode, ref_ready;
 };
+
+#define REF_DOWN (1ull << 63)
 
 /* ---- small pieces of the reference logic ---------------------------------------------- */
 
@@ -137,14 +144,23 @@ b200_ext_plan_t *b200_ext_plan_create(const b200_ext_opt_t *opt, int64_t l_pac, 
 	b200_ext_plan_t *p = calloc(1, sizeof(*p));
 	if (!p) return 0;
 	p->opt = *opt; p->l_pac = l_pac; p->pac = pac;
+	{
+		const char *e = getenv("KSW_B200_REF");                  /* default of the mode; b200_ext_plan_set_device_ref overrides */
+		p->ref_mode = e && e[0] == '1';
+	}
 	return p;
+}
+
+void b200_ext_plan_set_device_ref(b200_ext_plan_t *p, int on)
+{
+	if (p->chains.n == 0) { p->ref_mode = on != 0; p->ref_ready = 0; }       /* only between batches */
 }
 
 void b200_ext_plan_destroy(b200_ext_plan_t *p)
 {
 	if (!p) return;
 	free(p->reads.a); free(p->chains.a); free(p->seeds.a); free(p->ext.a);
-	free(p->qpool.a); free(p->tpool.a); free(p->jobs.a); free(p->res.a); free(p->owner.a);
+	free(p->qpool.a); free(p->tpool.a); free(p->jobs.a); free(p->rjobs.a); free(p->res.a); free(p->owner.a);
 	free(p->items.a); free(p->read_item0.a);
 	if (p->rstate.a) {
 		size_t r;
@@ -209,15 +225,21 @@ int b200_ext_plan_add_chain(b200_ext_plan_t *p, int read, const b200_chain_t *c)
 		else lo = p->l_pac;
 	}
 	ch.read = read; ch.n = c->n; ch.seed0 = p->seeds.n; ch.rmax0 = lo; ch.rmax1 = hi;
-	/* the window, forward and reversed (bns_get_seq, bwamem.c:757) */
-	vec_reserve(p->tpool, p->tpool.n + 2 * (size_t)(hi - lo));
-	ch.r_fwd = p->tpool.n;
-	rlen = b200_get_ref_slice(p->l_pac, p->pac, lo, hi, p->tpool.a + p->tpool.n);
-	assert(rlen == hi - lo);
-	p->tpool.n += (size_t)rlen;
-	ch.r_rev = p->tpool.n;
-	for (k = 0; k < rlen; ++k) p->tpool.a[ch.r_rev + k] = p->tpool.a[ch.r_fwd + (rlen - 1 - k)];
-	p->tpool.n += (size_t)rlen;
+	if (p->ref_mode) {
+		/* the GPU slices the resident .pac: nothing to materialise (the window never bridges the strands, see above) */
+		ch.r_fwd = ch.r_rev = 0;
+		(void)rlen; (void)k;
+	} else {
+		/* the window, forward and reversed (bns_get_seq, bwamem.c:757) */
+		vec_reserve(p->tpool, p->tpool.n + 2 * (size_t)(hi - lo));
+		ch.r_fwd = p->tpool.n;
+		rlen = b200_get_ref_slice(p->l_pac, p->pac, lo, hi, p->tpool.a + p->tpool.n);
+		assert(rlen == hi - lo);
+		p->tpool.n += (size_t)rlen;
+		ch.r_rev = p->tpool.n;
+		for (k = 0; k < rlen; ++k) p->tpool.a[ch.r_rev + k] = p->tpool.a[ch.r_fwd + (rlen - 1 - k)];
+		p->tpool.n += (size_t)rlen;
+	}
 	/* seeds and their (still empty) extension records */
 	vec_reserve(p->seeds, p->seeds.n + (size_t)c->n);
 	vec_reserve(p->ext, p->ext.n + (size_t)c->n);
@@ -260,7 +282,8 @@ static void left_job(const b200_ext_plan_t *p, const chain_rec_t *ch, const b200
 	const int64_t rlen = ch->rmax1 - ch->rmax0, tmp = s->rbeg - ch->rmax0;
 	j->q_off = rd->q_rev + (uint64_t)(rd->l_query - s->qbeg);
 	j->qlen = s->qbeg;
-	j->t_off = ch->r_rev + (uint64_t)(rlen - tmp);
+	/* rs[i] = rseq[tmp-1-i] = reference base (s->rbeg - 1 - i) of the doubled space */
+	j->t_off = p->ref_mode ? ((uint64_t)(s->rbeg - 1) | REF_DOWN) : ch->r_rev + (uint64_t)(rlen - tmp);
 	j->tlen = (int32_t)tmp;
 	j->h0 = s->len * p->opt.a;
 	j->w = w;
@@ -275,7 +298,7 @@ static void right_job(const b200_ext_plan_t *p, const chain_rec_t *ch, const b20
 	assert(re >= 0);
 	j->q_off = rd->q_fwd + (uint64_t)qe;
 	j->qlen = rd->l_query - qe;
-	j->t_off = ch->r_fwd + (uint64_t)re;
+	j->t_off = p->ref_mode ? (uint64_t)(s->rbeg + s->len) : ch->r_fwd + (uint64_t)re;
 	j->tlen = (int32_t)(ch->rmax1 - ch->rmax0 - re);
 	j->h0 = h0;
 	j->w = w;
@@ -310,12 +333,36 @@ static void dump_jobs(const b200_ext_plan_t *p, const ksw_b200_cfg_t *cfg)
 	pthread_mutex_unlock(&dump_mu);
 }
 
+/* submits p->jobs[0..n) and waits for p->res[0..n) */
+static int submit_jobs(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, size_t n)
+{
+	size_t k;
+	vec_reserve(p->res, n);
+	if (!p->ref_mode) {
+		dump_jobs(p, cfg);
+		return ksw_b200_extend_batch(ctx, cfg, (int64_t)n, p->jobs.a, p->qpool.a, p->tpool.a, p->res.a);
+	}
+	if (!p->ref_ready) {
+		const int rc = ksw_b200_ref_set(ctx, p->pac, p->l_pac);  /* shared per device; a no-op after the first context */
+		if (rc) return rc;
+		p->ref_ready = 1;
+	}
+	vec_reserve(p->rjobs, n);
+	for (k = 0; k < n; ++k) {
+		const ksw_b200_job_t *j = &p->jobs.a[k];
+		ksw_b200_rjob_t *r = &p->rjobs.a[k];
+		memset(r, 0, sizeof(*r));
+		r->q_off = j->q_off; r->q_step = 1;                       /* the read is stored forward and reversed */
+		r->t_pos = (int64_t)(j->t_off & ~REF_DOWN); r->t_step = (j->t_off & REF_DOWN) ? -1 : 1;
+		r->qlen = j->qlen; r->tlen = j->tlen; r->h0 = j->h0; r->w = j->w;
+	}
+	return ksw_b200_extend_batch_ref(ctx, cfg, (int64_t)n, p->rjobs.a, p->qpool.a, p->qpool.n, p->res.a);
+}
+
 static int run_jobs(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg)
 {
 	if (p->jobs.n == 0) return 0;
-	dump_jobs(p, cfg);
-	vec_reserve(p->res, p->jobs.n);
-	return ksw_b200_extend_batch(ctx, cfg, (int64_t)p->jobs.n, p->jobs.a, p->qpool.a, p->tpool.a, p->res.a);
+	return submit_jobs(p, ctx, cfg, p->jobs.n);
 }
 
 int b200_ext_plan_run(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx)
@@ -632,9 +679,7 @@ int b200_ext_plan_run_rounds(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx)
 	}
 	while (p->jobs.n) {
 		size_t n_jobs = p->jobs.n, w = 0;
-		dump_jobs(p, &cfg);
-		vec_reserve(p->res, n_jobs);
-		rc = ksw_b200_extend_batch(ctx, &cfg, (int64_t)n_jobs, p->jobs.a, p->qpool.a, p->tpool.a, p->res.a);
+		rc = submit_jobs(p, ctx, &cfg, n_jobs);
 		if (rc) return rc;
 		++p->st_rounds;
 		for (k = 0; k < n_jobs; ++k) {

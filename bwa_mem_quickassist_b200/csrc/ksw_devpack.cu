@@ -192,6 +192,137 @@ ksw_pack_kernel(const ksw_b200_job_t *__restrict__ raw, long long n, const uint8
 	}
 }
 
+// ---- jobs against a reference kept on the device (ksw_b200_extend_batch_ref) -------------------
+// The target of a job is a run of the doubled reference coordinate space [0, 2 l_pac) read upwards or downwards from
+// t_pos; base x of that space is what bns_get_seq produces (bwa-0.7.8/bntseq.c:355-376): the 2-bit .pac base for
+// x < l_pac (_get_pac, bntseq.c:192), and 3 - pac(2 l_pac - 1 - x) for the reverse strand.  The query is a run of the
+// byte-coded read pool, upwards or downwards from q_off.  No window is materialised on the host.
+__device__ __forceinline__ uint32_t ref_base(const uint8_t *__restrict__ pac, long long l_pac, long long x)
+{
+	const bool rev = x >= l_pac;
+	const long long k = rev ? (l_pac << 1) - 1 - x : x;
+	const uint32_t b = (pac[k >> 2] >> ((~k & 3) << 1)) & 3u;
+	return rev ? 3u - b : b;
+}
+
+__global__ void __launch_bounds__(256)
+ksw_prep_ref_kernel(const ksw_b200_rjob_t *__restrict__ raw, long long n, const KswScoring S, long long l_pac, unsigned long long qbytes,
+                    DevJob *__restrict__ jobs, uint32_t *__restrict__ offs, DevPackStats *__restrict__ stats)
+{
+	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	uint32_t my_units = 0, cls = 0xffu;
+	unsigned long long my_nmask = 0;
+	int my_qlen = 0;
+	bool bad = false;
+	if (k < n) {
+		const ksw_b200_rjob_t j = raw[k];
+		DevJob d;
+		d.seq_off = 0; d.idx = (uint32_t)k; d.qlen = j.qlen; d.tlen = j.tlen;
+		d.h0 = j.h0 < 0 ? 0 : j.h0;                                                    // ksw.c:384
+		d.nmask_off = 0;
+		bool ok = j.qlen >= 1 && j.tlen >= 0 && (j.q_step == 1 || j.q_step == -1) && (j.t_step == 1 || j.t_step == -1);
+		if (ok) {
+			// both ends of both runs must exist, and the target must stay on one strand (bwamem.c:752-755)
+			const long long q_last = (long long)j.q_off + (long long)j.q_step * (j.qlen - 1);
+			const long long t_last = j.t_pos + (long long)j.t_step * (j.tlen - 1);
+			ok = q_last >= 0 && (unsigned long long)q_last < qbytes && j.q_off < qbytes;
+			if (j.tlen > 0) ok = ok && j.t_pos >= 0 && t_last >= 0 && j.t_pos < (l_pac << 1) && t_last < (l_pac << 1) &&
+			                     ((j.t_pos < l_pac) == (t_last < l_pac));
+		}
+		if (!ok) {
+			bad = true;
+			d.qlen = 1; d.tlen = 0; d.w = 0; d.flags = KSW_CLASS_THREAD << KSW_CLASS_SHIFT;
+		} else {
+			d.w = ksw_clamp_w_expr(j.qlen, S.maxsc, S.o_del, S.e_del, S.o_ins, S.e_ins, j.w, S.end_bonus);
+			cls = ksw_job_class(S, j.qlen, d.h0);
+			d.flags = cls << KSW_CLASS_SHIFT;
+			my_units = ksw_job_units(j.qlen, j.tlen);
+			my_nmask = ksw_words1(j.qlen);                                             // the reference holds no N (bntseq.c:228)
+			my_qlen = j.qlen;
+		}
+		jobs[k] = d;
+	}
+	uint32_t incl = my_units;
+	for (int o = 1; o < 32; o <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += v;
+	}
+	const uint32_t warp_units = __shfl_sync(0xffffffffu, incl, 31);
+	unsigned long long base = 0;
+	if (lane == 0 && warp_units) base = atomicAdd(&stats->units, (unsigned long long)warp_units);
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (k < n) offs[k] = (uint32_t)(base + incl - my_units);
+	for (int o = 16; o > 0; o >>= 1) my_nmask += __shfl_down_sync(0xffffffffu, my_nmask, o);
+	if (lane == 0 && my_nmask) atomicAdd(&stats->nmask_words, my_nmask);
+	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&stats->bad, 1u);
+	for (uint32_t c = 0; c < KSW_N_CLASSES; ++c) {
+		const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+		if (!m) continue;
+		int q = cls == c ? my_qlen : 0;
+		for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_down_sync(0xffffffffu, q, o); q = q > v ? q : v; }
+		if (lane == 0) { atomicAdd(&stats->class_n[c], (unsigned)__popc(m)); atomicMax(&stats->class_qmax[c], q); }
+	}
+}
+
+__global__ void __launch_bounds__(KSW_PACK_THREADS)
+ksw_pack_ref_kernel(const ksw_b200_rjob_t *__restrict__ raw, long long n, const uint8_t *__restrict__ qraw, const uint8_t *__restrict__ pac,
+                    long long l_pac, const uint32_t *__restrict__ offs, DevJob *__restrict__ jobs, uint32_t *__restrict__ pool,
+                    uint32_t *__restrict__ npool, DevPackStats *__restrict__ stats)
+{
+	const int sub = threadIdx.x & (KSW_PACK_LANES - 1);
+	const unsigned grp = 0xffffu << (threadIdx.x & 16);
+	const long long k = ((long long)blockIdx.x * KSW_PACK_THREADS + threadIdx.x) / KSW_PACK_LANES;
+	if (k >= n) return;
+	const ksw_b200_rjob_t j = raw[k];
+	if (j.qlen < 1 || j.tlen < 0) return;                                              // (a batch with such a job is rejected after prep)
+	const uint32_t qw = ksw_words2(j.qlen), tw = ksw_words2(j.tlen), total = ksw_job_units(j.qlen, j.tlen) * 4u;
+	const uint32_t off = offs[k];
+	uint32_t *out = pool + (size_t)off * 4;
+	bool qn = false;
+	for (uint32_t wi = sub; wi < total; wi += KSW_PACK_LANES) {
+		uint32_t word = 0;
+		if (wi < qw) {
+			const int lim = j.qlen - 16 * (int)wi < 16 ? j.qlen - 16 * (int)wi : 16;
+			const long long q0 = (long long)j.q_off + (long long)j.q_step * 16 * (long long)wi;
+			for (int x = 0; x < lim; ++x) {
+				const uint32_t c = qraw[q0 + (long long)j.q_step * x];
+				if (c > 3u) qn = true; else word |= c << (2 * x);
+			}
+		} else if (wi < qw + tw) {
+			const uint32_t ti = wi - qw;
+			const int lim = j.tlen - 16 * (int)ti < 16 ? j.tlen - 16 * (int)ti : 16;
+			const long long t0 = j.t_pos + (long long)j.t_step * 16 * (long long)ti;
+			for (int x = 0; x < lim; ++x) word |= ref_base(pac, l_pac, t0 + (long long)j.t_step * x) << (2 * x);
+		}
+		out[wi] = word;
+	}
+	qn = (__ballot_sync(grp, qn) & grp) != 0;
+	if (!qn) {
+		if (sub == 0) jobs[k].seq_off = off;
+		return;
+	}
+	const uint32_t qmw = ksw_words1(j.qlen);
+	uint32_t base = 0;
+	if (sub == 0) base = atomicAdd(&stats->nmask_used, qmw);
+	base = __shfl_sync(grp, base, threadIdx.x & 16);
+	for (uint32_t mi = sub; mi < qmw; mi += KSW_PACK_LANES) {
+		uint32_t m = 0;
+		const int lim = j.qlen - 32 * (int)mi < 32 ? j.qlen - 32 * (int)mi : 32;
+		for (int x = 0; x < lim; ++x) if (qraw[(long long)j.q_off + (long long)j.q_step * (32 * (long long)mi + x)] > 3) m |= 1u << x;
+		npool[base + mi] = m;
+	}
+	if (sub == 0) {
+		DevJob d = jobs[k];
+		d.seq_off = off;
+		d.nmask_off = base;
+		d.flags |= KSW_FLAG_QN;
+		if (((d.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK) == 0u)
+			d.flags = (d.flags & ~(KSW_CLASS_MASK << KSW_CLASS_SHIFT)) | (1u << KSW_CLASS_SHIFT);
+		jobs[k] = d;
+	}
+}
+
 // sorted_keys: the binning keys in ascending order (ksw_bin.cu): class c occupies [range[c], range[c+1])
 __global__ void ksw_range_kernel(const uint16_t *__restrict__ sorted_keys, long long n, uint32_t *__restrict__ range)
 {
@@ -232,5 +363,26 @@ cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw
 cudaError_t ksw_launch_ranges(const uint16_t *sorted_keys, int64_t n, uint32_t *range, cudaStream_t st)
 {
 	ksw_range_kernel<<<1, 32, 0, st>>>(sorted_keys, (long long)n, range);
+	return cudaGetLastError();
+}
+
+cudaError_t ksw_launch_prep_ref(const void *raw_jobs, int64_t n, const KswScoring &S, int64_t l_pac, uint64_t qbytes, DevJob *jobs,
+                                uint32_t *offs, DevPackStats *stats, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(DevPackStats), st);
+	if (e != cudaSuccess) return e;
+	ksw_prep_ref_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const ksw_b200_rjob_t *)raw_jobs, (long long)n, S, (long long)l_pac,
+	                                                               (unsigned long long)qbytes, jobs, offs, stats);
+	return cudaGetLastError();
+}
+
+cudaError_t ksw_launch_pack_ref(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *pac, int64_t l_pac, const uint32_t *offs,
+                                DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	const long long per_block = KSW_PACK_THREADS / KSW_PACK_LANES;
+	ksw_pack_ref_kernel<<<(unsigned)((n + per_block - 1) / per_block), KSW_PACK_THREADS, 0, st>>>(
+	    (const ksw_b200_rjob_t *)raw_jobs, (long long)n, qraw, pac, (long long)l_pac, offs, jobs, pool, npool, stats);
 	return cudaGetLastError();
 }

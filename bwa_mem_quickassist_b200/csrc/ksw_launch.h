@@ -58,3 +58,9 @@ cudaError_t ksw_launch_pack(const void *raw_jobs, int64_t n, const uint8_t *qraw
                             DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st);
 // range[c] = first entry of kernel class c in the binned order (c = 0..KSW_N_CLASSES; the last one is n)
 cudaError_t ksw_launch_ranges(const uint16_t *sorted_keys, int64_t n, uint32_t *range, cudaStream_t st);
+
+// jobs against a reference kept on the device (ksw_b200_rjob_t records, 2-bit .pac in HBM): same products as prep / pack
+cudaError_t ksw_launch_prep_ref(const void *raw_jobs, int64_t n, const KswScoring &S, int64_t l_pac, uint64_t qbytes, DevJob *jobs,
+                                uint32_t *offs, DevPackStats *stats, cudaStream_t st);
+cudaError_t ksw_launch_pack_ref(const void *raw_jobs, int64_t n, const uint8_t *qraw, const uint8_t *pac, int64_t l_pac, const uint32_t *offs,
+                                DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st);

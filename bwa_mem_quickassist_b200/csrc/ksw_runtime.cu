@@ -99,6 +99,15 @@ struct Slot {
 	bool host_packed = false;              // pinned-caller pipeline: this chunk was packed on the host threads
 };
 
+// a reference (.pac) resident on a device, shared by the contexts of that device
+struct RefEntry {
+	int device = -1;
+	const uint8_t *host = nullptr;
+	int64_t l_pac = 0;
+	void *dev = nullptr;
+	int refs = 0;
+};
+
 struct AsyncReq {
 	ksw_b200_cfg_t cfg;
 	int64_t n = 0;
@@ -135,6 +144,8 @@ struct ksw_b200_ctx {
 	int hybrid = 1;                        // a second lane packs chunks on the host threads (KSW_B200_HYBRID=0: device packing only)
 	Slot hslot[KSW_N_HSLOTS];                         // that lane's staging / device buffers (events only; it uses the shared streams)
 	double host_ms_per_job = 0, dev_ms_per_job = 0;   // measured pace of the two lanes (0 = not measured yet)
+	RefEntry *ref = nullptr;               // ksw_b200_ref_set
+	PinnedBuf h_rq;                        // ksw_b200_extend_batch_ref: staging of a pageable read pool
 	std::thread worker;
 	std::mutex mu;
 	std::condition_variable cv;
@@ -169,6 +180,21 @@ KswPool *pool_of(ksw_b200_ctx *ctx)
 	if (ctx->pool && ctx->pool->size() != ctx->pack_threads) { delete ctx->pool; ctx->pool = nullptr; }
 	if (!ctx->pool) ctx->pool = new KswPool(ctx->pack_threads);
 	return ctx->pool;
+}
+
+std::mutex g_ref_mu;
+std::vector<RefEntry *> g_refs;
+
+void ref_release(ksw_b200_ctx *ctx)
+{
+	if (!ctx->ref) return;
+	std::lock_guard<std::mutex> lk(g_ref_mu);
+	if (--ctx->ref->refs == 0) {
+		cudaFree(ctx->ref->dev);
+		g_refs.erase(std::remove(g_refs.begin(), g_refs.end(), ctx->ref), g_refs.end());
+		delete ctx->ref;
+	}
+	ctx->ref = nullptr;
 }
 
 int fast_qmax_enabled()
@@ -470,6 +496,8 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 		if (s.stream) cudaStreamDestroy(s.stream);
 	}
 	ctx->d_qraw.release(); ctx->d_traw.release();
+	ctx->h_rq.release();
+	ref_release(ctx);
 	for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
 	for (Slot &s : ctx->hslot) {
 		batch_release_buffers(&s.batch);
@@ -1069,6 +1097,120 @@ int ksw_b200_wait(ksw_b200_ctx_t *ctx)
 	std::unique_lock<std::mutex> lk(ctx->mu);
 	ctx->cv.wait(lk, [&] { return !ctx->req_pending && !ctx->req_running; });
 	return ctx->async_rc;
+}
+
+// ---- reference resident on the device ----
+int ksw_b200_ref_set(ksw_b200_ctx_t *ctx, const uint8_t *pac, int64_t l_pac)
+{
+	if (!ctx || !pac || l_pac < 1) return 1;
+	CU(cudaSetDevice(ctx->device));
+	ref_release(ctx);
+	std::lock_guard<std::mutex> lk(g_ref_mu);
+	for (RefEntry *r : g_refs)
+		if (r->device == ctx->device && r->host == pac && r->l_pac == l_pac) { ++r->refs; ctx->ref = r; return 0; }
+	RefEntry *r = new RefEntry();
+	r->device = ctx->device; r->host = pac; r->l_pac = l_pac; r->refs = 1;
+	const size_t bytes = (size_t)(l_pac / 4 + 1);
+	cudaError_t e = cudaMalloc(&r->dev, bytes + 16);
+	if (e == cudaSuccess) e = cudaMemcpy(r->dev, pac, bytes, cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) {
+		if (r->dev) cudaFree(r->dev);
+		delete r;
+		return fail(ctx, 100 + (int)e, std::string("ksw_b200_ref_set: ") + cudaGetErrorString(e));
+	}
+	g_refs.push_back(r);
+	ctx->ref = r;
+	return 0;
+}
+
+// Synchronous; the caller's arrays may be pageable (they are small: 40 B per job plus the reads).  Per chunk on slot 0's
+// stream: records + (once) the read pool H2D, prep, totals home, pack from the resident .pac, bin, kernels, results home.
+int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
+                              const uint8_t *qpool, size_t qbytes, ksw_b200_res_t *res)
+{
+	if (!ctx || !cfg || n < 0) return 1;
+	if (n == 0) return 0;
+	if (!jobs || !res || !qpool) return 1;
+	if (!ctx->ref) return fail(ctx, 5, "ksw_b200_extend_batch_ref: no reference on the device (call ksw_b200_ref_set first)");
+	if (cfg->m != 5) return fail(ctx, 2, "ksw_b200: only m == 5 is supported (every reference caller passes 5)");
+	CU(cudaSetDevice(ctx->device));
+	Slot &s = ctx->slot[0];
+	ksw_b200_batch *b = &s.batch;
+	KswScoring S;
+	ksw_scoring_from_cfg(cfg, fast_qmax_enabled(), S);
+	KswParams P;
+	ksw_params_from_cfg(cfg, P);
+	int64_t h2d = 0;
+	// the reads
+	CU(ctx->d_qraw.reserve(qbytes + 64));
+	{
+		const uint8_t *src = qpool;
+		if (!is_pinned(qpool)) {
+			CU(ctx->h_rq.reserve(qbytes));
+			memcpy(ctx->h_rq.p, qpool, qbytes);
+			src = (const uint8_t *)ctx->h_rq.p;
+		}
+		CU(cudaMemcpyAsync(ctx->d_qraw.p, src, qbytes, cudaMemcpyHostToDevice, s.stream));
+		h2d += (int64_t)qbytes;
+	}
+	const int64_t chunk = ctx->chunk_jobs;
+	for (int64_t first = 0; first < n; first += chunk) {
+		const int64_t nc = std::min(chunk, n - first);
+		const size_t n1 = (size_t)nc;
+		CU(s.d_rawjobs.reserve(sizeof(ksw_b200_rjob_t) * n1));
+		CU(s.d_offs.reserve(sizeof(uint32_t) * n1));
+		CU(s.d_stats.reserve(sizeof(DevPackStats)));
+		CU(s.h_stats.reserve(sizeof(DevPackStats)));
+		CU(s.h_jobs.reserve(sizeof(ksw_b200_rjob_t) * n1));
+		CU(s.h_res.reserve(sizeof(DevRes) * n1));
+		CU(b->d_jobs.reserve(sizeof(DevJob) * n1));
+		memcpy(s.h_jobs.p, jobs + first, sizeof(ksw_b200_rjob_t) * n1);
+		CU(cudaMemcpyAsync(s.d_rawjobs.p, s.h_jobs.p, sizeof(ksw_b200_rjob_t) * n1, cudaMemcpyHostToDevice, s.stream));
+		h2d += (int64_t)(sizeof(ksw_b200_rjob_t) * n1);
+		CU(ksw_launch_prep_ref(s.d_rawjobs.p, nc, S, ctx->ref->l_pac, qbytes, (DevJob *)b->d_jobs.p, (uint32_t *)s.d_offs.p,
+		                       (DevPackStats *)s.d_stats.p, s.stream));
+		CU(cudaMemcpyAsync(s.h_stats.p, s.d_stats.p, sizeof(DevPackStats), cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+		const DevPackStats st = *(const DevPackStats *)s.h_stats.p;
+		if (st.bad) return fail(ctx, 2, "ksw_b200_extend_batch_ref: job with bad lengths / steps, a run outside its pool, or a target bridging the strands");
+		if (st.units > 0xffffffffull) return fail(ctx, 2, "ksw_b200: packed pool exceeds 64 GiB");
+		b->n = nc; b->n_fast = 0;
+		for (int c = 0; c < KSW_FAST_CLASSES; ++c) {
+			b->fast_class_n[c] = st.class_n[c];
+			b->fast_class_qmax[c] = st.class_qmax[c];
+			b->n_fast += st.class_n[c];
+		}
+		b->n_warp = st.class_n[KSW_CLASS_WARP]; b->qmax_warp = st.class_qmax[KSW_CLASS_WARP];
+		b->n_generic = st.class_n[KSW_CLASS_THREAD];
+		b->qmax_generic = st.class_qmax[KSW_CLASS_THREAD];
+		b->pool_bytes = (size_t)st.units * 16; b->npool_bytes = (size_t)st.nmask_words * 4;
+		b->P = P;
+		b->dev_ranges = true;
+		CU(b->d_pool.reserve(std::max<size_t>(b->pool_bytes, 16)));
+		CU(b->d_npool.reserve(std::max<size_t>(b->npool_bytes, 16)));
+		CU(b->d_res.reserve(sizeof(DevRes) * n1));
+		CU(b->d_cells.reserve(sizeof(uint32_t) * n1));
+		CU(b->d_order.reserve(sizeof(uint32_t) * n1));
+		CU(b->d_keys.reserve(sizeof(uint16_t) * 2 * n1));
+		CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
+		CU(b->d_sort_tmp.reserve(std::max<size_t>(ksw_bin_temp_bytes(nc), 16)));
+		CU(b->d_range.reserve(sizeof(uint32_t) * (KSW_N_CLASSES + 1)));
+		CU(ksw_launch_pack_ref(s.d_rawjobs.p, nc, (const uint8_t *)ctx->d_qraw.p, (const uint8_t *)ctx->ref->dev, ctx->ref->l_pac,
+		                       (const uint32_t *)s.d_offs.p, (DevJob *)b->d_jobs.p, (uint32_t *)b->d_pool.p, (uint32_t *)b->d_npool.p,
+		                       (DevPackStats *)s.d_stats.p, s.stream));
+		CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, nc, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
+		                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, s.stream));
+		CU(ksw_launch_ranges((const uint16_t *)b->d_keys.p + n1, nc, (uint32_t *)b->d_range.p, s.stream));
+		ctx->launches += 5;
+		int rc = enqueue_kernels(ctx, s, b);
+		if (rc) return rc;
+		CU(cudaMemcpyAsync(s.h_res.p, b->d_res.p, sizeof(DevRes) * n1, cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+		memcpy(res + first, s.h_res.p, sizeof(DevRes) * n1);
+	}
+	ctx->last_h2d = h2d;
+	ctx->last_d2h = (int64_t)(sizeof(DevRes) * (size_t)n);
+	return 0;
 }
 
 // Multi-GPU form: jobs are independent, so the batch is cut into n_ctx contiguous ranges of (nearly)

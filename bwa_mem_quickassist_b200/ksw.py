@@ -17,6 +17,8 @@ JOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen",
                    ("h0", "<i4"), ("w", "<i4")])            # ksw_b200_job_t
 RES_DT = np.dtype([("score", "<i4"), ("qle", "<i4"), ("tle", "<i4"), ("gtle", "<i4"),
                    ("gscore", "<i4"), ("max_off", "<i4")])  # ksw_b200_res_t
+RJOB_DT = np.dtype([("q_off", "<u8"), ("t_pos", "<i8"), ("qlen", "<i4"), ("tlen", "<i4"), ("h0", "<i4"), ("w", "<i4"),
+                    ("q_step", "i1"), ("t_step", "i1"), ("reserved", "i1", (6,))])   # ksw_b200_rjob_t
 # banded global alignment with backtrace
 GJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"),
                     ("reserved", "<i4")])                   # ksw_b200_gjob_t
@@ -97,6 +99,8 @@ def load_library():
     lib.ksw_b200_host_unregister.argtypes = [vp]
     lib.ksw_b200_extend_batch_async.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     lib.ksw_b200_wait.argtypes = [vp]
+    lib.ksw_b200_ref_set.argtypes = [vp, vp, i64]
+    lib.ksw_b200_extend_batch_ref.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
     lib.ksw_b200_batch_upload.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(vp)]
     lib.ksw_b200_batch_run.argtypes = [vp, vp]
     lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
@@ -238,6 +242,22 @@ class KswB200:
 
     def wait(self):
         self._check(self.lib.ksw_b200_wait(self.ctx), "ksw_b200_wait")
+
+    def ref_set(self, pac: np.ndarray, l_pac: int):
+        """ksw_b200_ref_set: the forward-strand 2-bit .pac (l_pac/4+1 bytes) goes to this context's device."""
+        pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        assert pac.nbytes >= l_pac // 4 + 1
+        self._pac_keepalive = pac
+        self._check(self.lib.ksw_b200_ref_set(self.ctx, _p(pac), int(l_pac)), "ksw_b200_ref_set")
+
+    def extend_batch_ref(self, cfg: Cfg, rjobs, qpool) -> np.ndarray:
+        """ksw_b200_extend_batch_ref: targets are runs of the doubled reference space, sliced on the device."""
+        rjobs = np.ascontiguousarray(rjobs, dtype=RJOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        res = np.zeros(rjobs.shape[0], dtype=RES_DT)
+        self._check(self.lib.ksw_b200_extend_batch_ref(self.ctx, C.byref(cfg), rjobs.shape[0], _p(rjobs), _p(qpool), qpool.nbytes,
+                                                       _p(res)), "ksw_b200_extend_batch_ref")
+        return res
 
     def global_batch(self, cfg: Cfg, jobs, qpool, tpool):
         """ksw_b200_global_batch: banded global alignment + backtrace of every job (GJOB_DT).  Returns

@@ -79,6 +79,12 @@ void b200_ext_plan_destroy(b200_ext_plan_t *p);
 void b200_ext_plan_reset(b200_ext_plan_t *p);                 /* forget reads/chains, keep the memory */
 
 /* registers a read (query = codes 0..4, as mem_align1_core encodes them, bwamem.c:1093-1094); returns its handle */
+/* device-reference mode: on != 0 -> the plan no longer unpacks and copies the chains' reference
+ * windows (bns_get_seq, bwamem.c:757); its jobs name their targets by coordinate and the GPU slices the .pac it keeps
+ * (ksw_b200_ref_set is called for the run's context on first use; ksw_b200_extend_batch_ref runs the passes).  Same
+ * regions, bit for bit.  Only between batches (after create or reset).  Default: off, or KSW_B200_REF=1 in the
+ * environment. */
+void b200_ext_plan_set_device_ref(b200_ext_plan_t *p, int on);
 int b200_ext_plan_add_read(b200_ext_plan_t *p, int l_query, const uint8_t *query);
 /* registers one chain of that read and the left/right job of every one of its seeds; returns the chain
  * handle (>= 0), or -1 for an empty chain (mem_chain2aln returns at once, bwamem.c:738) */

@@ -119,6 +119,28 @@ int ksw_b200_extend_batch_async(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
                                 ksw_b200_res_t *res);
 int ksw_b200_wait(ksw_b200_ctx_t *ctx);
 
+/* ---- extension against a reference kept on the device ------------------------------------- */
+/* Replaces bns_get_seq (bwa-0.7.8/bntseq.c:355-376) + the window slicing of mem_chain2aln (bwamem.c:740-758, 813-817,
+ * 844) on the host: the forward-strand 2-bit .pac (bwa_idx_load, bwa.c:291: l_pac/4+1 bytes, base k in byte k/4 at bits
+ * 2*(~k&3), bntseq.c:191-192) is uploaded once per device (shared by all contexts of that device), and a job names its
+ * target as a run of the doubled coordinate space [0, 2*l_pac): x < l_pac is the forward strand, x >= l_pac the
+ * reverse strand = 3 - pac(2*l_pac - 1 - x).  A left extension (bwamem.c:813-817) reads both sequences downwards. */
+typedef struct {
+	uint64_t q_off;            /* byte offset in qpool of the FIRST query base (codes 0..4) */
+	int64_t  t_pos;            /* coordinate of the FIRST target base in the doubled reference space */
+	int32_t  qlen, tlen;       /* qlen >= 1, tlen >= 0; the target run must stay on one strand (bwamem.c:752-755) */
+	int32_t  h0, w;
+	int8_t   q_step, t_step;   /* +1: the run goes upwards from q_off / t_pos, -1: downwards */
+	int8_t   reserved[6];
+} ksw_b200_rjob_t;
+
+/* pac is copied to the device; the host buffer is not needed afterwards.  Calling it again with the same pointer and
+ * length on another context of the same device shares the copy. */
+int ksw_b200_ref_set(ksw_b200_ctx_t *ctx, const uint8_t *pac, int64_t l_pac);
+/* results as ksw_b200_extend_batch on the same sequences; qpool holds the reads (byte codes), qpool_bytes its size */
+int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
+                              const uint8_t *qpool, size_t qpool_bytes, ksw_b200_res_t *res);
+
 /* bytes the last ksw_b200_extend_batch / ksw_b200_extend_batch_async call copied host->device and device->host */
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

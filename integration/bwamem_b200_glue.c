@@ -79,6 +79,13 @@ static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bn
 		memcpy(eo.mat, opt->mat, 25);
 		t->plan = b200_ext_plan_create(&eo, bns->l_pac, pac);
 		t->pac = pac;
+		/* the .pac stays on the GPU (one copy per device, shared by the workers' contexts) and the extension jobs name their
+		 * targets by coordinate: no bns_get_seq / window copies in pass 1.  KSW_B200_REF=0: the plan
+		 * materialises the windows on the host as before (A/B switch) */
+		{
+			const char *e = getenv("KSW_B200_REF");
+			b200_ext_plan_set_device_ref(t->plan, !(e && e[0] == '0'));
+		}
 	}
 	return t;
 }

@@ -75,3 +75,14 @@ def test_batched_driver_matches_golden_and_oracle(gpu_ctx, oracle_built):
         assert K.regs_equal(K.run_chain_gpu(gpu_ctx, cs), want[:2]), seed
         rnd = K.run_chain_driver(gpu_ctx.lib, cs, ctx=gpu_ctx.ctx, rounds=True)       # strategy B on the GPU
         assert K.regs_equal(rnd[:2], want[:2]) and rnd[2] == want[2], seed
+
+
+def test_host_driver_device_reference_mode_cpu(oracle_built, monkeypatch):
+    """SURVEY.md 8(f) rank 3 on the host side: in device-reference mode the driver materialises no reference window and
+    names every target by its coordinate in the doubled reference space (ksw_b200_rjob_t).  Linked against the stub,
+    which slices the .pac the way bns_get_seq does, it must still produce the reference's regions."""
+    monkeypatch.setenv("KSW_B200_REF", "1")
+    lib = K.ext_emu_lib()
+    for name, (cs, want) in K.load_chain_golden().items():
+        assert K.regs_equal(K.run_chain_driver(lib, cs)[:2], want), ("speculative, device reference", name)
+        assert K.regs_equal(K.run_chain_driver(lib, cs, rounds=True)[:2], want), ("rounds, device reference", name)
