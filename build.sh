@@ -13,8 +13,11 @@ done
 if [ ! -f build/ksw_pack.o ] || [ -n "$(find csrc ../include -newer build/ksw_pack.o | head -1)" ]; then
   g++ -O3 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c csrc/ksw_pack.cpp -o build/ksw_pack.o
 fi
+if [ ! -f build/ksw_queue.o ] || [ -n "$(find csrc ../include -newer build/ksw_queue.o | head -1)" ]; then
+  g++ -O2 -std=c++17 -fPIC -Wall -c csrc/ksw_queue.cpp -o build/ksw_queue.o
+fi
 if [ ! -f build/bwamem_ext.o ] || [ -n "$(find csrc ../include -newer build/bwamem_ext.o | head -1)" ]; then
   gcc -O2 -std=gnu99 -fPIC -Wall -c csrc/bwamem_ext.c -o build/bwamem_ext.o
 fi
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libksw_b200.so build/ksw_generic.o build/ksw_warp.o build/ksw_fast.o build/ksw_pair.o build/ksw_bin.o build/ksw_devpack.o build/ksw_global.o build/ksw_runtime.o build/ksw_pack.o build/bwamem_ext.o -Xlinker -Bsymbolic-functions -lcudart_static -lpthread -ldl -lrt
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libksw_b200.so build/ksw_generic.o build/ksw_warp.o build/ksw_fast.o build/ksw_pair.o build/ksw_bin.o build/ksw_devpack.o build/ksw_global.o build/ksw_runtime.o build/ksw_pack.o build/ksw_queue.o build/bwamem_ext.o -Xlinker -Bsymbolic-functions -lcudart_static -lpthread -ldl -lrt
 echo "built $(pwd)/libksw_b200.so"

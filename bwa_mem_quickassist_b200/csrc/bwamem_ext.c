@@ -94,6 +94,7 @@ struct b200_ext_plan {
 	 * doubled-space coordinate of its first target base (bit 63: the run goes downwards) and the GPU slices the resident
 	 * .pac (ksw_b200_extend_batch_ref) */
 	int ref_mode, ref_ready;
+	ksw_b200_queue_t *queue;           /* device-reference mode: submit through the GPU's shared queue instead of a private context */
 };
 
 #define REF_DOWN (1ull << 63)
@@ -150,6 +151,8 @@ b200_ext_plan_t *b200_ext_plan_create(const b200_ext_opt_t *opt, int64_t l_pac, 
 	}
 	return p;
 }
+
+void b200_ext_plan_set_queue(b200_ext_plan_t *p, ksw_b200_queue_t *q) { p->queue = q; }
 
 void b200_ext_plan_set_device_ref(b200_ext_plan_t *p, int on)
 {
@@ -342,7 +345,7 @@ static int submit_jobs(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx, const ksw_b200_c
 		dump_jobs(p, cfg);
 		return ksw_b200_extend_batch(ctx, cfg, (int64_t)n, p->jobs.a, p->qpool.a, p->tpool.a, p->res.a);
 	}
-	if (!p->ref_ready) {
+	if (!p->ref_ready && !p->queue) {
 		const int rc = ksw_b200_ref_set(ctx, p->pac, p->l_pac);  /* shared per device; a no-op after the first context */
 		if (rc) return rc;
 		p->ref_ready = 1;
@@ -356,6 +359,8 @@ static int submit_jobs(b200_ext_plan_t *p, ksw_b200_ctx_t *ctx, const ksw_b200_c
 		r->t_pos = (int64_t)(j->t_off & ~REF_DOWN); r->t_step = (j->t_off & REF_DOWN) ? -1 : 1;
 		r->qlen = j->qlen; r->tlen = j->tlen; r->h0 = j->h0; r->w = j->w;
 	}
+	if (p->queue)                                                /* the queue's owner has put the reference on its device */
+		return ksw_b200_queue_extend_ref(p->queue, cfg, (int64_t)n, p->rjobs.a, p->qpool.a, p->qpool.n, p->res.a);
 	return ksw_b200_extend_batch_ref(ctx, cfg, (int64_t)n, p->rjobs.a, p->qpool.a, p->qpool.n, p->res.a);
 }
 

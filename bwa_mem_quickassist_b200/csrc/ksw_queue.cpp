@@ -1,0 +1,247 @@
+// ksw_queue.cpp — one submission queue per GPU shared by all host threads (include/ksw_b200.h; SURVEY.md 8(f) rank 1,
+// the part the rounds scheduler left open: cross-thread batch coalescing).  Built on the public C ABI only: the queue
+// owns one context and a server thread; submitters block on a condition variable; the server takes everything that is
+// pending for the same kind of work and the same scoring, runs it as one GPU batch, and wakes the submitters.
+// No delay is added to collect work: while the GPU runs batch k the next submissions pile up and become batch k+1.
+// Two servers (two contexts) per queue, so that the copies and the device-side packing of one merged batch overlap
+// the kernels of the other.
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ksw_b200.h"
+
+namespace {
+
+struct Sub {                           // one blocked submitter
+	int kind = 0;                      // 0: extension against the resident reference, 1: global alignment
+	ksw_b200_cfg_t cfg;
+	int64_t n = 0;
+	const ksw_b200_rjob_t *rjobs = nullptr;
+	const ksw_b200_gjob_t *gjobs = nullptr;
+	const uint8_t *qpool = nullptr, *tpool = nullptr;
+	size_t qbytes = 0, tbytes = 0;
+	ksw_b200_res_t *res = nullptr;
+	ksw_b200_gres_t *gres = nullptr;
+	uint32_t *cigar = nullptr;         // malloc'd for the submitter
+	int64_t n_cigar = 0;
+	int rc = 0;
+	bool done = false;
+	std::condition_variable cv;
+};
+
+bool same_cfg(const ksw_b200_cfg_t &a, const ksw_b200_cfg_t &b)
+{
+	return memcmp(a.mat, b.mat, 25) == 0 && a.m == b.m && a.o_del == b.o_del && a.e_del == b.e_del && a.o_ins == b.o_ins &&
+	       a.e_ins == b.e_ins && a.zdrop == b.zdrop && a.end_bonus == b.end_bonus;
+}
+
+} // namespace
+
+#define KSW_QUEUE_SERVERS 2             /* two contexts per GPU: the copies and the packing of one merged batch run under the
+                                         * kernels of the other */
+struct Server {
+	ksw_b200_ctx_t *ctx = nullptr;
+	std::thread th;
+	// merged global-alignment batch
+	std::vector<ksw_b200_gjob_t> gj;
+	std::vector<ksw_b200_gres_t> gr;
+	std::vector<uint8_t> gq, gt;
+};
+
+struct ksw_b200_queue {
+	Server srv[KSW_QUEUE_SERVERS];
+	std::mutex mu;
+	std::condition_variable cv_work;
+	std::deque<Sub *> pending;
+	bool stop = false;
+	std::string err;
+	int64_t n_batches = 0, n_subs = 0;
+};
+
+namespace {
+
+void run_extend(Server *q, std::vector<Sub *> &grp)
+{
+	std::vector<ksw_b200_rseg_t> segs(grp.size());
+	for (size_t i = 0; i < grp.size(); ++i) {
+		segs[i].n = grp[i]->n; segs[i].jobs = grp[i]->rjobs; segs[i].qpool = grp[i]->qpool;
+		segs[i].qpool_bytes = grp[i]->qbytes; segs[i].res = grp[i]->res;
+	}
+	const int rc = ksw_b200_extend_batch_ref_segs(q->ctx, &grp[0]->cfg, (int)segs.size(), segs.data());
+	for (Sub *s : grp) s->rc = rc;
+}
+
+void run_global(Server *q, std::vector<Sub *> &grp)
+{
+	// merge: job records with rebased offsets, the pools one after the other (their sizes are the jobs' extents)
+	size_t total = 0, nq = 0, nt = 0;
+	for (Sub *s : grp) {
+		total += (size_t)s->n;
+		size_t qb = 0, tb = 0;
+		for (int64_t k = 0; k < s->n; ++k) {
+			qb = std::max<size_t>(qb, (size_t)s->gjobs[k].q_off + (size_t)std::max(s->gjobs[k].qlen, 0));
+			tb = std::max<size_t>(tb, (size_t)s->gjobs[k].t_off + (size_t)std::max(s->gjobs[k].tlen, 0));
+		}
+		s->qbytes = qb; s->tbytes = tb;
+		nq += qb; nt += tb;
+	}
+	q->gj.resize(total); q->gr.resize(total); q->gq.resize(nq ? nq : 1); q->gt.resize(nt ? nt : 1);
+	size_t at = 0, qa = 0, ta = 0;
+	for (Sub *s : grp) {
+		if (s->qbytes) memcpy(q->gq.data() + qa, s->qpool, s->qbytes);
+		if (s->tbytes) memcpy(q->gt.data() + ta, s->tpool, s->tbytes);
+		for (int64_t k = 0; k < s->n; ++k) {
+			ksw_b200_gjob_t j = s->gjobs[k];
+			j.q_off += qa; j.t_off += ta;
+			q->gj[at + (size_t)k] = j;
+		}
+		at += (size_t)s->n; qa += s->qbytes; ta += s->tbytes;
+	}
+	const uint32_t *pool = nullptr;
+	int64_t n_cig = 0;
+	const int rc = ksw_b200_global_batch(q->ctx, &grp[0]->cfg, (int64_t)total, q->gj.data(), q->gq.data(), q->gt.data(), q->gr.data(), &pool, &n_cig);
+	at = 0;
+	for (Sub *s : grp) {
+		s->rc = rc;
+		if (rc == 0) {
+			int64_t ops = 0;
+			for (int64_t k = 0; k < s->n; ++k) ops += q->gr[at + (size_t)k].n_cigar;
+			s->cigar = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(ops > 0 ? ops : 1));
+			int64_t w = 0;
+			for (int64_t k = 0; k < s->n; ++k) {
+				const ksw_b200_gres_t &r = q->gr[at + (size_t)k];
+				s->gres[k].score = r.score; s->gres[k].n_cigar = r.n_cigar; s->gres[k].cigar_off = w;
+				if (r.n_cigar) memcpy(s->cigar + w, pool + r.cigar_off, sizeof(uint32_t) * (size_t)r.n_cigar);
+				w += r.n_cigar;
+			}
+			s->n_cigar = ops;
+		}
+		at += (size_t)s->n;
+	}
+}
+
+void server_main(ksw_b200_queue *q, Server *me)
+{
+	std::vector<Sub *> grp;
+	for (;;) {
+		grp.clear();
+		{
+			std::unique_lock<std::mutex> lk(q->mu);
+			q->cv_work.wait(lk, [&] { return q->stop || !q->pending.empty(); });
+			if (q->pending.empty()) return;                          // stop, and nothing left to serve
+			Sub *first = q->pending.front();
+			for (auto it = q->pending.begin(); it != q->pending.end();) {
+				if ((*it)->kind == first->kind && same_cfg((*it)->cfg, first->cfg)) { grp.push_back(*it); it = q->pending.erase(it); }
+				else ++it;
+			}
+		}
+		if (grp[0]->kind == 0) run_extend(me, grp); else run_global(me, grp);
+		{
+			std::unique_lock<std::mutex> lk(q->mu);
+			if (grp[0]->rc) q->err = ksw_b200_strerror(me->ctx);
+			++q->n_batches; q->n_subs += (int64_t)grp.size();
+			for (Sub *s : grp) { s->done = true; s->cv.notify_one(); }
+		}
+	}
+}
+
+int submit(ksw_b200_queue *q, Sub &s)
+{
+	std::unique_lock<std::mutex> lk(q->mu);
+	if (q->stop) return 1;
+	q->pending.push_back(&s);
+	q->cv_work.notify_one();
+	s.cv.wait(lk, [&] { return s.done; });
+	return s.rc;
+}
+
+} // namespace
+
+extern "C" {
+
+int ksw_b200_queue_create(int device, ksw_b200_queue_t **out)
+{
+	if (!out) return 1;
+	*out = nullptr;
+	ksw_b200_queue *q = new ksw_b200_queue();
+	for (Server &sv : q->srv) {
+		const int rc = ksw_b200_ctx_create(device, &sv.ctx);
+		if (rc) {
+			for (Server &x : q->srv) if (x.ctx) ksw_b200_ctx_destroy(x.ctx);
+			delete q;
+			return rc;
+		}
+		ksw_b200_ctx_set_pack_threads(sv.ctx, 1);
+	}
+	for (Server &sv : q->srv) sv.th = std::thread(server_main, q, &sv);
+	*out = q;
+	return 0;
+}
+
+void ksw_b200_queue_destroy(ksw_b200_queue_t *q)
+{
+	if (!q) return;
+	{
+		std::unique_lock<std::mutex> lk(q->mu);
+		q->stop = true;
+	}
+	q->cv_work.notify_all();
+	for (Server &sv : q->srv) sv.th.join();
+	for (Server &sv : q->srv) ksw_b200_ctx_destroy(sv.ctx);
+	delete q;
+}
+
+int ksw_b200_queue_ref_set(ksw_b200_queue_t *q, const uint8_t *pac, int64_t l_pac)
+{
+	if (!q) return 1;
+	std::unique_lock<std::mutex> lk(q->mu);
+	for (Server &sv : q->srv) {                                      // one copy per device: the second context shares it
+		const int rc = ksw_b200_ref_set(sv.ctx, pac, l_pac);
+		if (rc) { q->err = ksw_b200_strerror(sv.ctx); return rc; }
+	}
+	return 0;
+}
+
+int ksw_b200_queue_extend_ref(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
+                              const uint8_t *qpool, size_t qpool_bytes, ksw_b200_res_t *res)
+{
+	if (!q || !cfg || n < 0) return 1;
+	if (n == 0) return 0;
+	if (!jobs || !qpool || !res) return 1;
+	Sub s;
+	s.kind = 0; s.cfg = *cfg; s.n = n; s.rjobs = jobs; s.qpool = qpool; s.qbytes = qpool_bytes; s.res = res;
+	return submit(q, s);
+}
+
+int ksw_b200_queue_global(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
+                          uint32_t **cigar_pool, int64_t *n_cigar_total)
+{
+	if (!q || !cfg || n < 0 || !cigar_pool || !n_cigar_total) return 1;
+	*cigar_pool = nullptr; *n_cigar_total = 0;
+	if (n == 0) return 0;
+	if (!jobs || !res) return 1;
+	Sub s;
+	s.kind = 1; s.cfg = *cfg; s.n = n; s.gjobs = jobs; s.qpool = qpool; s.tpool = tpool; s.gres = res;
+	const int rc = submit(q, s);
+	if (rc == 0) { *cigar_pool = s.cigar; *n_cigar_total = s.n_cigar; }
+	else free(s.cigar);
+	return rc;
+}
+
+const char *ksw_b200_queue_strerror(const ksw_b200_queue_t *q) { return q ? q->err.c_str() : "null queue"; }
+
+void ksw_b200_queue_stats(const ksw_b200_queue_t *q, int64_t *n_batches, int64_t *n_submissions)
+{
+	if (!q) return;
+	if (n_batches) *n_batches = q->n_batches;
+	if (n_submissions) *n_submissions = q->n_subs;
+}
+
+} // extern "C"

@@ -1123,14 +1123,16 @@ int ksw_b200_ref_set(ksw_b200_ctx_t *ctx, const uint8_t *pac, int64_t l_pac)
 	return 0;
 }
 
-// Synchronous; the caller's arrays may be pageable (they are small: 40 B per job plus the reads).  Per chunk on slot 0's
-// stream: records + (once) the read pool H2D, prep, totals home, pack from the resident .pac, bin, kernels, results home.
-int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
-                              const uint8_t *qpool, size_t qbytes, ksw_b200_res_t *res)
+// Synchronous; the callers' arrays may be pageable (they are small: 40 B per job plus the reads).  The batch may come
+// in several SEGMENTS (one per submitting host thread, ksw_queue.cpp) that run as one GPU batch: job records and read
+// pools are gathered into the slot's pinned staging (q_off rebased), and the results are scattered back.  Per round
+// (<= chunk_jobs jobs) on slot 0's stream: records + read pools H2D, prep, totals home, pack from the resident .pac,
+// bin, kernels, results home.
+int ksw_b200_extend_batch_ref_segs(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int n_segs, const ksw_b200_rseg_t *segs)
 {
-	if (!ctx || !cfg || n < 0) return 1;
-	if (n == 0) return 0;
-	if (!jobs || !res || !qpool) return 1;
+	if (!ctx || !cfg || n_segs < 0 || (n_segs > 0 && !segs)) return 1;
+	for (int g = 0; g < n_segs; ++g)
+		if (segs[g].n < 0 || (segs[g].n > 0 && (!segs[g].jobs || !segs[g].res || !segs[g].qpool))) return 1;
 	if (!ctx->ref) return fail(ctx, 5, "ksw_b200_extend_batch_ref: no reference on the device (call ksw_b200_ref_set first)");
 	if (cfg->m != 5) return fail(ctx, 2, "ksw_b200: only m == 5 is supported (every reference caller passes 5)");
 	CU(cudaSetDevice(ctx->device));
@@ -1140,23 +1142,30 @@ int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, in
 	ksw_scoring_from_cfg(cfg, fast_qmax_enabled(), S);
 	KswParams P;
 	ksw_params_from_cfg(cfg, P);
-	int64_t h2d = 0;
-	// the reads
-	CU(ctx->d_qraw.reserve(qbytes + 64));
-	{
-		const uint8_t *src = qpool;
-		if (!is_pinned(qpool)) {
-			CU(ctx->h_rq.reserve(qbytes));
-			memcpy(ctx->h_rq.p, qpool, qbytes);
-			src = (const uint8_t *)ctx->h_rq.p;
-		}
-		CU(cudaMemcpyAsync(ctx->d_qraw.p, src, qbytes, cudaMemcpyHostToDevice, s.stream));
-		h2d += (int64_t)qbytes;
-	}
+	int64_t h2d = 0, d2h = 0;
 	const int64_t chunk = ctx->chunk_jobs;
-	for (int64_t first = 0; first < n; first += chunk) {
-		const int64_t nc = std::min(chunk, n - first);
+	struct Piece { int seg; int64_t first, n; size_t qbase; };
+	std::vector<Piece> round;
+	int g = 0;
+	int64_t at = 0;                                                  // next job of segment g
+	while (g < n_segs) {
+		// one round: pieces of consecutive segments, <= chunk jobs in all; the read pool of every segment it touches
+		round.clear();
+		int64_t nc = 0;
+		size_t qbytes = 0;
+		while (g < n_segs && nc < chunk) {
+			const int64_t take = std::min(segs[g].n - at, chunk - nc);
+			if (take > 0) {
+				round.push_back(Piece{g, at, take, qbytes});
+				qbytes += (segs[g].qpool_bytes + 15) & ~(size_t)15;
+				nc += take; at += take;
+			}
+			if (at >= segs[g].n) { ++g; at = 0; }
+		}
+		if (nc == 0) break;
 		const size_t n1 = (size_t)nc;
+		CU(ctx->d_qraw.reserve(qbytes + 64));
+		CU(ctx->h_rq.reserve(std::max<size_t>(qbytes, 16)));
 		CU(s.d_rawjobs.reserve(sizeof(ksw_b200_rjob_t) * n1));
 		CU(s.d_offs.reserve(sizeof(uint32_t) * n1));
 		CU(s.d_stats.reserve(sizeof(DevPackStats)));
@@ -1164,9 +1173,20 @@ int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, in
 		CU(s.h_jobs.reserve(sizeof(ksw_b200_rjob_t) * n1));
 		CU(s.h_res.reserve(sizeof(DevRes) * n1));
 		CU(b->d_jobs.reserve(sizeof(DevJob) * n1));
-		memcpy(s.h_jobs.p, jobs + first, sizeof(ksw_b200_rjob_t) * n1);
+		{
+			ksw_b200_rjob_t *hj = (ksw_b200_rjob_t *)s.h_jobs.p;
+			int64_t k = 0;
+			for (const Piece &pc : round) {
+				memcpy((uint8_t *)ctx->h_rq.p + pc.qbase, segs[pc.seg].qpool, segs[pc.seg].qpool_bytes);
+				memcpy(hj + k, segs[pc.seg].jobs + pc.first, sizeof(ksw_b200_rjob_t) * (size_t)pc.n);
+				if (pc.qbase)
+					for (int64_t x = 0; x < pc.n; ++x) hj[k + x].q_off += pc.qbase;
+				k += pc.n;
+			}
+		}
+		CU(cudaMemcpyAsync(ctx->d_qraw.p, ctx->h_rq.p, qbytes, cudaMemcpyHostToDevice, s.stream));
 		CU(cudaMemcpyAsync(s.d_rawjobs.p, s.h_jobs.p, sizeof(ksw_b200_rjob_t) * n1, cudaMemcpyHostToDevice, s.stream));
-		h2d += (int64_t)(sizeof(ksw_b200_rjob_t) * n1);
+		h2d += (int64_t)(qbytes + sizeof(ksw_b200_rjob_t) * n1);
 		CU(ksw_launch_prep_ref(s.d_rawjobs.p, nc, S, ctx->ref->l_pac, qbytes, (DevJob *)b->d_jobs.p, (uint32_t *)s.d_offs.p,
 		                       (DevPackStats *)s.d_stats.p, s.stream));
 		CU(cudaMemcpyAsync(s.h_stats.p, s.d_stats.p, sizeof(DevPackStats), cudaMemcpyDeviceToHost, s.stream));
@@ -1206,11 +1226,29 @@ int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, in
 		if (rc) return rc;
 		CU(cudaMemcpyAsync(s.h_res.p, b->d_res.p, sizeof(DevRes) * n1, cudaMemcpyDeviceToHost, s.stream));
 		CU(cudaStreamSynchronize(s.stream));
-		memcpy(res + first, s.h_res.p, sizeof(DevRes) * n1);
+		d2h += (int64_t)(sizeof(DevRes) * n1);
+		{
+			const DevRes *hr = (const DevRes *)s.h_res.p;
+			int64_t k = 0;
+			for (const Piece &pc : round) {
+				memcpy(segs[pc.seg].res + pc.first, hr + k, sizeof(DevRes) * (size_t)pc.n);
+				k += pc.n;
+			}
+		}
 	}
 	ctx->last_h2d = h2d;
-	ctx->last_d2h = (int64_t)(sizeof(DevRes) * (size_t)n);
+	ctx->last_d2h = d2h;
 	return 0;
+}
+
+int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
+                              const uint8_t *qpool, size_t qbytes, ksw_b200_res_t *res)
+{
+	if (!ctx || !cfg || n < 0) return 1;
+	if (n == 0) return 0;
+	ksw_b200_rseg_t seg;
+	seg.n = n; seg.jobs = jobs; seg.qpool = qpool; seg.qpool_bytes = qbytes; seg.res = res;
+	return ksw_b200_extend_batch_ref_segs(ctx, cfg, 1, &seg);
 }
 
 // Multi-GPU form: jobs are independent, so the batch is cut into n_ctx contiguous ranges of (nearly)

@@ -99,6 +99,16 @@ def load_library():
     lib.ksw_b200_host_unregister.argtypes = [vp]
     lib.ksw_b200_extend_batch_async.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     lib.ksw_b200_wait.argtypes = [vp]
+    lib.ksw_b200_queue_create.argtypes = [i32, C.POINTER(vp)]
+    lib.ksw_b200_queue_destroy.argtypes = [vp]
+    lib.ksw_b200_queue_destroy.restype = None
+    lib.ksw_b200_queue_ref_set.argtypes = [vp, vp, i64]
+    lib.ksw_b200_queue_extend_ref.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
+    lib.ksw_b200_queue_global.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(i64)]
+    lib.ksw_b200_queue_strerror.argtypes = [vp]
+    lib.ksw_b200_queue_strerror.restype = C.c_char_p
+    lib.ksw_b200_queue_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.ksw_b200_queue_stats.restype = None
     lib.ksw_b200_ref_set.argtypes = [vp, vp, i64]
     lib.ksw_b200_extend_batch_ref.argtypes = [vp, vp, i64, vp, vp, C.c_size_t, vp]
     lib.ksw_b200_batch_upload.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(vp)]
@@ -316,6 +326,67 @@ class KswB200:
         ops, ms = C.c_double(0), C.c_float(0)
         self._check(self.lib.ksw_b200_dpx_peak(self.ctx, which, C.byref(ops), C.byref(ms)), "ksw_b200_dpx_peak")
         return ops.value, ms.value
+
+
+class KswQueue:
+    """ksw_b200_queue_t: one submission queue per GPU shared by any number of host threads (the calls block and release
+    the GIL, so Python threads submit concurrently)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.q = C.c_void_p()
+        rc = self.lib.ksw_b200_queue_create(device, C.byref(self.q))
+        if rc != 0:
+            raise KswB200Error(f"ksw_b200_queue_create(device={device}) failed with code {rc}")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise KswB200Error(f"{what} failed ({rc}): {self.lib.ksw_b200_queue_strerror(self.q).decode()}")
+
+    def ref_set(self, pac: np.ndarray, l_pac: int):
+        pac = np.ascontiguousarray(pac, dtype=np.uint8)
+        self._pac_keepalive = pac
+        self._check(self.lib.ksw_b200_queue_ref_set(self.q, _p(pac), int(l_pac)), "ksw_b200_queue_ref_set")
+
+    def extend_ref(self, cfg: Cfg, rjobs, qpool) -> np.ndarray:
+        rjobs = np.ascontiguousarray(rjobs, dtype=RJOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        res = np.zeros(rjobs.shape[0], dtype=RES_DT)
+        self._check(self.lib.ksw_b200_queue_extend_ref(self.q, C.byref(cfg), rjobs.shape[0], _p(rjobs), _p(qpool), qpool.nbytes, _p(res)),
+                    "ksw_b200_queue_extend_ref")
+        return res
+
+    def global_batch(self, cfg: Cfg, jobs, qpool, tpool):
+        jobs = np.ascontiguousarray(jobs, dtype=GJOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        tpool = np.ascontiguousarray(tpool, dtype=np.uint8)
+        res = np.zeros(jobs.shape[0], dtype=GRES_DT)
+        pool = C.POINTER(C.c_uint32)()
+        total = C.c_int64(0)
+        self._check(self.lib.ksw_b200_queue_global(self.q, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool), _p(tpool), _p(res),
+                                                   C.byref(pool), C.byref(total)), "ksw_b200_queue_global")
+        cig = np.ctypeslib.as_array(pool, shape=(total.value,)).copy() if total.value else np.zeros(0, np.uint32)
+        if pool:
+            libc = C.CDLL(None)
+            libc.free.argtypes = [C.c_void_p]
+            libc.free(pool)
+        return res, cig
+
+    def stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.lib.ksw_b200_queue_stats(self.q, C.byref(a), C.byref(b))
+        return {"batches": a.value, "submissions": b.value}
+
+    def close(self):
+        if self.q:
+            self.lib.ksw_b200_queue_destroy(self.q)
+            self.q = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def extend_batch_multi(ctxs, cfg: Cfg, jobs, qpool, tpool) -> np.ndarray:

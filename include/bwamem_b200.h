@@ -85,6 +85,9 @@ void b200_ext_plan_reset(b200_ext_plan_t *p);                 /* forget reads/ch
  * regions, bit for bit.  Only between batches (after create or reset).  Default: off, or KSW_B200_REF=1 in the
  * environment. */
 void b200_ext_plan_set_device_ref(b200_ext_plan_t *p, int on);
+/* device-reference mode only: the passes are submitted to the GPU's shared queue (ksw_b200_queue_t, whose owner has
+ * called ksw_b200_queue_ref_set) instead of the context given to the run functions, which may then be NULL */
+void b200_ext_plan_set_queue(b200_ext_plan_t *p, ksw_b200_queue_t *q);
 int b200_ext_plan_add_read(b200_ext_plan_t *p, int l_query, const uint8_t *query);
 /* registers one chain of that read and the left/right job of every one of its seeds; returns the chain
  * handle (>= 0), or -1 for an empty chain (mem_chain2aln returns at once, bwamem.c:738) */

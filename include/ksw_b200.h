@@ -141,6 +141,16 @@ int ksw_b200_ref_set(ksw_b200_ctx_t *ctx, const uint8_t *pac, int64_t l_pac);
 int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
                               const uint8_t *qpool, size_t qpool_bytes, ksw_b200_res_t *res);
 
+/* the same for a batch that arrives in several segments (one per submitting host thread): they run as ONE GPU batch */
+typedef struct {
+	int64_t n;
+	const ksw_b200_rjob_t *jobs;
+	const uint8_t *qpool;
+	size_t qpool_bytes;
+	ksw_b200_res_t *res;
+} ksw_b200_rseg_t;
+int ksw_b200_extend_batch_ref_segs(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int n_segs, const ksw_b200_rseg_t *segs);
+
 /* bytes the last ksw_b200_extend_batch / ksw_b200_extend_batch_async call copied host->device and device->host */
 int ksw_b200_ctx_last_transfer(const ksw_b200_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
@@ -192,6 +202,27 @@ typedef struct {
 int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
                           const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
                           const uint32_t **cigar_pool, int64_t *n_cigar_total);
+
+/* ---- one submission queue per GPU, shared by all host threads (cross-thread batch coalescing) - */
+/* The reference's workers (kt_for_batch, kthread_batch.c:18-56) each own a slice of the reads; with one private context
+ * per worker every worker launches its own small batches.  A queue owns ONE context on its device and a server thread:
+ * any number of host threads submit (blocking, thread-safe), and whatever has been submitted while the GPU was busy
+ * runs as one merged batch; every submitter gets exactly the results of its own jobs (same read -> same regs[i]).
+ * GPU memory is that of one context, however many threads submit. */
+typedef struct ksw_b200_queue ksw_b200_queue_t;
+int  ksw_b200_queue_create(int device, ksw_b200_queue_t **out);
+void ksw_b200_queue_destroy(ksw_b200_queue_t *q);
+int  ksw_b200_queue_ref_set(ksw_b200_queue_t *q, const uint8_t *pac, int64_t l_pac);
+/* as ksw_b200_extend_batch_ref */
+int  ksw_b200_queue_extend_ref(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_rjob_t *jobs,
+                               const uint8_t *qpool, size_t qpool_bytes, ksw_b200_res_t *res);
+/* as ksw_b200_global_batch, but the CIGAR pool is a malloc'd array the caller owns (free() it): *cigar_pool, *n_cigar_total */
+int  ksw_b200_queue_global(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
+                           const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
+                           uint32_t **cigar_pool, int64_t *n_cigar_total);
+const char *ksw_b200_queue_strerror(const ksw_b200_queue_t *q);
+/* batches the server has run and submissions they carried (for the record: submissions / batches = coalescing factor) */
+void ksw_b200_queue_stats(const ksw_b200_queue_t *q, int64_t *n_batches, int64_t *n_submissions);
 
 /* ---- measurement helper ------------------------------------------------------ */
 /* Issue-rate microbenchmark of the DPX family used by the kernels (VIADDMNMX.S16x2[.RELU],

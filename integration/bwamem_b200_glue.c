@@ -38,7 +38,8 @@
 #include "bwamem_b200.h"
 
 typedef struct {
-	ksw_b200_ctx_t *ctx;
+	ksw_b200_ctx_t *ctx;               /* private context (KSW_B200_QUEUE=0), else NULL */
+	ksw_b200_queue_t *queue;           /* the shared queue of this worker's GPU */
 	b200_ext_plan_t *plan;
 	const uint8_t *pac;
 } b200_thread_t;
@@ -60,12 +61,47 @@ static int b200_gpu_count(void)
 static double b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, b200_t_init;
 static void b200_add_time(double *acc, double dt) { __sync_synchronize(); { static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER; pthread_mutex_lock(&mu); *acc += dt; pthread_mutex_unlock(&mu); } }
 
+/* One submission queue per GPU shared by all workers (cross-thread batch coalescing): whatever the
+ * workers submit while the GPU is busy runs as one merged batch, and GPU memory is one context per GPU whatever -t is.
+ * KSW_B200_QUEUE=0 (or KSW_B200_REF=0, the queue needs the device-resident reference): one private context per worker. */
+#define B200_MAX_GPUS 64
+static ksw_b200_queue_t *b200_queue[B200_MAX_GPUS];
+static const uint8_t *b200_queue_pac[B200_MAX_GPUS];
+static pthread_mutex_t b200_queue_mu = PTHREAD_MUTEX_INITIALIZER;
+static int b200_queue_on(void)
+{
+	static int v = -1;
+	if (v < 0) {
+		const char *e = getenv("KSW_B200_QUEUE"), *r = getenv("KSW_B200_REF");
+		v = !(e && e[0] == '0') && !(r && r[0] == '0');
+	}
+	return v;
+}
+static ksw_b200_queue_t *b200_queue_for(int gpu, const bntseq_t *bns, const uint8_t *pac)
+{
+	ksw_b200_queue_t *q;
+	pthread_mutex_lock(&b200_queue_mu);
+	if (!b200_queue[gpu] && ksw_b200_queue_create(gpu, &b200_queue[gpu]) != 0)
+		err_fatal(__func__, "no usable CUDA device: the B200 extension path has no CPU fallback");
+	if (pac && b200_queue_pac[gpu] != pac) {
+		if (ksw_b200_queue_ref_set(b200_queue[gpu], pac, bns->l_pac) != 0) err_fatal(__func__, "cannot put the reference on GPU %d", gpu);
+		b200_queue_pac[gpu] = pac;
+	}
+	q = b200_queue[gpu];
+	pthread_mutex_unlock(&b200_queue_mu);
+	return q;
+}
+
 static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int tid)
 {
 	b200_thread_t *t;
 	if (tid < 0 || tid >= B200_MAX_WORKERS) err_fatal(__func__, "more than %d worker threads", B200_MAX_WORKERS);
 	t = &b200_workers[tid];
-	if (!t->ctx) {
+	if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
+	if (b200_queue_on()) {
+		if (b200_n_gpus < 1) err_fatal(__func__, "no usable CUDA device: the B200 extension path has no CPU fallback");
+		t->queue = b200_queue_for(tid % (b200_n_gpus < B200_MAX_GPUS ? b200_n_gpus : B200_MAX_GPUS), bns, pac);
+	} else if (!t->ctx) {
 		if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
 		if (b200_n_gpus < 1 || ksw_b200_ctx_create(tid % b200_n_gpus, &t->ctx) != 0)
 			err_fatal(__func__, "no usable CUDA device: the B200 extension path has no CPU fallback");
@@ -86,6 +122,7 @@ static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bn
 			const char *e = getenv("KSW_B200_REF");
 			b200_ext_plan_set_device_ref(t->plan, !(e && e[0] == '0'));
 		}
+		if (t->queue) b200_ext_plan_set_queue(t->plan, t->queue);
 	}
 	return t;
 }
@@ -245,6 +282,22 @@ int b200_global2_hook(int qlen, const uint8_t *query, int tlen, const uint8_t *t
 	}
 	/* miss: one job on the GPU (there is no CPU fallback in this mode) */
 	__sync_fetch_and_add(&b200_cig_misses, 1);
+	if (b200_queue_on()) {
+		/* through GPU 0's shared queue: concurrent misses of the pass-2 threads are merged into one batch there */
+		uint32_t *own = 0;
+		if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
+		memcpy(cfg.mat, mat, 25);
+		cfg.m = m; cfg.o_del = o_del; cfg.e_del = e_del; cfg.o_ins = o_ins; cfg.e_ins = e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
+		job.q_off = 0; job.t_off = 0; job.qlen = qlen; job.tlen = tlen; job.w = w; job.reserved = 0;
+		if (b200_n_gpus < 1 || ksw_b200_queue_global(b200_queue_for(0, 0, 0), &cfg, 1, &job, query, target, &r, &own, &total) != 0)
+			err_fatal(__func__, "GPU global alignment failed");
+		if (n_cigar_) *n_cigar_ = 0;
+		if (n_cigar_ && cigar_) {
+			if (!own) own = (uint32_t *)malloc(4);
+			*n_cigar_ = r.n_cigar; *cigar_ = own;
+		} else free(own);
+		return r.score;
+	}
 	pthread_mutex_lock(&miss_mu);
 	if (!ctx) {
 		if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
@@ -350,7 +403,12 @@ static void b200_cig_lookahead(b200_thread_t *t, int tid, worker_t *w, int start
 		const uint32_t *pool = 0;
 		int64_t total = 0, j;
 		if (cur.n > m_res) { m_res = cur.n; res = (ksw_b200_gres_t *)realloc(res, sizeof(ksw_b200_gres_t) * m_res); }
-		if (ksw_b200_global_batch(t->ctx, &cfg, cur.n, cur.jobs, cur.q, cur.t, res, &pool, &total) != 0)
+		uint32_t *own_pool = 0;
+		if (t->queue) {
+			if (ksw_b200_queue_global(t->queue, &cfg, cur.n, cur.jobs, cur.q, cur.t, res, &own_pool, &total) != 0)
+				err_fatal(__func__, "GPU global alignment failed: %s", ksw_b200_queue_strerror(t->queue));
+			pool = own_pool;
+		} else if (ksw_b200_global_batch(t->ctx, &cfg, cur.n, cur.jobs, cur.q, cur.t, res, &pool, &total) != 0)
 			err_fatal(__func__, "GPU global alignment failed: %s", ksw_b200_strerror(t->ctx));
 		__sync_fetch_and_add(&b200_cig_jobs, cur.n);
 		nxt.n = 0; nxt.nq = 0; nxt.nt = 0;
@@ -364,6 +422,7 @@ static void b200_cig_lookahead(b200_thread_t *t, int tid, worker_t *w, int start
 				b200_cig_push(&nxt, opt, w->bns, w->pac, (const uint8_t *)w->seqs[mt.read].seq, &mt);
 		}
 		{ b200_cig_batch_t x = cur; cur = nxt; nxt = x; }
+		free(own_pool);
 	}
 	free(cur.jobs); free(cur.meta); free(cur.q); free(cur.t);
 	free(nxt.jobs); free(nxt.meta); free(nxt.q); free(nxt.t);
@@ -422,7 +481,7 @@ static void worker1_b200(void *data, int start, int batch_size, int tid)
 	tp = realtime() - t0 - ts;
 	t1 = realtime();
 	rc = rounds ? b200_ext_plan_run_rounds(t->plan, t->ctx) : b200_ext_plan_run(t->plan, t->ctx);
-	if (rc != 0) err_fatal(__func__, "GPU extension pass failed (%d): %s", rc, ksw_b200_strerror(t->ctx));
+	if (rc != 0) err_fatal(__func__, "GPU extension pass failed (%d): %s", rc, t->queue ? ksw_b200_queue_strerror(t->queue) : ksw_b200_strerror(t->ctx));
 	b200_add_time(&b200_t_seed, ts); b200_add_time(&b200_t_plan, tp); b200_add_time(&b200_t_gpu, realtime() - t1);
 	t1 = realtime();
 	for (b = 0; b < batch_size; ++b) {
@@ -485,4 +544,9 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		        "global alignments so far: %lld computed ahead, %lld hits, %lld misses)\n", __func__, n,
 		        cputime() - ctime, realtime() - rtime, b200_t_init, b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, b200_t_cigar,
 		        t_pass1, b200_cig_jobs, b200_cig_hits, b200_cig_misses);
+	if (bwa_verbose >= 3 && b200_queue_on() && b200_queue[0]) {
+		int64_t nb = 0, ns = 0;
+		ksw_b200_queue_stats(b200_queue[0], &nb, &ns);
+		fprintf(stderr, "[M::%s] GPU 0 queue so far: %lld submissions of the workers ran as %lld merged batches\n", __func__, (long long)ns, (long long)nb);
+	}
 }

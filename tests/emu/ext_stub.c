@@ -62,3 +62,10 @@ int ksw_b200_extend_batch_ref(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *c, int6
 	}
 	return 0;
 }
+
+int ksw_b200_queue_extend_ref(ksw_b200_queue_t *q, const ksw_b200_cfg_t *c, int64_t n, const ksw_b200_rjob_t *jobs,
+                              const uint8_t *qpool, size_t qpool_bytes, ksw_b200_res_t *res)
+{
+	(void)q;
+	return ksw_b200_extend_batch_ref(0, c, n, jobs, qpool, qpool_bytes, res);
+}

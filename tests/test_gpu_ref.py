@@ -86,3 +86,61 @@ def test_chain_driver_in_device_reference_mode(gpu_ctx, oracle_built, monkeypatc
         assert K.regs_equal(K.run_chain_gpu(gpu_ctx, cs), want), name
         rnd = K.run_chain_driver(gpu_ctx.lib, cs, ctx=gpu_ctx.ctx, rounds=True)
         assert K.regs_equal(rnd[:2], want), ("rounds", name)
+
+
+def test_shared_queue_merges_submissions_of_many_threads(oracle_built):
+    """ksw_b200_queue_t (cross-thread coalescing): twelve host threads submit extension and
+    global-alignment batches at the same time; every thread must get exactly the results of its own jobs, and the
+    server must have run fewer GPU batches than there were submissions."""
+    import threading
+    rng = np.random.default_rng(5)
+    l_pac = 40_000
+    genome = rng.integers(0, 4, l_pac).astype(np.uint8)
+    pac = K.pack_pac(genome)
+    q = B.KswQueue(0)
+    q.ref_set(pac, l_pac)
+    cfg = K.make_cfg()
+    n_thr, rounds = 12, 4
+
+    def make(seed):
+        r = np.random.default_rng(seed)
+        n = int(r.integers(200, 900))
+        rj = np.zeros(n, dtype=B.RJOB_DT)
+        reads, qs, ts, at = [], [], [], 0
+        for k in range(n):
+            ql, tl = int(r.integers(20, 160)), int(r.integers(10, 260))
+            beg = int(r.integers(0, l_pac - tl))
+            t = genome[beg:beg + tl]
+            qq = K.mutate(r, t, 0.02, 0.005, max_indel=3)[:ql]
+            if len(qq) < ql:
+                qq = np.concatenate([qq, r.integers(0, 4, ql - len(qq)).astype(np.uint8)])
+            reads.append(qq); qs.append(qq); ts.append(t)
+            rj[k]["q_off"], rj[k]["q_step"], rj[k]["t_pos"], rj[k]["t_step"] = at, 1, beg, 1
+            rj[k]["qlen"], rj[k]["tlen"], rj[k]["h0"], rj[k]["w"] = ql, tl, int(r.integers(0, 80)), 100
+            at += ql
+        want = K.run_oracle(K._pools_from_lists(qs, ts, rj["h0"], rj["w"], cfg), threads=2)
+        g = K.gen_global(int(r.integers(50, 300)), seed=seed + 1000, max_q=150)
+        gwant = K.run_global_oracle(g, threads=2)
+        return rj, np.concatenate(reads), want, g, gwant
+
+    work = [[make(100 * t + i) for i in range(rounds)] for t in range(n_thr)]
+    errors = []
+
+    def body(t):
+        try:
+            for rj, qpool, want, g, gwant in work[t]:
+                got = q.extend_ref(cfg, rj, qpool)
+                mm = K.first_mismatch(want, got.view(K.RES_DT))
+                assert mm is None, ("extension", t, mm)
+                mm = K.global_mismatch(q.global_batch(g.cfg, g.jobs, g.qpool, g.tpool), gwant)
+                assert mm is None, ("global", t, mm)
+        except Exception as e:                       # noqa: BLE001 — reported by the main thread
+            errors.append(e)
+
+    th = [threading.Thread(target=body, args=(t,)) for t in range(n_thr)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    st = q.stats()
+    q.close()
+    assert not errors, errors[0]
+    assert st["submissions"] == 2 * n_thr * rounds and st["batches"] < st["submissions"], st
