@@ -105,15 +105,18 @@ ksw_fast_kernel(const DevJob *__restrict__ jobs, long long n_jobs, const uint32_
 			if (got) { ksw_fast_init_lane(L, jb, pool, npool); state = RUN; }
 		}
 		if (__all_sync(0xffffffffu, state == DONE)) break;
-		if (state == RUN) {
-			if (ksw_fast_row<T, KEYED>(L, M, K, mrow)) {
-				DevRes r;
-				ksw_fast_result(L, r);
-				res[L.idx] = r;
-				cells[L.idx] = L.cells;
-				state = IDLE;
+		// rows, until a lane runs out of work: one vote per row instead of the two of the supply logic above
+		do {
+			if (state == RUN) {
+				if (ksw_fast_row<T, KEYED>(L, M, K, mrow)) {
+					DevRes r;
+					ksw_fast_result(L, r);
+					res[L.idx] = r;
+					cells[L.idx] = L.cells;
+					state = IDLE;
+				}
 			}
-		}
+		} while (!__any_sync(0xffffffffu, state == IDLE));
 	}
 }
 

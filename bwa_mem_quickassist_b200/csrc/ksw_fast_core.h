@@ -282,7 +282,8 @@ static KSW_HD void ksw_fast_setup_quads(ksw_u4 *hq, uint32_t *sq, const int owne
 struct KswFastRowRegs {       // registers carried along a row
 	uint32_t X;               // lo half = Fs entering the quad's first column, hi half = 0
 	uint32_t Hc;              // hi half = H(i, c0-1): carry for the shifted H store (the previous quad's hB)
-	uint32_t m, zmin;         // running max (keys relative to the current quad if KEYED) / running min of the row, per half
+	uint32_t m, zmin;         // running max (keys relative to the current quad if KEYED) / running min of the row's interior quads, per half
+	uint32_t zminE;           // running min of the (at most two) edge quads' in-band cells
 	int mjl, mjh;             // !KEYED: last column where the lo / hi half reached its running max
 	uint32_t hA, hB;          // H of the last processed quad
 };
@@ -356,7 +357,7 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, ksw_u4 *dst, const KswFastCo
 		if (ph) R.mjh = c0 + 3;
 	}
 	// zero detector over the in-band cells
-	if (EDGE) R.zmin = min3_2(R.zmin, hA | (~keepA & 0x7fff7fffu), hB | (~keepB & 0x7fff7fffu));
+	if (EDGE) R.zminE = min3_2(R.zminE, hA | (~keepA & 0x7fff7fffu), hB | (~keepB & 0x7fff7fffu));
 	else R.zmin = min3_2(R.zmin, hA, hB);
 	// store: eh[j].h = H(i, j-1), eh[j].e = E(i+1, j)
 	ksw_u4 o;
@@ -386,14 +387,19 @@ static KSW_HD bool ksw_has_zero16(uint32_t x, uint32_t Bpk)
 	return ((x - 0x00010001u) & ~x & 0x80008000u) != 0u;
 }
 
-// the reference's trim scans (ksw.c:463-466) over the stored eh[].h, skipping whole zero-free quads
+// the reference's trim scans (ksw.c:463-466) over the stored eh[].h, skipping whole zero-free quads.  The stored quads
+// cq_lo..cq_hi (eh[] indices 4cq_lo .. 4cq_hi+3) are known to hold no zero (the row's interior quads had none) and are
+// jumped over without a look; cq_lo > cq_hi: nothing is known.
 template <int T>
-static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, const KswFastConst &K, int rarg, int lo, int hi, int &new_lo, int &new_hi)
+static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, const KswFastConst &K, int rarg, int lo, int hi, int cq_lo, int cq_hi,
+                                      int &new_lo, int &new_hi)
 {
 	int j = rarg;
 	while (j >= lo) {
+		const int qj = j >> 2;
+		if (qj >= cq_lo && qj <= cq_hi) { j = (cq_lo << 2) - 1; continue; }
 		if ((j & 3) == 3 && j - 3 >= lo) {
-			const ksw_u4 v = M.hq[(j >> 2) * T];
+			const ksw_u4 v = M.hq[qj * T];
 			if (!ksw_has_zero16(v.x, K.Bpk) && !ksw_has_zero16(v.z, K.Bpk)) { j -= 4; continue; }
 		}
 		if (*M.h16(j) == (uint16_t)K.B) break;
@@ -402,8 +408,10 @@ static KSW_HD void ksw_fast_trim_scan(const KswFastMem<T> &M, const KswFastConst
 	new_lo = j + 1;
 	j = rarg + 2;
 	while (j <= hi) {
+		const int qj = j >> 2;
+		if (qj >= cq_lo && qj <= cq_hi) { j = (cq_hi + 1) << 2; continue; }
 		if ((j & 3) == 0 && j + 3 <= hi) {
-			const ksw_u4 v = M.hq[(j >> 2) * T];
+			const ksw_u4 v = M.hq[qj * T];
 			if (!ksw_has_zero16(v.x, K.Bpk) && !ksw_has_zero16(v.z, K.Bpk)) { j += 4; continue; }
 		}
 		if (*M.h16(j) == (uint16_t)K.B) break;
@@ -451,7 +459,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 	const uint32_t left0pk = (uint32_t)(left0 + K.B) * 0x10001u;
 	KswFastRowRegs R;
 	R.X = (uint32_t)(K.B + K.oe_ins);                          // F = 0 entering the band (ksw.c:417), as Fs, high half clear
-	R.Hc = 0; R.m = KEYED ? KSW_KEY_INIT : 0u; R.zmin = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
+	R.Hc = 0; R.m = KEYED ? KSW_KEY_INIT : 0u; R.zmin = R.zminE = 0x7fff7fffu; R.mjl = -1; R.mjh = -1; R.hA = 0; R.hB = 0;
 	ksw_u4 *ph = M.hq + q0 * T;                                // running pointers: the loop needs no index arithmetic
 	const uint32_t *ps = M.sq + q0 * T;
 	ksw_u4 v = *ph;
@@ -519,15 +527,18 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		if (drop) return true;
 	}
 	// band trim (ksw.c:463-466)
-	const bool any_zero = ((R.zmin & 0xffffu) == (uint32_t)K.B) | ((R.zmin >> 16) == (uint32_t)K.B);
-	if (!any_zero) {
+	const bool zero_in = ((R.zmin & 0xffffu) == (uint32_t)K.B) | ((R.zmin >> 16) == (uint32_t)K.B);
+	const bool zero_edge = ((R.zminE & 0xffffu) == (uint32_t)K.B) | ((R.zminE >> 16) == (uint32_t)K.B);
+	if (!(zero_in | zero_edge)) {
 		// every eh[j].h for j in (lo, hi] is non-zero, so only the first-column slot eh[lo].h can stop the
 		// downward scan, and the upward scan runs off the end
 		L.lo = left0 ? lo : lo + 1;
 		L.hi = hi + 1;
 	} else {
+		// the columns of the interior quads q0+1 .. q1-1 are stored one slot to the right (eh[j].h = H(i, j-1)): if none of
+		// them is zero, the stored quads q0+2 .. q1-1 hold no zero
 		int nl, nh;
-		ksw_fast_trim_scan<T>(M, K, rarg, lo, hi, nl, nh);
+		ksw_fast_trim_scan<T>(M, K, rarg, lo, hi, zero_in ? 1 : q0 + 2, zero_in ? 0 : q1 - 1, nl, nh);
 		L.lo = nl; L.hi = nh;
 	}
 	L.i = i + 1;
