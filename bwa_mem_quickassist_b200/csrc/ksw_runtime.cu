@@ -1258,6 +1258,8 @@ int ksw_b200_extend_batch_multi(int n_ctx, ksw_b200_ctx_t **ctxs, const ksw_b200
                                 const ksw_b200_job_t *jobs, const uint8_t *qpool, const uint8_t *tpool, ksw_b200_res_t *res)
 {
 	if (n_ctx < 1 || !ctxs || !cfg || n < 0) return 1;
+	if (n > 0 && (!jobs || !res)) return 1;
+	for (int r = 0; r < n_ctx; ++r) if (!ctxs[r]) return 1;
 	if (n_ctx == 1) return ksw_b200_extend_batch(ctxs[0], cfg, n, jobs, qpool, tpool, res);
 	std::vector<int64_t> cut(n_ctx + 1, n);
 	{
@@ -1336,7 +1338,14 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 	KswParams P;
 	ksw_params_from_cfg(cfg, P);
 	const int64_t max_chunk_jobs = 1 << 18;
-	const size_t max_seq = (size_t)256 << 20, max_ops = (size_t)128 << 20, z_budget = (size_t)8 << 30;
+	const size_t max_seq = (size_t)256 << 20, max_ops = (size_t)128 << 20;
+	// direction-matrix slab: at most 8 GiB, and never more than a quarter of what the device has free right now (several
+	// contexts may share a GPU; a slab this context already holds counts as available to it)
+	size_t z_budget = (size_t)8 << 30;
+	{
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) z_budget = std::min(z_budget, std::max<size_t>((free_b + ctx->g_dz.cap) / 4, (size_t)256 << 20));
+	}
 	int64_t first = 0;
 	while (first < n) {
 		// chunk [first, last): as many jobs as the budgets allow (at least one)
