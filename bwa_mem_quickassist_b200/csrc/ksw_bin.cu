@@ -12,12 +12,8 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256)
-ksw_bin_keys_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__restrict__ keys, uint32_t *__restrict__ vals)
+__device__ __forceinline__ uint32_t ksw_bin_key(const DevJob &jb)
 {
-	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n) return;
-	const DevJob jb = jobs[k];
 	const uint32_t cls = (jb.flags >> KSW_CLASS_SHIFT) & KSW_CLASS_MASK;
 	// query length (6 bits; steps of 2 / 2 / 4 / 8 columns for the four classes): the band of a row is capped by it, and
 	// the lanes of a warp wait for the widest band in every row.  (It replaced the row count tlen/16: how long a job
@@ -29,8 +25,90 @@ ksw_bin_keys_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__re
 	const uint32_t h0 = (uint32_t)jb.h0;
 	const uint32_t hb = 127u - (h0 < 96u ? h0 : 96u + min((h0 - 96u) >> 4, 31u));   // 7 bits
 	// fast classes: cls << 13; warp-cooperative jobs 0x8000 | ..., thread-per-job jobs 0xC000 | ... (13 key bits below)
-	keys[k] = (uint16_t)((cls >= KSW_CLASS_GENERIC ? (cls == KSW_CLASS_WARP ? 0x8000u : 0xC000u) : (cls << 13)) | (tl << 7) | hb);
+	return (cls >= KSW_CLASS_GENERIC ? (cls == KSW_CLASS_WARP ? 0x8000u : 0xC000u) : (cls << 13)) | (tl << 7) | hb;
+}
+
+__device__ __forceinline__ uint32_t ksw_class_lowest_key(int c)
+{
+	return c >= (int)KSW_CLASS_GENERIC ? (c == (int)KSW_CLASS_WARP ? 0x8000u : 0xC000u) : ((uint32_t)c << 13);
+}
+
+__global__ void __launch_bounds__(256)
+ksw_bin_keys_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	keys[k] = (uint16_t)ksw_bin_key(jobs[k]);
 	vals[k] = (uint32_t)k;
+}
+
+// ---- the same binning as a counting sort WITHOUT shared memory (three kernels): the pinned-caller pipeline launches it
+// while the previous chunk's extension kernels fill every SM's shared memory, and a kernel that needs none still finds
+// room beside them (ksw_runtime.cu); the radix sort would wait for them to drain, and the next chunk's extension kernels
+// with it.  Equal keys come out in the order their jobs got there, which the kernels do not care about.
+__global__ void __launch_bounds__(256)
+ksw_bin_hist_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__restrict__ keys, uint32_t *__restrict__ hist)
+{
+	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = k < n;
+	uint32_t key = 0xffffffffu;
+	if (live) { key = ksw_bin_key(jobs[k]); keys[k] = (uint16_t)key; }
+	// one atomic per distinct key of the warp
+	const unsigned act = __ballot_sync(0xffffffffu, live);
+	if (!live) return;
+	const unsigned same = __match_any_sync(act, key);
+	if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&hist[key], (uint32_t)__popc(same));
+}
+
+#define KSW_BIN_SCAN_THREADS 512
+#define KSW_BIN_KEYS 65536
+__global__ void __launch_bounds__(KSW_BIN_SCAN_THREADS)
+ksw_bin_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ cursor, uint32_t *__restrict__ scratch,
+                    uint32_t *__restrict__ range, long long n)
+{
+	constexpr int PER = KSW_BIN_KEYS / KSW_BIN_SCAN_THREADS;        // 128 consecutive keys per thread
+	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+	const uint32_t *h = hist + (size_t)t * PER;
+	uint32_t sum = 0;
+	for (int i = 0; i < PER; ++i) sum += h[i];
+	uint32_t incl = sum;
+	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+	if (lane == 31) scratch[wid] = incl;                            // warp totals through global memory: no shared memory here
+	__threadfence_block();
+	__syncthreads();
+	if (wid == 0) {
+		uint32_t w = lane < KSW_BIN_SCAN_THREADS / 32 ? scratch[lane] : 0u, wi = w;
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+		if (lane < KSW_BIN_SCAN_THREADS / 32) scratch[32 + lane] = wi - w;
+	}
+	__threadfence_block();
+	__syncthreads();
+	uint32_t run = scratch[32 + wid] + incl - sum;                  // keys before this thread's first key
+	uint32_t *c = cursor + (size_t)t * PER;
+	for (int i = 0; i < PER; ++i) {
+		const uint32_t key = (uint32_t)t * PER + i;
+		// the first entry of every kernel class in the binned order (class bounds sit on multiples of 0x2000 / 0x4000)
+		for (int cl = 0; cl < KSW_N_CLASSES; ++cl) if (key == ksw_class_lowest_key(cl)) range[cl] = run;
+		c[i] = run;
+		run += h[i];
+	}
+	if (t == 0) range[KSW_N_CLASSES] = (uint32_t)n;
+}
+
+__global__ void __launch_bounds__(256)
+ksw_bin_scatter_kernel(const uint16_t *__restrict__ keys, long long n, uint32_t *__restrict__ cursor, uint32_t *__restrict__ order)
+{
+	const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = k < n;
+	const unsigned act = __ballot_sync(0xffffffffu, live);
+	if (!live) return;
+	const uint32_t key = keys[k];
+	const unsigned same = __match_any_sync(act, key);
+	const int leader = __ffs(same) - 1, lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(same));
+	base = __shfl_sync(same, base, leader);
+	order[base + __popc(same & ((1u << lane) - 1u))] = (uint32_t)k;
 }
 
 } // namespace
@@ -53,4 +131,20 @@ cudaError_t ksw_launch_bin(const DevJob *jobs, int64_t n, uint16_t *keys_in, uin
 	if (e != cudaSuccess) return e;
 	return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint16_t *)keys_in, keys_out, (const uint32_t *)vals_in, order,
 	                                       (int)n, 0, 16, st);
+}
+
+size_t ksw_bin_counting_bytes(void) { return sizeof(uint32_t) * (2 * (size_t)KSW_BIN_KEYS + 64); }
+
+cudaError_t ksw_launch_bin_counting(const DevJob *jobs, int64_t n, uint16_t *keys, void *work, uint32_t *order, uint32_t *range,
+                                    cudaStream_t st)
+{
+	if (n <= 0) return cudaSuccess;
+	uint32_t *hist = (uint32_t *)work, *cursor = hist + KSW_BIN_KEYS, *scratch = cursor + KSW_BIN_KEYS;
+	cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(uint32_t) * KSW_BIN_KEYS, st);
+	if (e != cudaSuccess) return e;
+	const unsigned blocks = (unsigned)((n + 255) / 256);
+	ksw_bin_hist_kernel<<<blocks, 256, 0, st>>>(jobs, (long long)n, keys, hist);
+	ksw_bin_scan_kernel<<<1, KSW_BIN_SCAN_THREADS, 0, st>>>(hist, cursor, scratch, range, (long long)n);
+	ksw_bin_scatter_kernel<<<blocks, 256, 0, st>>>(keys, (long long)n, cursor, order);
+	return cudaGetLastError();
 }

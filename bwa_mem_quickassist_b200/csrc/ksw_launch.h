@@ -50,6 +50,12 @@ size_t ksw_bin_temp_bytes(int64_t n);
 cudaError_t ksw_launch_bin(const DevJob *jobs, int64_t n, uint16_t *keys_in, uint16_t *keys_out, uint32_t *vals_in,
                            uint32_t *order, void *temp, size_t temp_bytes, cudaStream_t st);
 
+// the same order (up to the order of equal keys) by a counting sort that needs no shared memory, plus range[c] = first entry
+// of kernel class c (c = 0..KSW_N_CLASSES; the last one is n); work: ksw_bin_counting_bytes() bytes of device scratch
+size_t ksw_bin_counting_bytes(void);
+cudaError_t ksw_launch_bin_counting(const DevJob *jobs, int64_t n, uint16_t *keys, void *work, uint32_t *order, uint32_t *range,
+                                    cudaStream_t st);
+
 // device-side packing (ksw_devpack.cu): raw ksw_b200_job_t records + raw byte-coded sequences in HBM -> DevJob[] + 2-bit pool
 // prep: DevJob records (seq_off left 0), each job's offset in the 2-bit pool (offs), chunk totals (stats; zeroed first)
 cudaError_t ksw_launch_prep(const void *raw_jobs, int64_t n, const KswScoring &S, DevJob *jobs, uint32_t *offs,

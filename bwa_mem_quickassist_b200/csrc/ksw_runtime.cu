@@ -926,7 +926,7 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 			CU(b->d_order.reserve(sizeof(uint32_t) * n1));
 			CU(b->d_keys.reserve(sizeof(uint16_t) * 2 * n1));
 			CU(b->d_vals.reserve(sizeof(uint32_t) * n1));
-			CU(b->d_sort_tmp.reserve(std::max<size_t>(ksw_bin_temp_bytes(nc), 16)));
+			CU(b->d_sort_tmp.reserve(std::max<size_t>(std::max(ksw_bin_temp_bytes(nc), ksw_bin_counting_bytes()), 16)));
 			CU(b->d_range.reserve(sizeof(uint32_t) * (KSW_N_CLASSES + 1)));
 			// the chunk after next: its records travel ahead of this chunk's sequences, its prep kernel runs ahead of
 			// this chunk's kernels
@@ -951,11 +951,12 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 			// does and runs when those end
 			CU(ksw_launch_pack(s.d_rawjobs.p, nc, (const uint8_t *)ctx->d_qraw.p, (const uint8_t *)ctx->d_traw.p, (const uint32_t *)s.d_offs.p,
 			                   (DevJob *)b->d_jobs.p, (uint32_t *)b->d_pool.p, (uint32_t *)b->d_npool.p, (DevPackStats *)s.d_stats.p, pre));
-			CU(ksw_launch_bin((const DevJob *)b->d_jobs.p, nc, (uint16_t *)b->d_keys.p, (uint16_t *)b->d_keys.p + n1,
-			                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, pre));
-			CU(ksw_launch_ranges((const uint16_t *)b->d_keys.p + n1, nc, (uint32_t *)b->d_range.p, pre));
+			// binning as a counting sort without shared memory: it, too, runs beside the previous chunk's extension kernels,
+			// so this chunk's are ready to take over the SMs as those run out of jobs
+			CU(ksw_launch_bin_counting((const DevJob *)b->d_jobs.p, nc, (uint16_t *)b->d_keys.p, b->d_sort_tmp.p,
+			                           (uint32_t *)b->d_order.p, (uint32_t *)b->d_range.p, pre));
 			CU(cudaEventRecord(s.ev_packed, pre));
-			ctx->launches += 4;                                    // pack, key kernel, radix sort (one more), ranges
+			ctx->launches += 4;                                    // pack, histogram, scan, scatter
 			// extension kernels of consecutive chunks alternate between two streams: the next launch fills the SMs as
 			// the warps of the previous one run out of jobs
 			cudaStream_t ext = (ext_seq++ & 1) ? ctx->ext2_stream : ctx->main_stream;
