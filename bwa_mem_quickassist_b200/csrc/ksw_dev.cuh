@@ -48,6 +48,14 @@ struct DevGJob {
 };
 static_assert(sizeof(DevGJob) == 24, "DevGJob must be 24 bytes");
 
+// fast global-alignment kernel (ksw_gfast.cu): 32 jobs of similar size per warp; their H values go to one lane-interleaved slab
+struct DevGGroup {
+	long long z_off;    // first uint2 of the group's slab: element (row i, band quad r, lane l) at z_off + (i * nqb + r) * 32 + l
+	int32_t rows, nqb;  // longest target / widest band (in quads) of the group
+	int32_t first, n;   // the group's jobs are gorder[first .. first + n), n <= 32
+};
+static_assert(sizeof(DevGGroup) == 24, "DevGGroup must be 24 bytes");
+
 struct DevGRes {
 	int32_t   score, n_cigar;
 	long long cigar_off;  // first of the job's n_cigar operations in the chunk's CIGAR pool

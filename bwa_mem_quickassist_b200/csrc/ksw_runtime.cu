@@ -153,8 +153,8 @@ struct ksw_b200_ctx {
 	int async_rc = 0;
 	AsyncReq req;
 	// banded global alignment (ksw_b200_global_batch): staging, device buffers, the CIGAR pool handed to the caller
-	PinnedBuf g_hjobs, g_hseq, g_hres, g_hcig;
-	DevBuf g_djobs, g_dseq, g_dres, g_dcig, g_dused, g_deh, g_dqc, g_dz;
+	PinnedBuf g_hjobs, g_hseq, g_hres, g_hcig, g_horder, g_hgroups;
+	DevBuf g_djobs, g_dseq, g_dres, g_dcig, g_dused, g_deh, g_dqc, g_dz, g_dorder, g_dgroups, g_dzfast, g_dcounter;
 	std::vector<uint32_t> g_cigar;
 };
 
@@ -510,6 +510,8 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 	ctx->g_hjobs.release(); ctx->g_hseq.release(); ctx->g_hres.release(); ctx->g_hcig.release();
 	ctx->g_djobs.release(); ctx->g_dseq.release(); ctx->g_dres.release(); ctx->g_dcig.release(); ctx->g_dused.release();
 	ctx->g_deh.release(); ctx->g_dqc.release(); ctx->g_dz.release();
+	ctx->g_dorder.release(); ctx->g_dgroups.release(); ctx->g_dzfast.release(); ctx->g_dcounter.release();
+	ctx->g_horder.release(); ctx->g_hgroups.release();
 	delete ctx->pool;
 	delete ctx;
 }
@@ -1325,8 +1327,30 @@ int ksw_b200_clamp_w(int qlen, const int8_t *mat, int o_del, int e_del, int o_in
 	return ksw_clamp_w(qlen, ksw_mat_max(mat), o_del, e_del, o_ins, e_ins, w, end_bonus);
 }
 
-// ---- banded global alignment with backtrace (ksw_global.cu).  Synchronous, chunk by chunk on slot 0's stream: a chunk
-// is bounded by its sequence bytes, its worst-case CIGAR pool and the direction-matrix slab.
+// ---- banded global alignment with backtrace.  Synchronous, chunk by chunk on slot 0's stream: a chunk is bounded by its
+// sequence bytes, its worst-case CIGAR pool and the memory the kernels need per job.  Jobs the s16x2 form can hold
+// (ksw_gfast.cu: the band holds the end cell, values far inside int16) are sorted by target length and run in groups of 32
+// per warp; the rest go to the int32 thread-per-job kernel (ksw_global.cu).  KSW_B200_GLOBAL_FAST=0: everything int32.
+namespace {
+
+inline int gfast_nqb(int qlen, int w) { return (int)((std::min<long long>(qlen, 2LL * w + 1) + 6) / 4 + 1); }
+
+bool gfast_eligible(const ksw_b200_cfg_t *cfg, const ksw_b200_gjob_t &j)
+{
+	static const int on = [] { const char *e = getenv("KSW_B200_GLOBAL_FAST"); return !(e && e[0] == '0'); }();
+	if (!on) return false;
+	if (j.qlen < 1 || j.tlen < 1 || j.qlen > 1000 || j.tlen > 30000) return false;
+	if (std::abs(j.tlen - j.qlen) > j.w) return false;            // outside it the reference reads cells it never wrote
+	int amax = 0;
+	for (int i = 0; i < 25; ++i) amax = std::max(amax, std::abs((int)cfg->mat[i]));
+	if (amax > 100 || cfg->e_del < 0 || cfg->e_ins < 0 || cfg->o_del < 0 || cfg->o_ins < 0) return false;
+	if (cfg->o_del + cfg->e_del > 800 || cfg->o_ins + cfg->e_ins > 800) return false;
+	const long long span = (long long)j.qlen + j.tlen;
+	return span * std::max(amax, std::max(cfg->e_del, cfg->e_ins)) + cfg->o_del + cfg->o_ins + cfg->e_del + cfg->e_ins < 7000;
+}
+
+} // namespace
+
 int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
                           const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
                           const uint32_t **cigar_pool, int64_t *n_cigar_total)
@@ -1340,51 +1364,49 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 	ksw_params_from_cfg(cfg, P);
 	const int64_t max_chunk_jobs = 1 << 18;
 	const size_t max_seq = (size_t)256 << 20, max_ops = (size_t)128 << 20;
-	// direction-matrix slab: at most 8 GiB, and never more than a quarter of what the device has free right now (several
-	// contexts may share a GPU; a slab this context already holds counts as available to it)
+	// per-job device memory (H slab of the fast kernel / direction-matrix slab of the int32 kernel): at most 8 GiB, and never
+	// more than a quarter of what the device has free right now (several contexts may share a GPU; what this context
+	// already holds counts as available to it)
 	size_t z_budget = (size_t)8 << 30;
 	{
 		size_t free_b = 0, total_b = 0;
-		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) z_budget = std::min(z_budget, std::max<size_t>((free_b + ctx->g_dz.cap) / 4, (size_t)256 << 20));
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+			z_budget = std::min(z_budget, std::max<size_t>((free_b + ctx->g_dz.cap + ctx->g_dzfast.cap) / 4, (size_t)256 << 20));
 	}
+	std::vector<uint32_t> bucket;
 	int64_t first = 0;
 	while (first < n) {
 		// chunk [first, last): as many jobs as the budgets allow (at least one)
-		int64_t last = first;
-		size_t seq_bytes = 0, ops = 0;
-		int qmax = 0;
+		int64_t last = first, n_fast = 0;
+		size_t seq_bytes = 0, ops = 0, zfast = 0;
+		int qmax = 0, qmax_fast = 0;
 		long long zmax = 0;
 		while (last < n && last - first < max_chunk_jobs) {
 			const ksw_b200_gjob_t &j = jobs[last];
 			if (j.qlen < 0 || j.tlen < 0 || j.w < 0) return fail(ctx, 2, "ksw_b200_global_batch: job with qlen < 0, tlen < 0 or w < 0");
 			const size_t sb = (size_t)j.qlen + (size_t)j.tlen, so = sb + 2;
-			if (last > first && (seq_bytes + sb > max_seq || ops + so > max_ops)) break;
-			seq_bytes += sb; ops += so;
-			qmax = std::max(qmax, j.qlen);
-			const long long n_col = std::min<long long>(j.qlen, 2LL * j.w + 1);
-			zmax = std::max(zmax, n_col * j.tlen);
+			const bool fastj = gfast_eligible(cfg, j);
+			// the group slab is sized by the group's longest target and widest band: 15 % of slack on the job's own need
+			const size_t zj = fastj ? (size_t)((double)j.tlen * gfast_nqb(j.qlen, j.w) * 8.0 * 1.15) + 64 : 0;
+			if (last > first && (seq_bytes + sb > max_seq || ops + so > max_ops || zfast + zj > z_budget / 2)) break;
+			seq_bytes += sb; ops += so; zfast += zj;
+			if (fastj) { ++n_fast; qmax_fast = std::max(qmax_fast, j.qlen); }
+			else {
+				qmax = std::max(qmax, j.qlen);
+				const long long n_col = std::min<long long>(j.qlen, 2LL * j.w + 1);
+				zmax = std::max(zmax, n_col * j.tlen);
+			}
 			++last;
 		}
-		const int64_t m = last - first;
-		const long long zcap = zmax + qmax + 2;
-		// threads: bounded by the direction-matrix slab; every thread owns one column set and one z slab
-		int bps = 4;                                        // blocks per SM: 4 keeps the H/E slabs of a 150 bp batch inside L2
-		if (const char *ev = getenv("KSW_B200_GLOBAL_BPS")) bps = std::max(1, atoi(ev));     // tuning knob
-		size_t threads = (size_t)ctx->sm_count * bps * KSW_GENERIC_THREADS;
-		while (threads > KSW_GENERIC_THREADS && threads * (size_t)zcap > z_budget) threads >>= 1;
-		threads = std::min<size_t>(threads, (size_t)((m + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS) * KSW_GENERIC_THREADS);
-		const int n_blocks = (int)(threads / KSW_GENERIC_THREADS);
-		CU(ctx->g_hjobs.reserve(sizeof(DevGJob) * (size_t)m));
+		const int64_t m = last - first, n_slow = m - n_fast;
+		CU(ctx->g_hjobs.reserve(sizeof(DevGJob) * (size_t)(m + n_slow)));
 		CU(ctx->g_hseq.reserve(std::max<size_t>(seq_bytes, 16)));
 		CU(ctx->g_hres.reserve(sizeof(DevGRes) * (size_t)m));
-		CU(ctx->g_djobs.reserve(sizeof(DevGJob) * (size_t)m));
+		CU(ctx->g_djobs.reserve(sizeof(DevGJob) * (size_t)(m + n_slow)));
 		CU(ctx->g_dseq.reserve(std::max<size_t>(seq_bytes, 16)));
 		CU(ctx->g_dres.reserve(sizeof(DevGRes) * (size_t)m));
 		CU(ctx->g_dcig.reserve(sizeof(uint32_t) * ops));
 		CU(ctx->g_dused.reserve(sizeof(unsigned long long)));
-		CU(ctx->g_deh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
-		CU(ctx->g_dqc.reserve(threads * (size_t)(qmax + 1)));
-		CU(ctx->g_dz.reserve(threads * (size_t)zcap));
 		DevGJob *hj = (DevGJob *)ctx->g_hjobs.p;
 		uint8_t *hs = (uint8_t *)ctx->g_hseq.p;
 		{
@@ -1408,13 +1430,71 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			};
 			if (T == 1) body(0); else tp->run(T, body);
 		}
-		CU(cudaMemcpyAsync(ctx->g_djobs.p, hj, sizeof(DevGJob) * (size_t)m, cudaMemcpyHostToDevice, s.stream));
+		// the fast kernel's jobs: counting sort by target length (longest first), groups of 32, one slab per group
+		int n_groups = 0;
+		size_t zfast_units = 0;
+		if (n_fast > 0) {
+			CU(ctx->g_horder.reserve(sizeof(uint32_t) * (size_t)n_fast));
+			CU(ctx->g_hgroups.reserve(sizeof(DevGGroup) * (size_t)((n_fast + 31) / 32)));
+			uint32_t *ho = (uint32_t *)ctx->g_horder.p;
+			DevGGroup *hg = (DevGGroup *)ctx->g_hgroups.p;
+			const int NB = 4096;
+			bucket.assign(NB + 1, 0);
+			auto key = [&](const ksw_b200_gjob_t &j) { return NB - 1 - std::min(j.tlen, NB - 1); };
+			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, jobs[first + k])) ++bucket[key(jobs[first + k]) + 1];
+			for (int x = 0; x < NB; ++x) bucket[x + 1] += bucket[x];
+			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, jobs[first + k])) ho[bucket[key(jobs[first + k])]++] = (uint32_t)k;
+			for (int64_t f = 0; f < n_fast; f += 32) {
+				DevGGroup g;
+				g.first = (int32_t)f; g.n = (int32_t)std::min<int64_t>(32, n_fast - f); g.rows = 0; g.nqb = 0;
+				for (int x = 0; x < g.n; ++x) {
+					const ksw_b200_gjob_t &j = jobs[first + ho[f + x]];
+					g.rows = std::max(g.rows, j.tlen);
+					g.nqb = std::max(g.nqb, gfast_nqb(j.qlen, j.w));
+				}
+				g.z_off = (long long)zfast_units;
+				zfast_units += (size_t)g.rows * (size_t)g.nqb * 32;
+				hg[n_groups++] = g;
+			}
+			CU(ctx->g_dorder.reserve(sizeof(uint32_t) * (size_t)n_fast));
+			CU(ctx->g_dgroups.reserve(sizeof(DevGGroup) * (size_t)n_groups));
+			CU(ctx->g_dzfast.reserve(zfast_units * sizeof(uint2) + 256));
+			CU(ctx->g_dcounter.reserve(sizeof(unsigned)));
+		}
+		// the int32 kernel's jobs: a compacted copy of their records behind the chunk's
+		if (n_slow > 0) {
+			int64_t w2 = m;
+			for (int64_t k = 0; k < m; ++k) if (!gfast_eligible(cfg, jobs[first + k])) hj[w2++] = hj[k];
+		}
+		CU(cudaMemcpyAsync(ctx->g_djobs.p, hj, sizeof(DevGJob) * (size_t)(m + n_slow), cudaMemcpyHostToDevice, s.stream));
 		if (seq_bytes) CU(cudaMemcpyAsync(ctx->g_dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, s.stream));
 		CU(cudaMemsetAsync(ctx->g_dused.p, 0, sizeof(unsigned long long), s.stream));
-		CU(ksw_launch_global((const DevGJob *)ctx->g_djobs.p, m, (const uint8_t *)ctx->g_dseq.p, P, (int2 *)ctx->g_deh.p,
-		                     (uint8_t *)ctx->g_dqc.p, (uint8_t *)ctx->g_dz.p, zcap, n_blocks,
-		                     (unsigned long long *)ctx->g_dused.p, (uint32_t *)ctx->g_dcig.p, (DevGRes *)ctx->g_dres.p, s.stream));
-		ctx->launches++;
+		if (n_fast > 0) {
+			CU(cudaMemcpyAsync(ctx->g_dorder.p, ctx->g_horder.p, sizeof(uint32_t) * (size_t)n_fast, cudaMemcpyHostToDevice, s.stream));
+			CU(cudaMemcpyAsync(ctx->g_dgroups.p, ctx->g_hgroups.p, sizeof(DevGGroup) * (size_t)n_groups, cudaMemcpyHostToDevice, s.stream));
+			CU(ksw_launch_gfast((const DevGJob *)ctx->g_djobs.p, (const uint8_t *)ctx->g_dseq.p, P, (const uint32_t *)ctx->g_dorder.p,
+			                    (const DevGGroup *)ctx->g_dgroups.p, n_groups, qmax_fast, ctx->sm_count, (uint2 *)ctx->g_dzfast.p,
+			                    (unsigned *)ctx->g_dcounter.p, (unsigned long long *)ctx->g_dused.p, (uint32_t *)ctx->g_dcig.p,
+			                    (DevGRes *)ctx->g_dres.p, s.stream));
+			ctx->launches += 2;
+		}
+		if (n_slow > 0) {
+			const long long zcap = zmax + qmax + 2;
+			// threads: bounded by the direction-matrix slab; every thread owns one column set and one z slab
+			int bps = 4;                                        // blocks per SM: 4 keeps the H/E slabs of a 150 bp batch inside L2
+			if (const char *ev = getenv("KSW_B200_GLOBAL_BPS")) bps = std::max(1, atoi(ev));     // tuning knob
+			size_t threads = (size_t)ctx->sm_count * bps * KSW_GENERIC_THREADS;
+			while (threads > KSW_GENERIC_THREADS && threads * (size_t)zcap > z_budget / 2) threads >>= 1;
+			threads = std::min<size_t>(threads, (size_t)((n_slow + KSW_GENERIC_THREADS - 1) / KSW_GENERIC_THREADS) * KSW_GENERIC_THREADS);
+			const int n_blocks = (int)(threads / KSW_GENERIC_THREADS);
+			CU(ctx->g_deh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
+			CU(ctx->g_dqc.reserve(threads * (size_t)(qmax + 1)));
+			CU(ctx->g_dz.reserve(threads * (size_t)zcap));
+			CU(ksw_launch_global((const DevGJob *)ctx->g_djobs.p + m, n_slow, (const uint8_t *)ctx->g_dseq.p, P, (int2 *)ctx->g_deh.p,
+			                     (uint8_t *)ctx->g_dqc.p, (uint8_t *)ctx->g_dz.p, zcap, n_blocks,
+			                     (unsigned long long *)ctx->g_dused.p, (uint32_t *)ctx->g_dcig.p, (DevGRes *)ctx->g_dres.p, s.stream));
+			ctx->launches++;
+		}
 		unsigned long long used = 0;
 		CU(cudaMemcpyAsync(ctx->g_hres.p, ctx->g_dres.p, sizeof(DevGRes) * (size_t)m, cudaMemcpyDeviceToHost, s.stream));
 		CU(cudaMemcpyAsync(&used, ctx->g_dused.p, sizeof(used), cudaMemcpyDeviceToHost, s.stream));
