@@ -71,3 +71,27 @@ static KSW_HD uint32_t ksw_job_class(const KswScoring &S, int qlen, int h0)
 
 // 16-byte units of a job's packed sequences in the 2-bit pool: query words | target words, padded
 static KSW_HD uint32_t ksw_job_units(int qlen, int tlen) { return (ksw_words2(qlen) + ksw_words2(tlen) + 3) >> 2; }
+
+// ---- banded global alignment (ksw_global2): routing between the s16x2 kernel (ksw_gfast.cu) and the int32 kernel
+// what the batch's scoring costs per cell at most (0: the s16x2 form cannot hold this scoring at all)
+static inline int ksw_gfast_cell_cost(const int8_t *mat25, int o_del, int e_del, int o_ins, int e_ins)
+{
+	int amax = 0;
+	for (int i = 0; i < 25; ++i) { const int a = mat25[i] < 0 ? -mat25[i] : mat25[i]; amax = a > amax ? a : amax; }
+	if (amax > 100 || e_del < 0 || e_ins < 0 || o_del < 0 || o_ins < 0) return 0;
+	if (o_del + e_del > 800 || o_ins + e_ins > 800) return 0;
+	int c = amax > e_del ? amax : e_del;
+	c = c > e_ins ? c : e_ins;
+	return c > 1 ? c : 1;
+}
+// the band holds the end cell (outside that the reference reads cells it never wrote), the query's columns fit shared
+// memory, and every H / E / F value of the band stays within +-7000 of zero: inside int16 with the kernel's bias
+#define KSW_GFAST_MAX_QLEN 1000
+static inline bool ksw_gfast_eligible(int cell_cost, int o_del, int e_del, int o_ins, int e_ins, int qlen, int tlen, int w)
+{
+	if (!cell_cost || qlen < 1 || tlen < 1 || qlen > KSW_GFAST_MAX_QLEN || tlen > 30000) return false;
+	if ((tlen > qlen ? tlen - qlen : qlen - tlen) > w) return false;
+	return ((long long)qlen + tlen) * cell_cost + o_del + o_ins + e_del + e_ins < 7000;
+}
+// quads per band row, at most
+static inline int ksw_gfast_nqb(int qlen, int w) { const long long b = 2LL * w + 1; return (int)(((qlen < b ? qlen : b) + 6) / 4 + 1); }

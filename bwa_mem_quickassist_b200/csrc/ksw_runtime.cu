@@ -21,6 +21,7 @@
 #include "../../include/ksw_b200.h"
 #include "ksw_dev.cuh"
 #include "ksw_launch.h"
+#include "ksw_class.h"
 #include "ksw_pack.h"
 
 // ------------------------------------------------------------------ small helpers
@@ -1333,20 +1334,18 @@ int ksw_b200_clamp_w(int qlen, const int8_t *mat, int o_del, int e_del, int o_in
 // per warp; the rest go to the int32 thread-per-job kernel (ksw_global.cu).  KSW_B200_GLOBAL_FAST=0: everything int32.
 namespace {
 
-inline int gfast_nqb(int qlen, int w) { return (int)((std::min<long long>(qlen, 2LL * w + 1) + 6) / 4 + 1); }
+inline int gfast_nqb(int qlen, int w) { return ksw_gfast_nqb(qlen, w); }
 
-bool gfast_eligible(const ksw_b200_cfg_t *cfg, const ksw_b200_gjob_t &j)
+int gfast_cell_cost(const ksw_b200_cfg_t *cfg)
 {
-	static const int on = [] { const char *e = getenv("KSW_B200_GLOBAL_FAST"); return !(e && e[0] == '0'); }();
-	if (!on) return false;
-	if (j.qlen < 1 || j.tlen < 1 || j.qlen > 1000 || j.tlen > 30000) return false;
-	if (std::abs(j.tlen - j.qlen) > j.w) return false;            // outside it the reference reads cells it never wrote
-	int amax = 0;
-	for (int i = 0; i < 25; ++i) amax = std::max(amax, std::abs((int)cfg->mat[i]));
-	if (amax > 100 || cfg->e_del < 0 || cfg->e_ins < 0 || cfg->o_del < 0 || cfg->o_ins < 0) return false;
-	if (cfg->o_del + cfg->e_del > 800 || cfg->o_ins + cfg->e_ins > 800) return false;
-	const long long span = (long long)j.qlen + j.tlen;
-	return span * std::max(amax, std::max(cfg->e_del, cfg->e_ins)) + cfg->o_del + cfg->o_ins + cfg->e_del + cfg->e_ins < 7000;
+	const char *e = getenv("KSW_B200_GLOBAL_FAST");
+	if (e && e[0] == '0') return 0;
+	return ksw_gfast_cell_cost(cfg->mat, cfg->o_del, cfg->e_del, cfg->o_ins, cfg->e_ins);
+}
+
+inline bool gfast_eligible(const ksw_b200_cfg_t *cfg, int cell_cost, const ksw_b200_gjob_t &j)
+{
+	return ksw_gfast_eligible(cell_cost, cfg->o_del, cfg->e_del, cfg->o_ins, cfg->e_ins, j.qlen, j.tlen, j.w);
 }
 
 } // namespace
@@ -1374,6 +1373,7 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			z_budget = std::min(z_budget, std::max<size_t>((free_b + ctx->g_dz.cap + ctx->g_dzfast.cap) / 4, (size_t)256 << 20));
 	}
 	std::vector<uint32_t> bucket;
+	const int cell_cost = gfast_cell_cost(cfg);
 	int64_t first = 0;
 	while (first < n) {
 		// chunk [first, last): as many jobs as the budgets allow (at least one)
@@ -1385,7 +1385,7 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			const ksw_b200_gjob_t &j = jobs[last];
 			if (j.qlen < 0 || j.tlen < 0 || j.w < 0) return fail(ctx, 2, "ksw_b200_global_batch: job with qlen < 0, tlen < 0 or w < 0");
 			const size_t sb = (size_t)j.qlen + (size_t)j.tlen, so = sb + 2;
-			const bool fastj = gfast_eligible(cfg, j);
+			const bool fastj = gfast_eligible(cfg, cell_cost, j);
 			// the group slab is sized by the group's longest target and widest band: 15 % of slack on the job's own need
 			const size_t zj = fastj ? (size_t)((double)j.tlen * gfast_nqb(j.qlen, j.w) * 8.0 * 1.15) + 64 : 0;
 			if (last > first && (seq_bytes + sb > max_seq || ops + so > max_ops || zfast + zj > z_budget / 2)) break;
@@ -1441,9 +1441,9 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			const int NB = 4096;
 			bucket.assign(NB + 1, 0);
 			auto key = [&](const ksw_b200_gjob_t &j) { return NB - 1 - std::min(j.tlen, NB - 1); };
-			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, jobs[first + k])) ++bucket[key(jobs[first + k]) + 1];
+			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, cell_cost, jobs[first + k])) ++bucket[key(jobs[first + k]) + 1];
 			for (int x = 0; x < NB; ++x) bucket[x + 1] += bucket[x];
-			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, jobs[first + k])) ho[bucket[key(jobs[first + k])]++] = (uint32_t)k;
+			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, cell_cost, jobs[first + k])) ho[bucket[key(jobs[first + k])]++] = (uint32_t)k;
 			for (int64_t f = 0; f < n_fast; f += 32) {
 				DevGGroup g;
 				g.first = (int32_t)f; g.n = (int32_t)std::min<int64_t>(32, n_fast - f); g.rows = 0; g.nqb = 0;
@@ -1464,7 +1464,7 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		// the int32 kernel's jobs: a compacted copy of their records behind the chunk's
 		if (n_slow > 0) {
 			int64_t w2 = m;
-			for (int64_t k = 0; k < m; ++k) if (!gfast_eligible(cfg, jobs[first + k])) hj[w2++] = hj[k];
+			for (int64_t k = 0; k < m; ++k) if (!gfast_eligible(cfg, cell_cost, jobs[first + k])) hj[w2++] = hj[k];
 		}
 		CU(cudaMemcpyAsync(ctx->g_djobs.p, hj, sizeof(DevGJob) * (size_t)(m + n_slow), cudaMemcpyHostToDevice, s.stream));
 		if (seq_bytes) CU(cudaMemcpyAsync(ctx->g_dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, s.stream));

@@ -140,3 +140,56 @@ extern "C" int ksw_pair_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ks
 	if (steps_out) *steps_out = steps;
 	return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The fast global-alignment kernels' per-lane source (ksw_gfast_core.h) on the CPU: the DP rows with software DPX into a
+// per-job H slab, then the backtrack that recomputes the reference's direction bits from it.  res[k].cigar_off must be
+// preset (capacity qlen + tlen + 2 each, like the oracle's batch entry).  Jobs the runtime would route to the int32
+// kernel keep score = INT32_MIN.
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_class.h"
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_gfast_core.h"
+
+extern "C" int ksw_gfast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs, const uint8_t *qpool,
+                                   const uint8_t *tpool, ksw_b200_gres_t *res, uint32_t *cigar_pool, int64_t *n_fast_out)
+{
+	KswParams P;
+	ksw_params_from_cfg(cfg, P);
+	KswGConst C;
+	ksw_gfast_make_const(P, C);
+	ksw_u2 mrow[5];
+	for (int t = 0; t < 5; ++t) mrow[t] = ksw_gfast_matrow(P, t);
+	KswFastEdge edge[5];
+	for (int r = 0; r < 5; ++r) ksw_fast_edge_entry(r, edge[r]);
+	const int cost = ksw_gfast_cell_cost(cfg->mat, cfg->o_del, cfg->e_del, cfg->o_ins, cfg->e_ins);
+	int64_t n_fast = 0;
+	for (int64_t k = 0; k < n; ++k) {
+		const ksw_b200_gjob_t &j = jobs[k];
+		res[k].score = INT_MIN; res[k].n_cigar = 0;
+		if (!ksw_gfast_eligible(cost, cfg->o_del, cfg->e_del, cfg->o_ins, cfg->e_ins, j.qlen, j.tlen, j.w)) continue;
+		++n_fast;
+		const uint8_t *query = qpool + j.q_off, *target = tpool + j.t_off;
+		const int nq = (j.qlen >> 2) + 1, nqb = ksw_gfast_nqb(j.qlen, j.w);
+		std::vector<ksw_u4> hq(nq);
+		std::vector<uint32_t> sq(nq + 1);                          // the row loop prefetches one quad ahead
+		hq.reserve(nq + 1);
+		std::vector<ksw_u2> z((size_t)j.tlen * nqb);
+		for (auto &v : z) v.x = v.y = 0x5a5a5a5au;
+		hq.resize(nq + 1);
+		ksw_gfast_setup<1>(hq.data(), sq.data(), j.qlen, j.w, query, C);
+		for (int i = 0; i < j.tlen; ++i) {
+			const int t = target[i] > 4 ? 4 : target[i];
+			ksw_gfast_row<1>(hq.data(), sq.data(), edge, mrow[t], z.data() + (size_t)i * nqb, i, j.qlen, j.w, C);
+		}
+		res[k].score = ksw_gfast_score<1>(hq.data(), j.qlen);
+		KswGWalk<1> wk;
+		wk.z = z.data(); wk.query = query; wk.target = target; wk.mat = P.mat;
+		wk.qlen = j.qlen; wk.tlen = j.tlen; wk.w = j.w; wk.nqb = nqb;
+		wk.o_del = P.o_del; wk.e_del = P.e_del; wk.o_ins = P.o_ins; wk.e_ins = P.e_ins;
+		const int nc = wk.run([](int, int, int) {});
+		uint32_t *out = cigar_pool + res[k].cigar_off;
+		wk.run([&](int r, int op, int len) { out[nc - 1 - r] = (uint32_t)len << 4 | (uint32_t)op; });
+		res[k].n_cigar = nc;
+	}
+	if (n_fast_out) *n_fast_out = n_fast;
+	return 0;
+}

@@ -327,6 +327,22 @@ def emu_lib():
     return _libs["emu"]
 
 
+def run_global_emu(b):
+    """(res, pool, n_fast) from the CPU build of the fast global-alignment kernels' source (ksw_gfast_core.h); jobs outside
+    that kernel's eligibility keep score = INT32_MIN."""
+    lib = emu_lib()
+    lib.ksw_gfast_emu_batch.restype = C.c_int
+    lib.ksw_gfast_emu_batch.argtypes = [C.POINTER(Cfg), C.c_int64] + [C.c_void_p] * 5 + [C.POINTER(C.c_int64)]
+    res = np.zeros(b.n, dtype=GRES_DT)
+    cap = b.jobs["qlen"].astype(np.int64) + b.jobs["tlen"] + 2
+    res["cigar_off"] = np.concatenate([[0], np.cumsum(cap)[:-1]]) if b.n else 0
+    pool = np.zeros(int(cap.sum()) + 1, dtype=np.uint32)
+    nf = C.c_int64(0)
+    rc = lib.ksw_gfast_emu_batch(C.byref(b.cfg), b.n, _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), _ptr(res), _ptr(pool), C.byref(nf))
+    assert rc == 0
+    return res, pool, int(nf.value)
+
+
 def run_pair_emu(b: Batch, lanes: int = 3, order: int = 0):
     """Results of the product packer + the PAIR kernel's lane code (two jobs per lane) compiled for the CPU.
     Jobs outside class 0 come back with score == INT32_MIN.  Returns (res, cells, n_pair, lane_rows)."""

@@ -64,6 +64,36 @@ def test_global_identical_sequences_give_one_match_run(oracle_built):
     assert int(res["score"][0]) == 77 and K.cigars(res, pool)[0] == (77 << 4,)
 
 
+def test_global_fast_kernel_source_emulated_matches_oracle(oracle_built):
+    """ksw_gfast_core.h compiled for the CPU (software DPX): scores and CIGARs of every eligible job equal the oracle's."""
+    total = 0
+    cases = [(621, None, dict(max_q=180, w_extra=(0, 1, 2, 3))), (622, None, dict(max_q=400, w_extra=(3, 10, 50, 200), indel=(0.03, 0.08))),
+             (623, None, dict(max_q=16, w_extra=(0, 1, 5), n_frac=0.2)), (624, None, dict(max_q=1000, w_extra=(0, 7))),
+             (625, K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3), dict(max_q=250)),
+             (626, K.make_cfg(a=1, b=1, o_del=1, e_del=2, o_ins=2, e_ins=1), dict(max_q=40)),
+             (627, K.make_cfg(a=3, b=2, o_del=0, e_del=0, o_ins=0, e_ins=0), dict(max_q=60))]
+    for name, (b, want) in K.load_global_golden().items():
+        res, pool, nf = K.run_global_emu(b)
+        sel = np.flatnonzero(res["score"] != np.iinfo(np.int32).min)
+        assert (res["score"][sel] == want[0]["score"][sel]).all(), name
+        ca, cb = K.cigars(res, pool), K.cigars(*want)
+        assert all(ca[k] == cb[k] for k in sel), name
+        total += nf
+    for seed, cfg, kw in cases:
+        b = K.gen_global(1500 if kw["max_q"] < 500 else 200, seed=seed, cfg=cfg, **kw)
+        want = K.run_global_oracle(b)
+        res, pool, nf = K.run_global_emu(b)
+        sel = np.flatnonzero(res["score"] != np.iinfo(np.int32).min)
+        assert sel.size == nf
+        bad = sel[res["score"][sel] != want[0]["score"][sel]]
+        assert bad.size == 0, (seed, int(bad[0]), b.jobs[int(bad[0])], int(res["score"][bad[0]]), int(want[0]["score"][bad[0]]))
+        ca, cb = K.cigars(res, pool), K.cigars(*want)
+        for k in sel:
+            assert ca[k] == cb[k], (seed, int(k), b.jobs[int(k)], ca[k], cb[k])
+        total += nf
+    assert total > 5000
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_gpu_global_golden_and_fuzz(gpu_ctx, oracle_built):
@@ -105,6 +135,22 @@ def test_gpu_global_empty_batch_and_scalar_dropin(gpu_ctx, oracle_built):
         sc, got = B.ksw_global2(int(j["qlen"]), q, int(j["tlen"]), t, 5, K.cfg_mat(b.cfg), b.cfg.o_del, b.cfg.e_del,
                                 b.cfg.o_ins, b.cfg.e_ins, int(j["w"]))
         assert sc == int(want_res["score"][k]) and tuple(int(x) for x in got) == cig
+
+
+@pytest.mark.gpu
+def test_gpu_global_both_kernels_agree_with_oracle(gpu_ctx, oracle_built, monkeypatch):
+    """The s16x2 kernel (no direction matrix: the backtrack recomputes the reference's bits from H) and the int32 kernel on the
+    same jobs: narrow and wide bands, N bases, heavy indels, lengths on every quad boundary."""
+    for seed, kw in ((611, dict(max_q=180, w_extra=(0, 1, 2, 3))), (612, dict(max_q=400, w_extra=(3, 10, 50, 200), indel=(0.03, 0.08))),
+                     (613, dict(max_q=16, w_extra=(0, 1, 5), n_frac=0.2)), (614, dict(max_q=1000, w_extra=(0, 7)))):
+        b = K.gen_global(4000 if kw["max_q"] < 500 else 600, seed=seed, **kw)
+        want = K.run_global_oracle(b)
+        monkeypatch.delenv("KSW_B200_GLOBAL_FAST", raising=False)
+        mm = K.global_mismatch(gpu_ctx.global_batch(b.cfg, b.jobs, b.qpool, b.tpool), want)
+        assert mm is None, ("s16x2", seed, mm)
+        monkeypatch.setenv("KSW_B200_GLOBAL_FAST", "0")
+        mm = K.global_mismatch(gpu_ctx.global_batch(b.cfg, b.jobs, b.qpool, b.tpool), want)
+        assert mm is None, ("int32", seed, mm)
 
 
 def _degenerate_batch():
