@@ -81,7 +81,8 @@ ksw_gfast_dp_kernel(const DevGJob *__restrict__ jobs, const uint8_t *__restrict_
 __global__ void __launch_bounds__(128)
 ksw_gfast_trace_kernel(const DevGJob *__restrict__ jobs, const uint8_t *__restrict__ seq, const KswParams P, const uint32_t *__restrict__ gorder,
                        const DevGGroup *__restrict__ groups, const int n_groups, const uint2 *__restrict__ z,
-                       unsigned long long *__restrict__ pool_used, uint32_t *__restrict__ cigar_pool, DevGRes *__restrict__ res)
+                       uint32_t *__restrict__ scratch, unsigned long long *__restrict__ pool_used, uint32_t *__restrict__ cigar_pool,
+                       DevGRes *__restrict__ res)
 {
 	const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
 	if (g >= n_groups) return;
@@ -93,10 +94,13 @@ ksw_gfast_trace_kernel(const DevGJob *__restrict__ jobs, const uint8_t *__restri
 	wk.query = seq + jb.seq_off; wk.target = wk.query + jb.qlen; wk.mat = P.mat;
 	wk.qlen = jb.qlen; wk.tlen = jb.tlen; wk.w = jb.w; wk.nqb = grp.nqb;
 	wk.o_del = P.o_del; wk.e_del = P.e_del; wk.o_ins = P.o_ins; wk.e_ins = P.e_ins;
-	const int n = wk.run([](int, int, int) {});
+	// one walk: the operations come out last first, into the job's worst-case slot (qlen + tlen + 2 words at seq_off + 2 idx);
+	// then they are reversed into the dense pool
+	uint32_t *mine = scratch + jb.seq_off + 2ull * jb.idx;
+	const int n = wk.run([&](int r_idx, int op, int len) { mine[r_idx] = (uint32_t)len << 4 | (uint32_t)op; });
 	const unsigned long long off = atomicAdd(pool_used, (unsigned long long)n);
 	uint32_t *out = cigar_pool + off;
-	wk.run([&](int r_idx, int op, int len) { out[n - 1 - r_idx] = (uint32_t)len << 4 | (uint32_t)op; });
+	for (int r = 0; r < n; ++r) out[n - 1 - r] = mine[r];
 	res[jb.idx].n_cigar = n;
 	res[jb.idx].cigar_off = (long long)off;
 }
@@ -108,8 +112,8 @@ size_t ksw_gfast_smem_bytes(int qmax)
 }
 
 cudaError_t ksw_launch_gfast(const DevGJob *jobs, const uint8_t *seq, const KswParams &P, const uint32_t *gorder, const DevGGroup *groups,
-                             int n_groups, int qmax, int sm_count, uint2 *z, unsigned *counter, unsigned long long *pool_used,
-                             uint32_t *cigar_pool, DevGRes *res, cudaStream_t st)
+                             int n_groups, int qmax, int sm_count, uint2 *z, unsigned *counter, uint32_t *scratch,
+                             unsigned long long *pool_used, uint32_t *cigar_pool, DevGRes *res, cudaStream_t st)
 {
 	if (n_groups <= 0) return cudaSuccess;
 	const size_t smem = ksw_gfast_smem_bytes(qmax);
@@ -137,6 +141,6 @@ cudaError_t ksw_launch_gfast(const DevGJob *jobs, const uint8_t *seq, const KswP
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
 	const int tb = (n_groups * 32 + 127) / 128;
-	ksw_gfast_trace_kernel<<<tb, 128, 0, st>>>(jobs, seq, P, gorder, groups, n_groups, z, pool_used, cigar_pool, res);
+	ksw_gfast_trace_kernel<<<tb, 128, 0, st>>>(jobs, seq, P, gorder, groups, n_groups, z, scratch, pool_used, cigar_pool, res);
 	return cudaGetLastError();
 }

@@ -176,20 +176,38 @@ struct KswGWalk {
 		t = t > 4 ? 4 : t; q = q > 4 ? 4 : q;
 		return d <= KSW_G_MINF / 2 ? KSW_G_MINF : d + mat[t * 5 + q];
 	}
-	// the reference's walk (ksw.c:562-579); emit(r, op, len): r-th operation counted from the END of the alignment
+	KSW_HD int hload(int i, int k) const       // H(i,k) of a cell that IS inside the band: no checks, one load
+	{
+		const int beg = i > w ? i - w : 0;
+		const ksw_u2 v = z[((size_t)i * nqb + ((k >> 2) - (beg >> 2))) * T];
+		const uint32_t word = (k & 1) ? v.y : v.x;
+		return (int)((k & 2) ? (word >> 16) : (word & 0xffffu)) - KSW_G_BIAS;
+	}
+	// the reference's walk (ksw.c:562-579); emit(r, op, len): r-th operation counted from the END of the alignment.
+	// Per step one H load (the diagonal neighbour, which is the next cell's own H if the step is diagonal) and the two bases,
+	// all independent of each other: one memory latency per step.  (i-1,k-1) is always inside the band when i, k > 0:
+	// beg(i-1) >= beg(i)-1 and end(i-1) >= end(i)-1.
 	template <class F>
 	KSW_HD int run(F &&emit) const
 	{
 		int i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;        // the last cell (ksw.c:565)
 		int which = 0, n = 0, cur_op = -1, cur_len = 0, gapv = 0;
 		const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+		int hcur = hload(i, k);
 		while (i >= 0 && k >= 0) {
-			const int m = mcell(i, k);
+			const bool inb = i > 0 && k > 0;
+			const int dv = hload(inb ? i - 1 : 0, inb ? k - 1 : 0);
+			int t = target[i], q = query[k];
+			t = t > 4 ? 4 : t; q = q > 4 ? 4 : q;
+			const int sc = mat[t * 5 + q];
+			const int bnd = i == 0 ? (k == 0 ? 0 : ((k <= w && k <= qlen) ? -(o_ins + e_ins * k) : KSW_G_MINF))
+			                       : (i - 1 <= w ? -(o_del + e_del * i) : KSW_G_MINF);      // k == 0: H(i-1,-1)
+			const int d = inb ? dv : bnd;
+			const int m = d <= KSW_G_MINF / 2 ? KSW_G_MINF : d + sc;                       // M(i,k) = H(i-1,k-1) + S(i,k)
 			if (which == 0) {
-				const int h = hcell(i, k);
-				if (h == m) which = 0;
-				else {
-					// E(i,k) = max over the rows above of M(i',k) - oe_del - (i-1-i') e_del: does it reach h?
+				const int h = hcur;
+				if (h != m) {
+					// E(i,k) = max over the rows above of M(i',k) - oe_del - (i-1-i') e_del: does it reach h?  (E beats F on ties)
 					which = 2;
 					const int top = k - w > 0 ? k - w : 0;
 					for (int r = i - 1; r >= top; --r) {
@@ -208,6 +226,7 @@ struct KswGWalk {
 			const int op = which == 0 ? 0 : (which == 1 ? 2 : 1);                  // push_cigar, ksw.c:486-499
 			if (op == cur_op) ++cur_len;
 			else { if (cur_op >= 0) emit(n++, cur_op, cur_len); cur_op = op; cur_len = 1; }
+			if (which == 0) hcur = d;                                              // the diagonal neighbour is the next cell
 			if (which != 2) --i;
 			if (which != 1) --k;
 		}

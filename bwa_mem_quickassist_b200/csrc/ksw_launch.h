@@ -72,8 +72,9 @@ cudaError_t ksw_launch_pack_ref(const void *raw_jobs, int64_t n, const uint8_t *
                                 DevJob *jobs, uint32_t *pool, uint32_t *npool, DevPackStats *stats, cudaStream_t st);
 
 // fast banded global alignment (ksw_gfast.cu): s16x2 DP kernel (stores H, 2 bytes per band cell) + backtrack kernel that recomputes
-// the reference's direction bits from H; jobs[gorder[..]] in groups of 32; z: slab of the groups; counter: one device word
+// the reference's direction bits from H; jobs[gorder[..]] in groups of 32; z: slab of the groups; counter: one device word;
+// scratch: (sum of qlen + tlen + 2 over ALL jobs of the array) words
 size_t ksw_gfast_smem_bytes(int qmax);
 cudaError_t ksw_launch_gfast(const DevGJob *jobs, const uint8_t *seq, const KswParams &P, const uint32_t *gorder, const DevGGroup *groups,
-                             int n_groups, int qmax, int sm_count, uint2 *z, unsigned *counter, unsigned long long *pool_used,
-                             uint32_t *cigar_pool, DevGRes *res, cudaStream_t st);
+                             int n_groups, int qmax, int sm_count, uint2 *z, unsigned *counter, uint32_t *scratch,
+                             unsigned long long *pool_used, uint32_t *cigar_pool, DevGRes *res, cudaStream_t st);

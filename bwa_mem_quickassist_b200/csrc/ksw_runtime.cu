@@ -109,6 +109,21 @@ struct RefEntry {
 	int refs = 0;
 };
 
+// one chunk of ksw_b200_global_batch: page-locked staging, device buffers, completion event
+struct GStage {
+	PinnedBuf hjobs, hseq, hres, hcig, horder, hgroups, hused;
+	DevBuf djobs, dseq, dres, dcig, dused, dorder, dgroups;
+	cudaEvent_t e_start = nullptr, e_up = nullptr, e_kstart = nullptr, e_kern = nullptr, e_done = nullptr;
+	int64_t first = 0, m = 0;
+	bool busy = false;
+	void release()
+	{
+		hjobs.release(); hseq.release(); hres.release(); hcig.release(); horder.release(); hgroups.release(); hused.release();
+		djobs.release(); dseq.release(); dres.release(); dcig.release(); dused.release(); dorder.release(); dgroups.release();
+		for (cudaEvent_t *e : {&e_start, &e_up, &e_kstart, &e_kern, &e_done}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+	}
+};
+
 struct AsyncReq {
 	ksw_b200_cfg_t cfg;
 	int64_t n = 0;
@@ -154,9 +169,9 @@ struct ksw_b200_ctx {
 	int async_rc = 0;
 	AsyncReq req;
 	// banded global alignment (ksw_b200_global_batch): staging, device buffers, the CIGAR pool handed to the caller
-	PinnedBuf g_hjobs, g_hseq, g_hres, g_hcig, g_horder, g_hgroups;
-	DevBuf g_djobs, g_dseq, g_dres, g_dcig, g_dused, g_deh, g_dqc, g_dz, g_dorder, g_dgroups, g_dzfast, g_dcounter;
-	std::vector<uint32_t> g_cigar;
+	GStage g_st[2];                        // two chunks in flight: the host prepares one while the GPU works on the other
+	DevBuf g_deh, g_dqc, g_dz, g_dzfast, g_dcounter, g_dscratch;      // kernel scratch: used in stream order, one copy
+	std::vector<uint32_t> g_cigar, g_key, g_tmp, g_bucket;
 };
 
 namespace {
@@ -508,11 +523,8 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 	}
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-	ctx->g_hjobs.release(); ctx->g_hseq.release(); ctx->g_hres.release(); ctx->g_hcig.release();
-	ctx->g_djobs.release(); ctx->g_dseq.release(); ctx->g_dres.release(); ctx->g_dcig.release(); ctx->g_dused.release();
-	ctx->g_deh.release(); ctx->g_dqc.release(); ctx->g_dz.release();
-	ctx->g_dorder.release(); ctx->g_dgroups.release(); ctx->g_dzfast.release(); ctx->g_dcounter.release();
-	ctx->g_horder.release(); ctx->g_hgroups.release();
+	ctx->g_st[0].release(); ctx->g_st[1].release();
+	ctx->g_deh.release(); ctx->g_dqc.release(); ctx->g_dz.release(); ctx->g_dzfast.release(); ctx->g_dcounter.release(); ctx->g_dscratch.release();
 	delete ctx->pool;
 	delete ctx;
 }
@@ -1372,11 +1384,58 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
 			z_budget = std::min(z_budget, std::max<size_t>((free_b + ctx->g_dz.cap + ctx->g_dzfast.cap) / 4, (size_t)256 << 20));
 	}
-	std::vector<uint32_t> bucket;
+	for (GStage &st : ctx->g_st)
+		for (cudaEvent_t *e : {&st.e_start, &st.e_up, &st.e_kstart, &st.e_kern, &st.e_done}) if (!*e) CU(cudaEventCreate(e));
+	// whatever happens, no chunk stays in flight behind this call (its staging belongs to the context)
+	struct Drain {
+		ksw_b200_ctx *c; cudaStream_t a, b;
+		~Drain() { if (c->g_st[0].busy || c->g_st[1].busy) { cudaStreamSynchronize(c->up_stream); cudaStreamSynchronize(a); cudaStreamSynchronize(b); c->g_st[0].busy = c->g_st[1].busy = false; } }
+	} drain{ctx, s.stream, ctx->down_stream};
 	const int cell_cost = gfast_cell_cost(cfg);
+	const int NB = 4096, NQ = KSW_GFAST_MAX_QLEN / 4 + 4;                          // sort buckets: target length, band width in quads
+	const uint32_t KEY_SLOW = 0xffffffffu;
+	std::vector<uint32_t> &gkey = ctx->g_key, &tmp = ctx->g_tmp, &bucket = ctx->g_bucket;
+	if ((int64_t)gkey.size() < std::min<int64_t>(n, max_chunk_jobs)) gkey.resize((size_t)std::min<int64_t>(n, max_chunk_jobs));
+	double tr_plan = 0, tr_pack = 0, tr_sort = 0, tr_wait = 0, tr_out = 0, tr_up = 0, tr_kern = 0, tr_down = 0;   // KSW_B200_TRACE
+	auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+
+	// results of a finished chunk: CIGAR pool (its size is known only now) on the second stream, then the records
+	auto finish = [&](GStage &st) -> int {
+		double t0 = now();
+		CU(cudaEventSynchronize(st.e_done));
+		tr_wait += now() - t0; t0 = now();
+		if (ctx->trace) {
+			float a = 0, b = 0, c = 0;
+			cudaEventElapsedTime(&a, st.e_start, st.e_up); cudaEventElapsedTime(&b, st.e_kstart, st.e_kern); cudaEventElapsedTime(&c, st.e_kern, st.e_done);
+			tr_up += a; tr_kern += b; tr_down += c;
+		}
+		const unsigned long long used = *(const unsigned long long *)st.hused.p;
+		const size_t base = ctx->g_cigar.size();
+		if (used) {
+			CU(st.hcig.reserve(sizeof(uint32_t) * (size_t)used));
+			CU(cudaMemcpyAsync(st.hcig.p, st.dcig.p, sizeof(uint32_t) * (size_t)used, cudaMemcpyDeviceToHost, ctx->down_stream));
+			CU(cudaStreamSynchronize(ctx->down_stream));
+			ctx->g_cigar.insert(ctx->g_cigar.end(), (const uint32_t *)st.hcig.p, (const uint32_t *)st.hcig.p + used);
+		}
+		const DevGRes *hr = (const DevGRes *)st.hres.p;
+		for (int64_t k = 0; k < st.m; ++k) {
+			res[st.first + k].score = hr[k].score;
+			res[st.first + k].n_cigar = hr[k].n_cigar;
+			res[st.first + k].cigar_off = (int64_t)base + hr[k].cigar_off;
+		}
+		st.busy = false;
+		tr_out += now() - t0;
+		return 0;
+	};
+
 	int64_t first = 0;
+	int cur = 0;
 	while (first < n) {
-		// chunk [first, last): as many jobs as the budgets allow (at least one)
+		GStage &st = ctx->g_st[cur];
+		if (st.busy) { const int rc = finish(st); if (rc) return rc; }
+		double t0 = now();
+		// chunk [first, last): as many jobs as the budgets allow (at least one).  gkey: KEY_SLOW = int32 kernel, else the
+		// fast kernel's sort key (band width in quads, then target length; both descending)
 		int64_t last = first, n_fast = 0;
 		size_t seq_bytes = 0, ops = 0, zfast = 0;
 		int qmax = 0, qmax_fast = 0;
@@ -1386,29 +1445,36 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			if (j.qlen < 0 || j.tlen < 0 || j.w < 0) return fail(ctx, 2, "ksw_b200_global_batch: job with qlen < 0, tlen < 0 or w < 0");
 			const size_t sb = (size_t)j.qlen + (size_t)j.tlen, so = sb + 2;
 			const bool fastj = gfast_eligible(cfg, cell_cost, j);
+			const int nqb = fastj ? gfast_nqb(j.qlen, j.w) : 0;
 			// the group slab is sized by the group's longest target and widest band: 15 % of slack on the job's own need
-			const size_t zj = fastj ? (size_t)((double)j.tlen * gfast_nqb(j.qlen, j.w) * 8.0 * 1.15) + 64 : 0;
+			const size_t zj = fastj ? (size_t)((double)j.tlen * nqb * 8.0 * 1.15) + 64 : 0;
 			if (last > first && (seq_bytes + sb > max_seq || ops + so > max_ops || zfast + zj > z_budget / 2)) break;
 			seq_bytes += sb; ops += so; zfast += zj;
-			if (fastj) { ++n_fast; qmax_fast = std::max(qmax_fast, j.qlen); }
-			else {
+			if (fastj) {
+				++n_fast; qmax_fast = std::max(qmax_fast, j.qlen);
+				gkey[(size_t)(last - first)] = (uint32_t)(NQ - 1 - std::min(nqb, NQ - 1)) << 12 | (uint32_t)(NB - 1 - std::min(j.tlen, NB - 1));
+			} else {
 				qmax = std::max(qmax, j.qlen);
 				const long long n_col = std::min<long long>(j.qlen, 2LL * j.w + 1);
 				zmax = std::max(zmax, n_col * j.tlen);
+				gkey[(size_t)(last - first)] = KEY_SLOW;
 			}
 			++last;
 		}
 		const int64_t m = last - first, n_slow = m - n_fast;
-		CU(ctx->g_hjobs.reserve(sizeof(DevGJob) * (size_t)(m + n_slow)));
-		CU(ctx->g_hseq.reserve(std::max<size_t>(seq_bytes, 16)));
-		CU(ctx->g_hres.reserve(sizeof(DevGRes) * (size_t)m));
-		CU(ctx->g_djobs.reserve(sizeof(DevGJob) * (size_t)(m + n_slow)));
-		CU(ctx->g_dseq.reserve(std::max<size_t>(seq_bytes, 16)));
-		CU(ctx->g_dres.reserve(sizeof(DevGRes) * (size_t)m));
-		CU(ctx->g_dcig.reserve(sizeof(uint32_t) * ops));
-		CU(ctx->g_dused.reserve(sizeof(unsigned long long)));
-		DevGJob *hj = (DevGJob *)ctx->g_hjobs.p;
-		uint8_t *hs = (uint8_t *)ctx->g_hseq.p;
+		st.first = first; st.m = m;
+		tr_plan += now() - t0; t0 = now();
+		CU(st.hjobs.reserve(sizeof(DevGJob) * (size_t)(m + n_slow)));
+		CU(st.hseq.reserve(std::max<size_t>(seq_bytes, 16)));
+		CU(st.hres.reserve(sizeof(DevGRes) * (size_t)m));
+		CU(st.hused.reserve(sizeof(unsigned long long)));
+		CU(st.djobs.reserve(sizeof(DevGJob) * (size_t)(m + n_slow)));
+		CU(st.dseq.reserve(std::max<size_t>(seq_bytes, 16)));
+		CU(st.dres.reserve(sizeof(DevGRes) * (size_t)m));
+		CU(st.dcig.reserve(sizeof(uint32_t) * ops));
+		CU(st.dused.reserve(sizeof(unsigned long long)));
+		DevGJob *hj = (DevGJob *)st.hjobs.p;
+		uint8_t *hs = (uint8_t *)st.hseq.p;
 		{
 			// records (a running offset: serial, cheap), then the sequence bytes on the pack threads
 			size_t off = 0;
@@ -1430,25 +1496,30 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			};
 			if (T == 1) body(0); else tp->run(T, body);
 		}
-		// the fast kernel's jobs: counting sort by target length (longest first), groups of 32, one slab per group
+		tr_pack += now() - t0; t0 = now();
+		// the fast kernel's jobs: two counting-sort passes over the keys (least significant field first), groups of 32, one
+		// slab per group: the 32 lanes of a warp walk their rows in lockstep, so a group costs (longest target) x (widest band)
 		int n_groups = 0;
 		size_t zfast_units = 0;
 		if (n_fast > 0) {
-			CU(ctx->g_horder.reserve(sizeof(uint32_t) * (size_t)n_fast));
-			CU(ctx->g_hgroups.reserve(sizeof(DevGGroup) * (size_t)((n_fast + 31) / 32)));
-			uint32_t *ho = (uint32_t *)ctx->g_horder.p;
-			DevGGroup *hg = (DevGGroup *)ctx->g_hgroups.p;
-			const int NB = 4096;
+			CU(st.horder.reserve(sizeof(uint32_t) * (size_t)n_fast));
+			CU(st.hgroups.reserve(sizeof(DevGGroup) * (size_t)((n_fast + 31) / 32)));
+			uint32_t *ho = (uint32_t *)st.horder.p;
+			DevGGroup *hg = (DevGGroup *)st.hgroups.p;
+			tmp.resize((size_t)n_fast);
 			bucket.assign(NB + 1, 0);
-			auto key = [&](const ksw_b200_gjob_t &j) { return NB - 1 - std::min(j.tlen, NB - 1); };
-			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, cell_cost, jobs[first + k])) ++bucket[key(jobs[first + k]) + 1];
+			for (int64_t k = 0; k < m; ++k) if (gkey[k] != KEY_SLOW) ++bucket[(gkey[k] & 0xfffu) + 1];
 			for (int x = 0; x < NB; ++x) bucket[x + 1] += bucket[x];
-			for (int64_t k = 0; k < m; ++k) if (gfast_eligible(cfg, cell_cost, jobs[first + k])) ho[bucket[key(jobs[first + k])]++] = (uint32_t)k;
+			for (int64_t k = 0; k < m; ++k) if (gkey[k] != KEY_SLOW) tmp[bucket[gkey[k] & 0xfffu]++] = (uint32_t)k;
+			bucket.assign(NQ + 1, 0);
+			for (int64_t x = 0; x < n_fast; ++x) ++bucket[(gkey[tmp[x]] >> 12) + 1];
+			for (int x = 0; x < NQ; ++x) bucket[x + 1] += bucket[x];
+			for (int64_t x = 0; x < n_fast; ++x) ho[bucket[gkey[tmp[x]] >> 12]++] = tmp[x];
 			for (int64_t f = 0; f < n_fast; f += 32) {
 				DevGGroup g;
 				g.first = (int32_t)f; g.n = (int32_t)std::min<int64_t>(32, n_fast - f); g.rows = 0; g.nqb = 0;
 				for (int x = 0; x < g.n; ++x) {
-					const ksw_b200_gjob_t &j = jobs[first + ho[f + x]];
+					const DevGJob &j = hj[ho[f + x]];
 					g.rows = std::max(g.rows, j.tlen);
 					g.nqb = std::max(g.nqb, gfast_nqb(j.qlen, j.w));
 				}
@@ -1456,26 +1527,37 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 				zfast_units += (size_t)g.rows * (size_t)g.nqb * 32;
 				hg[n_groups++] = g;
 			}
-			CU(ctx->g_dorder.reserve(sizeof(uint32_t) * (size_t)n_fast));
-			CU(ctx->g_dgroups.reserve(sizeof(DevGGroup) * (size_t)n_groups));
+			CU(st.dorder.reserve(sizeof(uint32_t) * (size_t)n_fast));
+			CU(st.dgroups.reserve(sizeof(DevGGroup) * (size_t)n_groups));
 			CU(ctx->g_dzfast.reserve(zfast_units * sizeof(uint2) + 256));
 			CU(ctx->g_dcounter.reserve(sizeof(unsigned)));
+			CU(ctx->g_dscratch.reserve(sizeof(uint32_t) * ops));
 		}
 		// the int32 kernel's jobs: a compacted copy of their records behind the chunk's
 		if (n_slow > 0) {
 			int64_t w2 = m;
-			for (int64_t k = 0; k < m; ++k) if (!gfast_eligible(cfg, cell_cost, jobs[first + k])) hj[w2++] = hj[k];
+			for (int64_t k = 0; k < m; ++k) if (gkey[k] == KEY_SLOW) hj[w2++] = hj[k];
 		}
-		CU(cudaMemcpyAsync(ctx->g_djobs.p, hj, sizeof(DevGJob) * (size_t)(m + n_slow), cudaMemcpyHostToDevice, s.stream));
-		if (seq_bytes) CU(cudaMemcpyAsync(ctx->g_dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, s.stream));
-		CU(cudaMemsetAsync(ctx->g_dused.p, 0, sizeof(unsigned long long), s.stream));
+		tr_sort += now() - t0;
+		// uploads on their own stream: they overlap the previous chunk's kernels (this stage's buffers are free: its last
+		// chunk was finished above)
+		cudaStream_t up = ctx->up_stream;
+		CU(cudaEventRecord(st.e_start, up));
+		CU(cudaMemcpyAsync(st.djobs.p, hj, sizeof(DevGJob) * (size_t)(m + n_slow), cudaMemcpyHostToDevice, up));
+		if (seq_bytes) CU(cudaMemcpyAsync(st.dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, up));
+		CU(cudaMemsetAsync(st.dused.p, 0, sizeof(unsigned long long), up));
 		if (n_fast > 0) {
-			CU(cudaMemcpyAsync(ctx->g_dorder.p, ctx->g_horder.p, sizeof(uint32_t) * (size_t)n_fast, cudaMemcpyHostToDevice, s.stream));
-			CU(cudaMemcpyAsync(ctx->g_dgroups.p, ctx->g_hgroups.p, sizeof(DevGGroup) * (size_t)n_groups, cudaMemcpyHostToDevice, s.stream));
-			CU(ksw_launch_gfast((const DevGJob *)ctx->g_djobs.p, (const uint8_t *)ctx->g_dseq.p, P, (const uint32_t *)ctx->g_dorder.p,
-			                    (const DevGGroup *)ctx->g_dgroups.p, n_groups, qmax_fast, ctx->sm_count, (uint2 *)ctx->g_dzfast.p,
-			                    (unsigned *)ctx->g_dcounter.p, (unsigned long long *)ctx->g_dused.p, (uint32_t *)ctx->g_dcig.p,
-			                    (DevGRes *)ctx->g_dres.p, s.stream));
+			CU(cudaMemcpyAsync(st.dorder.p, st.horder.p, sizeof(uint32_t) * (size_t)n_fast, cudaMemcpyHostToDevice, up));
+			CU(cudaMemcpyAsync(st.dgroups.p, st.hgroups.p, sizeof(DevGGroup) * (size_t)n_groups, cudaMemcpyHostToDevice, up));
+		}
+		CU(cudaEventRecord(st.e_up, up));
+		CU(cudaStreamWaitEvent(s.stream, st.e_up, 0));
+		CU(cudaEventRecord(st.e_kstart, s.stream));
+		if (n_fast > 0) {
+			CU(ksw_launch_gfast((const DevGJob *)st.djobs.p, (const uint8_t *)st.dseq.p, P, (const uint32_t *)st.dorder.p,
+			                    (const DevGGroup *)st.dgroups.p, n_groups, qmax_fast, ctx->sm_count, (uint2 *)ctx->g_dzfast.p,
+			                    (unsigned *)ctx->g_dcounter.p, (uint32_t *)ctx->g_dscratch.p, (unsigned long long *)st.dused.p, (uint32_t *)st.dcig.p,
+			                    (DevGRes *)st.dres.p, s.stream));
 			ctx->launches += 2;
 		}
 		if (n_slow > 0) {
@@ -1490,30 +1572,25 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 			CU(ctx->g_deh.reserve(threads * (size_t)(qmax + 1) * sizeof(int2)));
 			CU(ctx->g_dqc.reserve(threads * (size_t)(qmax + 1)));
 			CU(ctx->g_dz.reserve(threads * (size_t)zcap));
-			CU(ksw_launch_global((const DevGJob *)ctx->g_djobs.p + m, n_slow, (const uint8_t *)ctx->g_dseq.p, P, (int2 *)ctx->g_deh.p,
+			CU(ksw_launch_global((const DevGJob *)st.djobs.p + m, n_slow, (const uint8_t *)st.dseq.p, P, (int2 *)ctx->g_deh.p,
 			                     (uint8_t *)ctx->g_dqc.p, (uint8_t *)ctx->g_dz.p, zcap, n_blocks,
-			                     (unsigned long long *)ctx->g_dused.p, (uint32_t *)ctx->g_dcig.p, (DevGRes *)ctx->g_dres.p, s.stream));
+			                     (unsigned long long *)st.dused.p, (uint32_t *)st.dcig.p, (DevGRes *)st.dres.p, s.stream));
 			ctx->launches++;
 		}
-		unsigned long long used = 0;
-		CU(cudaMemcpyAsync(ctx->g_hres.p, ctx->g_dres.p, sizeof(DevGRes) * (size_t)m, cudaMemcpyDeviceToHost, s.stream));
-		CU(cudaMemcpyAsync(&used, ctx->g_dused.p, sizeof(used), cudaMemcpyDeviceToHost, s.stream));
-		CU(cudaStreamSynchronize(s.stream));
-		const size_t base = ctx->g_cigar.size();
-		if (used) {
-			CU(ctx->g_hcig.reserve(sizeof(uint32_t) * (size_t)used));
-			CU(cudaMemcpyAsync(ctx->g_hcig.p, ctx->g_dcig.p, sizeof(uint32_t) * (size_t)used, cudaMemcpyDeviceToHost, s.stream));
-			CU(cudaStreamSynchronize(s.stream));
-			ctx->g_cigar.insert(ctx->g_cigar.end(), (const uint32_t *)ctx->g_hcig.p, (const uint32_t *)ctx->g_hcig.p + used);
-		}
-		const DevGRes *hr = (const DevGRes *)ctx->g_hres.p;
-		for (int64_t k = 0; k < m; ++k) {
-			res[first + k].score = hr[k].score;
-			res[first + k].n_cigar = hr[k].n_cigar;
-			res[first + k].cigar_off = (int64_t)base + hr[k].cigar_off;
-		}
+		CU(cudaEventRecord(st.e_kern, s.stream));
+		CU(cudaMemcpyAsync(st.hres.p, st.dres.p, sizeof(DevGRes) * (size_t)m, cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaMemcpyAsync(st.hused.p, st.dused.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaEventRecord(st.e_done, s.stream));
+		st.busy = true;
+		cur ^= 1;
 		first = last;
 	}
+	for (int k = 0; k < 2; ++k, cur ^= 1)                                             // the older chunk first
+		if (ctx->g_st[cur].busy) { const int rc = finish(ctx->g_st[cur]); if (rc) return rc; }
+	if (ctx->trace)
+		fprintf(stderr, "[ksw_b200] global_batch n=%lld: host plan %.2f  pack %.2f  sort %.2f  wait for GPU %.2f  results out %.2f ms | "
+		                "GPU h2d %.2f  kernels %.2f  d2h %.2f ms\n",
+		        (long long)n, tr_plan, tr_pack, tr_sort, tr_wait, tr_out, tr_up, tr_kern, tr_down);
 	if (cigar_pool) *cigar_pool = ctx->g_cigar.data();
 	if (n_cigar_total) *n_cigar_total = (int64_t)ctx->g_cigar.size();
 	return 0;

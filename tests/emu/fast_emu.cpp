@@ -185,9 +185,10 @@ extern "C" int ksw_gfast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const k
 		wk.z = z.data(); wk.query = query; wk.target = target; wk.mat = P.mat;
 		wk.qlen = j.qlen; wk.tlen = j.tlen; wk.w = j.w; wk.nqb = nqb;
 		wk.o_del = P.o_del; wk.e_del = P.e_del; wk.o_ins = P.o_ins; wk.e_ins = P.e_ins;
-		const int nc = wk.run([](int, int, int) {});
+		std::vector<uint32_t> rev((size_t)j.qlen + j.tlen + 2);
+		const int nc = wk.run([&](int r, int op, int len) { rev[r] = (uint32_t)len << 4 | (uint32_t)op; });
 		uint32_t *out = cigar_pool + res[k].cigar_off;
-		wk.run([&](int r, int op, int len) { out[nc - 1 - r] = (uint32_t)len << 4 | (uint32_t)op; });
+		for (int r = 0; r < nc; ++r) out[nc - 1 - r] = rev[r];
 		res[k].n_cigar = nc;
 	}
 	if (n_fast_out) *n_fast_out = n_fast;
