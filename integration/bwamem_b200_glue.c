@@ -201,7 +201,7 @@ static int b200_cigar_on(void) { return b200_cigar_mode() != 0; }
 static void *b200_arena_alloc(b200_arena_t *a, size_t n)
 {
 	n = (n + 15) & ~(size_t)15;
-	if (n > B200_ARENA_BLOCK) err_fatal(__func__, "entry of %ld bytes", (long)n);
+	if (n > B200_ARENA_BLOCK) return 0;                    /* too large to keep: the caller skips it (computed on demand later) */
 	if (a->n_blk == 0 || a->used + n > B200_ARENA_BLOCK) {
 		if (a->n_blk && a->cur + 1 < a->n_blk) ++a->cur;
 		else {
@@ -235,9 +235,12 @@ static uint64_t b200_cig_hash(int qlen, const uint8_t *q, int tlen, const uint8_
 static void b200_cig_insert(int tid, int qlen, const uint8_t *q, int tlen, const uint8_t *t, int w, int score, int n_cigar, const uint32_t *cigar)
 {
 	b200_cig_entry_t *e = (b200_cig_entry_t *)b200_arena_alloc(&b200_cig_arena[tid], sizeof(b200_cig_entry_t) + 4 * (size_t)n_cigar + qlen + tlen);
-	uint32_t *c = (uint32_t *)(e + 1);
-	uint8_t *p = (uint8_t *)(c + n_cigar);
+	uint32_t *c;
+	uint8_t *p;
 	b200_cig_entry_t **slot;
+	if (!e) return;
+	c = (uint32_t *)(e + 1);
+	p = (uint8_t *)(c + n_cigar);
 	e->hash = b200_cig_hash(qlen, q, tlen, t, w);
 	e->qlen = qlen; e->tlen = tlen; e->w = w; e->score = score; e->n_cigar = n_cigar;
 	memcpy(c, cigar, 4 * (size_t)n_cigar); memcpy(p, q, qlen); memcpy(p + qlen, t, tlen);

@@ -103,3 +103,54 @@ int ksw_ref_global_batch(const ref_cfg_t *cfg, int64_t n, const ref_gjob_t *jobs
 	free(tid); free(args);
 	return 0;
 }
+
+/* ---- the same for the reference's ksw_align2 (bwa-0.7.8/ksw.c:329, prototype and kswr_t ksw.h:30-36, 62) ---- */
+#include <string.h>
+typedef struct { int score; int te, qe; int score2, te2; int tb, qb; } ref_kswr_t;   /* layout of kswr_t, ksw.h:30-36 */
+struct _kswq_t;
+ref_kswr_t ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat, int o_del, int e_del,
+                      int o_ins, int e_ins, int xtra, struct _kswq_t **qry);
+
+typedef struct { uint64_t q_off, t_off; int32_t qlen, tlen, xtra, pad; } ref_ajob_t;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb, pad; } ref_ares_t;
+typedef struct {
+	const ref_cfg_t *cfg; const ref_ajob_t *jobs; const uint8_t *qpool, *tpool;
+	ref_ares_t *res; int64_t n, begin, stride;
+} aarg_t;
+
+static void *aworker(void *p)
+{
+	aarg_t *a = (aarg_t *)p;
+	const ref_cfg_t *c = a->cfg;
+	int64_t k;
+	for (k = a->begin; k < a->n; k += a->stride) {
+		const ref_ajob_t *j = &a->jobs[k];
+		/* the reference reverses both sequences in place and back (ksw.c:343-346): give it private copies */
+		uint8_t *q = (uint8_t *)malloc((size_t)j->qlen + 16), *t = (uint8_t *)malloc((size_t)j->tlen + 16);
+		ref_kswr_t r;
+		memcpy(q, a->qpool + j->q_off, (size_t)j->qlen); memcpy(t, a->tpool + j->t_off, (size_t)j->tlen);
+		r = ksw_align2(j->qlen, q, j->tlen, t, c->m, c->mat, c->o_del, c->e_del, c->o_ins, c->e_ins, j->xtra, 0);
+		a->res[k].score = r.score; a->res[k].te = r.te; a->res[k].qe = r.qe; a->res[k].score2 = r.score2; a->res[k].te2 = r.te2;
+		a->res[k].tb = r.tb; a->res[k].qb = r.qb; a->res[k].pad = 0;
+		free(q); free(t);
+	}
+	return 0;
+}
+
+int ksw_ref_align_batch(const ref_cfg_t *cfg, int64_t n, const ref_ajob_t *jobs, const uint8_t *qpool,
+                        const uint8_t *tpool, ref_ares_t *res, int n_threads)
+{
+	int t;
+	pthread_t *tid; aarg_t *args;
+	if (n_threads < 1) n_threads = 1;
+	tid = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
+	args = (aarg_t *)malloc(sizeof(aarg_t) * n_threads);
+	for (t = 0; t < n_threads; ++t) {
+		aarg_t a = { cfg, jobs, qpool, tpool, res, n, t, n_threads };
+		args[t] = a;
+		pthread_create(&tid[t], 0, aworker, &args[t]);
+	}
+	for (t = 0; t < n_threads; ++t) pthread_join(tid[t], 0);
+	free(tid); free(args);
+	return 0;
+}

@@ -29,6 +29,10 @@ assert JOB_DT.itemsize == 32 and RES_DT.itemsize == 24
 GJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"), ("reserved", "<i4")])
 GRES_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])
 assert GJOB_DT.itemsize == 32 and GRES_DT.itemsize == 16
+AJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("reserved", "<i4")])
+ARES_DT = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4"), ("reserved", "<i4")])
+assert AJOB_DT.itemsize == 32 and ARES_DT.itemsize == 32
+KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000      # ksw.h:6-9
 
 
 class Cfg(C.Structure):
@@ -85,6 +89,8 @@ def oracle_lib():
         lib.ksw_oracle_global_batch.restype = C.c_int
         lib.ksw_oracle_global_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_int]
+        lib.ksw_oracle_align_batch.restype = C.c_int
+        lib.ksw_oracle_align_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.ksw_oracle_clamp_w.restype = C.c_int
         lib.ksw_oracle_clamp_w.argtypes = [C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6
         _libs["oracle"] = lib
@@ -104,6 +110,9 @@ def ref_lib():
         lib.ksw_ref_global_batch.restype = C.c_int
         lib.ksw_ref_global_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int]
+        if hasattr(lib, "ksw_ref_align_batch"):
+            lib.ksw_ref_align_batch.restype = C.c_int
+            lib.ksw_ref_align_batch.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _libs["ref"] = lib
     return _libs["ref"]
 
@@ -719,3 +728,83 @@ def gen_global(n: int, seed: int, cfg: Cfg | None = None, max_q: int = 250, n_fr
     jobs["t_off"] = np.concatenate([[0], np.cumsum(tlen)[:-1]]) if n else 0
     jobs["qlen"], jobs["tlen"], jobs["w"] = qlen, tlen, ws
     return GBatch(cfg, jobs, np.ascontiguousarray(np.concatenate(qs)), np.ascontiguousarray(np.concatenate(ts)))
+
+
+# ------------------------------------------------------------------ local alignment (ksw_align2, mate rescue)
+@dataclass
+class ABatch:
+    cfg: Cfg
+    jobs: np.ndarray      # AJOB_DT
+    qpool: np.ndarray
+    tpool: np.ndarray
+
+    @property
+    def n(self) -> int:
+        return int(self.jobs.shape[0])
+
+
+def _run_align(fn, b: ABatch, threads: int):
+    res = np.zeros(b.n, dtype=ARES_DT)
+    rc = fn(C.byref(b.cfg), b.n, _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), _ptr(res), threads)
+    assert rc == 0
+    return res
+
+
+def run_align_oracle(b: ABatch, threads: int = 8):
+    """ARES_DT records from the CPU restatement oracle/ksw_align_oracle.c."""
+    return _run_align(oracle_lib().ksw_oracle_align_batch, b, threads)
+
+
+def run_align_ref(b: ABatch, threads: int = 8):
+    """The same from the reference's own ksw_align2 (oracle/_ref/libksw_ref.so)."""
+    return _run_align(ref_lib().ksw_ref_align_batch, b, threads)
+
+
+def align_mismatch(a: np.ndarray, b: np.ndarray):
+    for f in ("score", "te", "qe", "score2", "te2", "tb", "qb"):
+        bad = np.flatnonzero(a[f] != b[f])
+        if bad.size:
+            k = int(bad[0])
+            return k, f, tuple(int(a[x][k]) for x in ARES_DT.names[:7]), tuple(int(b[x][k]) for x in ARES_DT.names[:7])
+    return None
+
+
+def gen_align(n: int, seed: int, cfg: Cfg | None = None, max_q: int = 250, max_t: int = 900, flags=None, min_seed: int = 19,
+              n_frac: float = 0.01, copies=(0, 1, 1, 1, 2, 3)) -> ABatch:
+    """Jobs of the shape mem_matesw produces (bwamem_pair.c:128-150): the query is a read (or its reverse complement), the
+    target a reference window that holds 0, 1 or several mutated copies of it (the repeats feed the second-best list);
+    xtra as mem_matesw sets it — KSW_XSUBO | KSW_XSTART | (qlen * a < 250 ? KSW_XBYTE : 0) | min_seed_len * a — unless
+    `flags` gives a list of flag words to draw from (then the low 16 bits are drawn too)."""
+    rng = np.random.default_rng(seed)
+    cfg = cfg or make_cfg()
+    a = int(cfg_mat(cfg)[0])
+    qs, ts = [], []
+    jobs = np.zeros(n, dtype=AJOB_DT)
+    qo = to = 0
+    for k in range(n):
+        ql = int(rng.integers(1, max_q + 1)) if rng.random() < 0.2 else int(rng.integers(max(1, max_q // 3), max_q + 1))
+        q = rng.integers(0, 4, ql).astype(np.uint8)
+        tl = int(rng.integers(0, max_t + 1)) if rng.random() < 0.1 else int(rng.integers(max_t // 4, max_t + 1))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        for _ in range(int(rng.choice(copies))):
+            c = q.copy()
+            sub = rng.random(ql) < float(rng.choice([0.0, 0.02, 0.08, 0.2]))
+            c[sub] = (c[sub] + rng.integers(1, 4, int(sub.sum()))) & 3
+            if rng.random() < 0.4 and ql > 8:
+                p = int(rng.integers(2, ql - 2)); d = int(rng.integers(1, 6))
+                c = np.concatenate([c[:p], rng.integers(0, 4, d).astype(np.uint8), c[p:]]) if rng.random() < 0.5 else np.concatenate([c[:p], c[p + d:]])
+            if rng.random() < 0.3:
+                c = c[int(rng.integers(0, max(1, len(c) // 2))):]                 # a partial copy
+            if len(c) and tl > len(c):
+                p = int(rng.integers(0, tl - len(c)))
+                t[p:p + len(c)] = c
+        q[rng.random(ql) < n_frac] = 4
+        if tl: t[rng.random(tl) < n_frac] = 4
+        if flags is None:
+            xtra = KSW_XSUBO | KSW_XSTART | (KSW_XBYTE if ql * a < 250 else 0) | (min_seed * a)
+        else:
+            xtra = int(rng.choice(flags)) | int(rng.choice([0, 1, 10, 19, 30, 60, 200]))
+            if (xtra & KSW_XBYTE) and ql * max(a, 1) >= 250: xtra &= ~KSW_XBYTE        # byte overflow is outside the domain
+        jobs[k] = (qo, to, ql, tl, xtra, 0)
+        qs.append(q); ts.append(t); qo += ql; to += tl
+    return ABatch(cfg, jobs, np.concatenate(qs + [np.zeros(16, np.uint8)]), np.concatenate(ts + [np.zeros(16, np.uint8)]))

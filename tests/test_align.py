@@ -1,0 +1,42 @@
+"""Local alignment with start positions and second-best score: the reference's ksw_align2 (bwa-0.7.8/ksw.c:329-354, the
+striped SSE2 kernels ksw_u8 / ksw_i16), which mem_matesw calls for mate rescue (bwamem_pair.c:150).  SURVEY §8(f) rank 4.
+CPU tests pin the restatement (oracle/ksw_align_oracle.c) to the compiled reference; GPU tests compare the kernel with it."""
+import numpy as np
+import pytest
+import kswtest as K
+
+X = K.KSW_XBYTE, K.KSW_XSTOP, K.KSW_XSUBO, K.KSW_XSTART
+ALL_FLAGS = [0, K.KSW_XBYTE, K.KSW_XSTART, K.KSW_XSUBO, K.KSW_XSUBO | K.KSW_XSTART, K.KSW_XBYTE | K.KSW_XSUBO | K.KSW_XSTART,
+             K.KSW_XSTOP, K.KSW_XSTOP | K.KSW_XSTART, K.KSW_XBYTE | K.KSW_XSTOP | K.KSW_XSUBO | K.KSW_XSTART]
+CFGS = [None, K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3), K.make_cfg(a=1, b=1, o_del=1, e_del=2, o_ins=0, e_ins=1),
+        K.make_cfg(a=3, b=2, o_del=0, e_del=1, o_ins=0, e_ins=1), K.make_cfg(a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1)]
+
+
+def test_align_oracle_matches_compiled_reference(oracle_built):
+    if not K.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    n = 0
+    for seed, cfg in enumerate(CFGS):
+        b = K.gen_align(700, seed=700 + seed, cfg=cfg, max_q=150 if seed % 2 else 250)               # mem_matesw's flags
+        mm = K.align_mismatch(K.run_align_oracle(b), K.run_align_ref(b))
+        assert mm is None, ("matesw", seed, mm, b.jobs[mm[0]])
+        b = K.gen_align(700, seed=720 + seed, cfg=cfg, max_q=120, max_t=400, flags=ALL_FLAGS)         # every flag combination
+        mm = K.align_mismatch(K.run_align_oracle(b), K.run_align_ref(b))
+        assert mm is None, ("flags", seed, mm, b.jobs[mm[0]])
+        n += 2 * b.n
+    assert n >= 7000
+
+
+def test_align_oracle_known_answers(oracle_built):
+    """A read embedded once, exactly: score = qlen * a, ends and starts where it was put; embedded twice: the second-best
+    score is the same and points at the other copy."""
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 4, 80).astype(np.uint8)
+    t = rng.integers(0, 4, 600).astype(np.uint8)
+    t[100:180] = q
+    t[400:480] = q
+    jobs = np.zeros(1, dtype=K.AJOB_DT)
+    jobs[0] = (0, 0, 80, 600, K.KSW_XSUBO | K.KSW_XSTART | K.KSW_XBYTE | 19, 0)
+    r = K.run_align_oracle(K.ABatch(K.make_cfg(), jobs, np.concatenate([q, np.zeros(16, np.uint8)]), np.concatenate([t, np.zeros(16, np.uint8)])))[0]
+    assert (int(r["score"]), int(r["te"]), int(r["qe"]), int(r["tb"]), int(r["qb"])) == (80, 179, 79, 100, 0)
+    assert int(r["score2"]) == 80 and int(r["te2"]) == 479
