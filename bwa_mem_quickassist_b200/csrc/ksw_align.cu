@@ -1,0 +1,272 @@
+// ksw_align.cu — local alignment with start positions and second-best score: the reference's ksw_align2
+// (bwa-0.7.8/ksw.c:329-354) with its two striped SSE2 kernels ksw_u8 (ksw.c:110-236) and ksw_i16 (ksw.c:238-320), which
+// mem_matesw calls for mate rescue (bwamem_pair.c:150).  SURVEY §8(f) rank 4.
+//
+// The reference's results depend on its vector layout (E is computed before the lazy-F loop corrects H across lane
+// boundaries; the lazy-F loop stops when no lane can improve; the padding columns take part in the row maximum), so this
+// kernel keeps the layout: ONE SUB-WARP OF P LANES IS ONE 128-BIT VECTOR — P = 16 lanes for the byte kernel, 8 for the
+// 16-bit kernel; lane l owns the query segment l*slen .. l*slen+slen-1 exactly like SSE lane l (ksw.c:87-89), walks it
+// column by column with F in a register, and the byte shifts between lanes (_mm_slli_si128) are __shfl_up_sync.  A warp
+// runs 32/P jobs of similar size (the host sorts them) with warp-uniform control flow; every arithmetic step saturates the
+// way the SSE2 instruction it replaces does.  Per sub-warp, shared memory holds (H | E<<16) per column, the row copied at
+// the best score (Hmax, ksw.c:208-209) and the query profile (ksw.c:87-106); the second-best list (ksw.c:196-205) goes to
+// a per-warp scratch slab in HBM, one (score, row) pair per qualifying row at most.
+// Both passes of ksw_align2 run back to back in the same sub-warp: the forward pass, then — if KSW_XSTART asks for it and the
+// score passes the KSW_XSUBO threshold — the pass over the reversed prefixes with KSW_XSTOP (ksw.c:342-350), which, like the
+// reference, still walks all tlen rows (reversed prefix first) unless it stops at the score.
+#include <cuda_runtime.h>
+#include "ksw_dev.cuh"
+#include "ksw_launch.h"
+
+namespace {
+
+constexpr int XSTOP = 0x20000, XSUBO = 0x40000, XSTART = 0x80000;      // ksw.h:6-9
+constexpr unsigned FULL = 0xffffffffu;
+
+struct APass { int score, te, qe, score2, te2; };
+
+template <int P>
+__device__ __forceinline__ int sub_max(int v)
+{
+#pragma unroll
+	for (int o = P / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o, P));
+	return v;
+}
+
+// one call of ksw_u8 (P = 16) / ksw_i16 (P = 8) on the sub-warp's job; live = this sub-warp has a job in this pass.
+// rev: the sequences are the reversed prefixes query[qe1..0], target[te1..0] followed by target[te1+1..tlen) (ksw.c:343-345)
+template <int P>
+__device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, const int qlen, const uint8_t *__restrict__ target,
+                            const int tlen, const int xtra, const bool rev, const int qe1, const int te1, uint32_t *HE, uint16_t *HM,
+                            int8_t *PR, const int cap, uint2 *bs, const KswAlignParams &A, const int sub, const int sl)
+{
+	const int slen = live ? (qlen + P - 1) / P : 0;                       // ksw.c:68
+	const unsigned submask = (P == 16 ? 0xffffu : 0xffu) << (sub * P);
+	const int vmask = P == 16 ? 0xff : 0xffff;
+	const int oe_del = (A.o_del + A.e_del) & vmask, e_del = A.e_del & vmask;     // _mm_set1_epi8/16 truncate (ksw.c:131-134)
+	const int oe_ins = (A.o_ins + A.e_ins) & vmask, e_ins = A.e_ins & vmask;
+	const int shift = A.shift;
+	// query profile (ksw.c:87-106) and the zeroed H / E / Hmax rows (ksw.c:138-142)
+	for (int j = 0; j < slen; ++j) {
+		const int k = j + sl * slen;
+		int code = 4;
+		if (k < qlen) { code = rev ? query[qe1 - k] : query[k]; code = code > 4 ? 4 : code; }
+#pragma unroll
+		for (int a = 0; a < 5; ++a) PR[a * cap + j * P + sl] = k < qlen ? A.mat[a * 5 + code] : (int8_t)0;
+		HE[j * P + sl] = 0u;
+		HM[j * P + sl] = 0;
+	}
+	__syncwarp();
+	int slen_w = slen, rows_w = live ? tlen : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		slen_w = max(slen_w, __shfl_xor_sync(FULL, slen_w, o));
+		rows_w = max(rows_w, __shfl_xor_sync(FULL, rows_w, o));
+	}
+	const int minsc = (xtra & XSUBO) ? (xtra & 0xffff) : 0x10000;         // ksw.c:127-128
+	const int endsc = (xtra & XSTOP) ? (xtra & 0xffff) : 0x10000;
+	int gmax = 0, te = -1, n_b = 0, last_sc = 0, last_row = -2;
+	bool done = !live;
+	int t_next = 0;
+	if (live && tlen > 0) t_next = rev && 0 <= te1 ? target[te1] : target[0];
+	for (int i = 0; i < rows_w; ++i) {
+		const bool act = !done && i < tlen;
+		if (!__any_sync(FULL, act)) break;
+		int t = t_next;
+		t = t > 4 ? 4 : t;
+		if (act && i + 1 < tlen) t_next = rev && i + 1 <= te1 ? target[te1 - i - 1] : target[i + 1];
+		const int8_t *S = PR + t * cap;
+		// h = H(i-1, -1): the last vector shifted up by one lane (ksw.c:147-148)
+		const int hl = act ? (int)(HE[(slen - 1) * P + sl] & 0xffffu) : 0;
+		int h = __shfl_up_sync(FULL, hl, 1, P);
+		if (sl == 0) h = 0;
+		int f = 0, mx = 0;
+		for (int j = 0; j < slen_w; ++j) {
+			if (act && j < slen) {
+				const uint32_t w = HE[j * P + sl];
+				int e = (int)(w >> 16);
+				const int sc = S[j * P + sl];
+				int hv;
+				if (P == 16) {                                            // ksw.c:156-157
+					hv = min(255, h + ((sc + shift) & 0xff));
+					hv = max(0, hv - shift);
+				} else {                                                  // ksw.c:268 (signed saturating add)
+					hv = min(32767, max(-32768, h + sc));
+				}
+				hv = max(hv, max(e, f));                                  // ksw.c:159-160
+				mx = max(mx, hv);
+				e = max(max(0, e - e_del), max(0, hv - oe_del));          // ksw.c:164-167
+				f = max(max(0, f - e_ins), max(0, hv - oe_ins));          // ksw.c:169-171
+				HE[j * P + sl] = (uint32_t)hv | ((uint32_t)e << 16);
+				h = (int)(w & 0xffffu);                                   // H(i-1, j) for the next column
+			}
+		}
+		// the lazy-F loop (ksw.c:182-192 / 282-291): at most 16 rounds of slen steps; a round starts by shifting f up one
+		// lane; it ends for good at the first step after which no lane of the vector has f > H - oe_ins.  If every shifted
+		// f is zero the first step changes nothing and ends it, so it is skipped.
+		{
+			int fs = __shfl_up_sync(FULL, f, 1, P);
+			fs = sl == 0 ? 0 : fs;
+			const unsigned pos = __ballot_sync(FULL, act && fs > 0);
+			bool lz = act && (pos & submask) != 0u;
+			int jl = 0, kl = 0;
+			f = fs;
+			while (__any_sync(FULL, lz)) {
+				bool gt = false;
+				if (lz) {
+					const uint32_t w = HE[jl * P + sl];
+					int hv = max((int)(w & 0xffffu), f);
+					HE[jl * P + sl] = (w & 0xffff0000u) | (uint32_t)hv;
+					hv = max(0, hv - oe_ins);
+					f = max(0, f - e_ins);
+					gt = f > hv;
+				}
+				const unsigned more = __ballot_sync(FULL, gt);
+				if (lz) {
+					if ((more & submask) == 0u) lz = false;
+					else if (++jl == slen) { jl = 0; if (++kl == 16) lz = false; }
+				}
+				// the next round's shift (only sub-warps at a round start take it)
+				fs = __shfl_up_sync(FULL, f, 1, P);
+				if (lz && jl == 0) f = sl == 0 ? 0 : fs;
+			}
+		}
+		const int imax = sub_max<P>(mx);
+		if (act && imax >= minsc) {                                       // the second-best list, ksw.c:196-205
+			if (n_b == 0 || last_row + 1 != i) {
+				if (sl == 0) bs[n_b] = make_uint2((uint32_t)imax, (uint32_t)i);
+				++n_b; last_sc = imax; last_row = i;
+			} else if (last_sc < imax) {
+				if (sl == 0) bs[n_b - 1] = make_uint2((uint32_t)imax, (uint32_t)i);
+				last_sc = imax; last_row = i;
+			}
+		}
+		if (act && imax > gmax) {                                         // ksw.c:206-211
+			gmax = imax; te = i;
+			for (int j = 0; j < slen; ++j) HM[j * P + sl] = (uint16_t)(HE[j * P + sl] & 0xffffu);
+			if ((P == 16 && gmax + shift >= 255) || gmax >= endsc) done = true;
+		}
+		__syncwarp();
+	}
+	APass r;
+	r.score = P == 16 ? (gmax + shift < 255 ? gmax : 255) : gmax;          // ksw.c:214 / 309
+	r.te = te; r.qe = -1; r.score2 = -1; r.te2 = -1;
+	__syncwarp();
+	{
+		// qe: the smallest column among those holding the maximum of the kept row (ksw.c:218-221)
+		int best = -1, col = 0x7fffffff;
+		for (int j = 0; j < slen; ++j) {
+			const int v = HM[j * P + sl];
+			if (v > best) { best = v; col = j + sl * slen; }
+		}
+#pragma unroll
+		for (int o = P / 2; o > 0; o >>= 1) {
+			const int ob = __shfl_xor_sync(FULL, best, o, P), oc = __shfl_xor_sync(FULL, col, o, P);
+			if (ob > best || (ob == best && oc < col)) { best = ob; col = oc; }
+		}
+		if (P == 8 || r.score != 255) r.qe = col;
+		// second best: the first list entry with the highest score outside [te - d, te + d] (ksw.c:223-231)
+		int s2 = -1, idx2 = 0x7fffffff, row2 = -1;
+		if (live && n_b > 0 && (P == 8 || r.score != 255)) {
+			const int d = (r.score + A.qmax - 1) / A.qmax, low = te - d, high = te + d;
+			for (int x = sl; x < n_b; x += P) {
+				const uint2 en = bs[x];
+				const int e = (int)en.y;
+				if ((e < low || e > high) && (int)en.x > s2) { s2 = (int)en.x; idx2 = x; row2 = e; }
+			}
+		}
+#pragma unroll
+		for (int o = P / 2; o > 0; o >>= 1) {
+			const int os = __shfl_xor_sync(FULL, s2, o, P), oi = __shfl_xor_sync(FULL, idx2, o, P), orow = __shfl_xor_sync(FULL, row2, o, P);
+			if (os > s2 || (os == s2 && oi < idx2)) { s2 = os; idx2 = oi; row2 = orow; }
+		}
+		if (s2 >= 0) { r.score2 = s2; r.te2 = row2; }
+	}
+	__syncwarp();
+	return r;
+}
+
+template <int P>
+__global__ void __launch_bounds__(32)
+ksw_align_kernel(const DevAJob *__restrict__ jobs, const uint32_t *__restrict__ order, const int n_jobs, const uint8_t *__restrict__ seq,
+                 const KswAlignParams A, const int cap, uint2 *__restrict__ bscr, const int tcap, unsigned *__restrict__ counter,
+                 DevARes *__restrict__ res)
+{
+	constexpr int G = 32 / P;
+	extern __shared__ uint32_t asm_[];
+	const int lane = threadIdx.x, sub = lane / P, sl = lane % P;
+	uint32_t *HE = asm_ + sub * cap;
+	uint16_t *HM = reinterpret_cast<uint16_t *>(asm_ + G * cap) + sub * cap;
+	int8_t *PR = reinterpret_cast<int8_t *>(asm_ + G * cap + G * cap / 2) + sub * 5 * cap;
+	uint2 *bs = bscr + ((size_t)blockIdx.x * G + sub) * (size_t)tcap;
+	for (;;) {
+		unsigned g = 0;
+		if (lane == 0) g = atomicAdd(counter, 1u);
+		g = __shfl_sync(FULL, g, 0);
+		if ((long long)g * G >= n_jobs) break;
+		const int jidx = (int)g * G + sub;
+		const bool have = jidx < n_jobs;
+		DevAJob jb;
+		jb.seq_off = 0; jb.qlen = 1; jb.tlen = 0; jb.xtra = 0; jb.idx = 0;
+		if (have) jb = jobs[order[jidx]];
+		const uint8_t *query = seq + jb.seq_off, *target = query + jb.qlen;
+		const APass r = align_pass<P>(have, query, jb.qlen, target, jb.tlen, jb.xtra, false, 0, -1, HE, HM, PR, cap, bs, A, sub, sl);
+		// ksw.c:341: the start positions are wanted and the score passes the threshold; a saturated byte score (255) is outside the
+		// reference's defined behaviour (it goes on with qe = -1): the job ends here with score 255
+		const bool second = have && (jb.xtra & XSTART) && !((jb.xtra & XSUBO) && r.score < (jb.xtra & 0xffff)) && r.qe >= 0;
+		const APass rr = align_pass<P>(second, query, r.qe + 1, target, jb.tlen, XSTOP | r.score, true, r.qe, r.te, HE, HM, PR, cap, bs, A, sub, sl);
+		if (have && sl == 0) {
+			DevARes o;
+			o.score = r.score; o.te = r.te; o.qe = r.qe; o.score2 = r.score2; o.te2 = r.te2; o.tb = -1; o.qb = -1; o.pad = 0;
+			if (second && r.score == rr.score) { o.tb = r.te - rr.te; o.qb = r.qe - rr.qe; }      // ksw.c:348-349
+			res[jb.idx] = o;
+		}
+	}
+}
+
+template <int P>
+cudaError_t launch_one(const DevAJob *jobs, const uint32_t *order, int n_jobs, const uint8_t *seq, const KswAlignParams &A, int qmax,
+                       int tmax, int sm_count, void **bscr, size_t *bscr_cap, unsigned *counter, DevARes *res, cudaStream_t st)
+{
+	constexpr int G = 32 / P;
+	if (n_jobs <= 0) return cudaSuccess;
+	const int cap = ((qmax + 15) / 16) * 16;                              // >= slen * P for every job, and keeps the regions aligned
+	const size_t smem = (size_t)G * cap * 11;
+	int dev = 0, optin = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	if (e != cudaSuccess) return e;
+	if (smem > (size_t)optin) return cudaErrorInvalidValue;
+	e = cudaFuncSetAttribute(ksw_align_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_align_kernel<P>, 32, smem);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	int blocks = sm_count * per_sm;
+	const int groups = (n_jobs + G - 1) / G;
+	if (blocks > groups) blocks = groups;
+	const int tcap = tmax > 0 ? tmax : 1;
+	const size_t need = (size_t)blocks * G * (size_t)tcap * sizeof(uint2);
+	if (need > *bscr_cap) {
+		if (*bscr) { e = cudaFree(*bscr); *bscr = nullptr; *bscr_cap = 0; if (e != cudaSuccess) return e; }
+		e = cudaMalloc(bscr, need);
+		if (e != cudaSuccess) return e;
+		*bscr_cap = need;
+	}
+	e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+	if (e != cudaSuccess) return e;
+	ksw_align_kernel<P><<<blocks, 32, smem, st>>>(jobs, order, n_jobs, seq, A, cap, (uint2 *)*bscr, tcap, counter, res);
+	return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t ksw_launch_align(int bytes_per_score, const DevAJob *jobs, const uint32_t *order, int n_jobs, const uint8_t *seq,
+                             const KswAlignParams &A, int qmax, int tmax, int sm_count, void **bscr, size_t *bscr_cap,
+                             unsigned *counter, DevARes *res, cudaStream_t st)
+{
+	return bytes_per_score == 1 ? launch_one<16>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st)
+	                            : launch_one<8>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
+}

@@ -56,6 +56,22 @@ struct DevGGroup {
 };
 static_assert(sizeof(DevGGroup) == 24, "DevGGroup must be 24 bytes");
 
+// local alignment (ksw_align.cu): byte codes, query then target, like DevGJob
+struct DevAJob {
+	uint64_t seq_off;
+	int32_t  qlen, tlen, xtra;   // xtra: the reference's KSW_X* flags | threshold (ksw.h:6-9)
+	uint32_t idx;
+};
+static_assert(sizeof(DevAJob) == 24, "DevAJob must be 24 bytes");
+struct DevARes { int32_t score, te, qe, score2, te2, tb, qb, pad; };      // kswr_t, ksw.h:30-36
+static_assert(sizeof(DevARes) == 32, "DevARes must be 32 bytes");
+struct KswAlignParams {
+	int8_t  mat[25];
+	int8_t  pad[3];
+	int32_t o_del, e_del, o_ins, e_ins;
+	int32_t shift, qmax;         // ksw_qinit's q->shift and q->max (ksw.c:77-83)
+};
+
 struct DevGRes {
 	int32_t   score, n_cigar;
 	long long cigar_off;  // first of the job's n_cigar operations in the chunk's CIGAR pool

@@ -78,3 +78,10 @@ size_t ksw_gfast_smem_bytes(int qmax);
 cudaError_t ksw_launch_gfast(const DevGJob *jobs, const uint8_t *seq, const KswParams &P, const uint32_t *gorder, const DevGGroup *groups,
                              int n_groups, int qmax, int sm_count, uint2 *z, unsigned *counter, uint32_t *scratch,
                              unsigned long long *pool_used, uint32_t *cigar_pool, DevGRes *res, cudaStream_t st);
+
+// local alignment, the reference's ksw_align2 (ksw_align.cu): bytes_per_score 1 = the byte kernel (16 lanes per job), 2 = the
+// 16-bit kernel (8 lanes per job); jobs[order[0..n_jobs)] sorted by size; *bscr / *bscr_cap: scratch the launcher (re)allocates
+#define KSW_ALIGN_MAX_QLEN 4096
+cudaError_t ksw_launch_align(int bytes_per_score, const DevAJob *jobs, const uint32_t *order, int n_jobs, const uint8_t *seq,
+                             const KswAlignParams &A, int qmax, int tmax, int sm_count, void **bscr, size_t *bscr_cap,
+                             unsigned *counter, DevARes *res, cudaStream_t st);

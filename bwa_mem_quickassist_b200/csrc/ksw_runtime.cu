@@ -172,6 +172,11 @@ struct ksw_b200_ctx {
 	GStage g_st[2];                        // two chunks in flight: the host prepares one while the GPU works on the other
 	DevBuf g_deh, g_dqc, g_dz, g_dzfast, g_dcounter, g_dscratch;      // kernel scratch: used in stream order, one copy
 	std::vector<uint32_t> g_cigar, g_key, g_tmp, g_bucket;
+	// local alignment (ksw_b200_align_batch)
+	PinnedBuf a_hjobs, a_hseq, a_hres, a_horder;
+	DevBuf a_djobs, a_dseq, a_dres, a_dorder, a_dcounter;
+	void *a_bscr = nullptr;
+	size_t a_bscr_cap = 0;
 };
 
 namespace {
@@ -524,6 +529,9 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	ctx->g_st[0].release(); ctx->g_st[1].release();
+	ctx->a_hjobs.release(); ctx->a_hseq.release(); ctx->a_hres.release(); ctx->a_horder.release();
+	ctx->a_djobs.release(); ctx->a_dseq.release(); ctx->a_dres.release(); ctx->a_dorder.release(); ctx->a_dcounter.release();
+	if (ctx->a_bscr) { cudaFree(ctx->a_bscr); ctx->a_bscr = nullptr; ctx->a_bscr_cap = 0; }
 	ctx->g_deh.release(); ctx->g_dqc.release(); ctx->g_dz.release(); ctx->g_dzfast.release(); ctx->g_dcounter.release(); ctx->g_dscratch.release();
 	delete ctx->pool;
 	delete ctx;
@@ -1593,6 +1601,124 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
 		        (long long)n, tr_plan, tr_pack, tr_sort, tr_wait, tr_out, tr_up, tr_kern, tr_down);
 	if (cigar_pool) *cigar_pool = ctx->g_cigar.data();
 	if (n_cigar_total) *n_cigar_total = (int64_t)ctx->g_cigar.size();
+	return 0;
+}
+
+// ---- local alignment with start positions and second-best score (ksw_align.cu): the reference's ksw_align2.  Synchronous,
+// chunk by chunk on slot 0's stream.  Within a chunk the byte-kernel jobs (KSW_XBYTE) and the 16-bit jobs are each sorted
+// by (query length, target length): the 2 resp. 4 jobs that share a warp walk their rows in lockstep.
+int ksw_b200_align_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_ajob_t *jobs,
+                         const uint8_t *qpool, const uint8_t *tpool, ksw_b200_ares_t *res)
+{
+	if (!ctx || !cfg || n < 0 || (n > 0 && (!jobs || !res || !qpool || !tpool))) return fail(ctx, 1, "ksw_b200_align_batch: bad argument");
+	if (cfg->m != 5) return fail(ctx, 2, "ksw_b200: only m == 5 is supported (every reference caller passes 5)");
+	CU(cudaSetDevice(ctx->device));
+	Slot &s = ctx->slot[0];
+	KswAlignParams A;
+	memset(&A, 0, sizeof(A));
+	memcpy(A.mat, cfg->mat, 25);
+	A.o_del = cfg->o_del; A.e_del = cfg->e_del; A.o_ins = cfg->o_ins; A.e_ins = cfg->e_ins;
+	{
+		// ksw_qinit (ksw.c:77-83): shift = 256 - (most negative entry, at most 127) as a byte, max = largest entry (at least 0)
+		uint8_t shift = 127, mdiff = 0;
+		for (int a = 0; a < 25; ++a) {
+			if (cfg->mat[a] < (int8_t)shift) shift = (uint8_t)cfg->mat[a];
+			if (cfg->mat[a] > (int8_t)mdiff) mdiff = (uint8_t)cfg->mat[a];
+		}
+		A.qmax = mdiff;
+		A.shift = (uint8_t)(256 - shift);
+		if (A.qmax <= 0) return fail(ctx, 2, "ksw_b200_align_batch: the scoring matrix has no positive entry (the reference divides by it, ksw.c:224)");
+	}
+	const int64_t max_chunk_jobs = 1 << 20;
+	const size_t max_seq = (size_t)256 << 20;
+	std::vector<uint32_t> &tmp = ctx->g_tmp, &bucket = ctx->g_bucket;
+	int64_t first = 0;
+	while (first < n) {
+		int64_t last = first;
+		size_t seq_bytes = 0;
+		int64_t n_byte = 0;
+		int qmax[2] = {0, 0}, tmax[2] = {0, 0};
+		while (last < n && last - first < max_chunk_jobs) {
+			const ksw_b200_ajob_t &j = jobs[last];
+			if (j.qlen < 1 || j.tlen < 0) return fail(ctx, 2, "ksw_b200_align_batch: job with qlen < 1 or tlen < 0");
+			if (j.qlen > KSW_ALIGN_MAX_QLEN) return fail(ctx, 2, "ksw_b200_align_batch: query longer than 4096 (not supported by the mate-rescue kernel)");
+			const size_t sb = (size_t)j.qlen + (size_t)j.tlen;
+			if (last > first && seq_bytes + sb > max_seq) break;
+			seq_bytes += sb;
+			const int c = (j.xtra & 0x10000) ? 0 : 1;
+			n_byte += c == 0;
+			qmax[c] = std::max(qmax[c], j.qlen); tmax[c] = std::max(tmax[c], j.tlen);
+			++last;
+		}
+		const int64_t m = last - first;
+		CU(ctx->a_hjobs.reserve(sizeof(DevAJob) * (size_t)m));
+		CU(ctx->a_hseq.reserve(seq_bytes + 16));
+		CU(ctx->a_hres.reserve(sizeof(DevARes) * (size_t)m));
+		CU(ctx->a_horder.reserve(sizeof(uint32_t) * (size_t)m));
+		CU(ctx->a_djobs.reserve(sizeof(DevAJob) * (size_t)m));
+		CU(ctx->a_dseq.reserve(seq_bytes + 16));
+		CU(ctx->a_dres.reserve(sizeof(DevARes) * (size_t)m));
+		CU(ctx->a_dorder.reserve(sizeof(uint32_t) * (size_t)m));
+		CU(ctx->a_dcounter.reserve(sizeof(unsigned)));
+		DevAJob *hj = (DevAJob *)ctx->a_hjobs.p;
+		uint8_t *hs = (uint8_t *)ctx->a_hseq.p;
+		uint32_t *ho = (uint32_t *)ctx->a_horder.p;
+		{
+			size_t off = 0;
+			for (int64_t k = 0; k < m; ++k) {
+				const ksw_b200_ajob_t &j = jobs[first + k];
+				hj[k].seq_off = off; hj[k].qlen = j.qlen; hj[k].tlen = j.tlen; hj[k].xtra = j.xtra; hj[k].idx = (uint32_t)k;
+				off += (size_t)j.qlen + (size_t)j.tlen;
+			}
+			KswPool *tp = pool_of(ctx);
+			const int T = (int)std::max<int64_t>(1, std::min<int64_t>(tp->size(), m / 1024));
+			const int64_t per = (m + T - 1) / T;
+			auto body = [&](int t) {
+				const int64_t b = std::min<int64_t>(m, t * per), e = std::min<int64_t>(m, b + per);
+				for (int64_t k = b; k < e; ++k) {
+					const ksw_b200_ajob_t &j = jobs[first + k];
+					memcpy(hs + hj[k].seq_off, qpool + j.q_off, (size_t)j.qlen);
+					if (j.tlen) memcpy(hs + hj[k].seq_off + j.qlen, tpool + j.t_off, (size_t)j.tlen);
+				}
+			};
+			if (T == 1) body(0); else tp->run(T, body);
+		}
+		{
+			// order: byte-kernel jobs first, then the 16-bit ones; inside each by query length, then target length (descending):
+			// three stable counting-sort passes, least significant key first
+			const int NB = 4097;
+			tmp.resize((size_t)m);
+			auto pass = [&](const uint32_t *in, uint32_t *out, int nb, auto key) {
+				bucket.assign((size_t)nb + 1, 0);
+				for (int64_t x = 0; x < m; ++x) ++bucket[key(hj[in ? in[x] : (uint32_t)x]) + 1];
+				for (int x = 0; x < nb; ++x) bucket[x + 1] += bucket[x];
+				for (int64_t x = 0; x < m; ++x) { const uint32_t k = in ? in[x] : (uint32_t)x; out[bucket[key(hj[k])]++] = k; }
+			};
+			pass(nullptr, ho, NB, [&](const DevAJob &j) { return NB - 1 - std::min(j.tlen, NB - 1); });
+			pass(ho, tmp.data(), NB, [&](const DevAJob &j) { return NB - 1 - std::min(j.qlen, NB - 1); });
+			pass(tmp.data(), ho, 2, [&](const DevAJob &j) { return (j.xtra & 0x10000) ? 0 : 1; });
+		}
+		CU(cudaMemcpyAsync(ctx->a_djobs.p, hj, sizeof(DevAJob) * (size_t)m, cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemcpyAsync(ctx->a_dseq.p, hs, seq_bytes, cudaMemcpyHostToDevice, s.stream));
+		CU(cudaMemcpyAsync(ctx->a_dorder.p, ho, sizeof(uint32_t) * (size_t)m, cudaMemcpyHostToDevice, s.stream));
+		for (int c = 0; c < 2; ++c) {
+			const int64_t cnt = c == 0 ? n_byte : m - n_byte;
+			if (cnt <= 0) continue;
+			CU(ksw_launch_align(c == 0 ? 1 : 2, (const DevAJob *)ctx->a_djobs.p, (const uint32_t *)ctx->a_dorder.p + (c == 0 ? 0 : n_byte),
+			                    (int)cnt, (const uint8_t *)ctx->a_dseq.p, A, qmax[c], tmax[c], ctx->sm_count, &ctx->a_bscr, &ctx->a_bscr_cap,
+			                    (unsigned *)ctx->a_dcounter.p, (DevARes *)ctx->a_dres.p, s.stream));
+			ctx->launches++;
+		}
+		CU(cudaMemcpyAsync(ctx->a_hres.p, ctx->a_dres.p, sizeof(DevARes) * (size_t)m, cudaMemcpyDeviceToHost, s.stream));
+		CU(cudaStreamSynchronize(s.stream));
+		const DevARes *hr = (const DevARes *)ctx->a_hres.p;
+		for (int64_t k = 0; k < m; ++k) {
+			ksw_b200_ares_t &o = res[first + k];
+			o.score = hr[k].score; o.te = hr[k].te; o.qe = hr[k].qe; o.score2 = hr[k].score2; o.te2 = hr[k].te2; o.tb = hr[k].tb; o.qb = hr[k].qb;
+			o.reserved = 0;
+		}
+		first = last;
+	}
 	return 0;
 }
 

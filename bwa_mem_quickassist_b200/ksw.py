@@ -23,6 +23,10 @@ RJOB_DT = np.dtype([("q_off", "<u8"), ("t_pos", "<i8"), ("qlen", "<i4"), ("tlen"
 GJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("w", "<i4"),
                     ("reserved", "<i4")])                   # ksw_b200_gjob_t
 GRES_DT = np.dtype([("score", "<i4"), ("n_cigar", "<i4"), ("cigar_off", "<i8")])   # ksw_b200_gres_t
+AJOB_DT = np.dtype([("q_off", "<u8"), ("t_off", "<u8"), ("qlen", "<i4"), ("tlen", "<i4"), ("xtra", "<i4"), ("reserved", "<i4")])   # ksw_b200_ajob_t
+ARES_DT = np.dtype([("score", "<i4"), ("te", "<i4"), ("qe", "<i4"), ("score2", "<i4"), ("te2", "<i4"), ("tb", "<i4"), ("qb", "<i4"),
+                    ("reserved", "<i4")])                                          # ksw_b200_ares_t (kswr_t, ksw.h:30-36)
+KSW_XBYTE, KSW_XSTOP, KSW_XSUBO, KSW_XSTART = 0x10000, 0x20000, 0x40000, 0x80000   # ksw.h:6-9
 
 
 class KswB200Error(RuntimeError):
@@ -283,6 +287,17 @@ class KswB200:
                                                    _p(res), C.byref(pool), C.byref(total)), "ksw_b200_global_batch")
         cig = np.ctypeslib.as_array(pool, shape=(total.value,)).copy() if total.value else np.zeros(0, np.uint32)
         return res, cig
+
+    def align_batch(self, cfg: Cfg, jobs, qpool, tpool):
+        """ksw_b200_align_batch: the reference's ksw_align2 (local alignment, start positions, second-best score) for every
+        job (AJOB_DT; xtra = KSW_X* flags | threshold as mem_matesw passes them).  Returns res[ARES_DT]."""
+        jobs = np.ascontiguousarray(jobs, dtype=AJOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        tpool = np.ascontiguousarray(tpool, dtype=np.uint8)
+        res = np.zeros(jobs.shape[0], dtype=ARES_DT)
+        self._check(self.lib.ksw_b200_align_batch(self.ctx, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool), _p(tpool), _p(res)),
+                    "ksw_b200_align_batch")
+        return res
 
     def upload(self, cfg: Cfg, jobs, qpool, tpool) -> ResidentBatch:
         jobs, qpool, tpool = self._norm(jobs, qpool, tpool)

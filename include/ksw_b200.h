@@ -203,6 +203,33 @@ int ksw_b200_global_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_
                           const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
                           const uint32_t **cigar_pool, int64_t *n_cigar_total);
 
+/* ---- local alignment with start positions and second-best score ----------------------------- */
+/* Replaces the reference's ksw_align2 (bwa-0.7.8/ksw.h:62, ksw.c:329-354; the striped SSE2 kernels ksw_u8 / ksw_i16 of
+ * ksw.c:110-320), which mem_matesw calls once per rescue window (bwamem_pair.c:150).  Results are those of the reference
+ * bit for bit, including what its vector layout makes observable (see csrc/ksw_align.cu).  Sequences are byte codes 0..4.
+ * Domain: qlen >= 1 (<= 4096), and a KSW_XBYTE job must not saturate the byte kernel (qlen * max score + shift < 255, which
+ * mem_matesw guarantees, bwamem_pair.c:147): if it does, the job ends after the forward pass with score = 255, where the
+ * reference goes on with qe = -1 (undefined). */
+#define KSW_B200_XBYTE  0x10000    /* ksw.h:6-9: the flags of `xtra`; its low 16 bits are the score threshold */
+#define KSW_B200_XSTOP  0x20000
+#define KSW_B200_XSUBO  0x40000
+#define KSW_B200_XSTART 0x80000
+typedef struct {
+	uint64_t q_off, t_off;     /* byte offsets into qpool / tpool */
+	int32_t  qlen, tlen;
+	int32_t  xtra;             /* as passed to ksw_align2 */
+	int32_t  reserved;
+} ksw_b200_ajob_t;
+
+typedef struct {               /* kswr_t, ksw.h:30-36 (unset fields are -1 like g_defr, ksw.c:43) */
+	int32_t score, te, qe, score2, te2, tb, qb;
+	int32_t reserved;
+} ksw_b200_ares_t;
+
+/* cfg: mat, m (= 5), o_del, e_del, o_ins, e_ins are used */
+int ksw_b200_align_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_ajob_t *jobs,
+                         const uint8_t *qpool, const uint8_t *tpool, ksw_b200_ares_t *res);
+
 /* ---- one submission queue per GPU, shared by all host threads (cross-thread batch coalescing) - */
 /* The reference's workers (kt_for_batch, kthread_batch.c:18-56) each own a slice of the reads; with one private context
  * per worker every worker launches its own small batches.  A queue owns ONE context on its device and a server thread:

@@ -40,3 +40,46 @@ def test_align_oracle_known_answers(oracle_built):
     r = K.run_align_oracle(K.ABatch(K.make_cfg(), jobs, np.concatenate([q, np.zeros(16, np.uint8)]), np.concatenate([t, np.zeros(16, np.uint8)])))[0]
     assert (int(r["score"]), int(r["te"]), int(r["qe"]), int(r["tb"]), int(r["qb"])) == (80, 179, 79, 100, 0)
     assert int(r["score2"]) == 80 and int(r["te2"]) == 479
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_gpu_align_matesw_shaped_jobs(gpu_ctx, oracle_built):
+    for seed, cfg in enumerate(CFGS):
+        b = K.gen_align(3000, seed=740 + seed, cfg=cfg, max_q=150 if seed % 2 else 250)
+        mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), K.run_align_oracle(b))
+        assert mm is None, (seed, mm, b.jobs[mm[0]])
+
+
+@pytest.mark.gpu
+def test_gpu_align_every_flag_combination(gpu_ctx, oracle_built):
+    for seed, cfg in enumerate(CFGS):
+        b = K.gen_align(3000, seed=760 + seed, cfg=cfg, max_q=120, max_t=400, flags=ALL_FLAGS)
+        mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), K.run_align_oracle(b))
+        assert mm is None, (seed, mm, b.jobs[mm[0]])
+
+
+@pytest.mark.gpu
+def test_gpu_align_edges(gpu_ctx, oracle_built):
+    """Empty batch, empty targets, one-base queries, queries on every vector-length boundary, a long query."""
+    res = gpu_ctx.align_batch(K.make_cfg(), np.zeros(0, dtype=K.AJOB_DT), np.zeros(16, np.uint8), np.zeros(16, np.uint8))
+    assert res.shape[0] == 0
+    rng = np.random.default_rng(11)
+    shapes = [(1, 0), (1, 1), (1, 40), (7, 0), (8, 30), (9, 30), (15, 64), (16, 64), (17, 64), (31, 90), (32, 90), (33, 90), (249, 700), (250, 700),
+              (1000, 1500), (4096, 300)]
+    qs, ts = [], []
+    jobs = np.zeros(2 * len(shapes), dtype=K.AJOB_DT)
+    qo = to = 0
+    for k, (ql, tl) in enumerate(shapes + shapes):
+        q = rng.integers(0, 4, ql).astype(np.uint8); t = rng.integers(0, 4, tl).astype(np.uint8)
+        if tl > ql + 2: t[1:1 + ql] = q
+        xtra = K.KSW_XSUBO | K.KSW_XSTART | 5 | (K.KSW_XBYTE if (k < len(shapes) and ql < 250) else 0)
+        jobs[k] = (qo, to, ql, tl, xtra, 0)
+        qs.append(q); ts.append(t); qo += ql; to += tl
+    b = K.ABatch(K.make_cfg(), jobs, np.concatenate(qs + [np.zeros(16, np.uint8)]), np.concatenate(ts + [np.zeros(16, np.uint8)]))
+    mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), K.run_align_oracle(b))
+    assert mm is None, (mm, b.jobs[mm[0]])
+    from bwa_mem_quickassist_b200 import KswB200Error
+    bad = jobs[:1].copy(); bad["qlen"] = 0
+    with pytest.raises(KswB200Error):
+        gpu_ctx.align_batch(b.cfg, bad, b.qpool, b.tpool)
