@@ -11,10 +11,19 @@
 // way the SSE2 instruction it replaces does.  Per sub-warp, shared memory holds (H | E<<16) per column, the row copied at
 // the best score (Hmax, ksw.c:208-209) and the query profile (ksw.c:87-106); the second-best list (ksw.c:196-205) goes to
 // a per-warp scratch slab in HBM, one (score, row) pair per qualifying row at most.
+// The lazy-F loop (ksw.c:182-192) is where the SSE2 code spends its time on a real alignment: up to 16 x slen steps per row,
+// each a load, a store and a vote.  When o_ins >= 1 its result has a closed form: the loop stops early only where every
+// lane's own main-loop F already dominates what is left of the carried one (at a stop f - e <= H' - oe, and H' was not raised
+// by f itself, else f - e <= f - oe would need o <= 0), so H' = max(H, carry) with the carry propagated all the way:
+// carry into lane s = max over s' < s of (final f of lane s') - e_ins * slen * (s - s' - 1), a max-plus prefix scan over the
+// lanes (log2 P shuffles), decaying by e_ins per column inside the lane.  The kernel does that scan once per row and applies
+// the carry when the row is READ (next row's diagonal, the Hmax copy) — no extra pass over the row.  With o_ins == 0 (or gap
+// costs that wrap in the byte kernel) the early stop is observable and the kernel runs the loop literally (LIT = true).
 // Both passes of ksw_align2 run back to back in the same sub-warp: the forward pass, then — if KSW_XSTART asks for it and the
 // score passes the KSW_XSUBO threshold — the pass over the reversed prefixes with KSW_XSTOP (ksw.c:342-350), which, like the
 // reference, still walks all tlen rows (reversed prefix first) unless it stops at the score.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "ksw_dev.cuh"
 #include "ksw_launch.h"
 
@@ -35,7 +44,7 @@ __device__ __forceinline__ int sub_max(int v)
 
 // one call of ksw_u8 (P = 16) / ksw_i16 (P = 8) on the sub-warp's job; live = this sub-warp has a job in this pass.
 // rev: the sequences are the reversed prefixes query[qe1..0], target[te1..0] followed by target[te1+1..tlen) (ksw.c:343-345)
-template <int P>
+template <int P, bool LIT>
 __device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, const int qlen, const uint8_t *__restrict__ target,
                             const int tlen, const int xtra, const bool rev, const int qe1, const int te1, uint32_t *HE, uint16_t *HM,
                             int8_t *PR, const int cap, uint2 *bs, const KswAlignParams &A, const int sub, const int sl)
@@ -69,6 +78,8 @@ __device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, 
 	bool done = !live;
 	int t_next = 0;
 	if (live && tlen > 0) t_next = rev && 0 <= te1 ? target[te1] : target[0];
+	const int decay = e_ins * slen;                                       // what a carried F loses across one whole lane
+	int G = 0;                                                            // carry into this lane's segment from the previous row's lazy-F loop
 	for (int i = 0; i < rows_w; ++i) {
 		const bool act = !done && i < tlen;
 		if (!__any_sync(FULL, act)) break;
@@ -77,10 +88,10 @@ __device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, 
 		if (act && i + 1 < tlen) t_next = rev && i + 1 <= te1 ? target[te1 - i - 1] : target[i + 1];
 		const int8_t *S = PR + t * cap;
 		// h = H(i-1, -1): the last vector shifted up by one lane (ksw.c:147-148)
-		const int hl = act ? (int)(HE[(slen - 1) * P + sl] & 0xffffu) : 0;
+		const int hl = act ? max((int)(HE[(slen - 1) * P + sl] & 0xffffu), G - e_ins * (slen - 1)) : 0;
 		int h = __shfl_up_sync(FULL, hl, 1, P);
 		if (sl == 0) h = 0;
-		int f = 0, mx = 0;
+		int f = 0, mx = 0, c = G;
 		for (int j = 0; j < slen_w; ++j) {
 			if (act && j < slen) {
 				const uint32_t w = HE[j * P + sl];
@@ -98,13 +109,24 @@ __device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, 
 				e = max(max(0, e - e_del), max(0, hv - oe_del));          // ksw.c:164-167
 				f = max(max(0, f - e_ins), max(0, hv - oe_ins));          // ksw.c:169-171
 				HE[j * P + sl] = (uint32_t)hv | ((uint32_t)e << 16);
-				h = (int)(w & 0xffffu);                                   // H(i-1, j) for the next column
+				h = max((int)(w & 0xffffu), c);                           // H'(i-1, j): the stored H with the previous row's carry
+				c -= e_ins;
 			}
 		}
-		// the lazy-F loop (ksw.c:182-192 / 282-291): at most 16 rounds of slen steps; a round starts by shifting f up one
-		// lane; it ends for good at the first step after which no lane of the vector has f > H - oe_ins.  If every shifted
-		// f is zero the first step changes nothing and ends it, so it is skipped.
-		{
+		if (!LIT) {
+			// closed form of the lazy-F loop: carry into lane s = max over s' < s of f_end(s') - decay * (s - s' - 1)
+			int v = __shfl_up_sync(FULL, f, 1, P);
+			v = sl == 0 ? 0 : v;
+#pragma unroll
+			for (int d = 1; d < P; d <<= 1) {
+				const int o = __shfl_up_sync(FULL, v, d, P);
+				if (sl >= d) v = max(v, o - decay * d);
+			}
+			G = act ? max(v, 0) : 0;
+		} else {
+			// the lazy-F loop as it is (ksw.c:182-192 / 282-291): at most 16 rounds of slen steps; a round starts by shifting
+			// f up one lane; it ends for good at the first step after which no lane of the vector has f > H - oe_ins.  If
+			// every shifted f is zero the first step changes nothing and ends it, so it is skipped.
 			int fs = __shfl_up_sync(FULL, f, 1, P);
 			fs = sl == 0 ? 0 : fs;
 			const unsigned pos = __ballot_sync(FULL, act && fs > 0);
@@ -141,9 +163,10 @@ __device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, 
 				last_sc = imax; last_row = i;
 			}
 		}
-		if (act && imax > gmax) {                                         // ksw.c:206-211
+		if (act && imax > gmax) {                                         // ksw.c:206-211 (the kept row is H after the lazy-F loop)
 			gmax = imax; te = i;
-			for (int j = 0; j < slen; ++j) HM[j * P + sl] = (uint16_t)(HE[j * P + sl] & 0xffffu);
+			int cc = G;
+			for (int j = 0; j < slen; ++j, cc -= e_ins) HM[j * P + sl] = (uint16_t)max((int)(HE[j * P + sl] & 0xffffu), cc);
 			if ((P == 16 && gmax + shift >= 255) || gmax >= endsc) done = true;
 		}
 		__syncwarp();
@@ -186,7 +209,7 @@ __device__ APass align_pass(const bool live, const uint8_t *__restrict__ query, 
 	return r;
 }
 
-template <int P>
+template <int P, bool LIT>
 __global__ void __launch_bounds__(32)
 ksw_align_kernel(const DevAJob *__restrict__ jobs, const uint32_t *__restrict__ order, const int n_jobs, const uint8_t *__restrict__ seq,
                  const KswAlignParams A, const int cap, uint2 *__restrict__ bscr, const int tcap, unsigned *__restrict__ counter,
@@ -210,11 +233,11 @@ ksw_align_kernel(const DevAJob *__restrict__ jobs, const uint32_t *__restrict__ 
 		jb.seq_off = 0; jb.qlen = 1; jb.tlen = 0; jb.xtra = 0; jb.idx = 0;
 		if (have) jb = jobs[order[jidx]];
 		const uint8_t *query = seq + jb.seq_off, *target = query + jb.qlen;
-		const APass r = align_pass<P>(have, query, jb.qlen, target, jb.tlen, jb.xtra, false, 0, -1, HE, HM, PR, cap, bs, A, sub, sl);
+		const APass r = align_pass<P, LIT>(have, query, jb.qlen, target, jb.tlen, jb.xtra, false, 0, -1, HE, HM, PR, cap, bs, A, sub, sl);
 		// ksw.c:341: the start positions are wanted and the score passes the threshold; a saturated byte score (255) is outside the
 		// reference's defined behaviour (it goes on with qe = -1): the job ends here with score 255
 		const bool second = have && (jb.xtra & XSTART) && !((jb.xtra & XSUBO) && r.score < (jb.xtra & 0xffff)) && r.qe >= 0;
-		const APass rr = align_pass<P>(second, query, r.qe + 1, target, jb.tlen, XSTOP | r.score, true, r.qe, r.te, HE, HM, PR, cap, bs, A, sub, sl);
+		const APass rr = align_pass<P, LIT>(second, query, r.qe + 1, target, jb.tlen, XSTOP | r.score, true, r.qe, r.te, HE, HM, PR, cap, bs, A, sub, sl);
 		if (have && sl == 0) {
 			DevARes o;
 			o.score = r.score; o.te = r.te; o.qe = r.qe; o.score2 = r.score2; o.te2 = r.te2; o.tb = -1; o.qb = -1; o.pad = 0;
@@ -224,7 +247,7 @@ ksw_align_kernel(const DevAJob *__restrict__ jobs, const uint32_t *__restrict__ 
 	}
 }
 
-template <int P>
+template <int P, bool LIT>
 cudaError_t launch_one(const DevAJob *jobs, const uint32_t *order, int n_jobs, const uint8_t *seq, const KswAlignParams &A, int qmax,
                        int tmax, int sm_count, void **bscr, size_t *bscr_cap, unsigned *counter, DevARes *res, cudaStream_t st)
 {
@@ -238,10 +261,10 @@ cudaError_t launch_one(const DevAJob *jobs, const uint32_t *order, int n_jobs, c
 	e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 	if (e != cudaSuccess) return e;
 	if (smem > (size_t)optin) return cudaErrorInvalidValue;
-	e = cudaFuncSetAttribute(ksw_align_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+	e = cudaFuncSetAttribute(ksw_align_kernel<P, LIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_align_kernel<P>, 32, smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_align_kernel<P, LIT>, 32, smem);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
 	int blocks = sm_count * per_sm;
@@ -257,7 +280,7 @@ cudaError_t launch_one(const DevAJob *jobs, const uint32_t *order, int n_jobs, c
 	}
 	e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
 	if (e != cudaSuccess) return e;
-	ksw_align_kernel<P><<<blocks, 32, smem, st>>>(jobs, order, n_jobs, seq, A, cap, (uint2 *)*bscr, tcap, counter, res);
+	ksw_align_kernel<P, LIT><<<blocks, 32, smem, st>>>(jobs, order, n_jobs, seq, A, cap, (uint2 *)*bscr, tcap, counter, res);
 	return cudaGetLastError();
 }
 
@@ -267,6 +290,12 @@ cudaError_t ksw_launch_align(int bytes_per_score, const DevAJob *jobs, const uin
                              const KswAlignParams &A, int qmax, int tmax, int sm_count, void **bscr, size_t *bscr_cap,
                              unsigned *counter, DevARes *res, cudaStream_t st)
 {
-	return bytes_per_score == 1 ? launch_one<16>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st)
-	                            : launch_one<8>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
+	// the closed form of the lazy-F loop needs o_ins >= 1 after the truncation the vector constants go through (ksw.c:131-134)
+	const int vmask = bytes_per_score == 1 ? 0xff : 0xffff;
+	const bool lit = !((A.e_ins & vmask) < ((A.o_ins + A.e_ins) & vmask)) || A.e_ins < 0 || A.o_ins < 0 || getenv("KSW_B200_ALIGN_LITERAL") != nullptr;
+	if (bytes_per_score == 1)
+		return lit ? launch_one<16, true>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st)
+		           : launch_one<16, false>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
+	return lit ? launch_one<8, true>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st)
+	           : launch_one<8, false>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
 }
