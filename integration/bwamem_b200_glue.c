@@ -370,39 +370,19 @@ static void b200_cig_push(b200_cig_batch_t *B, const mem_opt_t *opt, const bntse
 	free(rseq);
 }
 
-static void b200_cig_lookahead(b200_thread_t *t, int tid, worker_t *w, int start, int batch_size)
+/* runs the collected jobs in up to three rounds of growing bands (the do-while of bwamem.c:1194-1200) and fills the table */
+static void b200_cig_rounds(b200_thread_t *t, int tid, worker_t *w, b200_cig_batch_t *first)
 {
 	const mem_opt_t *opt = w->opt;
-	b200_cig_batch_t cur, nxt;
+	b200_cig_batch_t cur = *first, nxt;
 	ksw_b200_cfg_t cfg;
 	ksw_b200_gres_t *res = 0;
 	int64_t m_res = 0;
-	int b, round;
-	size_t k;
-	memset(&cur, 0, sizeof(cur)); memset(&nxt, 0, sizeof(nxt));
+	int round;
+	memset(&nxt, 0, sizeof(nxt));
 	memcpy(cfg.mat, opt->mat, 25);
 	cfg.m = 5; cfg.o_del = opt->o_del; cfg.e_del = opt->e_del; cfg.o_ins = opt->o_ins; cfg.e_ins = opt->e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
-	for (b = 0; b < batch_size; ++b) {
-		bseq1_t *s = &w->seqs[start + b];
-		const mem_alnreg_v *regs = &w->regs[start + b];
-		for (k = 0; k < regs->n; ++k) {
-			const mem_alnreg_t *ar = &regs->a[k];
-			b200_cig_meta_t mt;
-			int tmp, w2;
-			if (ar->rb < 0 || ar->re < 0 || ar->score < opt->T) continue;     /* never printed (bwamem.c:1015, bwamem_pair.c) */
-			mt.qb = ar->qb; mt.qe = ar->qe; mt.rb = ar->rb; mt.re = ar->re;
-			/* mem_reg2aln, bwamem.c:1183-1191 */
-			if (bwa_fix_xref2(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->w, w->bns, w->pac, (uint8_t *)s->seq,
-			                  &mt.qb, &mt.qe, &mt.rb, &mt.re) < 0) continue;
-			tmp = infer_bw(mt.qe - mt.qb, mt.re - mt.rb, ar->truesc, opt->a, opt->o_del, opt->e_del);
-			w2 = infer_bw(mt.qe - mt.qb, mt.re - mt.rb, ar->truesc, opt->a, opt->o_ins, opt->e_ins);
-			w2 = w2 > tmp ? w2 : tmp;
-			if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
-			mt.w2 = w2; mt.truesc = ar->truesc; mt.last_sc = -(1 << 30); mt.read = start + b;
-			b200_cig_push(&cur, opt, w->bns, w->pac, (const uint8_t *)s->seq, &mt);
-		}
-	}
-	for (round = 0; round < 3 && cur.n > 0; ++round) {                           /* the do-while of bwamem.c:1194-1200 */
+	for (round = 0; round < 3 && cur.n > 0; ++round) {
 		const uint32_t *pool = 0;
 		int64_t total = 0, j;
 		if (cur.n > m_res) { m_res = cur.n; res = (ksw_b200_gres_t *)realloc(res, sizeof(ksw_b200_gres_t) * m_res); }
@@ -430,6 +410,289 @@ static void b200_cig_lookahead(b200_thread_t *t, int tid, worker_t *w, int start
 	free(cur.jobs); free(cur.meta); free(cur.q); free(cur.t);
 	free(nxt.jobs); free(nxt.meta); free(nxt.q); free(nxt.t);
 	free(res);
+	memset(first, 0, sizeof(*first));
+}
+
+/* one region as mem_reg2aln will see it (bwamem.c:1183-1191): the first band it tries */
+static void b200_cig_push_region(b200_cig_batch_t *B, worker_t *w, int read, int qb, int qe, int64_t rb, int64_t re, int truesc, int reg_w)
+{
+	const mem_opt_t *opt = w->opt;
+	b200_cig_meta_t mt;
+	int tmp, w2;
+	mt.qb = qb; mt.qe = qe; mt.rb = rb; mt.re = re;
+	if (bwa_fix_xref2(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, opt->w, w->bns, w->pac, (uint8_t *)w->seqs[read].seq,
+	                  &mt.qb, &mt.qe, &mt.rb, &mt.re) < 0) return;
+	tmp = infer_bw(mt.qe - mt.qb, mt.re - mt.rb, truesc, opt->a, opt->o_del, opt->e_del);
+	w2 = infer_bw(mt.qe - mt.qb, mt.re - mt.rb, truesc, opt->a, opt->o_ins, opt->e_ins);
+	w2 = w2 > tmp ? w2 : tmp;
+	if (w2 > opt->w) w2 = w2 < reg_w ? w2 : reg_w;
+	mt.w2 = w2; mt.truesc = truesc; mt.last_sc = -(1 << 30); mt.read = read;
+	b200_cig_push(B, opt, w->bns, w->pac, (const uint8_t *)w->seqs[read].seq, &mt);
+}
+
+static void b200_cig_lookahead(b200_thread_t *t, int tid, worker_t *w, int start, int batch_size)
+{
+	const mem_opt_t *opt = w->opt;
+	b200_cig_batch_t cur;
+	int b;
+	size_t k;
+	memset(&cur, 0, sizeof(cur));
+	for (b = 0; b < batch_size; ++b) {
+		const mem_alnreg_v *regs = &w->regs[start + b];
+		for (k = 0; k < regs->n; ++k) {
+			const mem_alnreg_t *ar = &regs->a[k];
+			/* single-end output never prints a region below -T (bwamem.c:1015); the paired path can (mem_sam_pe takes the pair
+			 * mem_pair chose, bwamem_pair.c:290-300) */
+			if (ar->rb < 0 || ar->re < 0 || (ar->score < opt->T && !(opt->flag & MEM_F_PE))) continue;
+			b200_cig_push_region(&cur, w, start + b, ar->qb, ar->qe, ar->rb, ar->re, ar->truesc, ar->w);
+		}
+	}
+	b200_cig_rounds(t, tid, w, &cur);
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Mate-rescue look-ahead.  mem_matesw (bwamem_pair.c:109-176) runs one local alignment (ksw_align2)
+ * per anchor region and admissible orientation whose pair is not yet consistent.  Its inputs — the mate (or its reverse
+ * complement) and the reference window [rb, re) derived from the anchor and the insert-size statistics — are all known
+ * once pass 1 and mem_pestat are done, so between mem_pestat and pass 2 the workers compute, for every pair, the jobs
+ * mem_sam_pe can ask for (a superset: orientations that a rescue found earlier in the same pair makes it skip are still
+ * computed), run them in batches on the GPU (ksw_b200_align_batch) and store the results in a table keyed by the EXACT
+ * inputs of ksw_align2 (flags, query bytes, window bytes).  bwamem_pair.c is compiled, unedited, with
+ * -Dksw_align2=b200_align2_hook: hit -> the stored kswr_t; miss -> one GPU call for that job.  KSW_B200_RESCUE=0: off
+ * (the hook calls the reference's own ksw_align2). */
+typedef struct b200_aln_entry {
+	struct b200_aln_entry *next;
+	uint64_t hash;
+	int32_t qlen, tlen, xtra;
+	kswr_t r;
+	/* followed by: uint8_t query[qlen]; uint8_t target[tlen] */
+} b200_aln_entry_t;
+static b200_aln_entry_t **b200_aln_table;
+static b200_arena_t b200_aln_arena[B200_MAX_WORKERS];
+static long long b200_aln_hits, b200_aln_misses, b200_aln_jobs;
+static double b200_t_rescue;
+static ksw_b200_ctx_t *b200_aln_ctx[B200_MAX_GPUS];
+static pthread_mutex_t b200_aln_mu[B200_MAX_GPUS];
+static pthread_once_t b200_aln_once = PTHREAD_ONCE_INIT;
+static void b200_aln_init(void) { int g; for (g = 0; g < B200_MAX_GPUS; ++g) pthread_mutex_init(&b200_aln_mu[g], 0); }
+
+static int b200_rescue_on(void)
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("KSW_B200_RESCUE"); v = !(e && e[0] == '0'); }
+	return v;
+}
+
+static void b200_aln_reset(void)                         /* single-threaded: called between chunks */
+{
+	int t;
+	if (!b200_aln_table) b200_aln_table = (b200_aln_entry_t **)calloc(B200_CIG_BUCKETS, sizeof(void *));
+	else memset(b200_aln_table, 0, sizeof(void *) * B200_CIG_BUCKETS);
+	for (t = 0; t < B200_MAX_WORKERS; ++t) { b200_aln_arena[t].cur = 0; b200_aln_arena[t].used = 0; }
+}
+
+static uint64_t b200_aln_hash(int qlen, const uint8_t *q, int tlen, const uint8_t *t, int xtra)
+{
+	uint64_t h = 1469598103934665603ull ^ ((uint64_t)(uint32_t)qlen << 32 | (uint32_t)tlen) ^ ((uint64_t)(uint32_t)xtra * 0x9E3779B97F4A7C15ull);
+	int i;
+	for (i = 0; i < qlen; ++i) h = (h ^ q[i]) * 1099511628211ull;
+	for (i = 0; i + 8 <= tlen; i += 8) { uint64_t x; memcpy(&x, t + i, 8); h = (h ^ x) * 1099511628211ull; }
+	for (; i < tlen; ++i) h = (h ^ t[i]) * 1099511628211ull;
+	return h;
+}
+
+static const b200_aln_entry_t *b200_aln_find(uint64_t h, int qlen, const uint8_t *q, int tlen, const uint8_t *t, int xtra)
+{
+	const b200_aln_entry_t *e;
+	if (!b200_aln_table) return 0;
+	for (e = b200_aln_table[h & (B200_CIG_BUCKETS - 1)]; e; e = e->next) {
+		const uint8_t *p = (const uint8_t *)(e + 1);
+		if (e->hash != h || e->qlen != qlen || e->tlen != tlen || e->xtra != xtra) continue;
+		if (memcmp(p, q, qlen) != 0 || memcmp(p + qlen, t, tlen) != 0) continue;
+		return e;
+	}
+	return 0;
+}
+
+static void b200_aln_insert(int tid, int qlen, const uint8_t *q, int tlen, const uint8_t *t, int xtra, const ksw_b200_ares_t *r)
+{
+	b200_aln_entry_t *e = (b200_aln_entry_t *)b200_arena_alloc(&b200_aln_arena[tid], sizeof(b200_aln_entry_t) + (size_t)qlen + tlen);
+	uint8_t *p;
+	b200_aln_entry_t **slot;
+	if (!e) return;
+	p = (uint8_t *)(e + 1);
+	e->hash = b200_aln_hash(qlen, q, tlen, t, xtra);
+	e->qlen = qlen; e->tlen = tlen; e->xtra = xtra;
+	e->r.score = r->score; e->r.te = r->te; e->r.qe = r->qe; e->r.score2 = r->score2; e->r.te2 = r->te2; e->r.tb = r->tb; e->r.qb = r->qb;
+	memcpy(p, q, qlen); memcpy(p + qlen, t, tlen);
+	slot = &b200_aln_table[e->hash & (B200_CIG_BUCKETS - 1)];
+	do { e->next = *(b200_aln_entry_t * volatile *)slot; } while (!__sync_bool_compare_and_swap(slot, e->next, e));
+}
+
+/* one batch on GPU `gpu` through that GPU's alignment context (shared by the workers: the GPU runs one batch at a time anyway) */
+static void b200_aln_run(int gpu, const mem_opt_t *opt, int64_t n, const ksw_b200_ajob_t *jobs, const uint8_t *q, const uint8_t *t, ksw_b200_ares_t *res)
+{
+	ksw_b200_cfg_t cfg;
+	pthread_once(&b200_aln_once, b200_aln_init);
+	memcpy(cfg.mat, opt->mat, 25);
+	cfg.m = 5; cfg.o_del = opt->o_del; cfg.e_del = opt->e_del; cfg.o_ins = opt->o_ins; cfg.e_ins = opt->e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
+	pthread_mutex_lock(&b200_aln_mu[gpu]);
+	if (!b200_aln_ctx[gpu]) {
+		if (ksw_b200_ctx_create(gpu, &b200_aln_ctx[gpu]) != 0) err_fatal(__func__, "no usable CUDA device: the B200 path has no CPU fallback");
+		ksw_b200_ctx_set_pack_threads(b200_aln_ctx[gpu], 2);
+	}
+	if (ksw_b200_align_batch(b200_aln_ctx[gpu], &cfg, n, jobs, q, t, res) != 0)
+		err_fatal(__func__, "GPU local alignment failed: %s", ksw_b200_strerror(b200_aln_ctx[gpu]));
+	pthread_mutex_unlock(&b200_aln_mu[gpu]);
+}
+
+static const mem_opt_t *b200_aln_opt;                  /* the options of the running mem_process_seqs (for the miss path) */
+
+kswr_t b200_align2_hook(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat, int o_del, int e_del,
+                        int o_ins, int e_ins, int xtra, kswq_t **qry)
+{
+	kswr_t r;
+	ksw_b200_ajob_t job;
+	ksw_b200_ares_t ar;
+	const mem_opt_t *opt = b200_aln_opt;
+	if (!b200_rescue_on() || qry || m != 5 || qlen < 1 || qlen > 4096 || !opt || memcmp(mat, opt->mat, 25) != 0 || o_del != opt->o_del ||
+	    e_del != opt->e_del || o_ins != opt->o_ins || e_ins != opt->e_ins)
+		return ksw_align2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra, qry);   /* not mem_matesw's call */
+	{
+		const b200_aln_entry_t *e = b200_aln_find(b200_aln_hash(qlen, query, tlen, target, xtra), qlen, query, tlen, target, xtra);
+		if (e) { __sync_fetch_and_add(&b200_aln_hits, 1); return e->r; }
+	}
+	/* miss: one job on the GPU */
+	__sync_fetch_and_add(&b200_aln_misses, 1);
+	if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
+	if (b200_n_gpus < 1) err_fatal(__func__, "no usable CUDA device: the B200 path has no CPU fallback");
+	job.q_off = 0; job.t_off = 0; job.qlen = qlen; job.tlen = tlen; job.xtra = xtra; job.reserved = 0;
+	b200_aln_run(0, opt, 1, &job, query, target, &ar);
+	r.score = ar.score; r.te = ar.te; r.qe = ar.qe; r.score2 = ar.score2; r.te2 = ar.te2; r.tb = ar.tb; r.qb = ar.qb;
+	return r;
+}
+
+typedef struct { int64_t rb; int read, is_rev; } b200_aln_meta_t;        /* window start, index of the mate in seqs[], strand */
+typedef struct { ksw_b200_ajob_t *jobs; b200_aln_meta_t *meta; int64_t n, m; uint8_t *q, *t; size_t nq, mq, nt, mt; } b200_aln_batch_t;
+
+/* the orientation of two hits and their distance (the reference's mem_infer_dir, bwamem_pair.c:27-35, is static there) */
+static int b200_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist)
+{
+	const int r1 = b1 >= l_pac, r2 = b2 >= l_pac;
+	const int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;         /* hit 2 on the strand of hit 1 */
+	*dist = p2 > b1 ? p2 - b1 : b1 - p2;
+	return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
+}
+
+/* the jobs mem_matesw(opt, l_pac, pac, pes, a, l_ms, ms, ma) can run, with `ma` as it is before any rescue (bwamem_pair.c:112-150) */
+static void b200_aln_push_matesw(b200_aln_batch_t *B, const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4],
+                                 const mem_alnreg_t *a, int l_ms, const uint8_t *ms, const mem_alnreg_v *ma, int mate_read)
+{
+	const int64_t l_pac = bns->l_pac;
+	int skip[4], r;
+	size_t i;
+	if (l_ms < 1 || l_ms > 4096) return;
+	for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+	for (i = 0; i < ma->n; ++i) {
+		int64_t dist;
+		r = b200_infer_dir(l_pac, a->rb, ma->a[i].rb, &dist);
+		if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+	}
+	for (r = 0; r < 4; ++r) {
+		const int is_rev = (r >> 1) != (r & 1), is_larger = !(r >> 1);
+		int64_t rb, re, len;
+		uint8_t *ref;
+		int k;
+		if (skip[r]) continue;
+		if (!is_rev) {
+			rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
+			re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
+		} else {
+			rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
+			re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
+		}
+		if (rb < 0) rb = 0;
+		if (re > l_pac << 1) re = l_pac << 1;
+		ref = bns_get_seq(l_pac, pac, rb, re, &len);
+		if (len == re - rb && len >= 0) {
+			if (B->n == B->m) {
+				B->m = B->m ? B->m << 1 : 1024;
+				B->jobs = (ksw_b200_ajob_t *)realloc(B->jobs, sizeof(ksw_b200_ajob_t) * B->m);
+				B->meta = (b200_aln_meta_t *)realloc(B->meta, sizeof(b200_aln_meta_t) * B->m);
+			}
+			if (B->nq + l_ms > B->mq) { B->mq = (B->mq ? B->mq << 1 : 1 << 18) + l_ms; B->q = (uint8_t *)realloc(B->q, B->mq); }
+			if (B->nt + len > B->mt) { B->mt = (B->mt ? B->mt << 1 : 1 << 20) + len; B->t = (uint8_t *)realloc(B->t, B->mt); }
+			if (is_rev) for (k = 0; k < l_ms; ++k) B->q[B->nq + l_ms - 1 - k] = ms[k] < 4 ? 3 - ms[k] : 4;
+			else memcpy(B->q + B->nq, ms, l_ms);
+			memcpy(B->t + B->nt, ref, len);
+			B->jobs[B->n].q_off = B->nq; B->jobs[B->n].t_off = B->nt; B->jobs[B->n].qlen = l_ms; B->jobs[B->n].tlen = (int)len;
+			B->jobs[B->n].xtra = KSW_XSUBO | KSW_XSTART | (l_ms * opt->a < 250 ? KSW_XBYTE : 0) | (opt->min_seed_len * opt->a);
+			B->jobs[B->n].reserved = 0;
+			B->meta[B->n].rb = rb; B->meta[B->n].read = mate_read; B->meta[B->n].is_rev = is_rev;
+			B->nq += l_ms; B->nt += len; ++B->n;
+		}
+		free(ref);
+	}
+}
+
+/* kt_for_batch body over PAIRS [start, start + batch_size): collect, run on this worker's GPU, fill the table */
+static void worker_rescue_b200(void *data, int start, int batch_size, int tid)
+{
+	worker_t *w = (worker_t *)data;
+	const mem_opt_t *opt = w->opt;
+	b200_aln_batch_t B;
+	ksw_b200_ares_t *res;
+	double t0 = realtime();
+	int p, i;
+	int64_t k;
+	size_t j;
+	memset(&B, 0, sizeof(B));
+	if (b200_n_gpus < 0) b200_n_gpus = b200_gpu_count();
+	for (p = start; p < start + batch_size; ++p) {
+		const bseq1_t *s = &w->seqs[p << 1];
+		const mem_alnreg_v *a = &w->regs[p << 1];
+		for (i = 0; i < 2; ++i) {                                          /* mem_sam_pe, bwamem_pair.c:254-261 */
+			int n_anchor = 0;
+			for (j = 0; j < a[i].n && n_anchor < opt->max_matesw; ++j) {
+				if (a[i].a[j].score < a[i].a[0].score - opt->pen_unpaired) continue;
+				++n_anchor;
+				b200_aln_push_matesw(&B, opt, w->bns, w->pac, w->pes, &a[i].a[j], s[!i].l_seq, (const uint8_t *)s[!i].seq, &a[!i], (p << 1) + !i);
+			}
+		}
+	}
+	if (B.n > 0) {
+		res = (ksw_b200_ares_t *)malloc(sizeof(ksw_b200_ares_t) * B.n);
+		b200_aln_run(tid % (b200_n_gpus < B200_MAX_GPUS ? b200_n_gpus : B200_MAX_GPUS), opt, B.n, B.jobs, B.q, B.t, res);
+		for (k = 0; k < B.n; ++k)
+			b200_aln_insert(tid, B.jobs[k].qlen, B.q + B.jobs[k].q_off, B.jobs[k].tlen, B.t + B.jobs[k].t_off, B.jobs[k].xtra, &res[k]);
+		__sync_fetch_and_add(&b200_aln_jobs, B.n);
+		if (b200_cigar_mode() == 1) {
+			/* the regions these rescues can add (bwamem_pair.c:151-160: truesc = 0 and w = 0 after the memset) will ask pass 2
+			 * for their CIGAR like any other: compute those ahead too, or every one of them is a single-job miss */
+			b200_cig_batch_t C;
+			const int64_t l_pac = w->bns->l_pac;
+			double t1 = realtime();
+			memset(&C, 0, sizeof(C));
+			for (k = 0; k < B.n; ++k) {
+				const ksw_b200_ares_t *x = &res[k];
+				const b200_aln_meta_t *mt = &B.meta[k];
+				const int l_ms = B.jobs[k].qlen;
+				int qb, qe;
+				int64_t rb, re;
+				if (x->score < opt->min_seed_len || x->qb < 0) continue;
+				qb = mt->is_rev ? l_ms - (x->qe + 1) : x->qb;
+				qe = mt->is_rev ? l_ms - x->qb : x->qe + 1;
+				rb = mt->is_rev ? (l_pac << 1) - (mt->rb + x->te + 1) : mt->rb + x->tb;
+				re = mt->is_rev ? (l_pac << 1) - (mt->rb + x->tb) : mt->rb + x->te + 1;
+				b200_cig_push_region(&C, w, mt->read, qb, qe, rb, re, 0, 0);
+			}
+			b200_cig_rounds(b200_thread_state(opt, w->bns, w->pac, tid), tid, w, &C);
+			b200_add_time(&b200_t_cigar, realtime() - t1);
+		}
+		free(res);
+	}
+	free(B.jobs); free(B.meta); free(B.q); free(B.t);
+	b200_add_time(&b200_t_rescue, realtime() - t0);
 }
 
 typedef struct { int handle; int short_ok; mem_alnreg_t short_reg; } b200_chain_state_t;
@@ -539,14 +802,22 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
 		else mem_pestat(opt, bns->l_pac, n, regs, pes);
 	}
+	b200_aln_opt = opt;
+	if ((opt->flag & MEM_F_PE) && !(opt->flag & MEM_F_NO_RESCUE) && b200_rescue_on()) {           /* mate-rescue look-ahead */
+		b200_aln_reset();
+		/* few pairs need rescue, and a GPU batch should carry thousands of jobs: one slice of the chunk's pairs per thread */
+		const int per = ((n >> 1) + opt->n_threads - 1) / opt->n_threads;
+		kt_for_batch(opt->n_threads, worker_rescue_b200, &w, n >> 1, per > 2048 ? per : 2048);
+	}
 	kt_for(opt->n_threads, worker2, &w, (opt->flag & MEM_F_PE) ? n >> 1 : n);          /* pass 2: unchanged */
 	free(regs);
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f CPU sec, %.3f real sec (extension on B200; thread-seconds so far: "
 		        "init %.2f, seed+chain %.2f, plan %.2f, gpu passes %.2f, replay %.2f, cigar look-ahead %.2f; pass1 %.3f s real; "
-		        "global alignments so far: %lld computed ahead, %lld hits, %lld misses)\n", __func__, n,
+		        "global alignments so far: %lld computed ahead, %lld hits, %lld misses; mate-rescue alignments: look-ahead %.2f thread-s, "
+		        "%lld computed ahead, %lld hits, %lld misses)\n", __func__, n,
 		        cputime() - ctime, realtime() - rtime, b200_t_init, b200_t_seed, b200_t_plan, b200_t_gpu, b200_t_replay, b200_t_cigar,
-		        t_pass1, b200_cig_jobs, b200_cig_hits, b200_cig_misses);
+		        t_pass1, b200_cig_jobs, b200_cig_hits, b200_cig_misses, b200_t_rescue, b200_aln_jobs, b200_aln_hits, b200_aln_misses);
 	if (bwa_verbose >= 3 && b200_queue_on() && b200_queue[0]) {
 		int64_t nb = 0, ns = 0;
 		ksw_b200_queue_stats(b200_queue[0], &nb, &ns);

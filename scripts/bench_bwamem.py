@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--genome", type=int, default=0, help="override the genome length of the selected configs (bp)")
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads (SE) / pairs (PE) of the selected configs")
     ap.add_argument("--no-cigar-off", action="store_true", help="skip the extra run with the CIGAR look-ahead off")
+    ap.add_argument("--rescue-off", action="store_true", help="one more run with the mate-rescue look-ahead off (KSW_B200_RESCUE=0)")
     ap.add_argument("--gpus", type=int, default=0, help="KSW_B200_GPUS of the B200-bound build (0 = all visible)")
     a = ap.parse_args()
     sc = a.scale
@@ -53,6 +54,8 @@ def main():
         ("config1 SE100 1Mbp 1%sub 0.1%indel", dict(genome=1_000_000, pe=False, n=int(4_000_000 * sc), L=100, sub=0.01, indel=0.001, imax=1)),
         ("config3-shape PE150 (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(1_500_000 * sc), L=150, sub=0.01, indel=0.001, imax=1)),
         ("config4-shape PE250 high-indel (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(600_000 * sc), L=250, sub=0.03, indel=0.002, imax=12)),
+        # one mate of 15 % of the pairs cannot be seeded, 3 % are junk: mem_matesw's local alignments dominate pass 2
+        ("rescue PE150, 15 % of the pairs need mate rescue (10 Mbp genome)", dict(genome=10_000_000, pe=True, n=int(1_000_000 * sc), L=150, sub=0.01, indel=0.001, imax=1, rescue=0.15, junk=0.03)),
     ]
     if a.only:
         cfgs = [(n, c) for n, c in cfgs if a.only in n]
@@ -68,7 +71,8 @@ def main():
             S.bwa_index(fa)
             if c["pe"]:
                 reads = [os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq")]
-                S.write_reads_fast(reads, g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"])
+                S.write_reads_fast(reads, g, c["n"], c["L"], seed=2, sub=c["sub"], indel=c["indel"], indel_max=c["imax"],
+                                   rescue_frac=c.get("rescue", 0.0), junk_frac=c.get("junk", 0.0))
                 n_reads = 2 * c["n"]
             else:
                 reads = [os.path.join(d, "r.fq")]
@@ -87,6 +91,18 @@ def main():
                 env0 = dict(env or os.environ, KSW_B200_CIGAR="0")
                 t_b200_0, e_b200_0 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200_0.sam"), a.threads, extra=["-b", str(a.batch)], env=env0)
                 ok0, _ = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200_0.sam"))
+            rescue = None
+            if c["pe"]:
+                import re
+                mm = re.findall(r"mate-rescue alignments: look-ahead ([\d.]+) thread-s, (\d+) computed ahead, (\d+) hits, (\d+) misses", e_b200)
+                rescue = {"lookahead_thread_s": float(mm[-1][0]), "computed_ahead": int(mm[-1][1]), "hits": int(mm[-1][2]), "misses": int(mm[-1][3])} if mm else None
+                if a.rescue_off and rescue is not None:
+                    env1 = dict(env or os.environ, KSW_B200_RESCUE="0")
+                    t1, e1 = timed(S.BWA_B200, fa, reads, os.path.join(d, "b200_1.sam"), a.threads, extra=["-b", str(a.batch)], env=env1)
+                    ok1, _ = S.sam_equal(os.path.join(d, "stock.sam"), os.path.join(d, "b200_1.sam"))
+                    c1 = chunk_times(e1)
+                    rescue.update(off_wall_s=round(t1, 3), off_sam_identical_minus_PG=bool(ok1),
+                                  off_steady_reads_per_s=round(sum(r for r, _ in c1[1:]) / max(sum(t for _, t in c1[1:]), 1e-9)) if len(c1) > 1 else None)
             cb0 = chunk_times(e_b200_0)
             sb0 = sum(r for r, _ in cb0[1:]) / max(sum(t for _, t in cb0[1:]), 1e-9) if len(cb0) > 1 else None
             cs, cb = chunk_times(e_stock), chunk_times(e_b200)
@@ -102,6 +118,7 @@ def main():
                    "cigar_lookahead": {"computed_ahead_hits_misses": cigar_stats(e_b200),
                                        "off_wall_s": round(t_b200_0, 3), "off_steady_reads_per_s": round(sb0) if sb0 else None,
                                        "off_sam_identical_minus_PG": ok0},
+                   "mate_rescue_lookahead": rescue,
                    "n_gpus": a.gpus or "all visible", "genome_bp": c["genome"]}
             print(json.dumps(row), flush=True)
             rows.append(row)

@@ -181,8 +181,11 @@ def _write_fastq_fixed(path, prefix, reads):
     buf.tofile(path)
 
 
-def write_reads_fast(paths, genome, n, length, seed, sub=0.01, indel=0.001, indel_max=1, ins_mean=None, ins_sd=None, chunk=500_000):
-    """SE if len(paths) == 1 else PE (FR orientation, insert ~ N(ins_mean, ins_sd))."""
+def write_reads_fast(paths, genome, n, length, seed, sub=0.01, indel=0.001, indel_max=1, ins_mean=None, ins_sd=None, chunk=500_000,
+                     rescue_frac=0.0, rescue_sub=0.18, junk_frac=0.0):
+    """SE if len(paths) == 1 else PE (FR orientation, insert ~ N(ins_mean, ins_sd)).  PE only: in a fraction `rescue_frac`
+    of the pairs one mate (either, at random) gets `rescue_sub` more substitutions per base — too many for a 19 bp seed to survive in most of them, so
+    the aligner finds it only by mate rescue (mem_matesw) — and in `junk_frac` of the pairs one mate is random sequence."""
     rng = np.random.default_rng(seed)
     G = len(genome)
     pe = len(paths) == 2
@@ -208,6 +211,21 @@ def write_reads_fast(paths, genome, n, length, seed, sub=0.01, indel=0.001, inde
             b = np.where(rev[:, None], f1, f2)
             r1 = _mutate_matrix(rng, a, length, sub, indel, indel_max)
             r2 = _mutate_matrix(rng, b, length, sub, indel, indel_max)
+            if rescue_frac > 0 or junk_frac > 0:
+                u = rng.random(m)
+                which = rng.random(m) < 0.5
+                hard = u < rescue_frac
+                junk = (u >= rescue_frac) & (u < rescue_frac + junk_frac)
+                for r, sel in ((r1, which), (r2, ~which)):
+                    rows = np.flatnonzero(hard & sel)
+                    if rows.size:
+                        mut = rng.random((rows.size, length)) < rescue_sub
+                        blk = r[rows]
+                        blk[mut] = (blk[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+                        r[rows] = blk
+                    rows = np.flatnonzero(junk & sel)
+                    if rows.size:
+                        r[rows] = rng.integers(0, 4, size=(rows.size, length), dtype=np.uint8)
             for path, r in ((paths[0], r1), (paths[1], r2)):
                 tmp = path + ".part"
                 _write_fastq_fixed(tmp, f"p{done // chunk:03d}_", r)

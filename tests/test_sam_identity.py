@@ -123,3 +123,29 @@ def test_pe250_high_indel_byte_identical(tmp_path):
     S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_rounds.sam"), threads=4, env=env)
     ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_rounds.sam"))
     assert ok, ("rounds", why)
+
+
+@pytest.mark.gpu
+@need_b200
+def test_pe_mate_rescue_byte_identical(tmp_path):
+    """Pairs in which one mate cannot be seeded (18 % extra substitutions) or is junk: pass 2 finds it by mate rescue (mem_matesw ->
+    ksw_align2), which the B200-bound build computes ahead on the GPU.  The SAM must not change, most look-ups
+    must hit, and with the look-ahead off (the reference's own SSE2 ksw_align2) the SAM is the same again."""
+    import re
+    fa = str(tmp_path / "ref.fa")
+    g = S.write_genome(fa, 2_000_000, seed=41)
+    S.bwa_index(fa)
+    for L, n in ((150, 30000), (250, 12000)):                                   # byte kernel (150 * 1 < 250) and 16-bit kernel
+        f1, f2 = str(tmp_path / f"r1_{L}.fq"), str(tmp_path / f"r2_{L}.fq")
+        S.write_reads_fast([f1, f2], g, n, L, seed=42 + L, sub=0.01, indel=0.002, indel_max=3, rescue_frac=0.2, junk_frac=0.05)
+        S.bwa_mem(S.BWA_STOCK, fa, [f1, f2], str(tmp_path / "stock.sam"), threads=4)
+        err = S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200.sam"), threads=4)
+        ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200.sam"))
+        assert ok, (L, why)
+        mm = re.findall(r"mate-rescue alignments: look-ahead [\d.]+ thread-s, (\d+) computed ahead, (\d+) hits, (\d+) misses", err)
+        assert mm, err[-600:]
+        ahead, hits, misses = (int(x) for x in mm[-1])
+        assert ahead > n // 10 and hits > n // 10 and misses <= hits // 50, (L, ahead, hits, misses)
+        S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_off.sam"), threads=4, env=dict(os.environ, KSW_B200_RESCUE="0"))
+        ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_off.sam"))
+        assert ok, ("rescue look-ahead off", L, why)
