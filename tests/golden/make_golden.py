@@ -1,5 +1,5 @@
 """Generates tests/golden/ksw_extend_golden.npz from the REFERENCE's own ksw_extend2, ksw_global_golden.npz from its
-ksw_global2 (oracle/_ref/libksw_ref.so = bwa-0.7.8/ksw.c compiled unmodified by oracle/Makefile) and
+ksw_global2, ksw_align_golden.npz from its ksw_align2 (oracle/_ref/libksw_ref.so = bwa-0.7.8/ksw.c compiled unmodified by oracle/Makefile) and
 chain2aln_golden.npz from its mem_chain2aln (oracle/_ref/libbwa_ref.so).
 
 Run in the build container (where /root/reference is mounted):  python tests/golden/make_golden.py
@@ -62,6 +62,29 @@ def main():
         out[f"{name}.cigar"] = cig.astype(np.uint32)
         print("global", name, b.n, "jobs", len(cig), "operations")
     path = os.path.join(HERE, "ksw_global_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+    # local alignment (mate rescue): kswr_t records from the reference's own ksw_align2 (striped SSE2 kernels)
+    flags = [0, K.KSW_XBYTE, K.KSW_XSTART, K.KSW_XSUBO, K.KSW_XSUBO | K.KSW_XSTART, K.KSW_XBYTE | K.KSW_XSUBO | K.KSW_XSTART,
+             K.KSW_XSTOP, K.KSW_XSTOP | K.KSW_XSTART, K.KSW_XBYTE | K.KSW_XSTOP | K.KSW_XSUBO | K.KSW_XSTART]
+    asets = {
+        "matesw150": K.gen_align(500, seed=301, max_q=150, max_t=700),
+        "matesw250": K.gen_align(300, seed=302, max_q=250, max_t=900),
+        "flags": K.gen_align(600, seed=303, max_q=100, max_t=300, flags=flags),
+        "asym": K.gen_align(300, seed=304, cfg=K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3), max_q=120, max_t=400),
+        "zero_open": K.gen_align(300, seed=305, cfg=K.make_cfg(a=3, b=2, o_del=0, e_del=1, o_ins=0, e_ins=1), max_q=80, max_t=300, flags=flags),
+    }
+    out = {}
+    for name, b in asets.items():
+        res = K.run_align_ref(b, threads=4)
+        out[f"{name}.cfg"] = np.frombuffer(bytes(b.cfg), dtype=np.uint8).copy()
+        out[f"{name}.jobs"] = b.jobs
+        out[f"{name}.qpool"] = b.qpool
+        out[f"{name}.tpool"] = b.tpool
+        out[f"{name}.res"] = res
+        print("align", name, b.n, "jobs")
+    path = os.path.join(HERE, "ksw_align_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 

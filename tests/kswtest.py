@@ -808,3 +808,16 @@ def gen_align(n: int, seed: int, cfg: Cfg | None = None, max_q: int = 250, max_t
         jobs[k] = (qo, to, ql, tl, xtra, 0)
         qs.append(q); ts.append(t); qo += ql; to += tl
     return ABatch(cfg, jobs, np.concatenate(qs + [np.zeros(16, np.uint8)]), np.concatenate(ts + [np.zeros(16, np.uint8)]))
+
+
+ALIGN_GOLDEN = os.path.join(ROOT, "tests", "golden", "ksw_align_golden.npz")
+
+
+def load_align_golden():
+    """{name: (ABatch, res)} from the committed fixture made from the compiled reference's ksw_align2."""
+    z = np.load(ALIGN_GOLDEN)
+    out = {}
+    for nm in sorted({k.split(".")[0] for k in z.files}):
+        cfg = Cfg.from_buffer_copy(z[f"{nm}.cfg"].tobytes())
+        out[nm] = (ABatch(cfg, z[f"{nm}.jobs"].astype(AJOB_DT), z[f"{nm}.qpool"], z[f"{nm}.tpool"]), z[f"{nm}.res"].astype(ARES_DT))
+    return out

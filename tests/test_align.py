@@ -27,6 +27,16 @@ def test_align_oracle_matches_compiled_reference(oracle_built):
     assert n >= 7000
 
 
+def test_align_oracle_matches_golden_vectors(oracle_built):
+    """The committed fixture (tests/golden/make_golden.py: outputs of the reference's own ksw_align2) — runs anywhere."""
+    n = 0
+    for name, (b, want) in K.load_align_golden().items():
+        mm = K.align_mismatch(K.run_align_oracle(b), want)
+        assert mm is None, (name, mm)
+        n += b.n
+    assert n >= 2000
+
+
 def test_align_oracle_known_answers(oracle_built):
     """A read embedded once, exactly: score = qlen * a, ends and starts where it was put; embedded twice: the second-best
     score is the same and points at the other copy."""
@@ -43,6 +53,13 @@ def test_align_oracle_known_answers(oracle_built):
 
 
 # ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_gpu_align_golden_vectors(gpu_ctx):
+    for name, (b, want) in K.load_align_golden().items():
+        mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), want)
+        assert mm is None, (name, mm)
+
+
 @pytest.mark.gpu
 def test_gpu_align_matesw_shaped_jobs(gpu_ctx, oracle_built):
     for seed, cfg in enumerate(CFGS):
