@@ -247,6 +247,252 @@ ksw_align_kernel(const DevAJob *__restrict__ jobs, const uint32_t *__restrict__ 
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same algorithm with TWO SSE lanes per thread as the halves of s16x2 registers (closed-form lazy-F only): thread t of a
+// job's T = P/2 threads holds lanes 2t (low half) and 2t+1 (high half).  Every per-cell operation of the reference is
+// element-wise, so each becomes one DPX instruction on both lanes: the saturating byte add is VIADDMNMX(h, S, 255) followed by
+// VIADDMNMX(., -shift, 0), the unsigned saturating subtractions are VIADDMNMX.RELU, H = VIMNMX3(h, E, F).  The profile is not
+// stored: a column keeps a 16-bit PRMT selector (two query codes) and the row's scores sit in two registers as bytes, like
+// the extension kernel's look-up.  One 16-byte shared-memory word per column pair: {H, E, selector, Hmax}.  Jobs per warp:
+// 4 (byte kernel) / 8 (16-bit kernel).  Used when o_ins >= 1 and, for the 16-bit kernel, no score can reach the int16
+// saturation (qlen * max score <= 32000); everything else takes the int32 kernel above.
+__device__ __forceinline__ uint32_t apk2(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
+__device__ __forceinline__ uint32_t aprmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+
+template <int P>
+__device__ APass align_pass2(const bool live, const uint8_t *__restrict__ query, const int qlen, const uint8_t *__restrict__ target,
+                             const int tlen, const int xtra, const bool rev, const int qe1, const int te1, uint4 *C, uint2 *bs,
+                             const uint2 *mrow, const KswAlignParams &A, const int tl)
+{
+	constexpr int T = P / 2;
+	const int slen = live ? (qlen + P - 1) / P : 0;                       // ksw.c:68
+	const int vmask = P == 16 ? 0xff : 0xffff;
+	const int e_ins = A.e_ins & vmask;
+	const uint32_t n_ed = apk2(-(A.e_del & vmask)), n_oed = apk2(-((A.o_del + A.e_del) & vmask));
+	const uint32_t n_ei = apk2(-e_ins), n_oei = apk2(-((A.o_ins + A.e_ins) & vmask));
+	const uint32_t n_shift = apk2(-A.shift), k255 = apk2(255), floor1 = apk2(-1), low16 = apk2(-32768);
+	// per column pair: the PRMT selector of the two query codes (padding columns: code 5 = the table's score-0 entry), zeroed rows
+	for (int j = 0; j < slen; ++j) {
+		uint32_t sel = 0;
+#pragma unroll
+		for (int hlf = 0; hlf < 2; ++hlf) {
+			const int k = j + (2 * tl + hlf) * slen;
+			uint32_t code = 5;
+			if (k < qlen) { code = rev ? query[qe1 - k] : query[k]; code = code > 4 ? 4 : code; }
+			// byte kernel: value byte, then a zero byte (7); 16-bit kernel: value byte, then its sign
+			const uint32_t nib = P == 16 ? (code | 0x70u) : (code | ((8u | code) << 4));
+			sel |= nib << (8 * hlf);
+		}
+		C[j * T + tl] = make_uint4(0u, 0u, sel, 0u);
+	}
+	__syncwarp();
+	int slen_w = slen, rows_w = live ? tlen : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		slen_w = max(slen_w, __shfl_xor_sync(FULL, slen_w, o));
+		rows_w = max(rows_w, __shfl_xor_sync(FULL, rows_w, o));
+	}
+	const int minsc = (xtra & XSUBO) ? (xtra & 0xffff) : 0x10000;
+	const int endsc = (xtra & XSTOP) ? (xtra & 0xffff) : 0x10000;
+	int gmax = 0, te = -1, n_b = 0, last_sc = 0, last_row = -2;
+	bool done = !live;
+	int t_next = 0;
+	if (live && tlen > 0) t_next = rev && 0 <= te1 ? target[te1] : target[0];
+	const int decay = min(e_ins * slen, 40000);                           // what a carried F loses across one whole lane
+	const uint32_t n_last = apk2(-min(e_ins * (slen - 1), 32767));        // ... across a lane's columns but the last
+	uint32_t G = 0;                                                       // carries into this thread's two lanes (previous row)
+	for (int i = 0; i < rows_w; ++i) {
+		const bool act = !done && i < tlen;
+		if (!__any_sync(FULL, act)) break;
+		int t = t_next;
+		t = t > 4 ? 4 : t;
+		if (act && i + 1 < tlen) t_next = rev && i + 1 <= te1 ? target[te1 - i - 1] : target[i + 1];
+		const uint2 mr = mrow[t];
+		// h = H(i-1, -1): the last vector shifted up by one lane (ksw.c:147-148): low half <- previous thread's high half,
+		// high half <- own low half
+		const uint32_t hl = act ? __vmaxs2(C[(slen - 1) * T + tl].x, __viaddmax_s16x2(G, n_last, floor1)) : 0u;
+		uint32_t prev = __shfl_up_sync(FULL, hl, 1, T);
+		if (tl == 0) prev = 0u;
+		uint32_t h = aprmt(prev, hl, 0x5432u);
+		uint32_t f = 0u, mx = 0u, c = G;
+		for (int j = 0; j < slen_w; ++j) {
+			if (act && j < slen) {
+				uint4 *cell = &C[j * T + tl];
+				const uint4 v = *cell;
+				const uint32_t S = aprmt(mr.x, mr.y, v.z);
+				uint32_t hv;
+				if (P == 16) hv = __viaddmax_s16x2(__viaddmin_s16x2(h, S, k255), n_shift, 0u);      // ksw.c:156-157
+				else hv = __viaddmax_s16x2(h, S, low16);                                            // ksw.c:268 (cannot saturate here)
+				hv = __vimax3_s16x2(hv, v.y, f);                                                    // ksw.c:159-160
+				mx = __vmaxs2(mx, hv);
+				const uint32_t e = __viaddmax_s16x2(v.y, n_ed, __viaddmax_s16x2_relu(hv, n_oed, 0u));   // ksw.c:164-167
+				f = __viaddmax_s16x2(f, n_ei, __viaddmax_s16x2_relu(hv, n_oei, 0u));                   // ksw.c:169-171
+				*reinterpret_cast<uint2 *>(cell) = make_uint2(hv, e);
+				h = __vmaxs2(v.x, c);                                     // H'(i-1, j): the stored H with the previous row's carry
+				c = __viaddmax_s16x2(c, n_ei, floor1);
+			}
+		}
+		{
+			// closed form of the lazy-F loop (see above), two lanes per thread: x(t) = carry into lane 2t
+			const int flo = (int)(f & 0xffffu), fhi = (int)(f >> 16);
+			int v = max(fhi, flo - decay);
+			v = __shfl_up_sync(FULL, v, 1, T);
+			if (tl == 0) v = 0;
+#pragma unroll
+			for (int d = 1; d < T; d <<= 1) {
+				const int o = __shfl_up_sync(FULL, v, d, T);
+				if (tl >= d) v = max(v, o - 2 * decay * d);
+			}
+			const int glo = max(v, 0), ghi = max(max(flo, v - decay), 0);
+			G = act ? ((uint32_t)glo | ((uint32_t)ghi << 16)) : 0u;
+		}
+		int imax = max((int)(mx & 0xffffu), (int)(mx >> 16));
+#pragma unroll
+		for (int o = T / 2; o > 0; o >>= 1) imax = max(imax, __shfl_xor_sync(FULL, imax, o, T));
+		if (act && imax >= minsc) {                                       // the second-best list, ksw.c:196-205
+			if (n_b == 0 || last_row + 1 != i) {
+				if (tl == 0) bs[n_b] = make_uint2((uint32_t)imax, (uint32_t)i);
+				++n_b; last_sc = imax; last_row = i;
+			} else if (last_sc < imax) {
+				if (tl == 0) bs[n_b - 1] = make_uint2((uint32_t)imax, (uint32_t)i);
+				last_sc = imax; last_row = i;
+			}
+		}
+		if (act && imax > gmax) {                                         // ksw.c:206-211
+			gmax = imax; te = i;
+			uint32_t cc = G;
+			for (int j = 0; j < slen; ++j) {
+				C[j * T + tl].w = __vmaxs2(C[j * T + tl].x, cc);
+				cc = __viaddmax_s16x2(cc, n_ei, floor1);
+			}
+			if ((P == 16 && gmax + A.shift >= 255) || gmax >= endsc) done = true;
+		}
+		__syncwarp();
+	}
+	APass r;
+	r.score = P == 16 ? (gmax + A.shift < 255 ? gmax : 255) : gmax;
+	r.te = te; r.qe = -1; r.score2 = -1; r.te2 = -1;
+	__syncwarp();
+	{
+		int best = -1, col = 0x7fffffff;
+		for (int j = 0; j < slen; ++j) {
+			const uint32_t w = C[j * T + tl].w;
+			const int vlo = (int)(w & 0xffffu), vhi = (int)(w >> 16), clo = j + 2 * tl * slen, chi = clo + slen;
+			if (vlo > best || (vlo == best && clo < col)) { best = vlo; col = clo; }
+			if (vhi > best || (vhi == best && chi < col)) { best = vhi; col = chi; }
+		}
+#pragma unroll
+		for (int o = T / 2; o > 0; o >>= 1) {
+			const int ob = __shfl_xor_sync(FULL, best, o, T), oc = __shfl_xor_sync(FULL, col, o, T);
+			if (ob > best || (ob == best && oc < col)) { best = ob; col = oc; }
+		}
+		if (P == 8 || r.score != 255) r.qe = col;
+		int s2 = -1, idx2 = 0x7fffffff, row2 = -1;
+		if (live && n_b > 0 && (P == 8 || r.score != 255)) {
+			const int d = (r.score + A.qmax - 1) / A.qmax, low = te - d, high = te + d;
+			for (int x = tl; x < n_b; x += T) {
+				const uint2 en = bs[x];
+				const int e = (int)en.y;
+				if ((e < low || e > high) && (int)en.x > s2) { s2 = (int)en.x; idx2 = x; row2 = e; }
+			}
+		}
+#pragma unroll
+		for (int o = T / 2; o > 0; o >>= 1) {
+			const int os = __shfl_xor_sync(FULL, s2, o, T), oi = __shfl_xor_sync(FULL, idx2, o, T), orow = __shfl_xor_sync(FULL, row2, o, T);
+			if (os > s2 || (os == s2 && oi < idx2)) { s2 = os; idx2 = oi; row2 = orow; }
+		}
+		if (s2 >= 0) { r.score2 = s2; r.te2 = row2; }
+	}
+	__syncwarp();
+	return r;
+}
+
+template <int P>
+__global__ void __launch_bounds__(32)
+ksw_align2x_kernel(const DevAJob *__restrict__ jobs, const uint32_t *__restrict__ order, const int n_jobs, const uint8_t *__restrict__ seq,
+                   const KswAlignParams A, const int cap, uint2 *__restrict__ bscr, const int tcap, unsigned *__restrict__ counter,
+                   DevARes *__restrict__ res)
+{
+	constexpr int T = P / 2, G = 32 / T;
+	extern __shared__ uint4 asm2_[];
+	const int lane = threadIdx.x, sub = lane / T, tl = lane % T;
+	uint2 *mrow = reinterpret_cast<uint2 *>(asm2_);                        // 5 rows of score bytes (+ the padding entry), then the jobs
+	uint4 *C = asm2_ + 4 + sub * cap;
+	if (lane < 5) {
+		// bytes 0..4: the scores of target base `lane` against query codes 0..4 (byte kernel: plus shift); byte 5: a padding column
+		uint32_t b[8];
+		for (int c = 0; c < 5; ++c) b[c] = P == 16 ? (uint32_t)((A.mat[lane * 5 + c] + A.shift) & 0xff) : (uint32_t)(uint8_t)A.mat[lane * 5 + c];
+		b[5] = P == 16 ? (uint32_t)(A.shift & 0xff) : 0u;
+		b[6] = b[7] = 0u;
+		mrow[lane] = make_uint2(b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24, b[4] | b[5] << 8);
+	}
+	__syncwarp();
+	uint2 *bs = bscr + ((size_t)blockIdx.x * G + sub) * (size_t)tcap;
+	for (;;) {
+		unsigned g = 0;
+		if (lane == 0) g = atomicAdd(counter, 1u);
+		g = __shfl_sync(FULL, g, 0);
+		if ((long long)g * G >= n_jobs) break;
+		const int jidx = (int)g * G + sub;
+		const bool have = jidx < n_jobs;
+		DevAJob jb;
+		jb.seq_off = 0; jb.qlen = 1; jb.tlen = 0; jb.xtra = 0; jb.idx = 0;
+		if (have) jb = jobs[order[jidx]];
+		const uint8_t *query = seq + jb.seq_off, *target = query + jb.qlen;
+		const APass r = align_pass2<P>(have, query, jb.qlen, target, jb.tlen, jb.xtra, false, 0, -1, C, bs, mrow, A, tl);
+		const bool second = have && (jb.xtra & XSTART) && !((jb.xtra & XSUBO) && r.score < (jb.xtra & 0xffff)) && r.qe >= 0;
+		const APass rr = align_pass2<P>(second, query, r.qe + 1, target, jb.tlen, XSTOP | r.score, true, r.qe, r.te, C, bs, mrow, A, tl);
+		if (have && tl == 0) {
+			DevARes o;
+			o.score = r.score; o.te = r.te; o.qe = r.qe; o.score2 = r.score2; o.te2 = r.te2; o.tb = -1; o.qb = -1; o.pad = 0;
+			if (second && r.score == rr.score) { o.tb = r.te - rr.te; o.qb = r.qe - rr.qe; }
+			res[jb.idx] = o;
+		}
+	}
+}
+
+template <int P>
+cudaError_t launch_2x(const DevAJob *jobs, const uint32_t *order, int n_jobs, const uint8_t *seq, const KswAlignParams &A, int qmax,
+                      int tmax, int sm_count, void **bscr, size_t *bscr_cap, unsigned *counter, DevARes *res, cudaStream_t st)
+{
+	constexpr int T = P / 2, G = 32 / T;
+	if (n_jobs <= 0) return cudaSuccess;
+	const int cap = ((qmax + P - 1) / P) * T;                             // uint4 words per job
+	const size_t smem = 64 + (size_t)G * cap * sizeof(uint4);
+	int dev = 0, optin = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	if (e != cudaSuccess) return e;
+	if (smem > (size_t)optin) return cudaErrorInvalidValue;
+	e = cudaFuncSetAttribute(ksw_align2x_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_align2x_kernel<P>, 32, smem);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	int blocks = sm_count * per_sm;
+	const int groups = (n_jobs + G - 1) / G;
+	if (blocks > groups) blocks = groups;
+	const int tcap = tmax > 0 ? tmax : 1;
+	const size_t need = (size_t)blocks * G * (size_t)tcap * sizeof(uint2);
+	if (need > *bscr_cap) {
+		if (*bscr) { e = cudaFree(*bscr); *bscr = nullptr; *bscr_cap = 0; if (e != cudaSuccess) return e; }
+		e = cudaMalloc(bscr, need);
+		if (e != cudaSuccess) return e;
+		*bscr_cap = need;
+	}
+	e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+	if (e != cudaSuccess) return e;
+	ksw_align2x_kernel<P><<<blocks, 32, smem, st>>>(jobs, order, n_jobs, seq, A, cap, (uint2 *)*bscr, tcap, counter, res);
+	return cudaGetLastError();
+}
+
 template <int P, bool LIT>
 cudaError_t launch_one(const DevAJob *jobs, const uint32_t *order, int n_jobs, const uint8_t *seq, const KswAlignParams &A, int qmax,
                        int tmax, int sm_count, void **bscr, size_t *bscr_cap, unsigned *counter, DevARes *res, cudaStream_t st)
@@ -293,9 +539,18 @@ cudaError_t ksw_launch_align(int bytes_per_score, const DevAJob *jobs, const uin
 	// the closed form of the lazy-F loop needs o_ins >= 1 after the truncation the vector constants go through (ksw.c:131-134)
 	const int vmask = bytes_per_score == 1 ? 0xff : 0xffff;
 	const bool lit = !((A.e_ins & vmask) < ((A.o_ins + A.e_ins) & vmask)) || A.e_ins < 0 || A.o_ins < 0 || getenv("KSW_B200_ALIGN_LITERAL") != nullptr;
-	if (bytes_per_score == 1)
+	// two SSE lanes per thread in s16x2 registers: every value must stay clear of the int16 saturation, the selectors need |score| <= 127
+	const char *e32 = getenv("KSW_B200_ALIGN_INT32");
+	const bool packed = !lit && !(e32 && e32[0] == '1') && A.e_del >= 0 && A.o_del >= 0 && (A.o_del + A.e_del) <= 30000 && (A.o_ins + A.e_ins) <= 30000 &&
+	                    (bytes_per_score == 1 || (long long)qmax * A.qmax <= 32000) &&
+	                    // its shared memory: 16 bytes per column pair, 4 (byte kernel) or 8 jobs per warp; longer queries take the int32 kernel
+	                    (bytes_per_score == 1 ? 64 + 4 * (size_t)((qmax + 15) / 16) * 8 * 16 : 64 + 8 * (size_t)((qmax + 7) / 8) * 4 * 16) <= (size_t)160 * 1024;
+	if (bytes_per_score == 1) {
+		if (packed) return launch_2x<16>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
 		return lit ? launch_one<16, true>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st)
 		           : launch_one<16, false>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
+	}
+	if (packed) return launch_2x<8>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
 	return lit ? launch_one<8, true>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st)
 	           : launch_one<8, false>(jobs, order, n_jobs, seq, A, qmax, tmax, sm_count, bscr, bscr_cap, counter, res, st);
 }

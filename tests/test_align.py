@@ -77,18 +77,22 @@ def test_gpu_align_every_flag_combination(gpu_ctx, oracle_built):
 
 
 @pytest.mark.gpu
-def test_gpu_align_literal_lazy_f_loop_agrees(gpu_ctx, oracle_built, monkeypatch):
-    """The kernel's closed form of the lazy-F loop (default when o_ins >= 1) and the loop run literally (KSW_B200_ALIGN_LITERAL)
-    on the same jobs, scorings with o_ins >= 1 only."""
+def test_gpu_align_three_kernel_forms_agree(gpu_ctx, oracle_built, monkeypatch):
+    """The packed kernel (two SSE lanes per thread in s16x2 registers, closed-form lazy-F loop: the default when o_ins >= 1), the
+    int32 kernel with the closed form (KSW_B200_ALIGN_INT32=1) and the int32 kernel running the lazy-F loop literally
+    (KSW_B200_ALIGN_LITERAL=1) on the same jobs; scorings with o_ins >= 1 only."""
     for seed, cfg in ((780, None), (781, K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3)), (782, K.make_cfg(a=1, b=1, o_del=3, e_del=2, o_ins=1, e_ins=1))):
         b = K.gen_align(2000, seed=seed, cfg=cfg, max_q=250)
         want = K.run_align_oracle(b)
-        monkeypatch.delenv("KSW_B200_ALIGN_LITERAL", raising=False)
-        mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), want)
-        assert mm is None, ("closed form", seed, mm, b.jobs[mm[0]])
-        monkeypatch.setenv("KSW_B200_ALIGN_LITERAL", "1")
-        mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), want)
-        assert mm is None, ("literal", seed, mm, b.jobs[mm[0]])
+        for name, env in (("packed", {}), ("int32", {"KSW_B200_ALIGN_INT32": "1"}), ("literal", {"KSW_B200_ALIGN_LITERAL": "1"})):
+            monkeypatch.delenv("KSW_B200_ALIGN_INT32", raising=False)
+            monkeypatch.delenv("KSW_B200_ALIGN_LITERAL", raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            mm = K.align_mismatch(gpu_ctx.align_batch(b.cfg, b.jobs, b.qpool, b.tpool), want)
+            assert mm is None, (name, seed, mm, b.jobs[mm[0]])
+    monkeypatch.delenv("KSW_B200_ALIGN_INT32", raising=False)
+    monkeypatch.delenv("KSW_B200_ALIGN_LITERAL", raising=False)
 
 
 @pytest.mark.gpu
