@@ -53,6 +53,8 @@ def read_batches(path: str, limit: int = 10 ** 9):
 def merge(batches, end_bonus=None):
     """the passes of many worker batches as ONE batch (optionally only those with the given end_bonus, i.e. one side)"""
     sel = [b for b in batches if end_bonus is None or b[0].end_bonus == end_bonus]
+    if not sel:
+        raise ValueError("no job batches in the trace (was the run made with KSW_B200_DUMP and KSW_B200_REF=0?)")
     jobs, qs, ts, qo, to = [], [], [], 0, 0
     for cfg, j, q, t in sel:
         j = j.copy(); j["q_off"] += qo; j["t_off"] += to
@@ -146,7 +148,9 @@ def harvest(mix: str, n_reads: int, genome_len: int = 2_000_000, seed: int = 1, 
     try:
         fa, reads = write_synthetic(d, genome_len, n_reads, seed, **MIXES[mix])
         subprocess.run([BWA_B200, "index", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        env = dict(os.environ, KSW_B200_DUMP=os.path.join(d, "jobs"))
+        # KSW_B200_REF=0: the host driver materialises the reference windows (with the reference resident on the device a job
+        # is a coordinate, and there is nothing to trace for offline replay)
+        env = dict(os.environ, KSW_B200_DUMP=os.path.join(d, "jobs"), KSW_B200_REF="0")
         t = threads or min(os.cpu_count() or 4, 16)
         with open(os.devnull, "wb") as nul:
             subprocess.run([BWA_B200, "mem", "-t", str(t), fa, *reads], check=True, stdout=nul, stderr=subprocess.PIPE, env=env)

@@ -11,7 +11,7 @@ paths=["$D/r1.fq","$D/r2.fq"] if "$1"=="pe" else ["$D/r1.fq"]
 S.write_reads_fast(paths, g, $2, $3, seed=2, sub=$4, indel=$5, indel_max=$6)
 PY
 READS="$D/r1.fq"; [ "$1" = pe ] && READS="$D/r1.fq $D/r2.fq"
-KSW_B200_DUMP=$D/jobs integration/_bin/bwa_b200 mem -t 1 -b 1000000 $D/ref.fa $READS > /dev/null 2> $D/err; tail -2 $D/err
+KSW_B200_REF=0 KSW_B200_DUMP=$D/jobs integration/_bin/bwa_b200 mem -t 1 -b 1000000 $D/ref.fa $READS > /dev/null 2> $D/err; tail -2 $D/err
 ls -la $D/*.bin
 python scripts/bench_jobs.py $D/jobs.*.bin
 rm -rf $D
