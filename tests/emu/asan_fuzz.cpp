@@ -12,10 +12,65 @@
 #include "../../bwa_mem_quickassist_b200/csrc/ksw_pack.h"
 #include "../../bwa_mem_quickassist_b200/csrc/ksw_fast_core.h"
 #include "../../bwa_mem_quickassist_b200/csrc/ksw_pair_core.h"
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_class.h"
+#include "../../bwa_mem_quickassist_b200/csrc/ksw_gfast_core.h"
 
 extern "C" int ksw_oracle_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
                                   int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
                                   int *qle, int *tle, int *gtle, int *gscore, int *max_off, int64_t *cells, int32_t *rows);
+
+extern "C" int ksw_oracle_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                                  int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t *cigar);
+
+// the fast global-alignment kernels' per-lane source (ksw_gfast_core.h): DP rows into an H slab of exactly the size the
+// runtime reserves per job (tlen x nqb quads), backtrack by recomputation, against the oracle's score and CIGAR
+static int gfast_fuzz(int n, std::mt19937 &rng, const ksw_b200_cfg_t &cfg, long long *n_run)
+{
+	auto U = [&](int lo, int hi) { return (int)(rng() % (unsigned)(hi - lo + 1)) + lo; };
+	KswParams P; ksw_params_from_cfg(&cfg, P);
+	KswGConst C; ksw_gfast_make_const(P, C);
+	ksw_u2 mrow[5];
+	for (int t = 0; t < 5; ++t) mrow[t] = ksw_gfast_matrow(P, t);
+	KswFastEdge edge[5];
+	for (int r = 0; r < 5; ++r) ksw_fast_edge_entry(r, edge[r]);
+	const int cost = ksw_gfast_cell_cost(cfg.mat, cfg.o_del, cfg.e_del, cfg.o_ins, cfg.e_ins);
+	int bad = 0;
+	for (int k = 0; k < n; ++k) {
+		const int ql = U(0, 3) == 0 ? U(1, 20) : U(1, 260);
+		std::vector<uint8_t> q(ql), t;
+		for (auto &x : q) x = (uint8_t)(U(0, 99) == 0 ? 4 : U(0, 3));
+		for (int j = 0; j < ql; ++j) {                              // the target: the query with substitutions and short indels
+			const int ev = U(0, 99);
+			if (ev < 3) continue;                                   // base missing from the target
+			if (ev < 6) t.push_back((uint8_t)U(0, 3));              // extra base
+			t.push_back(ev < 14 ? (uint8_t)U(0, 3) : q[j]);
+		}
+		if (t.empty()) t.push_back(0);
+		const int tl = (int)t.size(), w = abs(tl - ql) + U(0, 3) * U(0, 20);
+		if (!ksw_gfast_eligible(cost, cfg.o_del, cfg.e_del, cfg.o_ins, cfg.e_ins, ql, tl, w)) continue;
+		const int nq = (ql >> 2) + 1, nqb = ksw_gfast_nqb(ql, w);
+		std::vector<ksw_u4> hq(nq);                                 // exactly what the kernel gives a lane
+		std::vector<uint32_t> sq(nq);
+		std::vector<ksw_u2> z((size_t)tl * nqb);
+		ksw_gfast_setup<1>(hq.data(), sq.data(), ql, w, q.data(), C);
+		for (int i = 0; i < tl; ++i) ksw_gfast_row<1>(hq.data(), sq.data(), edge, mrow[t[i] > 4 ? 4 : t[i]], z.data() + (size_t)i * nqb, i, ql, w, C);
+		const int score = ksw_gfast_score<1>(hq.data(), ql);
+		KswGWalk<1> wk;
+		wk.z = z.data(); wk.query = q.data(); wk.target = t.data(); wk.mat = P.mat;
+		wk.qlen = ql; wk.tlen = tl; wk.w = w; wk.nqb = nqb;
+		wk.o_del = P.o_del; wk.e_del = P.e_del; wk.o_ins = P.o_ins; wk.e_ins = P.e_ins;
+		std::vector<uint32_t> rev((size_t)ql + tl + 2);
+		const int nc = wk.run([&](int r, int op, int len) { rev[r] = (uint32_t)len << 4 | (uint32_t)op; });
+		int n_ref = 0;
+		std::vector<uint32_t> cig((size_t)ql + tl + 2);
+		const int want = ksw_oracle_global2(ql, q.data(), tl, t.data(), 5, cfg.mat, cfg.o_del, cfg.e_del, cfg.o_ins, cfg.e_ins, w, &n_ref, cig.data());
+		bool ok = want == score && n_ref == nc;
+		for (int r = 0; ok && r < nc; ++r) ok = cig[r] == rev[nc - 1 - r];
+		if (!ok && bad++ < 5) fprintf(stderr, "global mismatch: qlen %d tlen %d w %d\n", ql, tl, w);
+		++*n_run;
+	}
+	return bad;
+}
 
 int main(int argc, char **argv)
 {
@@ -125,6 +180,8 @@ int main(int argc, char **argv)
 			}
 		}
 	}
-	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %lld through the pair lane, %d mismatches\n", n, n_fast, n_keyed, n_pair, bad);
+	long long n_glob = 0;
+	bad += gfast_fuzz(n / 4, rng, cfg, &n_glob);
+	printf("asan_fuzz: %d jobs, %lld on the fast path (%lld keyed), %lld through the pair lane, %lld global alignments, %d mismatches\n", n, n_fast, n_keyed, n_pair, n_glob, bad);
 	return bad ? 1 : 0;
 }
