@@ -67,7 +67,9 @@ static void b200_add_time(double *acc, double dt) { __sync_synchronize(); { stat
 #define B200_MAX_GPUS 64
 static ksw_b200_queue_t *b200_queue[B200_MAX_GPUS];
 static const uint8_t *b200_queue_pac[B200_MAX_GPUS];
-static pthread_mutex_t b200_queue_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t b200_queue_mu[B200_MAX_GPUS];        /* one per GPU: the queues of a multi-GPU box come up side by side */
+static pthread_once_t b200_queue_once = PTHREAD_ONCE_INIT;
+static void b200_queue_mu_init(void) { int g; for (g = 0; g < B200_MAX_GPUS; ++g) pthread_mutex_init(&b200_queue_mu[g], 0); }
 static int b200_queue_on(void)
 {
 	static int v = -1;
@@ -80,7 +82,8 @@ static int b200_queue_on(void)
 static ksw_b200_queue_t *b200_queue_for(int gpu, const bntseq_t *bns, const uint8_t *pac)
 {
 	ksw_b200_queue_t *q;
-	pthread_mutex_lock(&b200_queue_mu);
+	pthread_once(&b200_queue_once, b200_queue_mu_init);
+	pthread_mutex_lock(&b200_queue_mu[gpu]);
 	if (!b200_queue[gpu] && ksw_b200_queue_create(gpu, &b200_queue[gpu]) != 0)
 		err_fatal(__func__, "no usable CUDA device: the B200 extension path has no CPU fallback");
 	if (pac && b200_queue_pac[gpu] != pac) {
@@ -88,7 +91,7 @@ static ksw_b200_queue_t *b200_queue_for(int gpu, const bntseq_t *bns, const uint
 		b200_queue_pac[gpu] = pac;
 	}
 	q = b200_queue[gpu];
-	pthread_mutex_unlock(&b200_queue_mu);
+	pthread_mutex_unlock(&b200_queue_mu[gpu]);
 	return q;
 }
 
@@ -129,37 +132,52 @@ static b200_thread_t *b200_thread_state(const mem_opt_t *opt, const bntseq_t *bn
 
 /* CUDA context creation costs seconds on a large GPU, and so does the first launch of every kernel; start both while
  * `bwa mem` is still loading the index and parsing the first chunk of reads.  (glibc passes argc/argv to constructors.) */
+static void *b200_warmup_device(void *arg)
+{
+	const int d = (int)(intptr_t)arg;
+	ksw_b200_ctx_t *c = 0;
+	if (ksw_b200_ctx_create(d, &c) != 0) return 0;
+	{
+		/* one job per kernel (keyed, unkeyed, generic; binning; global alignment; local alignment): with lazy module loading the
+		 * first launch of every kernel costs tens of milliseconds, and 16 workers would queue up behind it in their first batch */
+		static const int qlens[3] = {20, 200, 600};
+		uint8_t seq[600];
+		ksw_b200_cfg_t cfg;
+		ksw_b200_job_t jobs[3];
+		ksw_b200_res_t res[3];
+		ksw_b200_gjob_t gj;
+		ksw_b200_gres_t gr;
+		ksw_b200_ajob_t aj[2];
+		ksw_b200_ares_t ar[2];
+		const uint32_t *pool;
+		int64_t total;
+		int i;
+		for (i = 0; i < 600; ++i) seq[i] = (uint8_t)((i * 7 + i / 5) & 3);
+		memset(&cfg, 0, sizeof(cfg));
+		bwa_fill_scmat(1, 4, cfg.mat);
+		cfg.m = 5; cfg.o_del = cfg.o_ins = 6; cfg.e_del = cfg.e_ins = 1; cfg.zdrop = 100; cfg.end_bonus = 5;
+		for (i = 0; i < 3; ++i) { jobs[i].q_off = 0; jobs[i].t_off = 0; jobs[i].qlen = qlens[i]; jobs[i].tlen = qlens[i]; jobs[i].h0 = 19; jobs[i].w = 100; }
+		ksw_b200_extend_batch(c, &cfg, 3, jobs, seq, seq, res);
+		gj.q_off = gj.t_off = 0; gj.qlen = gj.tlen = 100; gj.w = 10; gj.reserved = 0;
+		ksw_b200_global_batch(c, &cfg, 1, &gj, seq, seq, &gr, &pool, &total);
+		for (i = 0; i < 2; ++i) {                                   /* byte kernel and 16-bit kernel */
+			aj[i].q_off = 0; aj[i].t_off = 100; aj[i].qlen = 100; aj[i].tlen = 300; aj[i].reserved = 0;
+			aj[i].xtra = KSW_XSUBO | KSW_XSTART | (i == 0 ? KSW_XBYTE : 0) | 19;
+		}
+		ksw_b200_align_batch(c, &cfg, 2, aj, seq, seq, ar);
+	}
+	ksw_b200_ctx_destroy(c);
+	return 0;
+}
 static void *b200_warmup_thread(void *arg)
 {
-	int d, n = ksw_b200_device_count();
+	/* only the GPUs the run will use (KSW_B200_GPUS), all of them at the same time */
+	int d, n = b200_gpu_count();
+	pthread_t th[B200_MAX_GPUS];
 	(void)arg;
-	for (d = 0; d < n; ++d) {
-		ksw_b200_ctx_t *c = 0;
-		if (ksw_b200_ctx_create(d, &c) != 0) continue;
-		{
-			/* one job per kernel (keyed, unkeyed, generic; binning; global alignment): with lazy module loading the first
-			 * launch of every kernel costs tens of milliseconds, and 16 workers would queue up behind it in their first batch */
-			static const int qlens[3] = {20, 200, 600};
-			uint8_t seq[600];
-			ksw_b200_cfg_t cfg;
-			ksw_b200_job_t jobs[3];
-			ksw_b200_res_t res[3];
-			ksw_b200_gjob_t gj;
-			ksw_b200_gres_t gr;
-			const uint32_t *pool;
-			int64_t total;
-			int i;
-			for (i = 0; i < 600; ++i) seq[i] = (uint8_t)((i * 7 + i / 5) & 3);
-			memset(&cfg, 0, sizeof(cfg));
-			bwa_fill_scmat(1, 4, cfg.mat);
-			cfg.m = 5; cfg.o_del = cfg.o_ins = 6; cfg.e_del = cfg.e_ins = 1; cfg.zdrop = 100; cfg.end_bonus = 5;
-			for (i = 0; i < 3; ++i) { jobs[i].q_off = 0; jobs[i].t_off = 0; jobs[i].qlen = qlens[i]; jobs[i].tlen = qlens[i]; jobs[i].h0 = 19; jobs[i].w = 100; }
-			ksw_b200_extend_batch(c, &cfg, 3, jobs, seq, seq, res);
-			gj.q_off = gj.t_off = 0; gj.qlen = gj.tlen = 100; gj.w = 10; gj.reserved = 0;
-			ksw_b200_global_batch(c, &cfg, 1, &gj, seq, seq, &gr, &pool, &total);
-		}
-		ksw_b200_ctx_destroy(c);
-	}
+	if (n > B200_MAX_GPUS) n = B200_MAX_GPUS;
+	for (d = 0; d < n; ++d) if (pthread_create(&th[d], 0, b200_warmup_device, (void *)(intptr_t)d) != 0) th[d] = 0;
+	for (d = 0; d < n; ++d) if (th[d]) pthread_join(th[d], 0);
 	return 0;
 }
 __attribute__((constructor)) static void b200_warmup(int argc, char **argv)
