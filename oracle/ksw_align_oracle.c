@@ -41,8 +41,8 @@ static aln_res_t striped_pass(int size, int qlen, const uint8_t *query, int tlen
 	uint8_t shift8 = 127, mdiff = 0;
 	int a, i, j, l, qmax, shift;
 	int *prof, *base, *H0, *H1, *E, *Hmax, *h, *f, *mx, *swap;
-	uint64_t *b = 0;
-	int n_b = 0, m_b = 0, te = -1, gmax = 0;
+	int *sb_score = 0, *sb_row = 0;                         /* the second-best list: one (row maximum, row) entry per run of rows */
+	int n_b = 0, te = -1, gmax = 0;
 	const int minsc = (xtra & XSUBO) ? (xtra & 0xffff) : 0x10000;   /* ksw.c:127-128 */
 	const int endsc = (xtra & XSTOP) ? (xtra & 0xffff) : 0x10000;
 	/* _mm_set1_epi8 / _mm_set1_epi16 truncate the gap costs (ksw.c:131-134, 251-254) */
@@ -109,11 +109,14 @@ static aln_res_t striped_pass(int size, int qlen, const uint8_t *query, int tlen
 			}
 		}
 		for (l = 0; l < p; ++l) imax = imax2(imax, mx[l]);
-		if (imax >= minsc) {                                 /* ksw.c:196-205 */
-			if (n_b == 0 || (int32_t)b[n_b - 1] + 1 != i) {
-				if (n_b == m_b) { m_b = m_b ? m_b << 1 : 8; b = (uint64_t *)realloc(b, 8 * (size_t)m_b); }
-				b[n_b++] = (uint64_t)imax << 32 | (uint32_t)i;
-			} else if ((int)(b[n_b - 1] >> 32) < imax) b[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i;
+		if (imax >= minsc) {
+			/* ksw.c:196-205: a row whose maximum reaches the threshold opens a new entry unless it directly follows the row
+			 * the last entry names; in that case the entry is overwritten only by a larger maximum (and then names this row) */
+			const int follows = n_b > 0 && sb_row[n_b - 1] + 1 == i;
+			if (!follows) {
+				if (!sb_score) { sb_score = (int *)malloc(sizeof(int) * (size_t)(tlen + 1)); sb_row = (int *)malloc(sizeof(int) * (size_t)(tlen + 1)); }
+				sb_score[n_b] = imax; sb_row[n_b] = i; ++n_b;
+			} else if (sb_score[n_b - 1] < imax) { sb_score[n_b - 1] = imax; sb_row[n_b - 1] = i; }
 		}
 		if (imax > gmax) {                                   /* ksw.c:206-211 */
 			gmax = imax; te = i;
@@ -131,17 +134,14 @@ static aln_res_t striped_pass(int size, int qlen, const uint8_t *query, int tlen
 			if (Hmax[i] > max) max = Hmax[i], r.qe = col;
 			else if (Hmax[i] == max && col < r.qe) r.qe = col;
 		}
-		if (b) {
-			int low, high;
-			i = (r.score + qmax - 1) / qmax;
-			low = te - i; high = te + i;
-			for (i = 0; i < n_b; ++i) {
-				const int e = (int32_t)b[i];
-				if ((e < low || e > high) && (int)(b[i] >> 32) > r.score2) r.score2 = (int)(b[i] >> 32), r.te2 = e;
-			}
+		if (n_b > 0) {
+			/* the best entry at least ceil(score / max) rows away from the end of the best hit; the first one wins ties */
+			const int d = (r.score + qmax - 1) / qmax;
+			for (i = 0; i < n_b; ++i)
+				if ((sb_row[i] < te - d || sb_row[i] > te + d) && sb_score[i] > r.score2) r.score2 = sb_score[i], r.te2 = sb_row[i];
 		}
 	}
-	free(b); free(prof); free(base);
+	free(sb_score); free(sb_row); free(prof); free(base);
 	return r;
 }
 
