@@ -149,3 +149,11 @@ def test_pe_mate_rescue_byte_identical(tmp_path):
         S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_off.sam"), threads=4, env=dict(os.environ, KSW_B200_RESCUE="0"))
         ok, why = S.sam_equal(str(tmp_path / "stock.sam"), str(tmp_path / "b200_off.sam"))
         assert ok, ("rescue look-ahead off", L, why)
+        if L == 150:
+            # the options that change what mem_sam_pe does with rescue: -S (no rescue), -P (rescue but no pairing), -I (given
+            # insert-size distribution instead of mem_pestat's), -m (fewer rescue rounds)
+            for extra in (["-S"], ["-P"], ["-I", "380,40"], ["-m", "1"]):
+                S.bwa_mem(S.BWA_STOCK, fa, [f1, f2], str(tmp_path / "stock_x.sam"), threads=4, extra=extra)
+                S.bwa_mem(S.BWA_B200, fa, [f1, f2], str(tmp_path / "b200_x.sam"), threads=4, extra=extra)
+                ok, why = S.sam_equal(str(tmp_path / "stock_x.sam"), str(tmp_path / "b200_x.sam"))
+                assert ok, (extra, why)
