@@ -1,14 +1,15 @@
 // ksw_queue.cpp — one submission queue per GPU shared by all host threads (include/ksw_b200.h; SURVEY.md 8(f) rank 1,
 // the part the rounds scheduler left open: cross-thread batch coalescing).  Built on the public C ABI only.  The queue
-// owns two contexts ("lanes") on its device and NO thread of its own: a submitter that finds a lane free becomes the
+// owns a few contexts ("lanes", two by default) on its device and NO thread of its own: a submitter that finds a lane free becomes the
 // leader of a batch — it takes everything that is pending for the same kind of work and the same scoring (its own
 // submission or not), runs it as one GPU batch on that lane from its own thread, and wakes the submitters it served;
-// submitters that find both lanes busy sleep until they are served or a lane frees up.  No delay is added to collect
+// submitters that find every lane busy sleep until they are served or a lane frees up.  No delay is added to collect
 // work: while the lanes run, the next submissions pile up and become the next leader's batch.  (The first version had a
 // server thread per lane; with every core busy seeding, the hand-over to a sleeping server thread cost a scheduler
 // wake-up per batch, and a `bwa mem -t 16` chunk took anything between 2.2 and 3.4 s; led by the submitters
-// themselves it is as steady as private contexts.)  Two lanes, so that the copies and the device-side packing of one
-// merged batch overlap the kernels of the other.
+// themselves it is as steady as private contexts.)  Several lanes, so that the copies, the device-side packing and the
+// per-batch host work of one merged batch overlap the kernels of the others.
+#include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -46,8 +47,8 @@ bool same_cfg(const ksw_b200_cfg_t &a, const ksw_b200_cfg_t &b)
 
 } // namespace
 
-#define KSW_QUEUE_SERVERS 2             /* two contexts per GPU: the copies and the packing of one merged batch run under the
-                                         * kernels of the other */
+#define KSW_QUEUE_LANES 2               /* contexts per GPU (KSW_B200_QUEUE_LANES, 1..16): the copies, the device-side packing and
+                                         * the per-batch host work of one merged batch run under the kernels of the others */
 struct Server {
 	ksw_b200_ctx_t *ctx = nullptr;
 	bool busy = false;                 // a leader is running a batch on this lane
@@ -58,7 +59,7 @@ struct Server {
 };
 
 struct ksw_b200_queue {
-	Server srv[KSW_QUEUE_SERVERS];
+	std::vector<Server> srv;
 	std::mutex mu;
 	std::condition_variable cv_idle;   // destroy waits here for the lanes to drain
 	std::deque<Sub *> pending;
@@ -171,6 +172,9 @@ int ksw_b200_queue_create(int device, ksw_b200_queue_t **out)
 	if (!out) return 1;
 	*out = nullptr;
 	ksw_b200_queue *q = new ksw_b200_queue();
+	int lanes = KSW_QUEUE_LANES;
+	if (const char *e = getenv("KSW_B200_QUEUE_LANES")) lanes = std::max(1, std::min(16, atoi(e)));
+	q->srv.resize((size_t)lanes);
 	for (Server &sv : q->srv) {
 		const int rc = ksw_b200_ctx_create(device, &sv.ctx);
 		if (rc) {

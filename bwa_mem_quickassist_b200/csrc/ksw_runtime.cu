@@ -27,13 +27,18 @@
 // ------------------------------------------------------------------ small helpers
 namespace {
 
+// Growth of the grow-only buffers: a (re)allocation of device or page-locked memory synchronises the whole device, and
+// the batches a shared queue merges come in every size between one submission and sixteen, so small buffers double
+// (a handful of steps instead of dozens); large ones (a 10 M-job batch is gigabytes) get an eighth of slack.
+inline size_t grow_to(size_t bytes) { return bytes + std::max<size_t>(bytes / 8, std::min<size_t>(bytes, (size_t)32 << 20)) + 4096; }
+
 struct PinnedBuf {            // grow-only pinned host buffer
 	void *p = nullptr; size_t cap = 0;
 	cudaError_t reserve(size_t bytes) {
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFreeHost(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 8 + 4096;
+		size_t want = grow_to(bytes);
 		cudaError_t e = cudaMallocHost(&p, want);
 		if (e == cudaSuccess) cap = want;
 		return e;
@@ -47,7 +52,7 @@ struct DevBuf {               // grow-only device buffer
 		if (bytes <= cap) return cudaSuccess;
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
-		size_t want = bytes + bytes / 8 + 4096;
+		size_t want = grow_to(bytes);
 		cudaError_t e = cudaMalloc(&p, want);
 		if (e == cudaSuccess) cap = want;
 		return e;
