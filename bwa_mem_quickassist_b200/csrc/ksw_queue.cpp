@@ -23,11 +23,13 @@
 namespace {
 
 struct Sub {                           // one blocked submitter
-	int kind = 0;                      // 0: extension against the resident reference, 1: global alignment
+	int kind = 0;                      // 0: extension against the resident reference, 1: global alignment, 2: local alignment
 	ksw_b200_cfg_t cfg;
 	int64_t n = 0;
 	const ksw_b200_rjob_t *rjobs = nullptr;
 	const ksw_b200_gjob_t *gjobs = nullptr;
+	const ksw_b200_ajob_t *ajobs = nullptr;
+	ksw_b200_ares_t *ares = nullptr;
 	const uint8_t *qpool = nullptr, *tpool = nullptr;
 	size_t qbytes = 0, tbytes = 0;
 	ksw_b200_res_t *res = nullptr;
@@ -56,6 +58,9 @@ struct Server {
 	std::vector<ksw_b200_gjob_t> gj;
 	std::vector<ksw_b200_gres_t> gr;
 	std::vector<uint8_t> gq, gt;
+	// merged local-alignment batch (the byte pools above are shared: a lane runs one batch at a time)
+	std::vector<ksw_b200_ajob_t> aj;
+	std::vector<ksw_b200_ares_t> ar;
 };
 
 struct ksw_b200_queue {
@@ -130,6 +135,40 @@ void run_global(Server *q, std::vector<Sub *> &grp)
 	}
 }
 
+void run_align(Server *q, std::vector<Sub *> &grp)
+{
+	size_t total = 0, nq = 0, nt = 0;
+	for (Sub *s : grp) {
+		total += (size_t)s->n;
+		size_t qb = 0, tb = 0;
+		for (int64_t k = 0; k < s->n; ++k) {
+			qb = std::max<size_t>(qb, (size_t)s->ajobs[k].q_off + (size_t)std::max(s->ajobs[k].qlen, 0));
+			tb = std::max<size_t>(tb, (size_t)s->ajobs[k].t_off + (size_t)std::max(s->ajobs[k].tlen, 0));
+		}
+		s->qbytes = qb; s->tbytes = tb;
+		nq += qb; nt += tb;
+	}
+	q->aj.resize(total); q->ar.resize(total); q->gq.resize(nq ? nq : 1); q->gt.resize(nt ? nt : 1);
+	size_t at = 0, qa = 0, ta = 0;
+	for (Sub *s : grp) {
+		if (s->qbytes) memcpy(q->gq.data() + qa, s->qpool, s->qbytes);
+		if (s->tbytes) memcpy(q->gt.data() + ta, s->tpool, s->tbytes);
+		for (int64_t k = 0; k < s->n; ++k) {
+			ksw_b200_ajob_t j = s->ajobs[k];
+			j.q_off += qa; j.t_off += ta;
+			q->aj[at + (size_t)k] = j;
+		}
+		at += (size_t)s->n; qa += s->qbytes; ta += s->tbytes;
+	}
+	const int rc = ksw_b200_align_batch(q->ctx, &grp[0]->cfg, (int64_t)total, q->aj.data(), q->gq.data(), q->gt.data(), q->ar.data());
+	at = 0;
+	for (Sub *s : grp) {
+		s->rc = rc;
+		if (rc == 0) memcpy(s->ares, q->ar.data() + at, sizeof(ksw_b200_ares_t) * (size_t)s->n);
+		at += (size_t)s->n;
+	}
+}
+
 int submit(ksw_b200_queue *q, Sub &s)
 {
 	std::unique_lock<std::mutex> lk(q->mu);
@@ -152,7 +191,7 @@ int submit(ksw_b200_queue *q, Sub &s)
 		if (!q->pending.empty())                                      // other work is left and the other lane may be free
 			for (Server &sv : q->srv) if (!sv.busy) { q->pending.front()->cv.notify_one(); break; }
 		lk.unlock();
-		if (grp[0]->kind == 0) run_extend(lane, grp); else run_global(lane, grp);
+		if (grp[0]->kind == 0) run_extend(lane, grp); else if (grp[0]->kind == 1) run_global(lane, grp); else run_align(lane, grp);
 		lk.lock();
 		if (grp[0]->rc) q->err = ksw_b200_strerror(lane->ctx);
 		++q->n_batches; q->n_subs += (int64_t)grp.size();
@@ -240,6 +279,17 @@ int ksw_b200_queue_global(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_
 	if (rc == 0) { *cigar_pool = s.cigar; *n_cigar_total = s.n_cigar; }
 	else free(s.cigar);
 	return rc;
+}
+
+int ksw_b200_queue_align(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_ajob_t *jobs,
+                         const uint8_t *qpool, const uint8_t *tpool, ksw_b200_ares_t *res)
+{
+	if (!q || !cfg || n < 0) return 1;
+	if (n == 0) return 0;
+	if (!jobs || !qpool || !tpool || !res) return 1;
+	Sub s;
+	s.kind = 2; s.cfg = *cfg; s.n = n; s.ajobs = jobs; s.qpool = qpool; s.tpool = tpool; s.ares = res;
+	return submit(q, s);
 }
 
 const char *ksw_b200_queue_strerror(const ksw_b200_queue_t *q) { return q ? q->err.c_str() : "null queue"; }

@@ -387,6 +387,15 @@ class KswQueue:
             libc.free(pool)
         return res, cig
 
+    def align_batch(self, cfg: Cfg, jobs, qpool, tpool):
+        jobs = np.ascontiguousarray(jobs, dtype=AJOB_DT)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        tpool = np.ascontiguousarray(tpool, dtype=np.uint8)
+        res = np.zeros(jobs.shape[0], dtype=ARES_DT)
+        self._check(self.lib.ksw_b200_queue_align(self.q, C.byref(cfg), jobs.shape[0], _p(jobs), _p(qpool), _p(tpool), _p(res)),
+                    "ksw_b200_queue_align")
+        return res
+
     def stats(self):
         a, b = C.c_int64(0), C.c_int64(0)
         self.lib.ksw_b200_queue_stats(self.q, C.byref(a), C.byref(b))

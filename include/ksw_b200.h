@@ -232,10 +232,11 @@ int ksw_b200_align_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t
 
 /* ---- one submission queue per GPU, shared by all host threads (cross-thread batch coalescing) - */
 /* The reference's workers (kt_for_batch, kthread_batch.c:18-56) each own a slice of the reads; with one private context
- * per worker every worker launches its own small batches.  A queue owns ONE context on its device and a server thread:
- * any number of host threads submit (blocking, thread-safe), and whatever has been submitted while the GPU was busy
- * runs as one merged batch; every submitter gets exactly the results of its own jobs (same read -> same regs[i]).
- * GPU memory is that of one context, however many threads submit. */
+ * per worker every worker launches its own small batches.  A queue owns two contexts ("lanes") on its device and no thread:
+ * any number of host threads submit (blocking, thread-safe); a submitter that finds a lane free leads a batch — whatever
+ * has been submitted meanwhile, of the same kind and scoring, runs as ONE merged batch from its thread — and every submitter
+ * gets exactly the results of its own jobs (same read -> same regs[i]).  GPU memory is that of the lanes, however many
+ * threads submit (KSW_B200_QUEUE_LANES, default 2). */
 typedef struct ksw_b200_queue ksw_b200_queue_t;
 int  ksw_b200_queue_create(int device, ksw_b200_queue_t **out);
 void ksw_b200_queue_destroy(ksw_b200_queue_t *q);
@@ -247,8 +248,11 @@ int  ksw_b200_queue_extend_ref(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, i
 int  ksw_b200_queue_global(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_gjob_t *jobs,
                            const uint8_t *qpool, const uint8_t *tpool, ksw_b200_gres_t *res,
                            uint32_t **cigar_pool, int64_t *n_cigar_total);
+/* as ksw_b200_align_batch */
+int  ksw_b200_queue_align(ksw_b200_queue_t *q, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_ajob_t *jobs,
+                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_ares_t *res);
 const char *ksw_b200_queue_strerror(const ksw_b200_queue_t *q);
-/* batches the server has run and submissions they carried (for the record: submissions / batches = coalescing factor) */
+/* batches the queue has run and submissions they carried (for the record: submissions / batches = coalescing factor) */
 void ksw_b200_queue_stats(const ksw_b200_queue_t *q, int64_t *n_batches, int64_t *n_submissions);
 
 /* ---- measurement helper ------------------------------------------------------ */

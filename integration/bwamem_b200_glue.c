@@ -548,18 +548,23 @@ static void b200_aln_insert(int tid, int qlen, const uint8_t *q, int tlen, const
 }
 
 /* one batch on GPU `gpu` through that GPU's alignment context (shared by the workers: the GPU runs one batch at a time anyway) */
-static void b200_aln_run(int gpu, const mem_opt_t *opt, int64_t n, const ksw_b200_ajob_t *jobs, const uint8_t *q, const uint8_t *t, ksw_b200_ares_t *res)
+static void b200_aln_run(int gpu, const mem_opt_t *opt, int64_t n, const ksw_b200_ajob_t *jobs, const uint8_t *q_, const uint8_t *t, ksw_b200_ares_t *res)
 {
 	ksw_b200_cfg_t cfg;
 	pthread_once(&b200_aln_once, b200_aln_init);
 	memcpy(cfg.mat, opt->mat, 25);
 	cfg.m = 5; cfg.o_del = opt->o_del; cfg.e_del = opt->e_del; cfg.o_ins = opt->o_ins; cfg.e_ins = opt->e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
+	if (b200_queue_on()) {                                   /* through the GPU's shared queue: concurrent batches are merged there */
+		ksw_b200_queue_t *q = b200_queue_for(gpu, 0, 0);
+		if (ksw_b200_queue_align(q, &cfg, n, jobs, q_, t, res) != 0) err_fatal(__func__, "GPU local alignment failed: %s", ksw_b200_queue_strerror(q));
+		return;
+	}
 	pthread_mutex_lock(&b200_aln_mu[gpu]);
 	if (!b200_aln_ctx[gpu]) {
 		if (ksw_b200_ctx_create(gpu, &b200_aln_ctx[gpu]) != 0) err_fatal(__func__, "no usable CUDA device: the B200 path has no CPU fallback");
 		ksw_b200_ctx_set_pack_threads(b200_aln_ctx[gpu], 2);
 	}
-	if (ksw_b200_align_batch(b200_aln_ctx[gpu], &cfg, n, jobs, q, t, res) != 0)
+	if (ksw_b200_align_batch(b200_aln_ctx[gpu], &cfg, n, jobs, q_, t, res) != 0)
 		err_fatal(__func__, "GPU local alignment failed: %s", ksw_b200_strerror(b200_aln_ctx[gpu]));
 	pthread_mutex_unlock(&b200_aln_mu[gpu]);
 }

@@ -119,3 +119,30 @@ def test_gpu_align_edges(gpu_ctx, oracle_built):
     bad = jobs[:1].copy(); bad["qlen"] = 0
     with pytest.raises(KswB200Error):
         gpu_ctx.align_batch(b.cfg, bad, b.qpool, b.tpool)
+
+
+@pytest.mark.gpu
+def test_gpu_align_through_the_shared_queue(oracle_built):
+    """Eight threads submit slices of one job set to a queue at the same time: merged batches, everyone's own results."""
+    import threading
+    import bwa_mem_quickassist_b200 as B
+    b = K.gen_align(4000, seed=790, max_q=250)
+    want = K.run_align_oracle(b)
+    q = B.KswQueue(0)
+    got = np.zeros(b.n, dtype=K.ARES_DT)
+    errs = []
+
+    def work(t):
+        try:
+            for lo in range(t * 500, (t + 1) * 500, 125):
+                sl = b.jobs[lo:lo + 125]
+                got[lo:lo + 125] = q.align_batch(b.cfg, sl, b.qpool, b.tpool)
+        except Exception as e:                                     # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    assert K.align_mismatch(got, want) is None
+    st = q.stats()
+    assert st["submissions"] == 32 and st["batches"] <= 32
+    q.close()
