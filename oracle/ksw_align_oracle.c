@@ -32,8 +32,11 @@ static inline int imax2(int a, int b) { return a > b ? a : b; }
 static inline int imin2(int a, int b) { return a < b ? a : b; }
 
 /* one call of ksw_u8 (size 1) or ksw_i16 (size 2) including the profile of ksw_qinit */
+/* closed: 0 = the lazy-F loop as the reference runs it; 1 = its closed form, the claim the GPU kernel rests on when o_ins >= 1
+ * (H' = max(H, carry), carry into lane l = max over l' < l of f_end(l') - e_ins * slen * (l - l' - 1), decaying by e_ins per
+ * column): tests/test_align.py checks on the CPU that both give the same seven outputs */
 static aln_res_t striped_pass(int size, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
-                              int o_del, int e_del, int o_ins, int e_ins, int xtra)
+                              int o_del, int e_del, int o_ins, int e_ins, int xtra, int closed)
 {
 	const int p = size == 1 ? 16 : 8;                       /* values per vector, ksw.c:67 */
 	const int slen = (qlen + p - 1) / p, nlen = slen * p;   /* ksw.c:68 */
@@ -93,6 +96,14 @@ static aln_res_t striped_pass(int size, int qlen, const uint8_t *query, int tlen
 				f[l] = imax2(f[l], t);
 				h[l] = H0[j * p + l];
 			}
+		if (closed) {
+			int g = 0;                                       /* carry into lane l */
+			stop = 1;
+			for (l = 0; l < p; ++l) {
+				if (l > 0) g = imax2(imax2(0, g - e_ins_v * slen), f[l - 1]);
+				for (j = 0; j < slen; ++j) H1[j * p + l] = imax2(H1[j * p + l], g - e_ins_v * j);
+			}
+		}
 		for (k = 0; k < 16 && !stop; ++k) {                  /* the lazy-F loop, ksw.c:182-192 / 282-291 (16 rounds in both kernels) */
 			for (l = p - 1; l > 0; --l) f[l] = f[l - 1];
 			f[0] = 0;
@@ -149,17 +160,17 @@ static void revseq(int l, uint8_t *s) { int i; for (i = 0; i < l >> 1; ++i) { co
 
 /* ksw_align2 with qry == NULL (ksw.c:329-354): out = {score, te, qe, score2, te2, tb, qb}.  Domain: qlen >= 1, the
  * matrix has a positive entry, and no overflow of the byte kernel (score 255), where the reference goes on with qe = -1. */
-int ksw_oracle_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
-                      int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *out)
+static int align2_impl(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                       int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *out, int closed)
 {
 	const int size = (xtra & XBYTE) ? 1 : 2;
-	aln_res_t r = striped_pass(size, qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra), rr;
+	aln_res_t r = striped_pass(size, qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra, closed), rr;
 	if (!((xtra & XSTART) == 0 || ((xtra & XSUBO) && r.score < (xtra & 0xffff))) && r.qe >= 0) {
 		uint8_t *q = (uint8_t *)malloc((size_t)qlen + 1), *t = (uint8_t *)malloc((size_t)tlen + 1);
 		memcpy(q, query, (size_t)qlen); memcpy(t, target, (size_t)tlen);
 		revseq(r.qe + 1, q); revseq(r.te + 1, t);            /* ksw.c:343 */
 		/* NB the second pass still runs over all tlen rows (ksw.c:345), the reversed prefix first */
-		rr = striped_pass(size, r.qe + 1, q, tlen, t, m, mat, o_del, e_del, o_ins, e_ins, XSTOP | r.score);
+		rr = striped_pass(size, r.qe + 1, q, tlen, t, m, mat, o_del, e_del, o_ins, e_ins, XSTOP | r.score, closed);
 		if (r.score == rr.score) r.tb = r.te - rr.te, r.qb = r.qe - rr.qe;
 		free(q); free(t);
 	}
@@ -167,10 +178,23 @@ int ksw_oracle_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *t
 	return r.score;
 }
 
+int ksw_oracle_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                      int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *out)
+{
+	return align2_impl(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra, out, 0);
+}
+
+/* the same with the lazy-F loop replaced by its closed form (valid for o_ins >= 1; see striped_pass) */
+int ksw_oracle_align2_closed_form(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
+                                  int o_del, int e_del, int o_ins, int e_ins, int xtra, int32_t *out)
+{
+	return align2_impl(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra, out, 1);
+}
+
 /* ---- batch driver (same job / result records as include/ksw_b200.h: ksw_b200_ajob_t / ksw_b200_ares_t) ---- */
 typedef struct { int8_t mat[25]; int32_t m, o_del, e_del, o_ins, e_ins, zdrop, end_bonus; } ocfg_t;
 typedef struct { uint64_t q_off, t_off; int32_t qlen, tlen, xtra, pad; } ajob_t;
-typedef struct { const ocfg_t *cfg; const ajob_t *jobs; const uint8_t *qpool, *tpool; aln_res_t *res; int64_t n, begin, stride; } aarg_t;
+typedef struct { const ocfg_t *cfg; const ajob_t *jobs; const uint8_t *qpool, *tpool; aln_res_t *res; int64_t n, begin, stride; int closed; } aarg_t;
 
 static void *aworker(void *p_)
 {
@@ -180,16 +204,16 @@ static void *aworker(void *p_)
 	for (k = a->begin; k < a->n; k += a->stride) {
 		const ajob_t *j = &a->jobs[k];
 		int32_t o[7];
-		ksw_oracle_align2(j->qlen, a->qpool + j->q_off, j->tlen, a->tpool + j->t_off, c->m, c->mat, c->o_del, c->e_del, c->o_ins,
-		                  c->e_ins, j->xtra, o);
+		align2_impl(j->qlen, a->qpool + j->q_off, j->tlen, a->tpool + j->t_off, c->m, c->mat, c->o_del, c->e_del, c->o_ins,
+		            c->e_ins, j->xtra, o, a->closed);
 		memcpy(&a->res[k], o, sizeof(o));
 		a->res[k].pad = 0;
 	}
 	return 0;
 }
 
-int ksw_oracle_align_batch(const ocfg_t *cfg, int64_t n, const ajob_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
-                           aln_res_t *res, int n_threads)
+static int align_batch_impl(const ocfg_t *cfg, int64_t n, const ajob_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
+                            aln_res_t *res, int n_threads, int closed)
 {
 	int t;
 	pthread_t *tid; aarg_t *args;
@@ -197,11 +221,23 @@ int ksw_oracle_align_batch(const ocfg_t *cfg, int64_t n, const ajob_t *jobs, con
 	tid = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
 	args = (aarg_t *)malloc(sizeof(aarg_t) * n_threads);
 	for (t = 0; t < n_threads; ++t) {
-		aarg_t a = { cfg, jobs, qpool, tpool, res, n, t, n_threads };
+		aarg_t a = { cfg, jobs, qpool, tpool, res, n, t, n_threads, closed };
 		args[t] = a;
 		pthread_create(&tid[t], 0, aworker, &args[t]);
 	}
 	for (t = 0; t < n_threads; ++t) pthread_join(tid[t], 0);
 	free(tid); free(args);
 	return 0;
+}
+
+int ksw_oracle_align_batch(const ocfg_t *cfg, int64_t n, const ajob_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
+                           aln_res_t *res, int n_threads)
+{
+	return align_batch_impl(cfg, n, jobs, qpool, tpool, res, n_threads, 0);
+}
+
+int ksw_oracle_align_batch_closed_form(const ocfg_t *cfg, int64_t n, const ajob_t *jobs, const uint8_t *qpool, const uint8_t *tpool,
+                                       aln_res_t *res, int n_threads)
+{
+	return align_batch_impl(cfg, n, jobs, qpool, tpool, res, n_threads, 1);
 }

@@ -755,6 +755,14 @@ def run_align_oracle(b: ABatch, threads: int = 8):
     return _run_align(oracle_lib().ksw_oracle_align_batch, b, threads)
 
 
+def run_align_oracle_closed_form(b: ABatch, threads: int = 8):
+    """The restatement with the lazy-F loop replaced by its closed form (what the GPU kernel computes when o_ins >= 1)."""
+    lib = oracle_lib()
+    lib.ksw_oracle_align_batch_closed_form.restype = C.c_int
+    lib.ksw_oracle_align_batch_closed_form.argtypes = [C.POINTER(Cfg), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return _run_align(lib.ksw_oracle_align_batch_closed_form, b, threads)
+
+
 def run_align_ref(b: ABatch, threads: int = 8):
     """The same from the reference's own ksw_align2 (oracle/_ref/libksw_ref.so)."""
     return _run_align(ref_lib().ksw_ref_align_batch, b, threads)

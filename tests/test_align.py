@@ -37,6 +37,23 @@ def test_align_oracle_matches_golden_vectors(oracle_built):
     assert n >= 2000
 
 
+def test_align_lazy_f_loop_closed_form_equals_the_loop(oracle_built):
+    """The claim the GPU kernel rests on, checked on the CPU: for o_ins >= 1 the reference's lazy-F loop, with
+    its early stop and its 16-round limit, gives the same results as H' = max(H, carry propagated all the way).  With o_ins = 0
+    it does not (the early stop becomes observable), which is why the kernel keeps the literal loop for that case."""
+    n = 0
+    for seed, cfg in enumerate([None, K.make_cfg(a=2, b=7, o_del=0, e_del=1, o_ins=11, e_ins=3), K.make_cfg(a=1, b=1, o_del=3, e_del=2, o_ins=1, e_ins=1),
+                                K.make_cfg(a=5, b=3, o_del=2, e_del=1, o_ins=1, e_ins=4), K.make_cfg(a=1, b=4, o_del=6, e_del=1, o_ins=6, e_ins=1)]):
+        for b in (K.gen_align(1200, seed=800 + seed, cfg=cfg, max_q=250), K.gen_align(800, seed=820 + seed, cfg=cfg, max_q=60, max_t=300, flags=ALL_FLAGS)):
+            mm = K.align_mismatch(K.run_align_oracle_closed_form(b), K.run_align_oracle(b))
+            assert mm is None, (seed, mm, b.jobs[mm[0]])
+            n += b.n
+    assert n >= 10000
+    # and the counter-example class: zero gap-open for insertions
+    b = K.gen_align(3000, seed=840, cfg=K.make_cfg(a=3, b=2, o_del=0, e_del=1, o_ins=0, e_ins=1), max_q=120, max_t=400)
+    assert K.align_mismatch(K.run_align_oracle_closed_form(b), K.run_align_oracle(b)) is not None
+
+
 def test_align_oracle_known_answers(oracle_built):
     """A read embedded once, exactly: score = qlen * a, ends and starts where it was put; embedded twice: the second-best
     score is the same and points at the other copy."""
