@@ -1815,4 +1815,33 @@ int ksw_global(int qlen, const uint8_t *query, int tlen, const uint8_t *target, 
 	return ksw_global2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, w, n_cigar_, cigar_);
 }
 
+// ksw.h:62-63.  The reference's kswr_t by value; qry (its cached query profile) is not used.
+ksw_b200_kswr_t ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat,
+                           int o_del, int e_del, int o_ins, int e_ins, int xtra, void **qry)
+{
+	(void)qry;
+	ksw_b200_ctx *ctx = scalar_ctx();
+	ksw_b200_cfg_t cfg;
+	memcpy(cfg.mat, mat, 25);
+	cfg.m = m; cfg.o_del = o_del; cfg.e_del = e_del; cfg.o_ins = o_ins; cfg.e_ins = e_ins; cfg.zdrop = 0; cfg.end_bonus = 0;
+	ksw_b200_ajob_t job;
+	job.q_off = 0; job.t_off = 0; job.qlen = qlen; job.tlen = tlen; job.xtra = xtra; job.reserved = 0;
+	ksw_b200_ares_t r;
+	const uint8_t none = 0;
+	const int rc = ksw_b200_align_batch(ctx, &cfg, 1, &job, query, tlen > 0 ? target : &none, &r);
+	if (rc) {
+		fprintf(stderr, "[ksw_b200] fatal: ksw_align2 failed on the GPU (%d): %s\n", rc, ksw_b200_strerror(ctx));
+		abort();
+	}
+	ksw_b200_kswr_t o;
+	o.score = r.score; o.te = r.te; o.qe = r.qe; o.score2 = r.score2; o.te2 = r.te2; o.tb = r.tb; o.qb = r.qb;
+	return o;
+}
+
+ksw_b200_kswr_t ksw_align(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat,
+                          int gapo, int gape, int xtra, void **qry)
+{
+	return ksw_align2(qlen, query, tlen, target, m, mat, gapo, gape, gapo, gape, xtra, qry);
+}
+
 } // extern "C"

@@ -459,3 +459,19 @@ def ksw_global2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, w
     libc.free.argtypes = [C.c_void_p]
     libc.free(C.cast(cig, C.c_void_p))
     return sc, out
+
+
+class _Kswr(C.Structure):                                # kswr_t, ksw.h:30-36
+    _fields_ = [(n, C.c_int) for n in ("score", "te", "qe", "score2", "te2", "tb", "qb")]
+
+
+def ksw_align2(qlen, query, tlen, target, m, mat, o_del, e_del, o_ins, e_ins, xtra):
+    """Scalar drop-in with the reference's argument order (ksw.h:63; qry = NULL).  Returns the kswr_t fields as a dict."""
+    lib = load_library()
+    lib.ksw_align2.restype = _Kswr
+    lib.ksw_align2.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    q = np.ascontiguousarray(query, dtype=np.uint8)
+    t = np.ascontiguousarray(target, dtype=np.uint8)
+    mt = np.ascontiguousarray(mat, dtype=np.int8)
+    r = lib.ksw_align2(qlen, _p(q), tlen, _p(t), m, _p(mt), o_del, e_del, o_ins, e_ins, xtra, None)
+    return {n: getattr(r, n) for n, _ in _Kswr._fields_}

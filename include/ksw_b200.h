@@ -226,6 +226,17 @@ typedef struct {               /* kswr_t, ksw.h:30-36 (unset fields are -1 like 
 	int32_t reserved;
 } ksw_b200_ares_t;
 
+/* Scalar drop-ins with the reference's signatures (ksw.h:62-63; kswr_t, ksw.h:30-36, by value).  One job = one GPU round
+ * trip; the sequences are not modified (the reference reverses them in place and back).  qry (the reference's cached query
+ * profile) is not used: if given, *qry is left as it is. */
+typedef struct { int score; int te, qe; int score2, te2; int tb, qb; } ksw_b200_kswr_t;
+#ifndef __AC_KSW_H              /* a unit that has included the reference's ksw.h already has these two, with kswr_t / kswq_t */
+ksw_b200_kswr_t ksw_align2(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat,
+                           int o_del, int e_del, int o_ins, int e_ins, int xtra, void **qry);
+ksw_b200_kswr_t ksw_align(int qlen, uint8_t *query, int tlen, uint8_t *target, int m, const int8_t *mat,
+                          int gapo, int gape, int xtra, void **qry);
+#endif
+
 /* cfg: mat, m (= 5), o_del, e_del, o_ins, e_ins are used */
 int ksw_b200_align_batch(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_ajob_t *jobs,
                          const uint8_t *qpool, const uint8_t *tpool, ksw_b200_ares_t *res);

@@ -163,3 +163,17 @@ def test_gpu_align_through_the_shared_queue(oracle_built):
     st = q.stats()
     assert st["submissions"] == 32 and st["batches"] <= 32
     q.close()
+
+
+@pytest.mark.gpu
+def test_gpu_align_scalar_dropin(oracle_built):
+    """ksw_align2 with the reference's signature (kswr_t by value), one job per call."""
+    import bwa_mem_quickassist_b200 as B
+    b = K.gen_align(30, seed=795, max_q=200, max_t=500)
+    want = K.run_align_oracle(b)
+    for k in range(b.n):
+        j = b.jobs[k]
+        q = b.qpool[int(j["q_off"]):int(j["q_off"]) + int(j["qlen"])]
+        t = b.tpool[int(j["t_off"]):int(j["t_off"]) + int(j["tlen"])]
+        r = B.ksw_align2(int(j["qlen"]), q, int(j["tlen"]), t, 5, K.cfg_mat(b.cfg), b.cfg.o_del, b.cfg.e_del, b.cfg.o_ins, b.cfg.e_ins, int(j["xtra"]))
+        assert tuple(r[f] for f in ("score", "te", "qe", "score2", "te2", "tb", "qb")) == tuple(int(want[f][k]) for f in ("score", "te", "qe", "score2", "te2", "tb", "qb")), k
