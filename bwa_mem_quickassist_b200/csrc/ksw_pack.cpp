@@ -6,6 +6,8 @@
 #include <cstring>
 #include <thread>
 
+int ksw_pack_force_words = 0;
+
 namespace {
 
 // splits [0,n) into contiguous ranges, one per pool thread (serial when pool is null or n is small)
@@ -61,7 +63,7 @@ inline uint32_t squeeze16(uint64_t a, uint64_t b)
 
 // 2-bit packing of `len` byte codes into ceil(len/16) words.  Returns true if a code > 3 (N) was seen; those bases
 // are stored as 0 and flagged in nmask (ceil(len/32) words), which is zeroed here on the first N and otherwise untouched.
-inline bool pack2(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
+inline bool pack2_words(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
 {
 	bool has_n = false;
 	const int full = len >> 4;
@@ -101,6 +103,47 @@ inline bool pack2(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
 		out[full] = ((a | b) & 0xFCFCFCFCFCFCFCFCull) ? slow_word(s + 16 * full, 16 * full, rem) : squeeze16(a, b);
 	}
 	return has_n;
+}
+
+#ifdef KSW_HAVE_PEXT
+#include <immintrin.h>
+// 64 byte codes per step: two multiply-adds fold four codes into one byte (c0 + 4 c1, then + 16 (c2 + 4 c3)), a narrowing
+// move gathers the sixteen bytes = four words of the 2-bit stream.  Bytes past the end are never touched (masked load)
+// and pack as 0.  WRITES WHOLE 16-BYTE GROUPS: up to three words past ceil(len/16) are zeroed (the caller's line buffer
+// has the room, and packs the query before the target).  An N anywhere sends the whole sequence down the word path.
+__attribute__((target("avx512f,avx512bw"))) bool pack2_avx512(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
+{
+	const __m512i not2 = _mm512_set1_epi8((char)0xFC), w14 = _mm512_set1_epi16(0x0401), w116 = _mm512_set1_epi32(0x00100001);
+	__mmask64 bad = 0;
+	int k = 0;
+	for (; k + 64 <= len; k += 64) {
+		const __m512i v = _mm512_loadu_si512((const void *)(s + k));
+		bad |= _mm512_test_epi8_mask(v, not2);
+		const __m512i y = _mm512_madd_epi16(_mm512_maddubs_epi16(v, w14), w116);
+		_mm_storeu_si128((__m128i *)(out + (k >> 4)), _mm512_cvtepi32_epi8(y));
+	}
+	if (k < len) {
+		const __m512i v = _mm512_maskz_loadu_epi8(~0ull >> (64 - (len - k)), (const void *)(s + k));
+		bad |= _mm512_test_epi8_mask(v, not2);
+		const __m512i y = _mm512_madd_epi16(_mm512_maddubs_epi16(v, w14), w116);
+		const __m128i r = _mm512_cvtepi32_epi8(y);
+		if (len - k > 32) _mm_storeu_si128((__m128i *)(out + (k >> 4)), r);
+		else _mm_storel_epi64((__m128i *)(out + (k >> 4)), r);
+	}
+	return bad ? pack2_words(s, len, out, nmask) : false;
+}
+const bool g_has_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && !getenv("KSW_B200_PACK_WORDS");
+#endif
+
+// how many words past ceil(len/16) pack2 may zero
+#define KSW_PACK2_SLACK 3
+
+inline bool pack2(const uint8_t *s, int len, uint32_t *out, uint32_t *nmask)
+{
+#ifdef KSW_HAVE_PEXT
+	if (g_has_avx512 && !ksw_pack_force_words) return pack2_avx512(s, len, out, nmask);
+#endif
+	return pack2_words(s, len, out, nmask);
 }
 
 } // namespace
@@ -222,7 +265,7 @@ int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_
 			const uint32_t qmw = ksw_words1(j.qlen), tmw = ksw_words1(j.tlen);
 			if (qm.size() < qmw) qm.resize(qmw);
 			if (tm.size() < tmw) tm.resize(tmw);
-			if (line.size() < units * 4u) line.resize(units * 4u);
+			if (line.size() < units * 4u + KSW_PACK2_SLACK) line.resize(units * 4u + KSW_PACK2_SLACK);
 			uint32_t *dst = line.data();
 			const bool qn = pack2(qpool + j.q_off, j.qlen, dst, qm.data());
 			const bool tn = pack2(tpool + j.t_off, j.tlen, dst + qw, tm.data());

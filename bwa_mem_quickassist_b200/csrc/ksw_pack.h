@@ -53,6 +53,10 @@ int ksw_pack_stream(KswPackStats &st, const ksw_b200_cfg_t *cfg, const ksw_b200_
                     const uint8_t *qpool, const uint8_t *tpool, DevJob *dj, uint32_t *pool,
                     std::vector<uint32_t> &nmask, KswPool *tp);
 
+// A/B and test switch: non-zero keeps the packer on its word-at-a-time path where the 64-byte SIMD path would run
+// (also KSW_B200_PACK_WORDS=1 in the environment at load time); the two paths write identical bytes
+extern int ksw_pack_force_words;
+
 void ksw_params_from_cfg(const ksw_b200_cfg_t *cfg, KswParams &P);
 void ksw_scoring_from_cfg(const ksw_b200_cfg_t *cfg, int fast_qmax, KswScoring &S);
 

@@ -68,7 +68,7 @@ double now_ms()
 } // namespace
 
 #define KSW_N_SLOTS 6
-#define KSW_N_HSLOTS 3
+#define KSW_N_HSLOTS 8         /* staging sets the host lane may own; it uses ctx->n_hslots of them */
 
 // ------------------------------------------------------------------ opaque types
 struct ksw_b200_batch {       // a packed batch in HBM + what the launcher needs to know about it
@@ -164,6 +164,10 @@ struct ksw_b200_ctx {
 	cudaStream_t up_stream = nullptr, pre_stream = nullptr, main_stream = nullptr, ext2_stream = nullptr, host_stream = nullptr, down_stream = nullptr, hdown_stream = nullptr;
 	int hybrid = 1;                        // a second lane packs chunks on the host threads (KSW_B200_HYBRID=0: device packing only)
 	Slot hslot[KSW_N_HSLOTS];                         // that lane's staging / device buffers (events only; it uses the shared streams)
+	int n_hslots = 3;                                 // how many of them it cycles through (KSW_B200_HSLOTS)
+	cudaStream_t hup_stream = nullptr;                // the host lane's own upload stream (KSW_B200_HUP=1; default: up_stream)
+	int hup = 0;
+	std::vector<int64_t> lead_jobs;                   // sizes of the call's first chunks (KSW_B200_LEAD=a,b,..; default chunk/4, chunk/2)
 	double host_ms_per_job = 0, dev_ms_per_job = 0;   // measured pace of the two lanes (0 = not measured yet)
 	RefEntry *ref = nullptr;               // ksw_b200_ref_set
 	PinnedBuf h_rq;                        // ksw_b200_extend_batch_ref: staging of a pageable read pool
@@ -473,6 +477,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ext2_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->hup_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -483,7 +488,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 			for (cudaEvent_t ev : {s.ev_jobs, s.ev_stats, s.ev_up, s.ev_packed, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
 		}
 		for (Slot &s : ctx->hslot) for (cudaEvent_t ev : {s.ev_up, s.ev_ext, s.ev_done}) if (ev) cudaEventDestroy(ev);
-		for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) if (st) cudaStreamDestroy(st);
+		for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream, ctx->hup_stream}) if (st) cudaStreamDestroy(st);
 		if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 		if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 		delete ctx;
@@ -494,6 +499,17 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	if (const char *s = getenv("KSW_B200_CHUNK")) ctx->chunk_jobs = ctx->async_chunk_jobs = std::max<int64_t>(1024, atoll(s));
 	if (const char *s = getenv("KSW_B200_TRACE")) ctx->trace = atoi(s);
 	if (const char *s = getenv("KSW_B200_HYBRID")) ctx->hybrid = atoi(s);
+	if (const char *s = getenv("KSW_B200_HSLOTS")) ctx->n_hslots = std::max(1, std::min(KSW_N_HSLOTS, atoi(s)));
+	if (const char *s = getenv("KSW_B200_HUP")) ctx->hup = atoi(s);
+	if (const char *s = getenv("KSW_B200_LEAD")) {
+		for (const char *p = s; *p;) {
+			char *end = nullptr;
+			const long long v = strtoll(p, &end, 10);
+			if (end == p) break;
+			if (v > 0) ctx->lead_jobs.push_back(v);
+			p = *end ? end + 1 : end;
+		}
+	}
 	*out = ctx;
 	return 0;
 }
@@ -524,7 +540,7 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 	ctx->d_qraw.release(); ctx->d_traw.release();
 	ctx->h_rq.release();
 	ref_release(ctx);
-	for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+	for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream, ctx->hup_stream}) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
 	for (Slot &s : ctx->hslot) {
 		batch_release_buffers(&s.batch);
 		s.h_jobs.release(); s.h_pool.release(); s.h_npool.release();
@@ -822,13 +838,14 @@ static void devpack_host_lane(ksw_b200_ctx_t *ctx, DevpackShared *sh, const ksw_
 		const long long ci = sh->next.fetch_add(1);
 		if (ci >= sh->n_chunks) break;
 		const int64_t first = sh->start[(size_t)ci], nc = sh->start[(size_t)ci + 1] - first;
-		Slot &s = ctx->hslot[k++ % KSW_N_HSLOTS];
+		Slot &s = ctx->hslot[k++ % ctx->n_hslots];
 		int rc = devpack_wait_slot(ctx, s);
 		double t_plan = 0, t_fill = 0;
-		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, &t_plan, &t_fill, ctx->up_stream, ctx->host_stream);
+		cudaStream_t hup = ctx->hup ? ctx->hup_stream : ctx->up_stream;
+		if (!rc) rc = pack_and_upload(ctx, s, cfg, nc, jobs + first, qpool, tpool, &s.batch, &t_plan, &t_fill, hup, ctx->host_stream);
 		const double dt = t_plan + t_fill;                           // packing proper: buffer growth (first calls) is not the lane's pace
 		ChunkTimes *tm = sh->times.empty() ? nullptr : &sh->times[(size_t)ci];
-		if (tm) { tm->lane = 1; tm->host_enq = now_ms() - sh->host_t0; cudaEventCreate(&tm->up); cudaEventRecord(tm->up, ctx->up_stream); }
+		if (tm) { tm->lane = 1; tm->host_enq = now_ms() - sh->host_t0; cudaEventCreate(&tm->up); cudaEventRecord(tm->up, hup); }
 		if (!rc) rc = devpack_finish_chunk(ctx, s, first, nc, res, ctx->host_stream, ctx->hdown_stream, tm);
 		if (rc) { int z = 0; sh->rc.compare_exchange_strong(z, rc); break; }
 		ctx->host_ms_per_job = ctx->host_ms_per_job <= 0 ? dt / (double)nc : 0.5 * ctx->host_ms_per_job + 0.5 * dt / (double)nc;
@@ -855,10 +872,11 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 	DevpackShared sh;
 	{
 		int64_t at = 0;
-		const int64_t lead[2] = {std::max<int64_t>(chunk / 4, 1024), std::max<int64_t>(chunk / 2, 1024)};
-		for (int i = 0; at < n; ++i) {
+		std::vector<int64_t> lead = ctx->lead_jobs;
+		if (lead.empty()) lead = {std::max<int64_t>(chunk / 4, 1024), std::max<int64_t>(chunk / 2, 1024)};
+		for (size_t i = 0; at < n; ++i) {
 			sh.start.push_back(at);
-			at += std::min<int64_t>(n - at, (i < 2 && n > 2 * chunk) ? lead[i] : chunk);
+			at += std::min<int64_t>(n - at, (i < lead.size() && n > 2 * chunk) ? std::max<int64_t>(lead[i], 1024) : chunk);
 		}
 		sh.start.push_back(n);
 		sh.n_chunks = (long long)sh.start.size() - 1;
@@ -876,7 +894,8 @@ static int extend_batch_devpack(ksw_b200_ctx_t *ctx, const ksw_b200_cfg_t *cfg, 
 		pool_of(ctx);                                               // created here, used by the host lane only
 		// the lane's pinned staging is sized here, from the average job, so that its first chunk does not pay for it
 		const size_t per_job = (size_t)((qbytes + tbytes) / (size_t)n) / 4 + 24;
-		for (Slot &hs : ctx->hslot) {
+		for (int i = 0; i < ctx->n_hslots; ++i) {
+			Slot &hs = ctx->hslot[i];
 			CU(hs.h_jobs.reserve(sizeof(DevJob) * (size_t)chunk));
 			CU(hs.h_pool.reserve(per_job * (size_t)chunk));
 		}
@@ -1035,7 +1054,7 @@ static int run_devpack(ksw_b200_ctx_t *ctx, const AsyncReq &r)
 	const int rc = extend_batch_devpack(ctx, &r.cfg, r.n, r.jobs, r.qpool, r.qbytes, r.tpool, r.tbytes, r.res);
 	if (rc) {
 		// leave the context reusable: nothing may stay in flight or marked busy after a failed call
-		for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream}) cudaStreamSynchronize(st);
+		for (cudaStream_t st : {ctx->up_stream, ctx->pre_stream, ctx->main_stream, ctx->ext2_stream, ctx->host_stream, ctx->down_stream, ctx->hdown_stream, ctx->hup_stream}) cudaStreamSynchronize(st);
 		for (Slot &s : ctx->slot) { cudaStreamSynchronize(s.stream); s.busy = false; }
 		for (Slot &s : ctx->hslot) s.busy = false;
 	}

@@ -194,3 +194,33 @@ extern "C" int ksw_gfast_emu_batch(const ksw_b200_cfg_t *cfg, int64_t n, const k
 	if (n_fast_out) *n_fast_out = n_fast;
 	return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The host packer alone: what ksw_pack_sizes + ksw_pack_stream write (job records, 2-bit pool, N side pool), with the
+// 64-byte SIMD path or the word-at-a-time path (force_words != 0), so that a test can compare the two byte for byte.
+// Returns 0, a packer error code, or -1 when an output array is too small.
+extern "C" int ksw_pack_emu(const ksw_b200_cfg_t *cfg, int64_t n, const ksw_b200_job_t *jobs, const uint8_t *qpool,
+                            const uint8_t *tpool, int force_words, int threads, void *dj_out, uint32_t *pool_out,
+                            int64_t pool_cap_words, int64_t *pool_words, uint32_t *nmask_out, int64_t nmask_cap_words,
+                            int64_t *nmask_words, int64_t *class_n_out)
+{
+	KswPool tp(threads);
+	KswPackStats st;
+	std::string err;
+	const int fast_qmax = KSW_FAST_CLASS_QMAX[KSW_FAST_CLASSES - 1];
+	int rc = ksw_pack_sizes(cfg, n, jobs, fast_qmax, &tp, st, err);
+	if (rc) return rc;
+	if ((int64_t)(st.pool_bytes / 4) > pool_cap_words) return -1;
+	std::vector<uint32_t> nmask;
+	const int saved = ksw_pack_force_words;
+	ksw_pack_force_words = force_words;
+	rc = ksw_pack_stream(st, cfg, jobs, fast_qmax, qpool, tpool, (DevJob *)dj_out, pool_out, nmask, &tp);
+	ksw_pack_force_words = saved;
+	if (rc) return rc;
+	if ((int64_t)nmask.size() > nmask_cap_words) return -1;
+	if (!nmask.empty()) memcpy(nmask_out, nmask.data(), nmask.size() * 4);
+	*pool_words = (int64_t)(st.pool_bytes / 4);
+	*nmask_words = (int64_t)nmask.size();
+	for (int c = 0; c < KSW_N_CLASSES; ++c) class_n_out[c] = st.class_n[c];
+	return 0;
+}

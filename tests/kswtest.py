@@ -378,6 +378,22 @@ def run_emu(b: Batch, threads: int = 4):
     return res, int(nf.value)
 
 
+def run_packer(b: Batch, force_words: bool, threads: int = 3):
+    """What the product's host packer writes for a batch: (job records as raw uint32[n, 8], 2-bit pool words, N side
+    pool words, jobs per kernel class), through the 64-byte SIMD path or the word-at-a-time path."""
+    cap = int((b.jobs["qlen"].astype(np.int64) + b.jobs["tlen"] + 94).sum() // 4 + 64)
+    dj = np.zeros((max(b.n, 1), 8), dtype=np.uint32)
+    pool = np.full(cap, 0xdeadbeef, dtype=np.uint32)
+    ncap = int((b.jobs["qlen"].astype(np.int64) + b.jobs["tlen"] + 64).sum() // 32 + 2 * b.n + 8)
+    nm = np.zeros(ncap, dtype=np.uint32)
+    pw, nw = C.c_int64(0), C.c_int64(0)
+    cn = (C.c_int64 * 6)()
+    rc = emu_lib().ksw_pack_emu(C.byref(b.cfg), C.c_int64(b.n), _ptr(b.jobs), _ptr(b.qpool), _ptr(b.tpool), int(force_words), threads,
+                                _ptr(dj), _ptr(pool), C.c_int64(cap), C.byref(pw), _ptr(nm), C.c_int64(ncap), C.byref(nw), cn)
+    assert rc == 0, rc
+    return dj[:b.n], pool[:pw.value].copy(), nm[:nw.value].copy(), [int(x) for x in cn]
+
+
 # ------------------------------------------------------------------ chains -> regions (mem_chain2aln level)
 SEED_DT = np.dtype([("rbeg", "<i8"), ("qbeg", "<i4"), ("len", "<i4")])                      # mem_seed_t
 REG_DT = np.dtype([("rb", "<i8"), ("re", "<i8"), ("qb", "<i4"), ("qe", "<i4"), ("score", "<i4"), ("truesc", "<i4"),

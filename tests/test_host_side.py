@@ -36,6 +36,41 @@ def test_fast_lane_source_fuzz_vs_oracle(oracle_built):
         assert mm is None, mm
 
 
+def test_packer_simd_path_writes_the_same_bytes_as_the_word_path(oracle_built):
+    """ksw_pack.cpp packs 64 byte codes per step where the CPU has AVX-512BW; that path, the word-at-a-time path and
+    a numpy restatement of the layout (ksw_dev.cuh: base k of a sequence in word k/16 at bits 2(k%16), N as 0 + mask
+    bit) must agree on every byte: job records, 2-bit pool, N side pool, class counts."""
+    cases = [K.gen_fuzz(3000, seed=311), K.gen_fuzz(600, seed=312, max_q=700), K.gen_config2(2000, seed=313),
+             K.gen_fuzz(1500, seed=314, max_q=70, n_frac=0.3), K.gen_adversarial()]
+    for b in cases:
+        dj_s, pool_s, nm_s, cn_s = K.run_packer(b, force_words=False)
+        dj_w, pool_w, nm_w, cn_w = K.run_packer(b, force_words=True)
+        assert cn_s == cn_w
+        assert np.array_equal(dj_s, dj_w) and np.array_equal(pool_s, pool_w) and np.array_equal(nm_s, nm_w)
+        # independent check of the pool: every job's query and target words
+        seq_off, flags, nmask_off = dj_s[:, 0].astype(np.int64), dj_s[:, 6], dj_s[:, 7].astype(np.int64)
+        for k in range(0, b.n, 7):
+            j = b.jobs[k]
+            at = seq_off[k] * 4
+            noff = nmask_off[k]
+            for bit, pool_in, off, ln in ((1, b.qpool, int(j["q_off"]), int(j["qlen"])), (2, b.tpool, int(j["t_off"]), int(j["tlen"]))):
+                codes = pool_in[off:off + ln].astype(np.uint32)
+                isn = codes > 3
+                pad = np.zeros((-ln) % 16, dtype=np.uint32)
+                c2 = np.concatenate([np.where(isn, 0, codes), pad]).reshape(-1, 16)
+                want = (c2 << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1).astype(np.uint32)
+                assert np.array_equal(pool_s[at:at + len(want)], want), (k, bit)
+                at += len(want)
+                assert bool(flags[k] & bit) == bool(isn.any()), (k, bit)
+                if isn.any():
+                    mpad = np.zeros((-ln) % 32, dtype=np.uint32)
+                    mw = (np.concatenate([isn.astype(np.uint32), mpad]).reshape(-1, 32) << np.arange(32, dtype=np.uint32)).sum(axis=1).astype(np.uint32)
+                    assert np.array_equal(nm_s[noff:noff + len(mw)], mw), (k, bit)
+                    noff += len(mw)
+            units = int(dj_s[k + 1, 0]) - int(seq_off[k]) if k + 1 < b.n else (len(pool_s) // 4 - int(seq_off[k]))
+            assert not pool_s[at:(int(seq_off[k]) + units) * 4].any(), k      # padding words are zero
+
+
 def test_packer_routes_out_of_range_jobs_to_generic(oracle_built):
     b = K.gen_fuzz(300, seed=306, h0_max=60000)
     got, n_fast = K.run_emu(b)
