@@ -148,7 +148,10 @@ struct ksw_b200_ctx {
 	int pack_threads = 8;
 	KswPool *pool = nullptr;               // (re)created lazily with pack_threads workers
 	int64_t chunk_jobs = 1 << 20;
-	int64_t async_chunk_jobs = 1 << 19;    // pinned-caller pipeline: shorter chunks, the two lanes share them one by one
+	// pinned-caller pipeline: shorter chunks, the two lanes share them one by one.  Config 2, 10 M jobs, 16 host threads, with
+	// the 64-byte host packer: 2^18 -> 40.4 ms per call, 393216 -> 40.8, 2^19 -> 42.3, 786432 -> 44.6, 2^20 -> 47.1
+	// (profiles/r2_e2e_knobs_sweep.txt): short chunks let the host lane take 17 of 40 instead of 7 of 21
+	int64_t async_chunk_jobs = 1 << 18;
 	int trace = 0;
 	std::atomic<long long> launches{0};
 	int64_t last_h2d = 0, last_d2h = 0;    // bytes moved by the last ksw_b200_extend_batch call
@@ -460,15 +463,29 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	ksw_b200_ctx *ctx = new ksw_b200_ctx();
 	ctx->device = device;
 	cudaError_t e = cudaSetDevice(device);
+	// the events a feeder thread sleeps on (chunk totals back, a slot's results home).  Blocking-sync events make those
+	// waits yield the core instead of spinning: the feeder threads of the pinned-caller pipeline wait most of a call, and
+	// on a box with few cores per GPU a spinning feeder takes a core away from the host lane's pack threads
+	// (measured with the process pinned to 4 cores: 43.8 -> 43.0 ms per 10 M config-2 jobs; with 16 cores 40.2 vs 40.5).
+	// Default: on when the box has fewer than 8 hardware threads per GPU.
+	unsigned wait_flags = cudaEventDisableTiming;
+	{
+		int n_dev = 1;
+		if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) n_dev = 1;
+		const unsigned hw0 = std::thread::hardware_concurrency();
+		bool blocking = hw0 && hw0 / (unsigned)n_dev < 8u;
+		if (const char *s = getenv("KSW_B200_BLOCKSYNC")) blocking = atoi(s) != 0;
+		if (blocking) wait_flags |= cudaEventBlockingSync;
+	}
 	for (int i = 0; i < KSW_N_SLOTS && e == cudaSuccess; ++i) {
 		Slot &s = ctx->slot[i];
 		e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
 		cudaEvent_t *evs[6] = {&s.ev_jobs, &s.ev_stats, &s.ev_up, &s.ev_packed, &s.ev_ext, &s.ev_done};
-		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, (ev == &s.ev_stats || ev == &s.ev_done) ? wait_flags : cudaEventDisableTiming);
 	}
 	for (Slot &s : ctx->hslot) {
 		cudaEvent_t *evs[3] = {&s.ev_up, &s.ev_ext, &s.ev_done};
-		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+		for (cudaEvent_t *ev : evs) if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, ev == &s.ev_done ? wait_flags : cudaEventDisableTiming);
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking);
