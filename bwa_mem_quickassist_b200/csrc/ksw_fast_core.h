@@ -61,6 +61,7 @@ __device__ __forceinline__ uint32_t addmax2_relu(uint32_t a, uint32_t b, uint32_
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 __device__ __forceinline__ uint32_t maxu2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
 __device__ __forceinline__ uint32_t addmaxu2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b, bool &ge_hi, bool &ge_lo) { return __vibmax_s16x2(a, b, &ge_hi, &ge_lo); }
@@ -96,6 +97,7 @@ KSW_EMU uint32_t addmaxu2(uint32_t a, uint32_t b, uint32_t c)   // max(a + b, c)
 	const uint32_t sl = (a + b) & 0xffffu, sh = ((a >> 16) + (b >> 16)) & 0xffffu, cl = c & 0xffffu, ch = c >> 16;
 	return (sl > cl ? sl : cl) | ((sh > ch ? sh : ch) << 16);
 }
+KSW_EMU uint32_t max3u2(uint32_t a, uint32_t b, uint32_t c) { return maxu2(maxu2(a, b), c); }
 KSW_EMU uint32_t min3_2(uint32_t a, uint32_t b, uint32_t c)
 {
 	return pk16(mn(mn(lo16(a), lo16(b)), lo16(c)), mn(mn(hi16(a), hi16(b)), hi16(c)));
@@ -129,11 +131,13 @@ KSW_EMU uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)   // PTX prmt.b32, gen
 #define KSW_KEY_RA 0x00020000u      /* columns of pair A relative to its quad: lo 0, hi 2 */
 #define KSW_KEY_RB 0x00030001u      /* pair B: lo 1, hi 3 */
 #define KSW_KEY_DEC 0xfffcfffcu     /* -4 in both halves: the running key maximum moves back one quad */
+#define KSW_KEY_STEP 0x00040004u    /* the same step as a 32-bit subtrahend */
 #define KSW_KEY_INIT 0x00800080u    /* 4 * 32 quads: never wraps below 0 and never beats a real key (>= 128 * B, B >= 1) */
 
 struct KswFastConst {
 	uint32_t neg_ei, neg_oei;                    // both halves: -e_ins, -(o_ins+e_ins)
 	uint32_t neg_2ei;                            // both halves: -2*e_ins
+	uint32_t neg_ed, neg_oed;                    // both halves: -e_del, -(o_del+e_del)
 	uint32_t ed32, oed32;                        // both halves: e_del, o_del+e_del (subtracted with 32-bit IADDs)
 	uint32_t Bpk;                                // both halves: the bias B = o_del+e_del carried by every H/E/F value
 	int32_t B;
@@ -142,6 +146,7 @@ struct KswFastConst {
 	// the compiler cannot fold (built from a kernel-parameter byte that is always 0), so that key = h*128 + column
 	// stays one multiply-add on the FMA pipe instead of a shift-add with an immediate on the ALU pipe.
 	uint32_t keyRA, keyRB;
+	uint32_t one;                                // 1, unfoldable like keyRA / keyRB
 };
 
 struct KswFastLane {
@@ -165,9 +170,11 @@ static KSW_HD void ksw_fast_make_const(const KswParams &P, KswFastConst &K)
 {
 	K.neg_ei = ksw_pk2(-P.e_ins); K.neg_oei = ksw_pk2(-(P.o_ins + P.e_ins)); K.neg_2ei = ksw_pk2(-2 * P.e_ins);
 	K.ed32 = ksw_pk2(P.e_del); K.oed32 = ksw_pk2(P.o_del + P.e_del);
+	K.neg_ed = ksw_pk2(-P.e_del); K.neg_oed = ksw_pk2(-(P.o_del + P.e_del));
 	K.B = P.o_del + P.e_del; K.Bpk = ksw_pk2(K.B);
 	K.o_del = P.o_del; K.e_del = P.e_del; K.e_ins = P.e_ins; K.oe_ins = P.o_ins + P.e_ins; K.zdrop = P.zdrop;
 	K.keyRA = KSW_KEY_RA + (uint32_t)(uint8_t)P.pad[0]; K.keyRB = KSW_KEY_RB + (uint32_t)(uint8_t)P.pad[0];
+	K.one = 1u + (uint32_t)(uint8_t)P.pad[0];
 }
 
 // row t of the scoring matrix as PRMT source bytes: x = mat[t][0..3], y = mat[t][4] (upper bytes 0)
@@ -339,12 +346,25 @@ static KSW_HD void ksw_fast_quad(KswFastRowRegs &R, ksw_u4 *dst, const KswFastCo
 #endif
 	const uint32_t hA = addmax2(FA, K.neg_oei, hpA), hB = addmax2(FB, K.neg_oei, hpB);   // max(F, h')
 	// E(i+1,j) = max(E - e_del, H - oe_del, 0); every half is >= B >= oe_del, so the 32-bit subtractions cannot borrow
+#ifdef KSW_V_E2
+	// two fused add-max per pair instead of two subtractions and a three-way maximum: one instruction fewer per pair, all on the ALU pipe
+	uint32_t eA = addmax2(v.y, K.neg_ed, addmax2(hA, K.neg_oed, K.Bpk));
+	uint32_t eB = addmax2(v.w, K.neg_ed, addmax2(hB, K.neg_oed, K.Bpk));
+#else
 	uint32_t eA = max3_2(v.y - K.ed32, hA - K.oed32, K.Bpk);
 	uint32_t eB = max3_2(v.w - K.ed32, hB - K.oed32, K.Bpk);
+#endif
 	// row maximum, ties to the last column (ksw.c:434)
 	if (KEYED) {
+#ifdef KSW_V_KEYMAX3
+		// one three-way maximum instead of two two-way ones; the running key moves back by four columns with a 32-bit
+		// subtraction (borrow-free: a half never falls below 4, see KSW_KEY_INIT), written as a multiply-add by a
+		// register the compiler cannot fold (always 1) so that it issues on the FMA pipe
+		R.m = max3u2(R.m * K.one - KSW_KEY_STEP, hA * 128u + K.keyRA, hB * 128u + K.keyRB);
+#else
 		R.m = addmaxu2(R.m, KSW_KEY_DEC, hA * 128u + K.keyRA);
 		R.m = maxu2(R.m, hB * 128u + K.keyRB);
+#endif
 	} else {
 		// per half (each half sees its columns in rising order)
 		const int c0 = q << 2;
@@ -471,11 +491,39 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 		uint32_t swn = ps[T];
 		ksw_fast_quad<T, KEYED, true>(R, ph, K, mr, q0, v, sw, eL.geA, eL.geB, eL.onlyA, eL.onlyB, left0pk, 0u, 0u);
 		ksw_u4 *const pl = M.hq + q1 * T;
+#ifdef KSW_V_PTRIMAD
+		// The interior quads q0+1 .. q1-1 by quad index: the index advances with a multiply-add by K.one (a register the
+		// compiler cannot fold), so it and the two addresses derived from it (index * stride + base) are computed on the
+		// FMA pipe instead of three pointer increments on the ALU pipe, which is the one the cells saturate.  Two quads
+		// per turn (an odd one first); (vn, swn) always hold the next quad.
+		uint32_t qi = (uint32_t)q0 + 1u;
+		const uint32_t qe = (uint32_t)q1;
+		if ((qe - qi) & 1u) {
+			ksw_u4 *p = M.hq + qi * T;
+			const uint32_t *s = M.sq + qi * T;
+			v = vn; sw = swn;
+			vn = p[T]; swn = s[T];
+			ksw_fast_quad<T, KEYED, false>(R, p, K, mr, (int)qi, v, sw, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+			qi = qi * K.one + 1u;
+		}
+		while (qi != qe) {
+			ksw_u4 *p = M.hq + qi * T;
+			const uint32_t *s = M.sq + qi * T;
+			v = vn; sw = swn;
+			const ksw_u4 v1 = p[T]; const uint32_t sw1 = s[T];
+			vn = p[2 * T]; swn = s[2 * T];
+			ksw_fast_quad<T, KEYED, false>(R, p, K, mr, (int)qi, v, sw, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+			ksw_fast_quad<T, KEYED, false>(R, p + T, K, mr, (int)qi + 1, v1, sw1, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+			qi = qi * K.one + 2u;
+		}
+#else
 		int q = q0 + 1;
 		ph += T; ps += T;
 #ifdef __CUDACC__
-#ifdef KSW_V_UNROLL4
+#if defined(KSW_V_UNROLL4)
 #pragma unroll 4
+#elif defined(KSW_V_UNROLL1)
+#pragma unroll 1
 #else
 #pragma unroll 2
 #endif
@@ -485,6 +533,7 @@ static KSW_HD bool ksw_fast_row(KswFastLane &L, const KswFastMem<T> &M, const Ks
 			vn = ph[T]; swn = ps[T];
 			ksw_fast_quad<T, KEYED, false>(R, ph, K, mr, q, v, sw, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
 		}
+#endif
 		ksw_fast_quad<T, KEYED, true>(R, pl, K, mr, q1, vn, swn, eR.ltA, eR.ltB, 0u, 0u, 0u, eR.onlyA, eR.onlyB);
 	}
 	// H(i, hi-1): the reference's h1 after the loop

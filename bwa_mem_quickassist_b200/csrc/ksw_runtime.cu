@@ -143,7 +143,7 @@ struct AsyncReq {
 struct ksw_b200_ctx {
 	int device = 0;
 	int sm_count = 148;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
 	std::string err;
 	int pack_threads = 8;
 	KswPool *pool = nullptr;               // (re)created lazily with pack_threads workers
@@ -566,6 +566,7 @@ void ksw_b200_ctx_destroy(ksw_b200_ctx_t *ctx)
 	}
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
 	ctx->g_st[0].release(); ctx->g_st[1].release();
 	ctx->a_hjobs.release(); ctx->a_hseq.release(); ctx->a_hres.release(); ctx->a_horder.release();
 	ctx->a_djobs.release(); ctx->a_dseq.release(); ctx->a_dres.release(); ctx->a_dorder.release(); ctx->a_dcounter.release();
@@ -626,12 +627,13 @@ int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b)
 	return enqueue_kernels(ctx, ctx->slot[0], b);
 }
 
-int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms)
+int ksw_b200_batch_run_timed2(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms, float *ms_ext)
 {
 	if (!ctx || !b || iters < 1 || !ms) return 1;
 	CU(cudaSetDevice(ctx->device));
 	Slot &s = ctx->slot[0];
 	const size_t n1 = (size_t)std::max<int64_t>(b->n, 1);
+	if (ms_ext && !ctx->ev_mid) CU(cudaEventCreate(&ctx->ev_mid));
 	for (int i = 0; i < iters; ++i) {
 		CU(cudaEventRecord(ctx->ev0, s.stream));
 		// a step is everything the GPU does for a packed batch: binning (key kernel + radix sort) and the extension kernels
@@ -640,13 +642,20 @@ int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters
 			                  (uint32_t *)b->d_vals.p, (uint32_t *)b->d_order.p, b->d_sort_tmp.p, b->d_sort_tmp.cap, s.stream));
 			ctx->launches += 2;
 		}
+		if (ms_ext) CU(cudaEventRecord(ctx->ev_mid, s.stream));
 		int rc = enqueue_kernels(ctx, s, b);
 		if (rc) return rc;
 		CU(cudaEventRecord(ctx->ev1, s.stream));
 		CU(cudaEventSynchronize(ctx->ev1));
 		CU(cudaEventElapsedTime(&ms[i], ctx->ev0, ctx->ev1));
+		if (ms_ext) CU(cudaEventElapsedTime(&ms_ext[i], ctx->ev_mid, ctx->ev1));
 	}
 	return 0;
+}
+
+int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms)
+{
+	return ksw_b200_batch_run_timed2(ctx, b, iters, ms, nullptr);
 }
 
 int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_res_t *res)

@@ -118,6 +118,7 @@ def load_library():
     lib.ksw_b200_batch_upload.argtypes = [vp, vp, i64, vp, vp, vp, C.POINTER(vp)]
     lib.ksw_b200_batch_run.argtypes = [vp, vp]
     lib.ksw_b200_batch_run_timed.argtypes = [vp, vp, i32, vp]
+    lib.ksw_b200_batch_run_timed2.argtypes = [vp, vp, i32, vp, vp]
     lib.ksw_b200_batch_download.argtypes = [vp, vp, vp]
     lib.ksw_b200_batch_download_cells.argtypes = [vp, vp, vp]
     lib.ksw_b200_ctx_last_transfer.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
@@ -314,6 +315,14 @@ class KswB200:
         self._check(self.lib.ksw_b200_batch_run_timed(self.ctx, batch.handle, iters, _p(ms)),
                     "ksw_b200_batch_run_timed")
         return ms
+
+    def run_timed2(self, batch: ResidentBatch, iters: int):
+        """(ms per step, ms of the extension kernels alone per step)"""
+        ms = np.zeros(iters, dtype=np.float32)
+        ext = np.zeros(iters, dtype=np.float32)
+        self._check(self.lib.ksw_b200_batch_run_timed2(self.ctx, batch.handle, iters, _p(ms), _p(ext)),
+                    "ksw_b200_batch_run_timed2")
+        return ms, ext
 
     def download(self, batch: ResidentBatch) -> np.ndarray:
         res = np.zeros(batch.n, dtype=RES_DT)

@@ -163,6 +163,9 @@ int ksw_b200_batch_run(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b);
 /* run `iters` times, each bracketed by CUDA events on the ctx stream; ms[i] = device time of run i.  A run is everything
  * the GPU does for a packed batch: the binning (key kernel + radix sort) and the extension kernels */
 int ksw_b200_batch_run_timed(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms);
+/* the same, and ms_ext[i] (if not NULL) = the part of run i spent in the extension kernels alone (an event between the
+ * binning and the first extension launch): the launch duration the roofline figure of the benchmark divides by */
+int ksw_b200_batch_run_timed2(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, int iters, float *ms, float *ms_ext);
 /* wait for the stream and copy results (caller's job order) to host */
 int ksw_b200_batch_download(ksw_b200_ctx_t *ctx, ksw_b200_batch_t *b, ksw_b200_res_t *res);
 /* visited DP cells per job (caller's order): sum over the rows the reference loop executes of

@@ -320,6 +320,7 @@ def load_global_golden():
 # ------------------------------------------------------------------ CPU emulation of the fast kernel source
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(EMU_DIR, "libfast_emu.so")
+EMU_SO = os.environ.get("KSW_EMU_SO", EMU_SO)
 
 
 def emu_lib():
