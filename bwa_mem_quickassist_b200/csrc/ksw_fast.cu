@@ -131,7 +131,7 @@ template <bool KEYED>
 static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                                  const KswParams &P, int qmax, int sm_count, unsigned long long *counter,
                                  const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st,
-                                 const uint32_t *drange, int c_lo, int c_hi)
+                                 const uint32_t *drange, int c_lo, int c_hi, int ctas_cap)
 {
 	const size_t smem = ksw_fast_smem_bytes(qmax);
 	// The dynamic shared-memory ceiling of the kernel is raised ONCE per device to the opt-in maximum and never lowered:
@@ -153,6 +153,8 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksw_fast_kernel<KEYED>, T, smem);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	if (ctas_cap > 0 && ctas_cap < per_sm) per_sm = ctas_cap;
+	else if (ctas_cap < 0 && per_sm + ctas_cap >= 6) per_sm += ctas_cap;      // leave -ctas_cap CTAs' worth of room per SM
 	if (const char *ev = getenv("KSW_B200_FAST_CTAS")) per_sm = atoi(ev) > 0 && atoi(ev) < per_sm ? atoi(ev) : per_sm;   // tuning knob
 	long long blocks = (long long)sm_count * per_sm;
 	const long long need = (n_jobs + T - 1) / T;
@@ -173,9 +175,9 @@ static cudaError_t launch_fast_t(const DevJob *jobs, int64_t n_jobs, const uint3
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter,
                             const uint32_t *order, DevRes *res, uint32_t *cells, cudaStream_t st,
-                            const uint32_t *drange, int c_lo, int c_hi)
+                            const uint32_t *drange, int c_lo, int c_hi, int ctas_per_sm_cap)
 {
 	if (n_jobs <= 0) return cudaSuccess;
-	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st, drange, c_lo, c_hi)
-	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st, drange, c_lo, c_hi);
+	return keyed ? launch_fast_t<true>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st, drange, c_lo, c_hi, ctas_per_sm_cap)
+	             : launch_fast_t<false>(jobs, n_jobs, pool, npool, P, qmax, sm_count, counter, order, res, cells, st, drange, c_lo, c_hi, ctas_per_sm_cap);
 }

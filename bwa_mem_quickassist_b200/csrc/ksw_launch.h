@@ -31,11 +31,13 @@ cudaError_t ksw_launch_dpx_peak(int which, unsigned *out, int n_blocks, int iter
 
 // fast s16x2 kernel over the jobs jobs[order[0..n_jobs)] whose qlen <= qmax; keyed: every job satisfies the class-0 bounds of
 // ksw_class.h; counter: one device uint64 scratch word.  drange != nullptr (device-packed batches): the launch covers
-// order[drange[c_lo] .. drange[c_hi]) instead, n_jobs is only the host's upper bound of that count
+// order[drange[c_lo] .. drange[c_hi]) instead, n_jobs is only the host's upper bound of that count.  ctas_per_sm_cap > 0:
+// at most that many CTAs per SM; < 0: that many fewer than fit, if at least six remain (the pinned-caller pipeline leaves
+// room for the next chunks' packing / binning kernels)
 cudaError_t ksw_launch_fast(const DevJob *jobs, int64_t n_jobs, const uint32_t *pool, const uint32_t *npool,
                             const KswParams &P, int qmax, bool keyed, int sm_count, unsigned long long *counter, const uint32_t *order,
                             DevRes *res, uint32_t *cells, cudaStream_t st,
-                            const uint32_t *drange = nullptr, int c_lo = 0, int c_hi = 0);
+                            const uint32_t *drange = nullptr, int c_lo = 0, int c_hi = 0, int ctas_per_sm_cap = 0);
 size_t ksw_fast_smem_bytes(int qmax);
 
 // pair kernel (two jobs per lane, ksw_pair.cu) over the class-0 jobs jobs[order[0..n_jobs)]: qlen <= qmax <= 124, biased

@@ -168,6 +168,13 @@ struct ksw_b200_ctx {
 	int hybrid = 1;                        // a second lane packs chunks on the host threads (KSW_B200_HYBRID=0: device packing only)
 	Slot hslot[KSW_N_HSLOTS];                         // that lane's staging / device buffers (events only; it uses the shared streams)
 	int n_hslots = 3;                                 // how many of them it cycles through (KSW_B200_HSLOTS)
+	// The extension kernel's CTAs per SM in this pipeline: negative = that many fewer than fit.  The launches of the chunks
+	// run while the next chunks are packed and binned; beside 13 extension CTAs an SM has room for ONE more CTA (1 KB of
+	// shared memory, 22 k registers), the packing / binning chain of a chunk then takes as long as the chunk's extension
+	// kernel, ends when that kernel's CTAs start to leave, and the next launch is never ready to fill the half-empty last
+	// wave.  Two CTAs fewer: 40.2 -> 38.2 ms per 10 M config-2 jobs (13: 40.2, 12: 39.6, 11: 38.2, 10: 38.6, 9: 39.0,
+	// 8: 39.8; profiles/r2_e2e_knobs_sweep.txt).  KSW_B200_ASYNC_CTAS=<n> sets an absolute number, 0 = as many as fit.
+	int async_fast_ctas = -2;
 	cudaStream_t hup_stream = nullptr;                // the host lane's own upload stream (KSW_B200_HUP=1; default: up_stream)
 	int hup = 0;
 	std::vector<int64_t> lead_jobs;                   // sizes of the call's first chunks (KSW_B200_LEAD=a,b,..; default chunk/4, chunk/2)
@@ -341,7 +348,7 @@ int ensure_generic_scratch(ksw_b200_ctx *ctx, Slot &s, int qmax, int &n_blocks)
 // Device-packed batches (b->dev_ranges): the class sizes are upper bounds (a class-0 job that holds an N has moved to
 // class 1 on the device), so class 1 counts as populated whenever class 0 is, and every launch takes its bounds from
 // b->d_range.
-int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t st = nullptr)
+int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t st = nullptr, int fast_ctas_cap = 0)
 {
 	if (!st) st = s.stream;
 	int64_t cn[KSW_FAST_CLASSES];
@@ -393,7 +400,7 @@ int enqueue_kernels(ksw_b200_ctx *ctx, Slot &s, ksw_b200_batch *b, cudaStream_t 
 		CU(ksw_launch_fast((const DevJob *)b->d_jobs.p, n_grp, (const uint32_t *)b->d_pool.p,
 		                   (const uint32_t *)b->d_npool.p, b->P, qmax, keyed, ctx->sm_count,
 		                   (unsigned long long *)s.d_counter.p + c, (const uint32_t *)b->d_order.p + (drange ? 0 : first),
-		                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, st, drange, c, e));
+		                   (DevRes *)b->d_res.p, (uint32_t *)b->d_cells.p, st, drange, c, e, fast_ctas_cap));
 		ctx->launches++;
 		first += n_grp;
 		c = e;
@@ -518,6 +525,7 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	if (const char *s = getenv("KSW_B200_HYBRID")) ctx->hybrid = atoi(s);
 	if (const char *s = getenv("KSW_B200_HSLOTS")) ctx->n_hslots = std::max(1, std::min(KSW_N_HSLOTS, atoi(s)));
 	if (const char *s = getenv("KSW_B200_HUP")) ctx->hup = atoi(s);
+	if (const char *s = getenv("KSW_B200_ASYNC_CTAS")) ctx->async_fast_ctas = atoi(s);
 	if (const char *s = getenv("KSW_B200_LEAD")) {
 		for (const char *p = s; *p;) {
 			char *end = nullptr;
@@ -827,7 +835,7 @@ static int devpack_finish_chunk(ksw_b200_ctx_t *ctx, Slot &s, int64_t first, int
                                 cudaStream_t down, ChunkTimes *tm = nullptr)
 {
 	if (tm) { cudaEventCreate(&tm->k0); cudaEventCreate(&tm->k1); cudaEventCreate(&tm->done); cudaEventRecord(tm->k0, lane); }
-	int rc = enqueue_kernels(ctx, s, &s.batch, lane);
+	int rc = enqueue_kernels(ctx, s, &s.batch, lane, ctx->async_fast_ctas);
 	if (rc) return rc;
 	if (tm) cudaEventRecord(tm->k1, lane);
 	CU(cudaEventRecord(s.ev_ext, lane));
