@@ -498,7 +498,15 @@ int ksw_b200_ctx_create(int device, ksw_b200_ctx_t **out)
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->hdown_stream, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking);
+	{
+		// KSW_B200_PRE_PRIO=1 (A/B knob): the packing / binning stream at the highest priority, so that its CTAs are placed
+		// before the next extension launch's when an SM frees up
+		int lo = 0, hi = 0;
+		const char *pp = getenv("KSW_B200_PRE_PRIO");
+		if (e == cudaSuccess && pp && atoi(pp) && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess)
+			e = cudaStreamCreateWithPriority(&ctx->pre_stream, cudaStreamNonBlocking, hi);
+		else if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking);
+	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ext2_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->hup_stream, cudaStreamNonBlocking);

@@ -23,17 +23,13 @@ ctx.close()
 print(f"resident kernels: {ms[1:].mean():.2f} ms", flush=True)
 pj, pq, pt = B.pinned_copy(jobs), B.pinned_copy(qpool), B.pinned_copy(tpool)
 pr = B.PinnedArray(n, B.RES_DT)
-KEYS = ("KSW_B200_ASYNC_CTAS", "KSW_B200_FAST_CTAS", "KSW_B200_BLOCKSYNC", "KSW_B200_HSLOTS", "KSW_B200_HUP", "KSW_B200_CHUNK", "KSW_B200_LEAD", "KSW_B200_HYBRID", "KSW_B200_PACK_WORDS")
+KEYS = ("KSW_B200_PRE_PRIO", "KSW_B200_ASYNC_CTAS", "KSW_B200_FAST_CTAS", "KSW_B200_BLOCKSYNC", "KSW_B200_HSLOTS", "KSW_B200_HUP", "KSW_B200_CHUNK", "KSW_B200_LEAD", "KSW_B200_HYBRID", "KSW_B200_PACK_WORDS")
 SETTINGS = [
     {},
-    {"KSW_B200_ASYNC_CTAS": "11"},
-    {"KSW_B200_ASYNC_CTAS": "10"},
-    {"KSW_B200_ASYNC_CTAS": "9"},
-    {"KSW_B200_ASYNC_CTAS": "8"},
-    {"KSW_B200_ASYNC_CTAS": "11", "KSW_B200_CHUNK": "524288"},
-    {"KSW_B200_ASYNC_CTAS": "10", "KSW_B200_CHUNK": "524288"},
-    {"KSW_B200_ASYNC_CTAS": "10", "KSW_B200_CHUNK": "393216"},
-    {"KSW_B200_ASYNC_CTAS": "10", "KSW_B200_HSLOTS": "5"},
+    {"KSW_B200_PRE_PRIO": "1"},
+    {"KSW_B200_PRE_PRIO": "1", "KSW_B200_ASYNC_CTAS": "12"},
+    {"KSW_B200_PRE_PRIO": "1", "KSW_B200_ASYNC_CTAS": "0"},
+    {"KSW_B200_ASYNC_CTAS": "0"},
     {},
 ]
 if len(sys.argv) > 3:
