@@ -62,35 +62,49 @@ ksw_bin_hist_kernel(const DevJob *__restrict__ jobs, long long n, uint16_t *__re
 
 #define KSW_BIN_SCAN_THREADS 512
 #define KSW_BIN_KEYS 65536
+// Exclusive scan of the 65536-entry histogram by ONE block without shared memory.  Each of the 16 warps owns 4096
+// consecutive keys and walks them 32 at a time, lane l on key base + 32 * step + l: every load and store of a warp is one
+// 128-byte line (the first form of this kernel gave each thread 128 consecutive keys: 32 lines per warp access, 0.11 ms —
+// the longest kernel of a chunk's packing / binning chain, which sits on the critical path of the pinned-caller pipeline).
 __global__ void __launch_bounds__(KSW_BIN_SCAN_THREADS)
 ksw_bin_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ cursor, uint32_t *__restrict__ scratch,
                     uint32_t *__restrict__ range, long long n)
 {
-	constexpr int PER = KSW_BIN_KEYS / KSW_BIN_SCAN_THREADS;        // 128 consecutive keys per thread
+	constexpr int WARPS = KSW_BIN_SCAN_THREADS / 32;                // 16
+	constexpr int PER_WARP = KSW_BIN_KEYS / WARPS;                  // 4096 keys per warp
+	constexpr int STEPS = PER_WARP / 32;                            // 128
 	const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-	const uint32_t *h = hist + (size_t)t * PER;
+	const uint32_t *h = hist + (size_t)wid * PER_WARP + lane;
+	// pass 1: the warp's total
 	uint32_t sum = 0;
-	for (int i = 0; i < PER; ++i) sum += h[i];
-	uint32_t incl = sum;
-	for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-	if (lane == 31) scratch[wid] = incl;                            // warp totals through global memory: no shared memory here
+#pragma unroll 8
+	for (int i = 0; i < STEPS; ++i) sum += h[i * 32];
+	for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+	if (lane == 0) scratch[wid] = sum;                              // warp totals through global memory: no shared memory here
 	__threadfence_block();
 	__syncthreads();
 	if (wid == 0) {
-		uint32_t w = lane < KSW_BIN_SCAN_THREADS / 32 ? scratch[lane] : 0u, wi = w;
+		uint32_t w = lane < WARPS ? scratch[lane] : 0u, wi = w;
 		for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-		if (lane < KSW_BIN_SCAN_THREADS / 32) scratch[32 + lane] = wi - w;
+		if (lane < WARPS) scratch[32 + lane] = wi - w;
 	}
 	__threadfence_block();
 	__syncthreads();
-	uint32_t run = scratch[32 + wid] + incl - sum;                  // keys before this thread's first key
-	uint32_t *c = cursor + (size_t)t * PER;
-	for (int i = 0; i < PER; ++i) {
-		const uint32_t key = (uint32_t)t * PER + i;
-		// the first entry of every kernel class in the binned order (class bounds sit on multiples of 0x2000 / 0x4000)
-		for (int cl = 0; cl < KSW_N_CLASSES; ++cl) if (key == ksw_class_lowest_key(cl)) range[cl] = run;
-		c[i] = run;
-		run += h[i];
+	// pass 2: exclusive prefix of every key; the first entry of every kernel class in the binned order (class bounds sit on
+	// multiples of 0x2000 / 0x4000)
+	uint32_t run = scratch[32 + wid];                               // keys before this warp's first key
+	uint32_t *c = cursor + (size_t)wid * PER_WARP + lane;
+#pragma unroll 4
+	for (int i = 0; i < STEPS; ++i) {
+		const uint32_t v = h[i * 32];
+		uint32_t incl = v;
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+		const uint32_t excl = run + incl - v;
+		c[i * 32] = excl;
+		const uint32_t key = (uint32_t)(wid * PER_WARP + i * 32 + lane);
+		if ((key & 0x1fffu) == 0u)
+			for (int cl = 0; cl < KSW_N_CLASSES; ++cl) if (key == ksw_class_lowest_key(cl)) range[cl] = excl;
+		run += __shfl_sync(0xffffffffu, incl, 31);
 	}
 	if (t == 0) range[KSW_N_CLASSES] = (uint32_t)n;
 }

@@ -26,9 +26,7 @@ pr = B.PinnedArray(n, B.RES_DT)
 KEYS = ("KSW_B200_PRE_PRIO", "KSW_B200_ASYNC_CTAS", "KSW_B200_FAST_CTAS", "KSW_B200_BLOCKSYNC", "KSW_B200_HSLOTS", "KSW_B200_HUP", "KSW_B200_CHUNK", "KSW_B200_LEAD", "KSW_B200_HYBRID", "KSW_B200_PACK_WORDS")
 SETTINGS = [
     {},
-    {"KSW_B200_PRE_PRIO": "1"},
-    {"KSW_B200_PRE_PRIO": "1", "KSW_B200_ASYNC_CTAS": "12"},
-    {"KSW_B200_PRE_PRIO": "1", "KSW_B200_ASYNC_CTAS": "0"},
+    {"KSW_B200_ASYNC_CTAS": "12"},
     {"KSW_B200_ASYNC_CTAS": "0"},
     {},
 ]
