@@ -28,6 +28,8 @@ SETTINGS = [
     {},
     {"KSW_B200_ASYNC_CTAS": "12"},
     {"KSW_B200_ASYNC_CTAS": "0"},
+    {"KSW_B200_CHUNK": "524288"},
+    {"KSW_B200_HYBRID": "0"},
     {},
 ]
 if len(sys.argv) > 3:
