@@ -5,6 +5,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 int ksw_pack_force_words = 0;
 
@@ -26,7 +29,6 @@ void parallel_ranges(KswPool *pool, int64_t n, F &&fn)
 }
 
 #if defined(__x86_64__) && defined(__GNUC__)
-#include <emmintrin.h>
 // The packed records go to pinned staging that the CPU never reads again: non-temporal 16-byte stores skip the
 // read-for-ownership of every destination line (a quarter of the packer's memory traffic).
 inline void stream16(void *dst, const void *src) { _mm_stream_si128((__m128i *)dst, _mm_loadu_si128((const __m128i *)src)); }
@@ -106,7 +108,6 @@ inline bool pack2_words(const uint8_t *s, int len, uint32_t *out, uint32_t *nmas
 }
 
 #ifdef KSW_HAVE_PEXT
-#include <immintrin.h>
 // 64 byte codes per step: two multiply-adds fold four codes into one byte (c0 + 4 c1, then + 16 (c2 + 4 c3)), a narrowing
 // move gathers the sixteen bytes = four words of the 2-bit stream.  Bytes past the end are never touched (masked load)
 // and pack as 0.  WRITES WHOLE 16-BYTE GROUPS: up to three words past ceil(len/16) are zeroed (the caller's line buffer
